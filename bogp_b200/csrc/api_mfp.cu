@@ -1,0 +1,357 @@
+// C-ABI entry points of Boundary A (matched-field objective): set-up and dispatch.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "bogp_internal.h"
+
+using bogp::cplx;
+
+namespace {
+
+template <typename T>
+int upload(bogp_modeset_s* h, std::vector<void*>& owner, const std::vector<T>& v, const T** out) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  BOGP_CUDA(cudaMalloc(&p, bytes));
+  owner.push_back(p);
+  if (!v.empty()) BOGP_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<const T*>(p);
+  (void)h;
+  return 0;
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    bogp::set_error("no CUDA device available (%s); libbogp_sm100 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return BOGP_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace
+
+namespace bogp {
+int ensure_scratch(bogp_modeset_s* h, size_t bytes) {
+  if (h->grid_scratch_bytes >= bytes) return 0;
+  if (h->grid_scratch) cudaFree(h->grid_scratch);
+  h->grid_scratch = nullptr;
+  h->grid_scratch_bytes = 0;
+  BOGP_CUDA(cudaMalloc(&h->grid_scratch, bytes));
+  h->grid_scratch_bytes = bytes;
+  return 0;
+}
+}  // namespace bogp
+
+extern "C" int bogp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  if (int rc = require_device()) return rc;
+  int dev = 0;
+  BOGP_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  BOGP_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return 0;
+}
+
+extern "C" int bogp_modeset_create(bogp_modeset_t* out, int F, int N, const int* M_host,
+                                   const double* k_re_host, const double* k_im_host,
+                                   const double* phi_rec_re_host, const double* phi_rec_im_host,
+                                   int nz_tab, double z0, double dz, const double* phi_src_re_host,
+                                   const double* phi_src_im_host, const double* rec_z_host,
+                                   double z_pivot) {
+  BOGP_REQUIRE(out != nullptr, "bogp_modeset_create: out is NULL");
+  *out = nullptr;
+  BOGP_REQUIRE(F >= 1 && F <= BOGP_MAX_TONALS, "bogp_modeset_create: F=%d outside [1,%d]", F, BOGP_MAX_TONALS);
+  BOGP_REQUIRE(N >= 1 && N <= 1024, "bogp_modeset_create: N=%d outside [1,1024]", N);
+  BOGP_REQUIRE(nz_tab >= 2 && dz > 0.0, "bogp_modeset_create: need nz_tab>=2 and dz>0");
+  BOGP_REQUIRE(M_host && k_re_host && k_im_host && phi_rec_re_host && phi_src_re_host && rec_z_host,
+               "bogp_modeset_create: NULL input");
+  for (int f = 0; f < F; ++f)
+    BOGP_REQUIRE(M_host[f] >= 1 && M_host[f] <= 512, "bogp_modeset_create: M[%d]=%d outside [1,512]", f, M_host[f]);
+  if (int rc = require_device()) return rc;
+
+  bogp_modeset_s* h = new bogp_modeset_s();
+  bogp::ModesetDev& d = h->dev;
+  std::memset(&d, 0, sizeof(d));
+  d.F = F; d.N = N; d.nz_tab = nz_tab; d.z0 = z0; d.dz = dz; d.z_pivot = z_pivot;
+  d.src_complex = phi_src_im_host != nullptr;
+  d.rec_complex = phi_rec_im_host != nullptr;
+  h->F = F; h->N = N;
+  h->M.assign(M_host, M_host + F);
+  h->phi_rec.resize(F);
+
+  int sumMp = 0, sumTab = 0, sumRec = 0;
+  for (int f = 0; f < F; ++f) {
+    bogp::TonalMeta& t = d.t[f];
+    t.M = M_host[f];
+    t.Mp = bogp::pad_to(t.M, 8);
+    t.offM = sumMp; t.offTab = sumTab; t.offRec = sumRec;
+    sumMp += t.Mp; sumTab += nz_tab * t.Mp; sumRec += N * t.Mp;
+    h->max_Mp = std::max(h->max_Mp, t.Mp);
+  }
+  std::vector<double> kre(sumMp, 1.0), kim(sumMp, 0.0);
+  std::vector<float> cre(sumMp, 0.f), cim(sumMp, 0.f);
+  std::vector<float> tab_re(sumTab, 0.f), tab_im(d.src_complex ? sumTab : 0, 0.f);
+  std::vector<float> rec_re(sumRec, 0.f), rec_im(d.rec_complex ? sumRec : 0, 0.f);
+  std::vector<float> recT_re(sumRec, 0.f), recT_im(d.rec_complex ? sumRec : 0, 0.f);
+  std::vector<float> lever(N);
+  for (int n = 0; n < N; ++n) lever[n] = (float)(z_pivot - rec_z_host[n]);
+
+  size_t ik = 0, irec = 0, isrc = 0;
+  for (int f = 0; f < F; ++f) {
+    const bogp::TonalMeta& t = d.t[f];
+    for (int m = 0; m < t.M; ++m) {
+      kre[t.offM + m] = k_re_host[ik + m];
+      kim[t.offM + m] = k_im_host[ik + m];
+      cplx c = 1.0 / std::sqrt(cplx(k_re_host[ik + m], k_im_host[ik + m]));
+      cre[t.offM + m] = (float)c.real();
+      cim[t.offM + m] = (float)c.imag();
+    }
+    h->phi_rec[f].resize((size_t)N * t.M);
+    for (int n = 0; n < N; ++n)
+      for (int m = 0; m < t.M; ++m) {
+        double re = phi_rec_re_host[irec + (size_t)n * t.M + m];
+        double im = d.rec_complex ? phi_rec_im_host[irec + (size_t)n * t.M + m] : 0.0;
+        h->phi_rec[f][(size_t)n * t.M + m] = cplx(re, im);
+        rec_re[t.offRec + (size_t)n * t.Mp + m] = (float)re;
+        if (d.rec_complex) rec_im[t.offRec + (size_t)n * t.Mp + m] = (float)im;
+        recT_re[t.offRec + (size_t)m * N + n] = (float)re;
+        if (d.rec_complex) recT_im[t.offRec + (size_t)m * N + n] = (float)im;
+      }
+    for (int i = 0; i < nz_tab; ++i)
+      for (int m = 0; m < t.M; ++m) {
+        tab_re[t.offTab + (size_t)i * t.Mp + m] = (float)phi_src_re_host[isrc + (size_t)i * t.M + m];
+        if (d.src_complex) tab_im[t.offTab + (size_t)i * t.Mp + m] = (float)phi_src_im_host[isrc + (size_t)i * t.M + m];
+      }
+    ik += t.M; irec += (size_t)N * t.M; isrc += (size_t)nz_tab * t.M;
+  }
+  int rc = 0;
+  rc |= upload(h, h->allocs, kre, &d.k_re);
+  rc |= upload(h, h->allocs, kim, &d.k_im);
+  rc |= upload(h, h->allocs, cre, &d.c_re);
+  rc |= upload(h, h->allocs, cim, &d.c_im);
+  rc |= upload(h, h->allocs, tab_re, &d.tab_re);
+  if (d.src_complex) rc |= upload(h, h->allocs, tab_im, &d.tab_im);
+  rc |= upload(h, h->allocs, rec_re, &d.rec_re);
+  if (d.rec_complex) rc |= upload(h, h->allocs, rec_im, &d.rec_im);
+  rc |= upload(h, h->allocs, recT_re, &d.recT_re);
+  if (d.rec_complex) rc |= upload(h, h->allocs, recT_im, &d.recT_im);
+  rc |= upload(h, h->allocs, lever, &d.rec_lever);
+  if (rc) { bogp_modeset_destroy(h); return BOGP_ERR_CUDA; }
+  *out = h;
+  return 0;
+}
+
+extern "C" int bogp_modeset_destroy(bogp_modeset_t h) {
+  if (!h) return 0;
+  for (void* p : h->allocs) cudaFree(p);
+  for (void* p : h->cov_allocs) cudaFree(p);
+  if (h->grid_scratch) cudaFree(h->grid_scratch);
+  delete h;
+  return 0;
+}
+
+extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, const double* K_im_host) {
+  BOGP_REQUIRE(h && K_re_host && K_im_host, "bogp_covariance_set: NULL argument");
+  const int F = h->F, N = h->N;
+  bogp::ModesetDev& d = h->dev;
+  const double tol = 1e-13;
+  std::vector<float> W, Wt, Ckre, Ckim;
+  h->max_rows = 0; h->max_J = 0;
+  for (int f = 0; f < F; ++f) {
+    bogp::TonalMeta& t = d.t[f];
+    const int M = t.M;
+    const std::vector<cplx>& Phi = h->phi_rec[f];   // [N, M]
+    // Hermitian part of K_f (the processor takes Re(w^H K w), which only sees (K + K^H)/2).
+    std::vector<cplx> K((size_t)N * N);
+    double trK = 0.0;
+    for (int a = 0; a < N; ++a)
+      for (int b = 0; b < N; ++b) {
+        size_t ab = (size_t)f * N * N + (size_t)a * N + b, ba = (size_t)f * N * N + (size_t)b * N + a;
+        K[(size_t)a * N + b] = 0.5 * (cplx(K_re_host[ab], K_im_host[ab]) + std::conj(cplx(K_re_host[ba], K_im_host[ba])));
+      }
+    for (int a = 0; a < N; ++a) trK += K[(size_t)a * N + a].real();
+    t.trK = (float)trK;
+    // G = Phi^H Phi, KP = K Phi, H = Phi^H K Phi   (all [M, M] / [N, M])
+    std::vector<cplx> G((size_t)M * M), KP((size_t)N * M), H((size_t)M * M);
+    for (int a = 0; a < M; ++a)
+      for (int b = a; b < M; ++b) {
+        cplx s = 0.0;
+        for (int n = 0; n < N; ++n) s += std::conj(Phi[(size_t)n * M + a]) * Phi[(size_t)n * M + b];
+        G[(size_t)a * M + b] = s;
+        G[(size_t)b * M + a] = std::conj(s);
+      }
+    for (int n = 0; n < N; ++n)
+      for (int m = 0; m < M; ++m) {
+        cplx s = 0.0;
+        for (int q = 0; q < N; ++q) s += K[(size_t)n * N + q] * Phi[(size_t)q * M + m];
+        KP[(size_t)n * M + m] = s;
+      }
+    for (int a = 0; a < M; ++a)
+      for (int b = a; b < M; ++b) {
+        cplx s = 0.0;
+        for (int n = 0; n < N; ++n) s += std::conj(Phi[(size_t)n * M + a]) * KP[(size_t)n * M + b];
+        H[(size_t)a * M + b] = s;
+        H[(size_t)b * M + a] = std::conj(s);
+      }
+    for (int a = 0; a < M; ++a) { G[(size_t)a * M + a] = G[(size_t)a * M + a].real(); H[(size_t)a * M + a] = H[(size_t)a * M + a].real(); }
+    std::vector<cplx> LG, LH, LK;
+    int rG = 0, rH = 0, rK = 0;
+    bogp::pivoted_cholesky(G, M, tol, LG, rG);
+    bogp::pivoted_cholesky(H, M, tol, LH, rH);
+    bogp::pivoted_cholesky(K, N, tol, LK, rK);
+    // Mode-space operator W: rows = R = LG^H (rG x M) then C = LH^H (rH x M); T = W a.
+    t.n_plain = d.rec_complex ? 0 : rG;
+    t.n_npair = d.rec_complex ? rG : 0;
+    t.n_qpair = rH;
+    t.rows = t.n_plain + 2 * t.n_npair + 2 * t.n_qpair;
+    t.offW = (int)W.size();
+    W.resize(W.size() + (size_t)t.rows * t.Mp, 0.f);
+    float* Wf = &W[t.offW];
+    int row = 0;
+    // R[j, m] = conj(LG[m, j])
+    if (!d.rec_complex) {
+      for (int j = 0; j < rG; ++j, ++row)
+        for (int m = 0; m < M; ++m) Wf[(size_t)row * t.Mp + m] = (float)LG[(size_t)m * M + j].real();
+    } else {
+      for (int j = 0; j < rG; ++j, ++row)
+        for (int m = 0; m < M; ++m) Wf[(size_t)row * t.Mp + m] = (float)LG[(size_t)m * M + j].real();
+      for (int j = 0; j < rG; ++j, ++row)
+        for (int m = 0; m < M; ++m) Wf[(size_t)row * t.Mp + m] = (float)(-LG[(size_t)m * M + j].imag());
+    }
+    for (int j = 0; j < rH; ++j, ++row)
+      for (int m = 0; m < M; ++m) Wf[(size_t)row * t.Mp + m] = (float)LH[(size_t)m * M + j].real();
+    for (int j = 0; j < rH; ++j, ++row)
+      for (int m = 0; m < M; ++m) Wf[(size_t)row * t.Mp + m] = (float)(-LH[(size_t)m * M + j].imag());
+    t.rowsP = bogp::pad_to(std::max(t.rows, 1), 32);
+    t.offWt = (int)Wt.size();
+    Wt.resize(Wt.size() + (size_t)t.Mp * t.rowsP, 0.f);
+    for (int r2 = 0; r2 < t.rows; ++r2)
+      for (int m = 0; m < M; ++m) Wt[t.offWt + (size_t)m * t.rowsP + r2] = Wf[(size_t)r2 * t.Mp + m];
+    // Receiver-space factor: num = || LK^H p ||^2 ; Ck[j, n] = conj(LK[n, j]); stored transposed [N][J]
+    t.J = rK;
+    t.offC = (int)Ckre.size();
+    for (int n = 0; n < N; ++n)
+      for (int j = 0; j < rK; ++j) {
+        Ckre.push_back((float)LK[(size_t)n * N + j].real());
+        Ckim.push_back((float)(-LK[(size_t)n * N + j].imag()));
+      }
+    h->max_rows = std::max(h->max_rows, t.rows);
+    h->max_J = std::max(h->max_J, t.J);
+  }
+  for (void* p : h->cov_allocs) cudaFree(p);
+  h->cov_allocs.clear();
+  int rc = 0;
+  rc |= upload(h, h->cov_allocs, W, &d.W);
+  rc |= upload(h, h->cov_allocs, Wt, &d.Wt);
+  rc |= upload(h, h->cov_allocs, Ckre, &d.CkT_re);
+  rc |= upload(h, h->cov_allocs, Ckim, &d.CkT_im);
+  if (rc) return BOGP_ERR_CUDA;
+  h->has_cov = true;
+  return 0;
+}
+
+static int check_modes(int atype, int mf) {
+  BOGP_REQUIRE(atype == BOGP_ATYPE_CBF || atype == BOGP_ATYPE_CBF_ML, "unknown atype %d", atype);
+  BOGP_REQUIRE(mf == BOGP_MF_MEAN || mf == BOGP_MF_PRODUCT, "unknown multifreq method %d", mf);
+  return 0;
+}
+
+extern "C" int bogp_bartlett_grid(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                                  const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                                  float* out_dev, void* stream) {
+  BOGP_REQUIRE(h && r_m_host && z_host && out_dev, "bogp_bartlett_grid: NULL argument");
+  BOGP_REQUIRE(h->has_cov, "bogp_bartlett_grid: call bogp_covariance_set first");
+  BOGP_REQUIRE(Nr >= 0 && Nz >= 0 && Nt >= 1, "bogp_bartlett_grid: bad sizes Nr=%d Nz=%d Nt=%d", Nr, Nz, Nt);
+  if (int rc = check_modes(atype, mf_method)) return rc;
+  if (Nr == 0 || Nz == 0) return 0;
+  for (int i = 0; i < Nr; ++i) BOGP_REQUIRE(r_m_host[i] > 0.0, "bogp_bartlett_grid: range[%d]=%g must be > 0", i, r_m_host[i]);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bool tilted = false;
+  if (tilt_deg_host)
+    for (int i = 0; i < Nt; ++i) tilted |= (tilt_deg_host[i] != 0.0);
+  else
+    BOGP_REQUIRE(Nt == 1, "bogp_bartlett_grid: Nt must be 1 when tilt is NULL");
+  if (engine == BOGP_ENGINE_UMMA) {
+    BOGP_REQUIRE(!tilted && Nt == 1, "bogp_bartlett_grid: the UMMA engine covers the vertical-array grid only");
+    if (!bogp::umma_supported(h)) { bogp::set_error("UMMA engine unsupported for this mode set / device"); return BOGP_ERR_UNSUPPORTED; }
+    return bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s);
+  }
+  if (engine == BOGP_ENGINE_AUTO && !tilted && Nt == 1 && bogp::umma_supported(h) && (long long)Nr * Nz >= 16384)
+    return bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s);
+  return bogp::launch_grid_simt(h, r_m_host, Nr, z_host, Nz, tilted ? tilt_deg_host : nullptr, Nt, atype, mf_method, out_dev, s);
+}
+
+extern "C" int bogp_bartlett_grid_host(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                                       const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                                       float* out_host, void* stream) {
+  BOGP_REQUIRE(out_host != nullptr, "bogp_bartlett_grid_host: out is NULL");
+  size_t n = (size_t)std::max(Nt, 1) * Nz * Nr;
+  if (n == 0) return 0;
+  float* tmp = nullptr;
+  BOGP_CUDA(cudaMalloc(&tmp, n * sizeof(float)));
+  int rc = bogp_bartlett_grid(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, tmp, stream);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) { bogp::set_error("bogp_bartlett_grid_host: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
+  }
+  cudaFree(tmp);
+  return rc;
+}
+
+// any(cand[:,2] != 0) on the device, so the tilt-free fast path is chosen without a host copy of cand.
+__global__ void any_tilt_kernel(const double* __restrict__ cand, long long C, int* flag) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  int any = 0;
+  for (; i < C; i += stride) any |= (cand[3 * i + 2] != 0.0);
+  if (__syncthreads_or(any) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+extern "C" int bogp_bartlett_points(bogp_modeset_t h, const double* cand_dev, long long C, int atype, int mf_method,
+                                    float* out_dev, void* stream) {
+  BOGP_REQUIRE(h && (C == 0 || (cand_dev && out_dev)), "bogp_bartlett_points: NULL argument");
+  BOGP_REQUIRE(h->has_cov, "bogp_bartlett_points: call bogp_covariance_set first");
+  BOGP_REQUIRE(C >= 0, "bogp_bartlett_points: C < 0");
+  if (int rc = check_modes(atype, mf_method)) return rc;
+  if (C == 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = bogp::ensure_scratch(h, 256)) return rc;
+  int* flag = static_cast<int*>(h->grid_scratch);
+  BOGP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+  int blocks = (int)std::min<long long>((C + 255) / 256, 1184);
+  any_tilt_kernel<<<blocks, 256, 0, s>>>(cand_dev, C, flag);
+  int any = 0;
+  BOGP_CUDA(cudaMemcpyAsync(&any, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  BOGP_CUDA(cudaStreamSynchronize(s));
+  return bogp::launch_points(h, cand_dev, C, atype, mf_method, any != 0, out_dev, s);
+}
+
+extern "C" int bogp_bartlett_points_host(bogp_modeset_t h, const double* cand_host, long long C, int atype,
+                                         int mf_method, float* out_host, void* stream) {
+  BOGP_REQUIRE(C >= 0 && (C == 0 || (cand_host && out_host)), "bogp_bartlett_points_host: bad argument");
+  if (C == 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  double* cd = nullptr;
+  float* od = nullptr;
+  BOGP_CUDA(cudaMalloc(&cd, (size_t)C * 3 * sizeof(double)));
+  if (cudaMalloc(&od, (size_t)C * sizeof(float)) != cudaSuccess) { cudaFree(cd); bogp::set_error("cudaMalloc failed"); return BOGP_ERR_CUDA; }
+  int rc = 0;
+  cudaError_t e = cudaMemcpyAsync(cd, cand_host, (size_t)C * 3 * sizeof(double), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { bogp::set_error("H2D: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
+  if (!rc) rc = bogp_bartlett_points(h, cd, C, atype, mf_method, od, stream);
+  if (!rc) {
+    e = cudaMemcpyAsync(out_host, od, (size_t)C * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { bogp::set_error("D2H: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
+  }
+  cudaFree(cd);
+  cudaFree(od);
+  return rc;
+}

@@ -1,0 +1,125 @@
+// Internal declarations shared by the translation units of libbogp_sm100.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <complex>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/bogp.h"
+
+namespace bogp {
+
+typedef std::complex<double> cplx;
+
+void set_error(const char* fmt, ...);
+
+#define BOGP_CUDA(call)                                                                      \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      bogp::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call,                  \
+                      cudaGetErrorString(e__));                                              \
+      return BOGP_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+#define BOGP_REQUIRE(cond, ...)                                                              \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      bogp::set_error(__VA_ARGS__);                                                          \
+      return BOGP_ERR_INVALID;                                                               \
+    }                                                                                        \
+  } while (0)
+
+inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------- host linear algebra (float64)
+// Pivoted Cholesky of a Hermitian PSD matrix A[n,n] (row-major): A ~= L L^H, L[n, rank] (row-major,
+// leading dimension n).  Stops when the largest remaining diagonal <= tol * max initial diagonal.
+int pivoted_cholesky(const std::vector<cplx>& A, int n, double tol, std::vector<cplx>& L, int& rank);
+// Dense Cholesky A = L L^T (real SPD, row-major, lower); returns false if not PD.
+bool cholesky_lower(std::vector<double>& A, int n);
+// In-place inverse of a lower-triangular matrix (row-major).
+void invert_lower(std::vector<double>& L, int n);
+
+// ---------------------------------------------------------------- device-side tables of one tonal
+// All per-tonal arrays are concatenated; `off*` give the element offsets.
+struct TonalMeta {
+  int M;         // modes
+  int Mp;        // modes padded to a multiple of 8 (zero-filled)
+  int rows;      // rows of the mode-space operator W
+  int rowsP;     // rows padded to a multiple of 32 (leading dimension of Wt)
+  int n_plain;   // rows [0, n_plain): norm rows, real operator           T = W a
+  int n_npair;   // next 2*n_npair rows: norm rows of a complex operator  T = (Wre + i Wim) a
+  int n_qpair;   // next 2*n_qpair rows: numerator (projection) rows      T = (Cre + i Cim) a
+  int J;         // rank of the receiver-space covariance factor
+  int offM;      // offset into [sum Mp] arrays
+  int offW;      // offset into W (rows * Mp floats)
+  int offWt;     // offset into Wt (Mp * rowsP floats)
+  int offTab;    // offset into phi_src table (nz_tab * Mp)
+  int offRec;    // offset into phi_rec (N * Mp)
+  int offC;      // offset into receiver-space factor (J * N complex)
+  float trK;     // trace of K_f (cbf_ml)
+};
+
+#define BOGP_MAX_TONALS 32
+
+struct ModesetDev {
+  int F, N, nz_tab;
+  double z0, dz, z_pivot;
+  bool src_complex, rec_complex;
+  TonalMeta t[BOGP_MAX_TONALS];
+  // [sum Mp]
+  const double* k_re;
+  const double* k_im;
+  const float* c_re;   // k^{-1/2}
+  const float* c_im;
+  // [sum nz_tab*Mp]
+  const float* tab_re;
+  const float* tab_im;   // null unless src_complex
+  // [sum N*Mp]
+  const float* rec_re;
+  const float* rec_im;   // null unless rec_complex
+  const float* recT_re;  // transposed copies [Mp][N] (coalesced over receivers)
+  const float* recT_im;
+  const float* rec_lever;   // [N]  (z_pivot - z_n)
+  // set by covariance_set
+  const float* W;        // [sum rows*Mp]   row-major (UMMA operand generation)
+  const float* Wt;       // [sum Mp*rowsP]  transposed (SIMT kernels)
+  const float* CkT_re;   // [sum N*J]       receiver-space factor, transposed [N][J]
+  const float* CkT_im;
+};
+
+}  // namespace bogp
+
+struct bogp_modeset_s {
+  bogp::ModesetDev dev;           // device pointers + metadata (passed by value to kernels)
+  std::vector<void*> allocs;      // every cudaMalloc owned by this handle
+  std::vector<void*> cov_allocs;  // allocations replaced at each covariance_set
+  // host copies (float64) kept for covariance_set
+  int F = 0, N = 0;
+  std::vector<int> M;
+  std::vector<std::vector<bogp::cplx>> phi_rec;   // per tonal [N*M]
+  bool has_cov = false;
+  int max_rows = 0, max_Mp = 0, max_J = 0;
+  // scratch for the grid paths (grown on demand)
+  void* grid_scratch = nullptr;
+  size_t grid_scratch_bytes = 0;
+};
+
+namespace bogp {
+// kernels_simt.cu
+int launch_points(const bogp_modeset_s* h, const double* cand_dev, long long C, int atype, int mf, bool any_tilt,
+                  float* out_dev, cudaStream_t s);
+int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz,
+                     const double* tilt_host, int Nt, int atype, int mf, float* out_dev, cudaStream_t s);
+// kernels_umma.cu
+int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype,
+                     int mf, float* out_dev, cudaStream_t s);
+bool umma_supported(const bogp_modeset_s* h);
+int ensure_scratch(bogp_modeset_s* h, size_t bytes);
+}  // namespace bogp

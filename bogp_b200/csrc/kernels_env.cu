@@ -1,0 +1,291 @@
+// Geoacoustic-inversion scoring (config 5): every candidate environment has its own mode set, so
+// nothing is shared between candidates and the kernel is HBM-bound: per (candidate, tonal) it streams
+// Phi_rec^T [Mmax, N] float32 once (4*N*M bytes) plus k and the source amplitudes.
+// Replaces the pool of MatchedFieldProcessor calls of ref/projects/swellex96_inv/data/bo/obj.py:28-30, 73-83.
+// Also: arg-max / arg-min reduction (ref/projects/swellex96_localization/data/collate.py:50).
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+
+#include "bogp_internal.h"
+#include "device_math.cuh"
+
+struct bogp_envbatch_s {
+  long long C = 0;
+  int F = 0, N = 0, Mmax = 0;
+  double *k_re = nullptr, *k_im = nullptr, *range = nullptr;
+  float *amp_re = nullptr, *amp_im = nullptr, *phiT = nullptr;
+  float *CkT_re = nullptr, *CkT_im = nullptr;   // [F][N][Jmax]
+  int* J = nullptr;                             // [F]
+  float* trK = nullptr;                         // [F]
+  int Jmax = 0;
+  bool has_cov = false;
+};
+
+namespace bogp {
+
+constexpr int kEnvWarps = 8;
+
+// One warp per candidate; lanes run over receivers (coalesced rows of Phi^T), modes are broadcast
+// from shared memory.
+__global__ void __launch_bounds__(kEnvWarps * 32)
+envbatch_kernel(long long C, int F, int N, int Mmax, const double* __restrict__ k_re, const double* __restrict__ k_im,
+                const float* __restrict__ amp_re, const float* __restrict__ amp_im, const float* __restrict__ phiT,
+                const double* __restrict__ range, const float* __restrict__ CkT_re, const float* __restrict__ CkT_im,
+                const int* __restrict__ Jf, const float* __restrict__ trK, int Jmax, int atype, int mf,
+                float* __restrict__ out) {
+  extern __shared__ float2 smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* a_s = smem + (size_t)warp * (Mmax + N);
+  float2* p_s = a_s + Mmax;
+  for (long long c = (long long)blockIdx.x * kEnvWarps + warp; c < C; c += (long long)gridDim.x * kEnvWarps) {
+    const double r = range[c];
+    const float rs = (float)rsqrt(r);
+    float acc = 0.f;
+    for (int f = 0; f < F; ++f) {
+      const size_t cf = (size_t)c * F + f;
+      for (int m = lane; m < Mmax; m += 32) {
+        const double kre = k_re[cf * Mmax + m], kim = k_im[cf * Mmax + m];
+        const float ar = amp_re[cf * Mmax + m], ai = amp_im ? amp_im[cf * Mmax + m] : 0.f;
+        float2 a = make_float2(0.f, 0.f);
+        if (ar != 0.f || ai != 0.f) {
+          // k^{-1/2} in float64 (one per mode), propagation with float64 phase reduction
+          const double mag = rsqrt(sqrt(kre * kre + kim * kim)), ang = -0.5 * atan2(kim, kre);
+          double s2, c2;
+          sincos(ang, &s2, &c2);
+          float s, co;
+          sincosf(reduce_phase(kre * r), &s, &co);
+          const float amp = expf((float)(kim * r)) * rs * (float)mag;
+          a = cmul(cmul(make_float2(ar, ai), make_float2((float)c2, (float)s2)), make_float2(amp * co, -amp * s));
+        }
+        a_s[m] = a;
+      }
+      __syncwarp();
+      const float* P = phiT + cf * (size_t)Mmax * N;
+      float norm = 0.f;
+      for (int n = lane; n < N; n += 32) {
+        float pr = 0.f, pi = 0.f;
+#pragma unroll 4
+        for (int m = 0; m < Mmax; ++m) {
+          const float ph = __ldg(P + (size_t)m * N + n);
+          const float2 a = a_s[m];
+          pr = fmaf(ph, a.x, pr);
+          pi = fmaf(ph, a.y, pi);
+        }
+        p_s[n] = make_float2(pr, pi);
+        norm += pr * pr + pi * pi;
+      }
+      __syncwarp();
+      float num = 0.f;
+      const int J = Jf[f];
+      const float* cr = CkT_re + (size_t)f * N * Jmax;
+      const float* ci = CkT_im + (size_t)f * N * Jmax;
+      for (int j = lane; j < J; j += 32) {
+        float sr = 0.f, si = 0.f;
+        for (int n = 0; n < N; ++n) {
+          const float2 p = p_s[n];
+          const float a = __ldg(cr + (size_t)n * Jmax + j), b = __ldg(ci + (size_t)n * Jmax + j);
+          sr += a * p.x - b * p.y;
+          si += a * p.y + b * p.x;
+        }
+        num += sr * sr + si * si;
+      }
+      norm = warp_sum(norm);
+      num = warp_sum(num);
+      __syncwarp();
+      const float b = num / norm;
+      acc = combine_tonal(acc, atype == BOGP_ATYPE_CBF ? b : trK[f] - b, mf, f == 0);
+    }
+    if (lane == 0) out[c] = (mf == BOGP_MF_MEAN) ? acc / (float)F : acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ argmax
+struct ValIdx {
+  float v;
+  long long i;
+};
+
+template <bool MAX>
+__device__ __forceinline__ ValIdx better(ValIdx a, ValIdx b) {
+  // NaNs never win; ties go to the lower index (np.argmax / np.argmin: first occurrence)
+  const bool b_wins = (b.i >= 0) && ((a.i < 0) || (MAX ? b.v > a.v : b.v < a.v) || (b.v == a.v && b.i < a.i));
+  return b_wins ? b : a;
+}
+
+template <bool MAX>
+__device__ __forceinline__ ValIdx block_reduce(ValIdx x) {
+  __shared__ float sv[32];
+  __shared__ long long si[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ValIdx y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    x = better<MAX>(x, y);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[warp] = x.v; si[warp] = x.i; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    x.v = lane < nw ? sv[lane] : 0.f;
+    x.i = lane < nw ? si[lane] : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ValIdx y;
+      y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+      y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+      x = better<MAX>(x, y);
+    }
+  }
+  return x;
+}
+
+template <bool MAX>
+__global__ void argext_stage1(const float* __restrict__ x, long long n, float* __restrict__ pv, long long* __restrict__ pi) {
+  ValIdx best{0.f, -1};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    if (v == v) best = better<MAX>(best, ValIdx{v, i});
+  }
+  best = block_reduce<MAX>(best);
+  if (threadIdx.x == 0) { pv[blockIdx.x] = best.v; pi[blockIdx.x] = best.i; }
+}
+
+template <bool MAX>
+__global__ void argext_stage2(const float* __restrict__ pv, const long long* __restrict__ pi, int nb, float* ov, long long* oi) {
+  ValIdx best{0.f, -1};
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) best = better<MAX>(best, ValIdx{pv[i], pi[i]});
+  best = block_reduce<MAX>(best);
+  if (threadIdx.x == 0) { *ov = best.v; *oi = best.i; }
+}
+
+template <bool MAX>
+static int argext(const float* x_dev, long long n, float* val_host, long long* idx_host, cudaStream_t s) {
+  BOGP_REQUIRE(x_dev && val_host && idx_host && n >= 1, "bogp_arg%s_f32: bad argument", MAX ? "max" : "min");
+  const int nb = (int)std::max<long long>(1, std::min<long long>((n + 1023) / 1024, 592));
+  float* pv = nullptr;
+  BOGP_CUDA(cudaMalloc(&pv, (size_t)(nb + 1) * (sizeof(float) + sizeof(long long)) + 16));
+  long long* pi = reinterpret_cast<long long*>(pv + ((nb + 1 + 1) & ~1));
+  float* ov = pv + nb;
+  long long* oi = pi + nb;
+  argext_stage1<MAX><<<nb, 256, 0, s>>>(x_dev, n, pv, pi);
+  argext_stage2<MAX><<<1, 256, 0, s>>>(pv, pi, nb, ov, oi);
+  cudaError_t e = cudaMemcpyAsync(val_host, ov, sizeof(float), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(idx_host, oi, sizeof(long long), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(pv);
+  if (e != cudaSuccess) { set_error("bogp_argext: %s", cudaGetErrorString(e)); return BOGP_ERR_CUDA; }
+  return 0;
+}
+
+}  // namespace bogp
+
+extern "C" int bogp_argmax_f32(const float* x_dev, long long n, float* val_host, long long* idx_host, void* stream) {
+  return bogp::argext<true>(x_dev, n, val_host, idx_host, static_cast<cudaStream_t>(stream));
+}
+extern "C" int bogp_argmin_f32(const float* x_dev, long long n, float* val_host, long long* idx_host, void* stream) {
+  return bogp::argext<false>(x_dev, n, val_host, idx_host, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ env batch API
+template <typename T>
+static int dev_copy(T** dst, const T* src, size_t n) {
+  BOGP_CUDA(cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(T)));
+  if (n) BOGP_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int bogp_envbatch_create(bogp_envbatch_t* out, long long C, int F, int N, int Mmax, const double* k_re_host,
+                                    const double* k_im_host, const double* amp_re_host, const double* amp_im_host,
+                                    const float* phi_rec_T_host, const double* range_m_host) {
+  BOGP_REQUIRE(out, "bogp_envbatch_create: out is NULL");
+  *out = nullptr;
+  BOGP_REQUIRE(C >= 1 && F >= 1 && F <= BOGP_MAX_TONALS && N >= 1 && N <= 1024 && Mmax >= 1 && Mmax <= 1024,
+               "bogp_envbatch_create: bad sizes C=%lld F=%d N=%d Mmax=%d", C, F, N, Mmax);
+  BOGP_REQUIRE(k_re_host && k_im_host && amp_re_host && phi_rec_T_host && range_m_host, "bogp_envbatch_create: NULL input");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { bogp::set_error("no CUDA device available; no CPU fallback"); return BOGP_ERR_CUDA; }
+  bogp_envbatch_s* h = new bogp_envbatch_s();
+  h->C = C; h->F = F; h->N = N; h->Mmax = Mmax;
+  const size_t nm = (size_t)C * F * Mmax;
+  std::vector<float> ar(nm), ai(amp_im_host ? nm : 0);
+  for (size_t i = 0; i < nm; ++i) { ar[i] = (float)amp_re_host[i]; if (amp_im_host) ai[i] = (float)amp_im_host[i]; }
+  int rc = 0;
+  rc |= dev_copy(&h->k_re, k_re_host, nm);
+  rc |= dev_copy(&h->k_im, k_im_host, nm);
+  rc |= dev_copy(&h->amp_re, ar.data(), nm);
+  if (amp_im_host) rc |= dev_copy(&h->amp_im, ai.data(), nm);
+  rc |= dev_copy(&h->phiT, phi_rec_T_host, nm * N);
+  rc |= dev_copy(&h->range, range_m_host, (size_t)C);
+  if (rc) { bogp_envbatch_destroy(h); return BOGP_ERR_CUDA; }
+  *out = h;
+  return 0;
+}
+
+extern "C" int bogp_envbatch_set_covariance(bogp_envbatch_t h, const double* K_re_host, const double* K_im_host) {
+  BOGP_REQUIRE(h && K_re_host && K_im_host, "bogp_envbatch_set_covariance: NULL argument");
+  const int F = h->F, N = h->N;
+  std::vector<std::vector<bogp::cplx>> Ls(F);
+  std::vector<int> J(F);
+  std::vector<float> tr(F);
+  int Jmax = 1;
+  for (int f = 0; f < F; ++f) {
+    std::vector<bogp::cplx> K((size_t)N * N);
+    double t = 0.0;
+    for (int a = 0; a < N; ++a)
+      for (int b = 0; b < N; ++b) {
+        size_t ab = (size_t)f * N * N + (size_t)a * N + b, ba = (size_t)f * N * N + (size_t)b * N + a;
+        K[(size_t)a * N + b] = 0.5 * (bogp::cplx(K_re_host[ab], K_im_host[ab]) + std::conj(bogp::cplx(K_re_host[ba], K_im_host[ba])));
+      }
+    for (int a = 0; a < N; ++a) t += K[(size_t)a * N + a].real();
+    tr[f] = (float)t;
+    bogp::pivoted_cholesky(K, N, 1e-13, Ls[f], J[f]);
+    Jmax = std::max(Jmax, J[f]);
+  }
+  std::vector<float> cr((size_t)F * N * Jmax, 0.f), ci((size_t)F * N * Jmax, 0.f);
+  for (int f = 0; f < F; ++f)
+    for (int n = 0; n < N; ++n)
+      for (int j = 0; j < J[f]; ++j) {
+        cr[((size_t)f * N + n) * Jmax + j] = (float)Ls[f][(size_t)n * N + j].real();
+        ci[((size_t)f * N + n) * Jmax + j] = (float)(-Ls[f][(size_t)n * N + j].imag());
+      }
+  cudaFree(h->CkT_re); cudaFree(h->CkT_im); cudaFree(h->J); cudaFree(h->trK);
+  h->CkT_re = h->CkT_im = nullptr; h->J = nullptr; h->trK = nullptr;
+  int rc = 0;
+  rc |= dev_copy(&h->CkT_re, cr.data(), cr.size());
+  rc |= dev_copy(&h->CkT_im, ci.data(), ci.size());
+  rc |= dev_copy(&h->J, J.data(), (size_t)F);
+  rc |= dev_copy(&h->trK, tr.data(), (size_t)F);
+  if (rc) return BOGP_ERR_CUDA;
+  h->Jmax = Jmax;
+  h->has_cov = true;
+  return 0;
+}
+
+extern "C" int bogp_envbatch_bartlett(bogp_envbatch_t h, int atype, int mf_method, float* out_dev, void* stream) {
+  BOGP_REQUIRE(h && out_dev, "bogp_envbatch_bartlett: NULL argument");
+  BOGP_REQUIRE(h->has_cov, "bogp_envbatch_bartlett: call bogp_envbatch_set_covariance first");
+  BOGP_REQUIRE((atype == 0 || atype == 1) && (mf_method == 0 || mf_method == 1), "bogp_envbatch_bartlett: bad atype/mf");
+  const size_t smem = (size_t)bogp::kEnvWarps * (h->Mmax + h->N) * sizeof(float2);
+  BOGP_REQUIRE(smem <= 227 * 1024, "bogp_envbatch_bartlett: Mmax+N too large");
+  if (smem > 48 * 1024) BOGP_CUDA(cudaFuncSetAttribute(bogp::envbatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)std::max<long long>(1, std::min<long long>((h->C + bogp::kEnvWarps - 1) / bogp::kEnvWarps, (long long)sms * 8));
+  bogp::envbatch_kernel<<<grid, bogp::kEnvWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      h->C, h->F, h->N, h->Mmax, h->k_re, h->k_im, h->amp_re, h->amp_im, h->phiT, h->range, h->CkT_re, h->CkT_im, h->J,
+      h->trK, h->Jmax, atype, mf_method, out_dev);
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int bogp_envbatch_destroy(bogp_envbatch_t h) {
+  if (!h) return 0;
+  cudaFree(h->k_re); cudaFree(h->k_im); cudaFree(h->range); cudaFree(h->amp_re); cudaFree(h->amp_im);
+  cudaFree(h->phiT); cudaFree(h->CkT_re); cudaFree(h->CkT_im); cudaFree(h->J); cudaFree(h->trK);
+  delete h;
+  return 0;
+}

@@ -1,0 +1,283 @@
+"""Boundary B: exact-GP surrogate with the BoTorch ``Model`` interface, evaluated by libbogp_sm100.so.
+
+Mirrors what the reference uses from BoTorch/GPyTorch (all external to ref/):
+
+* ``SingleTaskGP(X, train_Y, likelihood=GaussianLikelihood(noise_constraint=Interval(1e-8, 1e-3)))`` and the
+  hand-rolled fit ``100 x AdamW(lr=0.1)`` on ``-mll`` (ref/projects/swellex96_inv/data/bo/ei.py:66-78);
+* the explicit Matern-5/2 ARD ``ScaleKernel`` (ref/projects/swellex96_inv/data/bo/baxus.py:310-319) and the RBF-ARD
+  surrogate ``LocalizationGP`` (ref/optimization/gpmodels.py:16-30): ``covar_module`` selects ``"matern52"``/``"rbf"``;
+* ``model.posterior(X)`` -> ``.mean [b,q,1]``, ``.variance [b,q,1]``, ``.covariance``, ``.rsample(...)``
+  (ref/projects/swellex96_localization/data/demo_1d.py:141; gpmodels.py:27-30).
+
+All posterior arithmetic is float64 on the GPU (``bogp_gp_posterior*``); the n x n factorisation happens once per
+hyper-parameter setting inside ``bogp_gp_create``.  The hyper-parameter fit (a "next" row) runs
+as torch float64 ops on the device the training data lives on.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+DT = torch.float64
+
+
+def _cuda_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("bogp_b200.gp needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+@dataclass
+class FitConfig:
+    """ei.py:66-78 on top of BoTorch<=0.11 ``SingleTaskGP`` priors [recalled, SURVEY App. A]."""
+
+    steps: int = 100
+    lr: float = 0.1
+    noise_bounds: Tuple[float, float] = (1e-8, 1e-3)
+    lengthscale_prior: Optional[Tuple[float, float]] = (3.0, 6.0)    # Gamma(concentration, rate)
+    outputscale_prior: Optional[Tuple[float, float]] = (2.0, 0.15)
+    weight_decay: float = 1e-2                                       # torch.optim.AdamW default
+
+
+class GPPosterior:
+    """What the reference reads from ``model.posterior(X)``."""
+
+    def __init__(self, mean: torch.Tensor, variance: torch.Tensor, covariance: Optional[torch.Tensor] = None):
+        self.mean = mean.unsqueeze(-1)            # [b, q, 1]
+        self.variance = variance.unsqueeze(-1)    # [b, q, 1]
+        self._cov = covariance                    # [b, q, q] or None (q = 1)
+
+    @property
+    def covariance(self) -> torch.Tensor:
+        if self._cov is None:
+            return self.variance.squeeze(-1).unsqueeze(-1)   # q = 1: [b, 1, 1]
+        return self._cov
+
+    @property
+    def stddev(self) -> torch.Tensor:
+        return self.variance.sqrt()
+
+    def rsample(self, sample_shape=torch.Size([1]), base_samples: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``mean + L z`` with ``L = chol(cov)``; ``base_samples[*sample_shape, b, q, 1]`` standard normal."""
+        mean = self.mean.squeeze(-1)                                  # [..., q]
+        if base_samples is None:
+            z = torch.randn(*sample_shape, *mean.shape, dtype=mean.dtype, device=mean.device)
+        else:
+            z = base_samples.to(mean)
+            if z.shape[-1] == 1 and z.ndim > mean.ndim:
+                z = z.squeeze(-1)
+        L = torch.linalg.cholesky(self.covariance)                    # [..., q, q]
+        return (mean + (L @ z.unsqueeze(-1)).squeeze(-1)).unsqueeze(-1)
+
+
+class SingleTaskGP:
+    """Exact GP: constant mean, ``outputscale * {Matern-5/2 | RBF}`` ARD kernel, homoskedastic noise."""
+
+    num_outputs = 1
+    _num_outputs = 1       # gpmodels.py:17
+
+    def __init__(self, train_X, train_Y, covar_module: str = "matern52", *, lengthscale=None,
+                 outputscale: Optional[float] = None, mean: float = 0.0, noise: Optional[float] = None,
+                 noise_bounds: Tuple[float, float] = (1e-8, 1e-3)):
+        if covar_module not in _lib.KERNEL:
+            raise ValueError(f"covar_module must be one of {sorted(_lib.KERNEL)}")
+        X = torch.as_tensor(train_X, dtype=DT)
+        Y = torch.as_tensor(train_Y, dtype=DT).reshape(-1)
+        if X.ndim != 2 or X.shape[0] != Y.shape[0]:
+            raise ValueError("train_X must be [n, d] and train_Y [n] or [n, 1]")
+        self.train_X, self.train_Y = X, Y
+        self.kind = covar_module
+        d = X.shape[1]
+        sp0 = math.log(2.0)                     # softplus(0): GPyTorch raw parameters start at 0 [recalled]
+        ls = torch.full((d,), sp0, dtype=DT) if lengthscale is None else torch.as_tensor(lengthscale, dtype=DT).reshape(-1)
+        self.lengthscale = ls.expand(d).clone() if ls.numel() == 1 else ls.clone()
+        self.outputscale = sp0 if outputscale is None else float(outputscale)
+        self.mean_const = float(mean)
+        self.noise_bounds = tuple(noise_bounds)
+        self.noise = 0.5 * (noise_bounds[0] + noise_bounds[1]) if noise is None else float(noise)
+        self._h: Optional[C.c_void_p] = None
+
+    # ------------------------------------------------------------------ device handle
+    def _invalidate(self):
+        if self._h is not None and self._h.value:
+            _lib.lib().bogp_gp_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self._invalidate()
+        except Exception:
+            pass
+
+    def handle(self) -> C.c_void_p:
+        if self._h is None:
+            self.device = _cuda_device()
+            X = np.ascontiguousarray(self.train_X.cpu().numpy(), dtype=np.float64)
+            y = np.ascontiguousarray(self.train_Y.cpu().numpy(), dtype=np.float64)
+            ls = np.ascontiguousarray(self.lengthscale.cpu().numpy(), dtype=np.float64)
+            h = C.c_void_p()
+            _lib.call("bogp_gp_create", C.byref(h), X.shape[0], X.shape[1], _lib.dptr(X), _lib.dptr(y),
+                      _lib.KERNEL[self.kind], _lib.dptr(ls), float(self.outputscale), float(self.mean_const),
+                      float(self.noise))
+            self._h = h
+        return self._h
+
+    @property
+    def jitter(self) -> float:
+        j = C.c_double()
+        _lib.call("bogp_gp_jitter", self.handle(), C.byref(j))
+        return j.value
+
+    def set_hyperparameters(self, *, lengthscale=None, outputscale=None, mean=None, noise=None) -> "SingleTaskGP":
+        if lengthscale is not None:
+            ls = torch.as_tensor(lengthscale, dtype=DT).reshape(-1)
+            self.lengthscale = ls.expand(self.train_X.shape[1]).clone() if ls.numel() == 1 else ls.clone()
+        if outputscale is not None:
+            self.outputscale = float(outputscale)
+        if mean is not None:
+            self.mean_const = float(mean)
+        if noise is not None:
+            self.noise = float(noise)
+        self._invalidate()
+        return self
+
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = True):
+        return self
+
+    # ------------------------------------------------------------------ posterior
+    def _prep(self, X) -> Tuple[torch.Tensor, Tuple[int, ...]]:
+        h = self.handle()  # noqa: F841  (sets self.device)
+        X = torch.as_tensor(X).to(device=self.device, dtype=DT)
+        d = self.train_X.shape[1]
+        if X.shape[-1] != d:
+            raise ValueError(f"X must have last dimension d={d}")
+        if X.ndim == 1:
+            X = X.unsqueeze(0)
+        if X.ndim == 2:
+            X = X.unsqueeze(1)           # [b, d] -> [b, 1, d]
+        batch_shape = tuple(X.shape[:-2])
+        return X.reshape(-1, X.shape[-2], d).contiguous(), batch_shape
+
+    def posterior(self, X, observation_noise: bool = False, posterior_transform=None) -> GPPosterior:
+        """``X[b, q, d]`` (or ``[b, d]``): marginal mean/variance, plus the joint covariance when q > 1."""
+        if posterior_transform is not None:
+            raise NotImplementedError("posterior_transform is not supported")
+        Xf, batch_shape = self._prep(X)
+        b, q, d = Xf.shape
+        stream = C.c_void_p(_lib.current_stream_ptr())
+        if q == 1:
+            mean = torch.empty(b, dtype=DT, device=self.device)
+            var = torch.empty(b, dtype=DT, device=self.device)
+            _lib.call("bogp_gp_posterior", self.handle(), C.c_void_p(Xf.data_ptr()), b, int(observation_noise),
+                      C.c_void_p(mean.data_ptr()), C.c_void_p(var.data_ptr()), stream)
+            return GPPosterior(mean.reshape(*batch_shape, 1), var.reshape(*batch_shape, 1))
+        mean, cov = joint_posterior(self, Xf, observation_noise)
+        var = torch.diagonal(cov, dim1=-2, dim2=-1).clamp_min(1e-10)
+        return GPPosterior(mean.reshape(*batch_shape, q), var.reshape(*batch_shape, q),
+                           cov.reshape(*batch_shape, q, q))
+
+    # gpmodels.py:27-30 ``forward(x) -> MultivariateNormal``: the prior is not on the hot path; expose the posterior
+    def __call__(self, X):
+        return self.posterior(X)
+
+
+class _JointPosterior(torch.autograd.Function):
+    """``(mean[b,q], cov[b,q,q])`` with the analytic backward of ``bogp_gp_posterior_joint_backward``."""
+
+    @staticmethod
+    def forward(ctx, X, model, observation_noise):
+        b, q, d = X.shape
+        mean = torch.empty(b, q, dtype=DT, device=X.device)
+        cov = torch.empty(b, q, q, dtype=DT, device=X.device)
+        Xc = X.detach().contiguous()
+        _lib.call("bogp_gp_posterior_joint", model.handle(), C.c_void_p(Xc.data_ptr()), b, q,
+                  C.c_void_p(mean.data_ptr()), C.c_void_p(cov.data_ptr()), C.c_void_p(_lib.current_stream_ptr()))
+        if observation_noise:
+            cov = cov + model.noise * torch.eye(q, dtype=DT, device=X.device)
+        ctx.model = model
+        ctx.save_for_backward(Xc)
+        return mean, cov
+
+    @staticmethod
+    def backward(ctx, gmean, gcov):
+        (Xc,) = ctx.saved_tensors
+        b, q, d = Xc.shape
+        gmean = torch.zeros(b, q, dtype=DT, device=Xc.device) if gmean is None else gmean.contiguous()
+        gcov = torch.zeros(b, q, q, dtype=DT, device=Xc.device) if gcov is None else gcov.contiguous()
+        grad = torch.empty_like(Xc)
+        _lib.call("bogp_gp_posterior_joint_backward", ctx.model.handle(), C.c_void_p(Xc.data_ptr()), b, q,
+                  C.c_void_p(gmean.data_ptr()), C.c_void_p(gcov.data_ptr()), C.c_void_p(grad.data_ptr()),
+                  C.c_void_p(_lib.current_stream_ptr()))
+        return grad, None, None
+
+
+def joint_posterior(model: SingleTaskGP, X: torch.Tensor, observation_noise: bool = False):
+    """Differentiable joint posterior over ``X[b, q, d]`` (CUDA float64)."""
+    return _JointPosterior.apply(X, model, observation_noise)
+
+
+# ---------------------------------------------------------------------------------------------- hyper-parameter fit
+def _kernel_matrix(kind: str, X: torch.Tensor, ls: torch.Tensor, os_: torch.Tensor) -> torch.Tensor:
+    a = X / ls
+    d2 = ((a.unsqueeze(-2) - a.unsqueeze(-3)) ** 2).sum(-1)
+    if kind == "rbf":
+        return os_ * torch.exp(-0.5 * d2)
+    r = torch.sqrt(d2.clamp_min(1e-30))
+    return os_ * (1.0 + math.sqrt(5.0) * r + (5.0 / 3.0) * d2) * torch.exp(-math.sqrt(5.0) * r)
+
+
+def _gamma_logpdf(x, conc, rate):
+    return conc * math.log(rate) - math.lgamma(conc) + (conc - 1.0) * torch.log(x) - rate * x
+
+
+def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), device=None) -> SingleTaskGP:
+    """The fit loop of ei.py:69-78: AdamW over the raw (unconstrained) parameters, initialised at 0.
+
+    ``-ExactMarginalLogLikelihood = -(log N(y | m, K + s2 I) + sum log-priors)/n``.  Runs as torch float64 ops on
+    ``device`` (default: the current CUDA device).  SURVEY 8(f) item 2: a hand-written batched Cholesky
+    forward/backward is the next row; this is the library-call stand-in until then.
+    """
+    dev = _cuda_device() if device is None else torch.device(device)
+    X = model.train_X.to(dev)
+    y = model.train_Y.to(dev)
+    n, d = X.shape
+    lo, hi = cfg.noise_bounds
+    raw = {k: torch.zeros(s, dtype=DT, device=dev, requires_grad=True)
+           for k, s in (("lengthscale", (d,)), ("outputscale", ()), ("noise", ()), ("mean", ()))}
+    opt = torch.optim.AdamW(list(raw.values()), lr=cfg.lr, weight_decay=cfg.weight_decay)
+    eye = torch.eye(n, dtype=DT, device=dev)
+    sp = torch.nn.functional.softplus
+    for _ in range(cfg.steps):
+        opt.zero_grad()
+        ls, os_ = sp(raw["lengthscale"]), sp(raw["outputscale"])
+        noise = lo + (hi - lo) * torch.sigmoid(raw["noise"])
+        Kxx = _kernel_matrix(model.kind, X, ls, os_) + noise * eye
+        L, info = torch.linalg.cholesky_ex(Kxx)
+        jit = 1e-8
+        while bool(info.any()) and jit <= 1e-6:      # gpytorch psd_safe_cholesky retries [recalled]
+            L, info = torch.linalg.cholesky_ex(Kxx + jit * eye)
+            jit *= 10.0
+        r = (y - raw["mean"]).unsqueeze(-1)
+        a = torch.cholesky_solve(r, L)
+        ll = -0.5 * (r * a).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * n * math.log(2.0 * math.pi)
+        if cfg.lengthscale_prior is not None:
+            ll = ll + _gamma_logpdf(ls, *cfg.lengthscale_prior).sum()
+        if cfg.outputscale_prior is not None:
+            ll = ll + _gamma_logpdf(os_, *cfg.outputscale_prior).sum()
+        (-ll / n).backward()
+        opt.step()
+    with torch.no_grad():
+        model.noise_bounds = (lo, hi)
+        model.set_hyperparameters(lengthscale=sp(raw["lengthscale"]).cpu(), outputscale=float(sp(raw["outputscale"])),
+                                  mean=float(raw["mean"]), noise=float(lo + (hi - lo) * torch.sigmoid(raw["noise"])))
+    return model

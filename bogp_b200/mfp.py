@@ -1,0 +1,319 @@
+"""Boundary A: the matched-field objective, host side (mirrors the TritonOA interface the reference calls).
+
+Reference interfaces mirrored here (all external to ref/, pinned by their call sites -- SURVEY 8b):
+
+* ``tritonoa.sp.mfp.MatchedFieldProcessor(runner, covariance_matrix, freq, parameters,
+  parameter_formatter=None, beamformer=beamformer, multifreq_method="mean")`` and its ``__call__(dict)``
+  (ref/projects/swellex96_localization/data/mfp.py:198-214, ref/projects/swellex96_inv/data/bo/obj.py:62-70,
+  ref/projects/swellex96_localization/conf/optimization/run.py:89-96);
+* ``tritonoa.at.models.kraken.runner.run_kraken(parameters) -> p[N, Nr]`` -- here :class:`ModeRunner`, a *mode
+  provider*: KRAKEN stays external on the host (north_star) and hands over a :class:`~bogp_b200.modes.ModeSet`;
+* ``tritonoa.sp.beamforming.beamformer(K, replica, atype)`` / ``covariance(d)``
+  (obj.py:68, ref/optimization/utils.py:23-32).
+
+The arithmetic runs in libbogp_sm100.so (fused modal sum + Bartlett + multi-frequency combine, no replica field in
+HBM).  There is no CPU fallback: an objective built from callables the library cannot fuse raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import partial
+from typing import Callable, Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .modes import ModeSet
+
+ArrayLike = Union[np.ndarray, Sequence[float]]
+
+
+def _split_planes(arrs: List[np.ndarray]):
+    """Concatenate per-tonal arrays into contiguous float64 re (and im, if any is complex) planes."""
+    cplx = any(np.iscomplexobj(a) for a in arrs)
+    re = np.ascontiguousarray(np.concatenate([np.real(a).ravel() for a in arrs]), dtype=np.float64)
+    im = (np.ascontiguousarray(np.concatenate([np.imag(a).ravel() for a in arrs]), dtype=np.float64)
+          if cplx else None)
+    return re, im
+
+
+class DeviceModeSet:
+    """A :class:`ModeSet` uploaded to the current CUDA device (``bogp_modeset_t`` handle)."""
+
+    def __init__(self, modes: ModeSet, covariance_matrix: Optional[np.ndarray] = None):
+        self.modes = modes
+        self._h = C.c_void_p()
+        M = np.asarray(modes.n_modes, dtype=np.int32)
+        k_re, k_im = _split_planes([np.asarray(k, dtype=np.complex128) for k in modes.k])
+        pr_re, pr_im = _split_planes(modes.phi_rec)
+        ps_re, ps_im = _split_planes(modes.phi_src_tab)
+        rec_z = np.ascontiguousarray(modes.rec_z, dtype=np.float64)
+        _lib.call("bogp_modeset_create", C.byref(self._h), modes.n_freq, modes.n_rec,
+                  M.ctypes.data_as(C.POINTER(C.c_int)), _lib.dptr(k_re), _lib.dptr(k_im), _lib.dptr(pr_re),
+                  _lib.dptr(pr_im), modes.nz_tab, float(modes.z0), float(modes.dz), _lib.dptr(ps_re),
+                  _lib.dptr(ps_im), _lib.dptr(rec_z), float(modes.z_pivot))
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        if covariance_matrix is not None:
+            self.set_covariance(covariance_matrix)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().bogp_modeset_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ inputs
+    def set_covariance(self, K: np.ndarray) -> None:
+        """``covariance_matrix`` of MatchedFieldProcessor: ``K[F, N, N]`` complex (utils.py:23-32, 42-56)."""
+        K = np.asarray(K)
+        F, N = self.modes.n_freq, self.modes.n_rec
+        if K.shape != (F, N, N):
+            raise ValueError(f"covariance_matrix must be [F={F}, N={N}, N={N}], got {K.shape}")
+        K_re = np.ascontiguousarray(K.real, dtype=np.float64)
+        K_im = np.ascontiguousarray(K.imag if np.iscomplexobj(K) else np.zeros_like(K_re), dtype=np.float64)
+        _lib.call("bogp_covariance_set", self._h, _lib.dptr(K_re), _lib.dptr(K_im))
+
+    # ------------------------------------------------------------------ evaluation
+    def bartlett_grid(self, r_km: ArrayLike, z: ArrayLike, tilt_deg: Optional[ArrayLike] = None, *,
+                      atype: str = "cbf", multifreq_method: str = "mean", engine: str = "auto",
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Ambiguity surface ``[Nz, Nr]`` (or ``[Nt, Nz, Nr]`` with a tilt axis), float32 on the device.
+
+        Replaces the row loop of ref/projects/swellex96_localization/data/mfp.py:213-214.
+        """
+        r_m = np.ascontiguousarray(1000.0 * np.atleast_1d(np.asarray(r_km, dtype=np.float64)))
+        zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
+        tt = None if tilt_deg is None else np.ascontiguousarray(np.atleast_1d(np.asarray(tilt_deg, dtype=np.float64)))
+        Nt = 1 if tt is None else len(tt)
+        shape = (len(zz), len(r_m)) if tt is None else (Nt, len(zz), len(r_m))
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
+        _lib.call("bogp_bartlett_grid", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz), _lib.dptr(tt), Nt,
+                  _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
+                  C.c_void_p(out.data_ptr()), C.c_void_p(_lib.current_stream_ptr()))
+        return out
+
+    def bartlett_grid_host(self, r_km: ArrayLike, z: ArrayLike, tilt_deg: Optional[ArrayLike] = None, *,
+                           atype: str = "cbf", multifreq_method: str = "mean", engine: str = "auto") -> np.ndarray:
+        """Same through the host-buffer entry point (device->host copy inside the call)."""
+        r_m = np.ascontiguousarray(1000.0 * np.atleast_1d(np.asarray(r_km, dtype=np.float64)))
+        zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
+        tt = None if tilt_deg is None else np.ascontiguousarray(np.atleast_1d(np.asarray(tilt_deg, dtype=np.float64)))
+        Nt = 1 if tt is None else len(tt)
+        shape = (len(zz), len(r_m)) if tt is None else (Nt, len(zz), len(r_m))
+        out = np.empty(shape, dtype=np.float32)
+        _lib.call("bogp_bartlett_grid_host", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz), _lib.dptr(tt),
+                  Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine], _lib.fptr(out),
+                  C.c_void_p(_lib.current_stream_ptr()))
+        return out
+
+    def bartlett_points(self, cand: Union[np.ndarray, torch.Tensor], *, atype: str = "cbf",
+                        multifreq_method: str = "mean") -> torch.Tensor:
+        """Scattered candidates ``cand[C, 3] = (range km, depth m, tilt deg)`` -> ``[C]`` float32 on the device."""
+        if not torch.is_tensor(cand):
+            cand = torch.as_tensor(np.asarray(cand, dtype=np.float64))
+        cand = cand.to(device=self.device, dtype=torch.float64).reshape(-1, 3).clone()
+        cand[:, 0] *= 1000.0
+        cand = cand.contiguous()
+        out = torch.empty(cand.shape[0], dtype=torch.float32, device=self.device)
+        _lib.call("bogp_bartlett_points", self._h, C.c_void_p(cand.data_ptr()), cand.shape[0], _lib.ATYPE[atype],
+                  _lib.MF_METHOD[multifreq_method], C.c_void_p(out.data_ptr()), C.c_void_p(_lib.current_stream_ptr()))
+        return out
+
+
+def argmax(x: torch.Tensor):
+    """``np.unravel_index(np.argmax(surface))`` (collate.py:50) on the device: ``(value, unravelled index)``."""
+    return _argext("bogp_argmax_f32", x)
+
+
+def argmin(x: torch.Tensor):
+    return _argext("bogp_argmin_f32", x)
+
+
+def _argext(fn: str, x: torch.Tensor):
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        raise ValueError("expected a contiguous float32 CUDA tensor")
+    val, idx = C.c_float(), C.c_longlong()
+    _lib.call(fn, C.c_void_p(x.data_ptr()), x.numel(), C.byref(val), C.byref(idx),
+              C.c_void_p(_lib.current_stream_ptr()))
+    return val.value, tuple(int(i) for i in np.unravel_index(idx.value, tuple(x.shape)))
+
+
+# ---------------------------------------------------------------------------------------------- tritonoa mirror
+def covariance(d: np.ndarray) -> np.ndarray:
+    """``tritonoa.sp.beamforming.covariance``: ``K = d d^H`` (utils.py:31; acoustics.py:116-124).  Host, set-up only."""
+    d = np.asarray(d, dtype=np.complex128).reshape(-1, 1)
+    return d @ d.conj().T
+
+
+def beamformer(K: np.ndarray, replica: np.ndarray, atype: str = "cbf") -> np.ndarray:
+    """Marker for ``tritonoa.sp.beamforming.beamformer``.
+
+    Inside :class:`MatchedFieldProcessor` the processor named by ``atype`` is fused into the CUDA kernel and this
+    function is never called with data; it exists so that ``partial(beamformer, atype="cbf_ml")`` (obj.py:68,
+    loc_tilt/conf/run.py:146) keeps working as the selector.
+    """
+    raise NotImplementedError(
+        "bogp_b200.mfp.beamformer is fused into the Bartlett kernels; pass it (or functools.partial of it) to "
+        "MatchedFieldProcessor instead of calling it on a replica field")
+
+
+class ModeRunner:
+    """``run_kraken`` stand-in: the mode provider for the fused kernels.
+
+    ``modes`` is either a :class:`ModeSet` (one fixed environment: localisation / tilt) or a callable
+    ``parameters -> ModeSet`` that runs the host normal-mode program for the environment in ``parameters``
+    (geoacoustic inversion, obj.py:73-83).  The modal sum itself happens on the GPU.
+    """
+
+    def __init__(self, modes: Union[ModeSet, Callable[[dict], ModeSet]]):
+        self.modes = modes
+
+    @property
+    def is_static(self) -> bool:
+        return isinstance(self.modes, ModeSet)
+
+    def modes_for(self, parameters: dict) -> ModeSet:
+        return self.modes if self.is_static else self.modes(parameters)
+
+    def __call__(self, parameters: dict):
+        raise NotImplementedError(
+            "ModeRunner does not materialise replica fields; use it as MatchedFieldProcessor(runner=...)")
+
+
+def _atype_of(bf: Callable) -> str:
+    """Recover ``atype`` from ``beamformer`` or ``partial(beamformer, atype=...)``."""
+    if bf is beamformer:
+        return "cbf"
+    if isinstance(bf, partial) and bf.func is beamformer and not bf.args:
+        extra = set(bf.keywords) - {"atype"}
+        if extra:
+            raise TypeError(f"unsupported beamformer keywords {sorted(extra)}")
+        return bf.keywords.get("atype", "cbf")
+    raise TypeError("MatchedFieldProcessor needs bogp_b200.mfp.beamformer (or functools.partial of it); "
+                    "arbitrary beamformer callables cannot be fused and there is no CPU fallback")
+
+
+class MatchedFieldProcessor:
+    """Drop-in for ``tritonoa.sp.mfp.MatchedFieldProcessor`` backed by the fused CUDA path.
+
+    ``__call__(parameters)`` accepts what the reference passes: a dict with scalar ``src_z`` and scalar or vector
+    ``rec_r`` [km] (mfp.py:214 -> ``ndarray[Nr]``; scalars -> ``float``), optionally ``tilt`` [deg].  It also accepts
+    a *list* of such dicts (the batch that obj.py:28-30 spreads over a process pool) and returns ``ndarray[C]``.
+    """
+
+    def __init__(self, runner: ModeRunner, covariance_matrix, freq: Sequence[float], parameters: dict,
+                 parameter_formatter: Optional[Callable] = None, beamformer: Callable = beamformer,
+                 multifreq_method: str = "mean"):
+        if not isinstance(runner, ModeRunner):
+            raise TypeError("runner must be a bogp_b200.mfp.ModeRunner (mode provider); the modal sum is fused "
+                            "into the CUDA kernel and there is no CPU fallback for arbitrary runner callables")
+        if multifreq_method not in _lib.MF_METHOD:
+            raise ValueError(f"unknown multifreq_method {multifreq_method!r}")
+        self.runner = runner
+        self.covariance_matrix = np.asarray(covariance_matrix)
+        self.freq = [float(f) for f in freq]
+        self.parameters = dict(parameters)
+        self.parameter_formatter = parameter_formatter
+        self.beamformer = beamformer
+        self.atype = _atype_of(beamformer)
+        if self.atype not in _lib.ATYPE:
+            raise ValueError(f"unknown beamformer atype {self.atype!r}")
+        self.multifreq_method = multifreq_method
+        if self.covariance_matrix.shape[0] != len(self.freq):
+            raise ValueError("covariance_matrix needs one [N, N] matrix per frequency")
+        self._dms: Optional[DeviceModeSet] = None
+
+    # pickling (hydra-zen partials, process pools): device handles are rebuilt lazily on the other side
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_dms"] = None
+        return st
+
+    # ------------------------------------------------------------------ internals
+    def _merged(self, parameters: dict) -> dict:
+        """Per-tonal merge exactly as the reference does it, then check the geometry is tonal-independent."""
+        merged = None
+        for f in self.freq:
+            title = f"{f:.1f}Hz"
+            if self.parameter_formatter is not None:
+                m = self.parameter_formatter(freq=f, title=title, fixed_parameters=self.parameters,
+                                             search_parameters=parameters)
+            else:
+                m = self.parameters | {"freq": f, "title": title} | parameters
+            if merged is None:
+                merged = m
+            else:
+                for key in ("src_z", "rec_r", "tilt"):
+                    if not np.array_equal(np.asarray(m.get(key, 0.0)), np.asarray(merged.get(key, 0.0))):
+                        raise ValueError(f"parameter {key!r} differs between tonals; cannot fuse")
+        return merged
+
+    def _select(self, modes: ModeSet) -> ModeSet:
+        idx = []
+        for f in self.freq:
+            hits = [i for i, g in enumerate(modes.freq) if abs(g - f) < 1e-9]
+            if not hits:
+                raise ValueError(f"mode set has no tonal at {f} Hz")
+            idx.append(hits[0])
+        return modes if idx == list(range(modes.n_freq)) else modes.select(idx)
+
+    def _device_modes(self) -> DeviceModeSet:
+        if self._dms is None:
+            self._dms = DeviceModeSet(self._select(self.runner.modes), self.covariance_matrix)
+        return self._dms
+
+    # ------------------------------------------------------------------ objective
+    def __call__(self, parameters: Union[dict, Sequence[dict]]):
+        if isinstance(parameters, dict):
+            return self._call_one(parameters)
+        return self._call_batch(list(parameters))
+
+    def _call_one(self, parameters: dict):
+        merged = self._merged(parameters)
+        if not self.runner.is_static:
+            return float(self._call_envs([merged])[0])
+        dms = self._device_modes()
+        rec_r = np.asarray(merged["rec_r"], dtype=np.float64)
+        src_z = np.asarray(merged["src_z"], dtype=np.float64)
+        tilt = float(merged.get("tilt", 0.0) or 0.0)
+        scalar = rec_r.ndim == 0 and src_z.ndim == 0
+        if src_z.ndim != 0:
+            raise ValueError("src_z must be a scalar (the reference evaluates one source depth per call)")
+        if scalar:
+            out = dms.bartlett_points(np.array([[float(rec_r), float(src_z), tilt]]), atype=self.atype,
+                                      multifreq_method=self.multifreq_method)
+            return float(out.cpu()[0])
+        out = dms.bartlett_grid(rec_r, [float(src_z)], [tilt] if tilt else None, atype=self.atype,
+                                multifreq_method=self.multifreq_method)
+        return out.reshape(-1).cpu().numpy().astype(np.float64)
+
+    def _call_batch(self, plist: List[dict]) -> np.ndarray:
+        merged = [self._merged(p) for p in plist]
+        if not self.runner.is_static:
+            return self._call_envs(merged)
+        cand = np.array([[float(np.asarray(m["rec_r"])), float(np.asarray(m["src_z"])),
+                          float(m.get("tilt", 0.0) or 0.0)] for m in merged], dtype=np.float64).reshape(-1, 3)
+        out = self._device_modes().bartlett_points(cand, atype=self.atype, multifreq_method=self.multifreq_method)
+        return out.cpu().numpy().astype(np.float64)
+
+    def _call_envs(self, merged: List[dict]) -> np.ndarray:
+        """Per-candidate environments: host mode provider per candidate, then one batched launch."""
+        from .envbatch import EnvBatch
+        mode_sets = [self._select(self.runner.modes_for(m)) for m in merged]
+        cand = np.array([[float(np.asarray(m["rec_r"])), float(np.asarray(m["src_z"])),
+                          float(m.get("tilt", 0.0) or 0.0)] for m in merged], dtype=np.float64).reshape(-1, 3)
+        if np.any(cand[:, 2] != 0.0):
+            raise NotImplementedError("tilt with per-candidate environments is not supported")
+        with EnvBatch(mode_sets, cand[:, 0], cand[:, 1], self.covariance_matrix) as eb:
+            out = eb.bartlett(atype=self.atype, multifreq_method=self.multifreq_method)
+        return out.cpu().numpy().astype(np.float64)

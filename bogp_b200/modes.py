@@ -165,3 +165,42 @@ def perturbed_pekeris_batch(freq: Sequence[float], rec_z: Sequence[float], depth
     """One ModeSet per candidate environment (config 5: geoacoustic inversion)."""
     return [pekeris_modes(freq, rec_z, depth=float(d), c_b=float(c), **kw)
             for d, c in zip(depths, c_bs)]
+
+
+def _outer(d: np.ndarray) -> np.ndarray:
+    d = np.asarray(d, dtype=np.complex128).reshape(-1, 1)
+    return d @ d.conj().T
+
+
+def synthetic_covariance(modes: ModeSet, src_z: float, rec_r_km: float, tilt_deg: float = 0.0,
+                         snapshots: int = 0, snr_db: float = 10.0, seed: int = 0) -> np.ndarray:
+    """Synthetic INPUT data: the covariance ``simulate_covariance`` (ref/optimization/utils.py:23-32) would hand to
+    the objective -- ``K_f = d d^H``, ``d = p/||p||`` at a known truth -- generated from a ModeSet.
+
+    This is a data generator (like :func:`pekeris_modes`), float64 on the host, one modal sum per tonal; it is
+    not part of the scored path.  ``snapshots > 0`` averages that many noisy snapshots
+    (rank > 1 covariance, the ``covariance_averaging: 8`` case of loc_tilt/conf/data/acoustics.yaml:56) and
+    renormalises to unit trace.
+    """
+    rng = np.random.default_rng(seed)
+    Ks = []
+    lever = modes.z_pivot - modes.rec_z
+    dr = -lever * np.sin(np.deg2rad(tilt_deg))
+    for f in range(modes.n_freq):
+        phi_s = modes.phi_src(f, src_z)[0]
+        rn = 1000.0 * float(rec_r_km) + dr                       # [N]
+        kr = modes.k[f][None, :] * rn[:, None]                   # [N, M]
+        p = np.sum(modes.phi_rec[f] * phi_s[None, :] * np.exp(-1j * kr) / np.sqrt(kr), axis=1)
+        d = p / np.linalg.norm(p)
+        if snapshots <= 0:
+            Ks.append(_outer(d))
+            continue
+        sigma = 10.0 ** (-snr_db / 20.0) / np.sqrt(modes.n_rec)
+        K = np.zeros((modes.n_rec, modes.n_rec), dtype=np.complex128)
+        for _ in range(snapshots):
+            noise = sigma * (rng.standard_normal(modes.n_rec) + 1j * rng.standard_normal(modes.n_rec)) / np.sqrt(2.0)
+            phase = np.exp(2j * np.pi * rng.random())
+            K += _outer(phase * d + noise)
+        K /= np.real(np.trace(K))
+        Ks.append(K)
+    return np.array(Ks)

@@ -1,0 +1,96 @@
+"""Boundary B: ``optimize_acqf``.
+
+Mirrors ``botorch.optim.optimize_acqf(acq_function, bounds, q, num_restarts, raw_samples)`` as called at
+ref/projects/swellex96_inv/data/bo/ei.py:81-92 (q=1, 40 restarts, 1024 raw samples, bounds [-1, 1]^d).  BoTorch's
+internals are RECALLED: scrambled-Sobol raw samples seeded from the torch RNG, Boltzmann restart
+selection (``initialize_q_batch[_nonneg]``), one joint SciPy L-BFGS-B over all restarts on ``-sum(acq)``, best
+restart returned.  The orchestration is host Python/SciPy as in BoTorch; every acquisition evaluation (value and
+gradient, all restarts at once) is one fused CUDA launch.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from scipy.optimize import minimize
+
+DT = torch.float64
+
+
+def draw_sobol_samples(bounds: torch.Tensor, n: int, q: int, seed: Optional[int] = None) -> torch.Tensor:
+    d = bounds.shape[-1]
+    eng = torch.quasirandom.SobolEngine(dimension=q * d, scramble=True, seed=seed)
+    u = eng.draw(n, dtype=DT).reshape(n, q, d)
+    return bounds[0] + (bounds[1] - bounds[0]) * u
+
+
+def _boltzmann(X: torch.Tensor, Y: torch.Tensor, n: int, eta: float = 2.0) -> torch.Tensor:
+    if n >= X.shape[0]:
+        return X
+    std = Y.std()
+    if float(std) == 0.0:
+        return X[torch.randperm(X.shape[0])[:n]]
+    max_idx = int(torch.argmax(Y))
+    etaZ = eta * (Y - Y.mean()) / std
+    w = torch.exp(etaZ)
+    while bool(torch.isinf(w).any()):
+        etaZ = etaZ * 0.5
+        w = torch.exp(etaZ)
+    idcs = torch.multinomial(w, n)
+    if max_idx not in idcs:
+        idcs[-1] = max_idx
+    return X[idcs]
+
+
+def _boltzmann_nonneg(X: torch.Tensor, Y: torch.Tensor, n: int, eta: float = 1.0, alpha: float = 1e-4) -> torch.Tensor:
+    if n >= X.shape[0]:
+        return X
+    max_val, max_idx = float(Y.max()), int(torch.argmax(Y))
+    if max_val <= 0.0:
+        return X[torch.randperm(X.shape[0])[:n]]
+    pos = Y >= alpha * max_val
+    while int(pos.sum()) < n:
+        alpha *= 0.1
+        pos = Y >= alpha * max_val
+    pos_idcs = torch.nonzero(pos).squeeze(-1)
+    w = torch.exp(eta * (Y[pos] / max_val - 1.0))
+    idcs = pos_idcs[torch.multinomial(w, n)]
+    if max_idx not in idcs:
+        idcs[-1] = max_idx
+    return X[idcs]
+
+
+def optimize_acqf(acq_function, bounds, q: int, num_restarts: int, raw_samples: int, options: Optional[dict] = None,
+                  return_best_only: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns ``(candidates[q, d], acq_value)`` as float64 CPU tensors."""
+    options = options or {}
+    bounds = torch.as_tensor(bounds, dtype=DT).cpu()
+    d = bounds.shape[-1]
+    seed = int(torch.randint(0, 10000, (1,)).item())
+    X_raw = draw_sobol_samples(bounds, raw_samples, q, seed)
+    with torch.no_grad():
+        Y_raw = acq_function(X_raw).detach().cpu()
+    init = _boltzmann_nonneg if getattr(acq_function, "nonneg", False) else _boltzmann
+    X0 = init(X_raw, Y_raw, num_restarts)
+    shape = X0.shape
+    lo = bounds[0].repeat(shape[0] * q).numpy()
+    hi = bounds[1].repeat(shape[0] * q).numpy()
+
+    def f_and_g(x: np.ndarray):
+        X = torch.from_numpy(x.copy()).reshape(shape).requires_grad_(True)
+        v = acq_function(X)
+        loss = -v.sum()
+        (g,) = torch.autograd.grad(loss, X)
+        return float(loss), g.reshape(-1).cpu().numpy().astype(np.float64)
+
+    x0 = np.clip(X0.reshape(-1).numpy().astype(np.float64), lo, hi)
+    res = minimize(f_and_g, x0, jac=True, method="L-BFGS-B", bounds=list(zip(lo, hi)),
+                   options={"maxiter": int(options.get("maxiter", 200))})
+    Xc = torch.from_numpy(np.clip(res.x, lo, hi)).reshape(shape)
+    with torch.no_grad():
+        vals = acq_function(Xc).detach().cpu()
+    if not return_best_only:
+        return Xc, vals
+    best = int(torch.argmax(vals))
+    return Xc[best], vals[best]

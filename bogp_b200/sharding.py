@@ -1,0 +1,96 @@
+"""Multi-GPU sharding of the candidate set: one process per GPU, no data-path collective.
+
+Candidates are independent, so every rank evaluates a contiguous slab of the flattened candidate index (for a
+grid: a block of source-depth rows; with a tilt axis: a block of (tilt, depth) rows) with replicated mode tables.
+The only exchange is the final reduction the reference does with ``np.unravel_index(np.argmax(surface))``
+(ref/projects/swellex96_localization/data/collate.py:50): an all-gather of one ``(value, flat index)`` pair per
+rank -- 16 bytes -- followed by a local reduce with np.argmax's first-occurrence tie rule.  Optionally the slabs
+themselves are all-gathered when every rank wants the full surface.
+
+Works over any ``torch.distributed`` backend (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def slab(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced ``[lo, hi)`` row range of ``rank`` (first ``n_rows % world`` ranks get one extra)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n_rows, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def combine_extrema(vals: torch.Tensor, idxs: torch.Tensor, maximize: bool = True) -> Tuple[float, int]:
+    """Reduce per-rank ``(value, global flat index)`` pairs; NaN / empty shards (index < 0) never win, ties go to
+    the lowest index (np.argmax: first occurrence)."""
+    best_v, best_i = float("nan"), -1
+    for v, i in zip(vals.tolist(), idxs.tolist()):
+        if i < 0 or v != v:
+            continue
+        better = best_i < 0 or (v > best_v if maximize else v < best_v) or (v == best_v and i < best_i)
+        if better:
+            best_v, best_i = v, int(i)
+    return best_v, best_i
+
+
+def allgather_extremum(local_val: float, local_idx: int, *, maximize: bool = True, device=None,
+                       group: Optional[dist.ProcessGroup] = None) -> Tuple[float, int]:
+    """All-gather the per-rank extremum pair and reduce locally (every rank returns the same answer)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return float(local_val), int(local_idx)
+    world = dist.get_world_size(group)
+    dev = torch.device("cpu") if device is None else torch.device(device)
+    v = torch.tensor([local_val], dtype=torch.float64, device=dev)
+    i = torch.tensor([local_idx], dtype=torch.int64, device=dev)
+    vs = torch.empty(world, dtype=torch.float64, device=dev)
+    is_ = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(vs, v, group=group) if dev.type == "cuda" else dist.all_gather(list(vs.split(1)), v, group=group)
+    dist.all_gather_into_tensor(is_, i, group=group) if dev.type == "cuda" else dist.all_gather(list(is_.split(1)), i, group=group)
+    return combine_extrema(vs.cpu(), is_.cpu(), maximize)
+
+
+def sharded_surface(evaluate_rows: Callable[[int, int], torch.Tensor], n_rows: int, n_cols: int, *,
+                    maximize: bool = True, gather_surface: bool = False,
+                    group: Optional[dist.ProcessGroup] = None):
+    """Evaluate rows ``[lo, hi)`` of an ``[n_rows, n_cols]`` surface on this rank and reduce the extremum globally.
+
+    ``evaluate_rows(lo, hi) -> tensor[hi-lo, n_cols]`` is the local hot path (the CUDA grid kernel on the GPU
+    box).  Returns ``(local_slab, (value, (row, col)), full_surface_or_None)``.
+    """
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    lo, hi = slab(n_rows, rank, world)
+    local = evaluate_rows(lo, hi)
+    if local.numel():
+        flat = local.reshape(-1)
+        clean = torch.where(torch.isnan(flat), torch.full_like(flat, float("-inf") if maximize else float("inf")), flat)
+        li = int(torch.argmax(clean) if maximize else torch.argmin(clean))
+        lv = float(flat[li])
+        gi = lo * n_cols + li
+        if lv != lv:
+            gi = -1
+    else:
+        lv, gi = float("nan"), -1
+    dev = local.device if local.is_cuda else None
+    val, idx = allgather_extremum(lv, gi, maximize=maximize, device=dev, group=group)
+    full = None
+    if gather_surface:
+        if world == 1:
+            full = local
+        else:
+            # slabs may differ by one row: pad to the largest, gather, trim
+            rows_max = slab(n_rows, 0, world)[1]
+            pad = torch.zeros(rows_max, n_cols, dtype=local.dtype, device=local.device)
+            pad[: hi - lo] = local
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad, group=group)
+            full = torch.cat([p[: slab(n_rows, r, world)[1] - slab(n_rows, r, world)[0]] for r, p in enumerate(parts)])
+    pos = tuple(int(x) for x in np.unravel_index(idx, (n_rows, n_cols))) if idx >= 0 else (-1, -1)
+    return local, (val, pos), full

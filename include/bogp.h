@@ -1,0 +1,155 @@
+/* bogp.h -- C ABI of libbogp_sm100.so: the B200-native hot path of NeptuneProjects/BOGP.
+ *
+ * The reference has no FFI of its own: its hot path is reached through two Python
+ * protocols.  Each entry point below names the reference interface it
+ * replaces; INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side.
+ *
+ *   Boundary A  objective callable  tritonoa.sp.mfp.MatchedFieldProcessor(...).__call__(dict)
+ *               built at ref/projects/swellex96_localization/data/mfp.py:198-204,
+ *               ref/projects/swellex96_inv/data/bo/obj.py:62-70,
+ *               ref/projects/swellex96_localization/conf/optimization/run.py:89-96
+ *   Boundary B  botorch Model.posterior / AcquisitionFunction.forward / optimize_acqf
+ *               used at ref/projects/swellex96_inv/data/bo/ei.py:65-92, ucb.py:82,
+ *               ref/projects/swellex96_localization/data/demo_1d.py:92-112,
+ *               ref/optimization/gpmodels.py:16-30
+ *
+ * Conventions: every function returns 0 on success, <0 on error (bogp_last_error() gives
+ * the text, thread-local).  Pointers named *_host are host memory, *_dev are device memory
+ * on the current CUDA device, caller-owned.  `stream` is a cudaStream_t passed as void*
+ * (NULL = legacy default stream).  Handles are not thread-safe; distinct handles are.
+ * Ranges are in METRES at this boundary (the Python objective takes km, mfp.py:214).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef BOGP_H
+#define BOGP_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOGP_OK 0
+#define BOGP_ERR_INVALID (-1)
+#define BOGP_ERR_CUDA (-2)
+#define BOGP_ERR_NUMERIC (-3)
+#define BOGP_ERR_UNSUPPORTED (-4)
+
+/* beamformer `atype` (tritonoa.sp.beamforming.beamformer; obj.py:68, loc_tilt/conf/run.py:146) */
+#define BOGP_ATYPE_CBF 0
+#define BOGP_ATYPE_CBF_ML 1
+/* MatchedFieldProcessor `multifreq_method` (loc_tilt/conf/run.py:263-264) */
+#define BOGP_MF_MEAN 0
+#define BOGP_MF_PRODUCT 1
+/* covariance kernels of the surrogate (baxus.py:310-319 Matern-5/2 ARD; gpmodels.py:22-24 RBF ARD) */
+#define BOGP_KERNEL_MATERN52 0
+#define BOGP_KERNEL_RBF 1
+/* analytic acquisitions (ei.py:80, logei.py:80, pi.py:81, ucb.py:82) */
+#define BOGP_ACQ_EI 0
+#define BOGP_ACQ_LOGEI 1
+#define BOGP_ACQ_PI 2
+#define BOGP_ACQ_UCB 3
+/* engine selection for the grid path */
+#define BOGP_ENGINE_AUTO 0
+#define BOGP_ENGINE_SIMT 1   /* CUDA-core kernel */
+#define BOGP_ENGINE_UMMA 2   /* tcgen05 3xTF32 kernel */
+
+typedef struct bogp_modeset_s* bogp_modeset_t;
+typedef struct bogp_envbatch_s* bogp_envbatch_t;
+typedef struct bogp_gp_s* bogp_gp_t;
+
+const char* bogp_last_error(void);
+int bogp_version(void);
+/* sm_count / compute capability of the current device; fails without a GPU. */
+int bogp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ Boundary A: matched-field objective
+ * Replaces the modal-sum half of tritonoa...run_kraken (the `runner` of MatchedFieldProcessor) for one
+ * environment: modes precomputed on the host (KRAKEN stays external), uploaded once.
+ *   M_host[F]                     modes per tonal
+ *   k_re/k_im_host[sum M]         horizontal wavenumbers
+ *   phi_rec_re/_im_host           per tonal row-major [N, M_f], concatenated; _im may be NULL (KRAKEN real modes)
+ *   phi_src_re/_im_host           per tonal row-major [nz_tab, M_f] on the mesh z0 + i*dz; _im may be NULL
+ *   rec_z_host[N], z_pivot        array geometry for the tilted-array path
+ */
+int bogp_modeset_create(bogp_modeset_t* out, int F, int N, const int* M_host,
+                        const double* k_re_host, const double* k_im_host,
+                        const double* phi_rec_re_host, const double* phi_rec_im_host,
+                        int nz_tab, double z0, double dz,
+                        const double* phi_src_re_host, const double* phi_src_im_host,
+                        const double* rec_z_host, double z_pivot);
+int bogp_modeset_destroy(bogp_modeset_t h);
+
+/* `covariance_matrix` argument of MatchedFieldProcessor: K[F, N, N] complex, row-major, split planes
+ * (layout [F,N,N] per ref/optimization/utils.py:23-32, 42-56).  Factorises K on the host (pivoted
+ * Cholesky, float64) into the projection rows the kernels consume. */
+int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, const double* K_im_host);
+
+/* Ambiguity surface: replaces the loop `for z in src_z: amb[zz,:] = MFP({"src_z": z, "rec_r": rvec})`
+ * (mfp.py:213-214) including runner + beamformer + multifreq combine.
+ * out_dev[Nt, Nz, Nr] float32 (Nt = 1 and tilt_deg_host = NULL for a vertical array). */
+int bogp_bartlett_grid(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                       const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                       float* out_dev, void* stream);
+/* Same, host output buffer (device->host copy inside; synchronises the stream). */
+int bogp_bartlett_grid_host(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                            const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                            float* out_host, void* stream);
+
+/* Scattered candidates (BO raw samples / trials): cand_dev[C, 3] float64 = (range m, depth m, tilt deg).
+ * Replaces one MatchedFieldProcessor.__call__ per candidate (obj.py:28-30). */
+int bogp_bartlett_points(bogp_modeset_t h, const double* cand_dev, long long C, int atype, int mf_method,
+                         float* out_dev, void* stream);
+int bogp_bartlett_points_host(bogp_modeset_t h, const double* cand_host, long long C, int atype,
+                              int mf_method, float* out_host, void* stream);
+
+/* Geoacoustic inversion (obj.py:73-83): candidate c has its OWN mode set (host KRAKEN run per candidate).
+ * Mode-major packing, padded to Mmax:  k_re/k_im_host[C, F, Mmax], amp_re/amp_im_host[C, F, Mmax] =
+ * phi_m(z_s) already evaluated at the candidate's source depth (0 for padded modes),
+ * phi_rec_T_host[C, F, Mmax, N] float32 (real modes).  range_m_host[C].  K is shared (bogp_envbatch_set_covariance). */
+int bogp_envbatch_create(bogp_envbatch_t* out, long long C, int F, int N, int Mmax,
+                         const double* k_re_host, const double* k_im_host,
+                         const double* amp_re_host, const double* amp_im_host,
+                         const float* phi_rec_T_host, const double* range_m_host);
+int bogp_envbatch_set_covariance(bogp_envbatch_t h, const double* K_re_host, const double* K_im_host);
+int bogp_envbatch_bartlett(bogp_envbatch_t h, int atype, int mf_method, float* out_dev, void* stream);
+int bogp_envbatch_destroy(bogp_envbatch_t h);
+
+/* np.unravel_index(np.argmax(surface)) (ref/projects/swellex96_localization/data/collate.py:50):
+ * first index of the maximum of x_dev[n]; NaNs are ignored. */
+int bogp_argmax_f32(const float* x_dev, long long n, float* val_host, long long* idx_host, void* stream);
+int bogp_argmin_f32(const float* x_dev, long long n, float* val_host, long long* idx_host, void* stream);
+
+/* ------------------------------------------------------------------ Boundary B: GP posterior + acquisition
+ * Replaces SingleTaskGP(X, Y, ...) in eval mode (ei.py:67; gpmodels.py:16-30): exact GP with constant mean,
+ * outputscale * {Matern-5/2 | RBF} ARD kernel, homoskedastic noise.  Factorises K_XX + noise*I = L L^T
+ * (float64, jitter retries 1e-8,1e-7,1e-6) and uploads L^-1 and alpha.  All GP arithmetic is float64. */
+int bogp_gp_create(bogp_gp_t* out, int n, int d, const double* X_host, const double* y_host, int kernel_kind,
+                   const double* lengthscale_host, double outputscale, double mean, double noise);
+int bogp_gp_destroy(bogp_gp_t g);
+/* jitter that had to be added to the diagonal (0 if none). */
+int bogp_gp_jitter(bogp_gp_t g, double* jitter_out);
+
+/* Model.posterior(X[b,1,d]).mean / .variance  (variance clamped at 1e-10 as gpytorch does for float64). */
+int bogp_gp_posterior(bogp_gp_t g, const double* Xs_dev, long long b, int observation_noise,
+                      double* mean_dev, double* var_dev, void* stream);
+/* AcquisitionFunction.forward(X[b,1,d]) -> out_dev[b]; grad_dev[b,d] = d out / d X (NULL to skip):
+ * fused posterior + EI/LogEI/PI/UCB epilogue (+ analytic backward for optimize_acqf's L-BFGS-B). */
+int bogp_gp_acq(bogp_gp_t g, int acq_kind, double best_f, double beta, const double* Xs_dev, long long b,
+                double* out_dev, double* grad_dev, void* stream);
+/* Joint posterior for q > 1: mean_dev[b,q], cov_dev[b,q,q]. */
+int bogp_gp_posterior_joint(bogp_gp_t g, const double* Xs_dev, long long b, int q,
+                            double* mean_dev, double* cov_dev, void* stream);
+/* Backward of the joint posterior: given d F/d mean [b,q] and d F/d cov [b,q,q] (entries of the full matrix; the
+ * kernel symmetrises), grad_dev[b,q,d] = d F/d X.  This is the autograd hook botorch's MC acquisitions use through
+ * Model.posterior (optimize_acqf's L-BFGS-B needs it). */
+int bogp_gp_posterior_joint_backward(bogp_gp_t g, const double* Xs_dev, long long b, int q,
+                                     const double* gmean_dev, const double* gcov_dev, double* grad_dev, void* stream);
+/* MC qEI (Ax Models.GPEI path, ref/optimization/strategy.py:61): base_dev[S,q] standard-normal QMC samples.
+ * out_dev[b]; grad_dev[b,q,d] or NULL. */
+int bogp_gp_qei(bogp_gp_t g, const double* Xs_dev, long long b, int q, const double* base_dev, int S,
+                double best_f, double* out_dev, double* grad_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOGP_H */

@@ -1,0 +1,105 @@
+"""CPU tier: host-side logic of both boundaries and the multi-rank reduction (gloo, world_size 2)."""
+import os
+import pickle
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from bogp_b200 import mfp, sharding
+from bogp_b200.modes import INV_TONALS_3, REC_Z_21, ModeSet, pekeris_modes
+
+
+def test_modeset_contract_and_interpolation():
+    m = pekeris_modes(INV_TONALS_3, REC_Z_21)
+    assert m.n_freq == 3 and m.n_rec == 21 and all(M > 0 for M in m.n_modes)
+    z = np.array([0.0, 0.1, 33.3, 216.9, 500.0, -3.0])
+    got = m.phi_src(1, z)
+    kz = (np.arange(1, m.n_modes[1] + 1) - 0.5) * np.pi / 217.0
+    exact = np.sqrt(2 / 217.0) * np.sin(np.outer(np.clip(z, 0, 217.0), kz))
+    np.testing.assert_allclose(got, exact, atol=3e-4)       # linear interpolation of a 0.25 m table (h^2 f''/8)
+    with pytest.raises(ValueError):
+        ModeSet([1.0], [np.ones(3, complex)], [np.ones((4, 2))], [np.ones((5, 3))], 0.0, 1.0, np.zeros(4))
+
+
+def test_mfp_constructor_mirrors_reference_and_rejects_unfusable():
+    m = pekeris_modes(INV_TONALS_3, REC_Z_21)
+    K = np.zeros((3, 21, 21), complex)
+    proc = mfp.MatchedFieldProcessor(runner=mfp.ModeRunner(m), covariance_matrix=K, freq=INV_TONALS_3,
+                                     parameters={"tilt": 0.0}, beamformer=partial(mfp.beamformer, atype="cbf_ml"),
+                                     multifreq_method="product")
+    assert proc.atype == "cbf_ml" and proc.multifreq_method == "product"
+    clone = pickle.loads(pickle.dumps(proc))                   # process pools / hydra-zen partials pickle it
+    assert clone.freq == proc.freq and clone._dms is None
+    with pytest.raises(TypeError):
+        mfp.MatchedFieldProcessor(lambda p: None, K, INV_TONALS_3, {})
+    with pytest.raises(TypeError):
+        mfp.MatchedFieldProcessor(mfp.ModeRunner(m), K, INV_TONALS_3, {}, beamformer=lambda K, p: 0.0)
+    with pytest.raises(ValueError):
+        mfp.MatchedFieldProcessor(mfp.ModeRunner(m), K, INV_TONALS_3, {}, multifreq_method="median")
+    with pytest.raises(ValueError):
+        mfp.MatchedFieldProcessor(mfp.ModeRunner(m), K[:2], INV_TONALS_3, {})
+    # per-tonal merge follows the reference: fixed | {freq, title} | search, or the formatter's signature
+    seen = []
+
+    def formatter(freq, title, fixed_parameters, search_parameters):
+        seen.append((freq, title))
+        return fixed_parameters | search_parameters
+
+    proc2 = mfp.MatchedFieldProcessor(mfp.ModeRunner(m), K, INV_TONALS_3, {"src_z": 60.0}, parameter_formatter=formatter)
+    merged = proc2._merged({"rec_r": 1.0})
+    assert merged["src_z"] == 60.0 and seen[0] == (148.0, "148.0Hz") and len(seen) == 3
+
+
+def test_slab_partition_is_balanced_and_complete():
+    for n in (0, 1, 7, 1000, 1001):
+        for w in (1, 2, 3, 8):
+            spans = [sharding.slab(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_combine_extrema_tie_and_nan_rules():
+    v = torch.tensor([0.5, float("nan"), 0.75, 0.75])
+    i = torch.tensor([3, 10, 40, 20])
+    assert sharding.combine_extrema(v, i) == (0.75, 20)           # first occurrence wins ties
+    assert sharding.combine_extrema(v, i, maximize=False) == (0.5, 3)
+    assert sharding.combine_extrema(torch.tensor([float("nan")]), torch.tensor([-1]))[1] == -1
+
+
+def _worker(rank, world, port, surf, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        S = torch.from_numpy(surf)
+        local, (val, pos), full = sharding.sharded_surface(lambda lo, hi: S[lo:hi].clone(), S.shape[0], S.shape[1],
+                                                           gather_surface=True)
+        lo, hi = sharding.slab(S.shape[0], rank, world)
+        assert local.shape[0] == hi - lo
+        q.put((rank, val, pos, bool(torch.equal(torch.nan_to_num(full, nan=-7.0), torch.nan_to_num(S, nan=-7.0)))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_argmax_gloo(world):
+    """N > 1 path on CPU: row slabs per rank, all-gather of (max, index), identical answer on every rank."""
+    rng = np.random.default_rng(5)
+    surf = rng.random((11, 17)).astype(np.float32)
+    surf[3, 4] = surf[9, 2] = 2.0                                # tie across ranks: the lower flat index wins
+    surf[0, 0] = np.nan
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, surf, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, val, pos, same in res:
+        assert val == 2.0 and pos == (3, 4) and same
