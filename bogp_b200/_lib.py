@@ -29,6 +29,7 @@ _ll = C.c_longlong
 SIGNATURES = {
     "bogp_last_error": (C.c_char_p, []),
     "bogp_version": (C.c_int, []),
+    "bogp_kernel_launches": (_ll, []),
     "bogp_device_info": (C.c_int, [_ip, _ip, _ip]),
     "bogp_modeset_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp, C.c_int, C.c_double,
                                       C.c_double, _dp, _dp, _dp, C.c_double]),

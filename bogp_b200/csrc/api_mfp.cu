@@ -327,6 +327,7 @@ extern "C" int bogp_bartlett_points(bogp_modeset_t h, const double* cand_dev, lo
   BOGP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
   int blocks = (int)std::min<long long>((C + 255) / 256, 1184);
   any_tilt_kernel<<<blocks, 256, 0, s>>>(cand_dev, C, flag);
+  bogp::count_launch();
   int any = 0;
   BOGP_CUDA(cudaMemcpyAsync(&any, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
   BOGP_CUDA(cudaStreamSynchronize(s));

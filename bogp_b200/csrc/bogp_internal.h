@@ -16,6 +16,8 @@ namespace bogp {
 typedef std::complex<double> cplx;
 
 void set_error(const char* fmt, ...);
+// Number of kernels this library has launched (bench.py reports it as gpu_launches).
+void count_launch(int n = 1);
 
 #define BOGP_CUDA(call)                                                                      \
   do {                                                                                       \

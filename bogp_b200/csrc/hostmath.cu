@@ -1,6 +1,7 @@
 // Host-side float64 linear algebra used at set-up time (factor the covariance / Gram matrices once;
 // the per-candidate work is all on the GPU).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 
 #include "bogp_internal.h"
@@ -19,6 +20,10 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* last_error_cstr() { return g_err.c_str(); }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int pivoted_cholesky(const std::vector<cplx>& A, int n, double tol, std::vector<cplx>& L, int& rank) {
   // Outer-product pivoted Cholesky; L is returned in ORIGINAL row order, column j = j-th pivot step.
@@ -96,3 +101,4 @@ void invert_lower(std::vector<double>& L, int n) {
 
 extern "C" const char* bogp_last_error(void) { return bogp::last_error_cstr(); }
 extern "C" int bogp_version(void) { return 100; }
+extern "C" long long bogp_kernel_launches(void) { return bogp::launches(); }

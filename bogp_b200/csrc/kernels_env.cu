@@ -171,7 +171,9 @@ static int argext(const float* x_dev, long long n, float* val_host, long long* i
   float* ov = pv + nb;
   long long* oi = pi + nb;
   argext_stage1<MAX><<<nb, 256, 0, s>>>(x_dev, n, pv, pi);
+  bogp::count_launch();
   argext_stage2<MAX><<<1, 256, 0, s>>>(pv, pi, nb, ov, oi);
+  bogp::count_launch();
   cudaError_t e = cudaMemcpyAsync(val_host, ov, sizeof(float), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaMemcpyAsync(idx_host, oi, sizeof(long long), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -278,6 +280,7 @@ extern "C" int bogp_envbatch_bartlett(bogp_envbatch_t h, int atype, int mf_metho
   bogp::envbatch_kernel<<<grid, bogp::kEnvWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       h->C, h->F, h->N, h->Mmax, h->k_re, h->k_im, h->amp_re, h->amp_im, h->phiT, h->range, h->CkT_re, h->CkT_im, h->J,
       h->trK, h->Jmax, atype, mf_method, out_dev);
+  bogp::count_launch();
   BOGP_CUDA(cudaGetLastError());
   return 0;
 }

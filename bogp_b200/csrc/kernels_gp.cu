@@ -461,6 +461,7 @@ static int launch_gp(const bogp_gp_s* g, const GpArgs& a, bool grad, cudaStream_
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
   const int grid = (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sms * per_sm));
   gp_eval_kernel<BC><<<grid, kGpThreads, smem, s>>>(dev, a);
+  bogp::count_launch();
   BOGP_CUDA(cudaGetLastError());
   return 0;
 }
@@ -650,6 +651,7 @@ extern "C" int bogp_gp_qei(bogp_gp_t g, const double* Xs_dev, long long b, int q
   if (!rc) {
     bogp::qei_kernel<<<(unsigned)((b + 3) / 4), 128, 0, s>>>(mean, cov, b, q, base_dev, S, best_f, out_dev,
                                                             grad_dev ? gmean : nullptr, grad_dev ? gcov : nullptr, fail);
+    bogp::count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) { bogp::set_error("bogp_gp_qei: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
   }

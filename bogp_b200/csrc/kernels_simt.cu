@@ -283,11 +283,13 @@ int launch_points(const bogp_modeset_s* h, const double* cand_dev, long long C, 
     const size_t smem = (size_t)kWarpsPerBlock * (aStride + tStride) * sizeof(float2);
     if (int rc = set_smem(points_modespace_kernel, smem)) return rc;
     points_modespace_kernel<<<grid_for(C, smem), kThreads, smem, s>>>(h->dev, cand_dev, C, atype, mf, out_dev, aStride, tStride);
+    bogp::count_launch();
   } else {
     const int qStride = h->max_Mp, pStride = h->N;
     const size_t smem = (size_t)kWarpsPerBlock * (qStride + pStride) * sizeof(float2);
     if (int rc = set_smem(points_tilt_kernel, smem)) return rc;
     points_tilt_kernel<<<grid_for(C, smem), kThreads, smem, s>>>(h->dev, cand_dev, C, atype, mf, out_dev, qStride, pStride);
+    bogp::count_launch();
   }
   BOGP_CUDA(cudaGetLastError());
   return 0;
@@ -312,11 +314,13 @@ int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
     dim3 tg(std::max(1, std::min(64, (int)(((long long)(Nr + Nz) * h->max_Mp + 255) / 256))), d.F);
     grid_tables_kernel<<<tg, 256, 0, s>>>(d, r_dev, Nr, z_dev, Nz, E, PZ);
+    bogp::count_launch();
     BOGP_CUDA(cudaGetLastError());
     const int aStride = h->max_Mp, tStride = pad_to(std::max(h->max_rows, 1), 32);
     const size_t smem = (size_t)kWarpsPerBlock * (aStride + tStride) * sizeof(float2);
     if (int rc = set_smem(grid_modespace_kernel, smem)) return rc;
     grid_modespace_kernel<<<grid_for((long long)Nr * Nz, smem), kThreads, smem, s>>>(d, E, PZ, Nr, Nz, atype, mf, out_dev, aStride, tStride);
+    bogp::count_launch();
     BOGP_CUDA(cudaGetLastError());
     return 0;
   }
@@ -331,6 +335,7 @@ int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
   BOGP_CUDA(cudaMemcpyAsync(t_dev, tilt_host, Nt * sizeof(double), cudaMemcpyHostToDevice, s));
   make_grid_candidates_kernel<<<std::max(1, (int)std::min<long long>((C + 255) / 256, 148 * 8)), 256, 0, s>>>(r_dev, Nr, z_dev, Nz, t_dev, Nt, cand);
+  bogp::count_launch();
   BOGP_CUDA(cudaGetLastError());
   return launch_points(h, cand, C, atype, mf, true, out_dev, s);
 }

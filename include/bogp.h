@@ -59,6 +59,8 @@ typedef struct bogp_gp_s* bogp_gp_t;
 
 const char* bogp_last_error(void);
 int bogp_version(void);
+/* Kernels launched by this library since load (monotonic; bench.py reports the per-step difference). */
+long long bogp_kernel_launches(void);
 /* sm_count / compute capability of the current device; fails without a GPU. */
 int bogp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -1,0 +1,221 @@
+"""GPU tier: the CUDA Bartlett path (through the C ABI) against the float64 oracle.
+
+Bar (BASELINE.json north_star): identical arg-max grid indices, Bartlett power within 1e-5 relative of the
+float64 reference (FP32 / 3xTF32 arithmetic vs FP64).  The relative error is taken against the surface scale
+max|B| for values far below it (a Bartlett sidelobe of 1e-4 next to a peak of 1 carries the same absolute FP32
+noise as the peak), i.e. |got - ref| <= RTOL * max(|ref|, FLOOR * max|ref|).
+"""
+from functools import partial
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bartlett as ob
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+RTOL = 1e-5
+FLOOR = 0.05
+
+
+def assert_parity(got, ref, rtol=RTOL, floor=FLOOR):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape
+    scale = np.maximum(np.abs(ref), floor * np.abs(ref).max())
+    err = np.abs(got - ref) / scale
+    assert np.isfinite(got).all()
+    assert err.max() <= rtol, f"max rel err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+@pytest.fixture(scope="module")
+def dms1(cfg1):
+    from bogp_b200.mfp import DeviceModeSet
+    return DeviceModeSet(cfg1["modes"], cfg1["K"])
+
+
+@pytest.fixture(scope="module")
+def dms2(cfg2_small):
+    from bogp_b200.mfp import DeviceModeSet
+    return DeviceModeSet(cfg2_small["modes"], cfg2_small["K"])
+
+
+@pytest.mark.parametrize("engine", ["simt", "auto"])
+def test_cfg1_surface_vs_golden(cfg1, dms1, engine):
+    from bogp_b200 import mfp
+    g = np.load(GOLD / "bartlett_cfg1.npz")
+    surf = dms1.bartlett_grid(cfg1["r"], cfg1["z"], engine=engine)
+    assert_parity(surf.cpu().numpy(), g["cbf_mean"])
+    val, pos = mfp.argmax(surf)
+    assert pos == tuple(g["argmax"])
+    ml = dms1.bartlett_grid(cfg1["r"], cfg1["z"], atype="cbf_ml", multifreq_method="product", engine=engine)
+    assert_parity(ml.cpu().numpy(), g["cbf_ml_product"], floor=1.0)   # product of (1 - B): absolute 1e-5 of O(1)
+    host = dms1.bartlett_grid_host(cfg1["r"], cfg1["z"], engine=engine)
+    np.testing.assert_array_equal(host, surf.cpu().numpy())
+
+
+@pytest.mark.parametrize("engine", ["simt", "auto"])
+def test_cfg2_shape_surface_vs_oracle(cfg2_small, dms2, engine):
+    """13 tonals, 64 receivers (SWellEx-96 shape); identical arg-max index."""
+    c = cfg2_small
+    ref = ob.ambiguity_surface(c["modes"], c["K"], c["r"], c["z"])
+    surf = dms2.bartlett_grid(c["r"], c["z"], engine=engine).cpu().numpy()
+    assert_parity(surf, ref)
+    assert np.unravel_index(surf.argmax(), surf.shape) == np.unravel_index(ref.argmax(), ref.shape)
+
+
+def test_truth_is_one_and_ml_zero(cfg2_small, dms2):
+    c = cfg2_small
+    cand = np.array([[c["truth"][0], c["truth"][1], 0.0]])
+    assert abs(float(dms2.bartlett_points(cand).cpu()[0]) - 1.0) < 2e-5
+    assert abs(float(dms2.bartlett_points(cand, atype="cbf_ml", multifreq_method="product").cpu()[0])) < 2e-5
+
+
+def test_points_tilt_rank8_vs_golden():
+    """Scattered candidates, tilted array, rank-8 covariance, 13 tonals."""
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    g = np.load(GOLD / "bartlett_points13.npz")
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    K8 = synthetic_covariance(modes, 60.0, 5.0, tilt_deg=1.5, snapshots=8, seed=3)
+    dms = DeviceModeSet(modes, K8)
+    got = dms.bartlett_points(g["cand"]).cpu().numpy()
+    assert_parity(got, g["cbf_mean"])
+    # zero-tilt rows go through the mode-space kernel when the whole batch is untilted: same numbers
+    got0 = dms.bartlett_points(g["cand"][:32]).cpu().numpy()
+    assert_parity(got0, g["cbf_mean"][:32])
+
+
+def test_grid_with_tilt_axis_matches_points(cfg1, dms1):
+    r, z, tilt = cfg1["r"][::10], cfg1["z"][::10], np.array([-2.0, 0.0, 1.0])
+    vol = dms1.bartlett_grid(r, z, tilt).cpu().numpy()
+    assert vol.shape == (3, len(z), len(r))
+    cand = np.array([[ri, zi, ti] for ti in tilt for zi in z for ri in r])
+    ref = ob.bartlett_points(cfg1["modes"], cfg1["K"], cand).reshape(vol.shape)
+    assert_parity(vol, ref)
+
+
+def test_complex_modes_krakenc_layout():
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import INV_TONALS_3, REC_Z_21, pekeris_modes, synthetic_covariance
+    modes = pekeris_modes(INV_TONALS_3, REC_Z_21, complex_modes=True)
+    K = synthetic_covariance(modes, 40.0, 2.2, snapshots=4, seed=1)
+    dms = DeviceModeSet(modes, K)
+    r, z = np.linspace(0.5, 6.0, 40), np.linspace(5.0, 190.0, 12)
+    ref = ob.ambiguity_surface(modes, K, r, z)
+    assert_parity(dms.bartlett_grid(r, z).cpu().numpy(), ref)
+    rng = np.random.default_rng(2)
+    cand = np.stack([rng.uniform(0.5, 6, 40), rng.uniform(5, 190, 40), rng.uniform(-3, 3, 40)], 1)
+    assert_parity(dms.bartlett_points(cand).cpu().numpy(), ob.bartlett_points(modes, K, cand))
+
+
+def test_matched_field_processor_is_drop_in(cfg1):
+    """Same constructor / call pattern as the reference loop (mfp.py:198-214) and the pooled objective (obj.py)."""
+    from bogp_b200 import mfp
+    m, K = cfg1["modes"], cfg1["K"]
+    ref_proc = ob.MatchedFieldProcessor(ob.make_runner(m), K, m.freq, {"tilt": 0.0})
+    gpu_proc = mfp.MatchedFieldProcessor(runner=mfp.ModeRunner(m), covariance_matrix=K, freq=m.freq,
+                                         parameters={"tilt": 0.0}, beamformer=mfp.beamformer)
+    rvec = cfg1["r"]
+    for zs in (10.0, 71.11, 150.5):
+        got = gpu_proc({"src_z": zs, "rec_r": rvec})
+        assert isinstance(got, np.ndarray) and got.shape == (len(rvec),) and got.dtype == np.float64
+        assert_parity(got, ref_proc({"src_z": zs, "rec_r": rvec}))
+    one = gpu_proc({"src_z": 71.11, "rec_r": 1.07})
+    assert isinstance(one, float) and abs(one - 1.0) < 2e-5
+    batch = [{"src_z": 20.0 + 3 * i, "rec_r": 0.5 + 0.2 * i, "tilt": 0.1 * i} for i in range(9)]
+    got = gpu_proc(batch)
+    ref = np.array([ref_proc(p) for p in batch])
+    assert_parity(got, ref)
+    # cbf_ml + product, subset of tonals (obj.py:62-70 flavour)
+    sub = [148.0, 388.0]
+    Ks = K[[0, 2]]
+    gp2 = mfp.MatchedFieldProcessor(mfp.ModeRunner(m), Ks, sub, {}, beamformer=partial(mfp.beamformer, atype="cbf_ml"),
+                                    multifreq_method="product")
+    rp2 = ob.MatchedFieldProcessor(ob.make_runner(m), Ks, sub, {}, beamformer=partial(ob.beamformer, atype="cbf_ml"),
+                                   multifreq_method="product")
+    assert_parity(gp2({"src_z": 55.0, "rec_r": rvec}), rp2({"src_z": 55.0, "rec_r": rvec}), floor=1.0)
+
+
+def test_envbatch_geoacoustic_scoring():
+    """Config 5 shape: every candidate has its own mode set (perturbed depth / bottom speed), 3 tonals, 21 elements."""
+    from bogp_b200.envbatch import EnvBatch
+    from bogp_b200 import mfp
+    from bogp_b200.modes import INV_TONALS_3, REC_Z_21, pekeris_modes, perturbed_pekeris_batch, synthetic_covariance
+    truth = pekeris_modes(INV_TONALS_3, REC_Z_21)
+    K = synthetic_covariance(truth, 71.11, 1.07)
+    rng = np.random.default_rng(4)
+    C = 48
+    depths = np.r_[217.0, rng.uniform(212.0, 222.0, C - 1)]
+    cbs = np.r_[1650.0, rng.uniform(1600.0, 1700.0, C - 1)]
+    sets = perturbed_pekeris_batch(INV_TONALS_3, REC_Z_21, depths, cbs)
+    r = np.r_[1.07, rng.uniform(0.9, 1.3, C - 1)]
+    zs = np.r_[71.11, rng.uniform(60.0, 80.0, C - 1)]
+    cand = np.stack([r, zs, np.zeros(C)], 1)
+    for atype, mf in (("cbf", "mean"), ("cbf_ml", "product")):
+        ref = ob.bartlett_envbatch(sets, K, cand, atype=atype, multifreq_method=mf)
+        with EnvBatch(sets, r, zs, K) as eb:
+            got = eb.bartlett(atype=atype, multifreq_method=mf).cpu().numpy()
+        assert_parity(got, ref, floor=1.0 if atype == "cbf_ml" else FLOOR)
+    assert abs(got[0]) < 2e-5                        # the true environment scores 0 under cbf_ml
+
+    # the objective protocol with a per-candidate mode provider (obj.py:73-83)
+    def provider(p):
+        return pekeris_modes(INV_TONALS_3, REC_Z_21, depth=p["h_w"], c_b=p["c_b"])
+
+    proc = mfp.MatchedFieldProcessor(mfp.ModeRunner(provider), K, INV_TONALS_3, {"src_z": 71.11, "rec_r": 1.07},
+                                     beamformer=partial(mfp.beamformer, atype="cbf_ml"), multifreq_method="product")
+    vals = proc([{"h_w": float(d), "c_b": float(c)} for d, c in zip(depths[:6], cbs[:6])])
+    ref6 = ob.bartlett_envbatch(sets[:6], K, np.array([[1.07, 71.11, 0.0]] * 6), atype="cbf_ml", multifreq_method="product")
+    assert_parity(vals, ref6, floor=1.0)
+
+
+def test_edge_cases(cfg1, dms1):
+    from bogp_b200 import _lib, mfp
+    empty = dms1.bartlett_grid(np.array([]), cfg1["z"])
+    assert empty.shape == (50, 0)
+    assert dms1.bartlett_points(np.zeros((0, 3))).shape == (0,)
+    one = dms1.bartlett_grid([1.07], [71.11])
+    assert one.shape == (1, 1) and abs(float(one.cpu()) - 1.0) < 2e-5
+    with pytest.raises(_lib.BogpError):
+        dms1.bartlett_grid([0.0, 1.0], [10.0])                 # non-positive range
+    with pytest.raises(KeyError):
+        dms1.bartlett_grid([1.0], [10.0], atype="mvdr")
+    # depths outside the table clamp to its ends (data contract)
+    lo = dms1.bartlett_points(np.array([[2.0, -5.0, 0.0], [2.0, 0.0, 0.0], [2.0, 400.0, 0.0], [2.0, 217.0, 0.0]])).cpu().numpy()
+    assert np.isnan(lo[:2]).all() or np.allclose(lo[0], lo[1], equal_nan=True)
+    x = torch.tensor([0.1, float("nan"), 0.7, 0.7, -1.0], device="cuda")
+    assert mfp.argmax(x) == (pytest.approx(0.7), (2,))
+    assert mfp.argmin(x) == (pytest.approx(-1.0), (4,))
+
+
+def test_full_size_surface_properties():
+    """BASELINE config 2 at full size (1000 x 1000 x 13 tonals): size-independent properties.
+
+    (a) the peak sits on the grid node nearest the truth with value ~1; (b) 0 <= B <= 1; (c) a random sample of
+    nodes matches the oracle; (d) SIMT and auto engines agree; (e) the grid equals the scattered-point kernel.
+    """
+    from bogp_b200 import mfp
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    r, z = np.linspace(0.1, 10.0, 1000), np.linspace(1.0, 200.0, 1000)
+    tr, tz = r[495], z[296]
+    K = synthetic_covariance(modes, tz, tr)
+    dms = DeviceModeSet(modes, K)
+    surf = dms.bartlett_grid(r, z)
+    val, pos = mfp.argmax(surf)
+    assert pos == (296, 495) and abs(val - 1.0) < 2e-5
+    s = surf.cpu().numpy()
+    assert s.min() >= 0.0 and s.max() <= 1.0 + 2e-5
+    rng = np.random.default_rng(9)
+    jj, ii = rng.integers(0, 1000, 300), rng.integers(0, 1000, 300)
+    cand = np.stack([r[ii], z[jj], np.zeros(300)], 1)
+    ref = ob.bartlett_points(modes, K, cand)
+    assert_parity(s[jj, ii], ref)
+    s2 = dms.bartlett_grid(r, z, engine="simt").cpu().numpy()
+    assert np.abs(s2 - s).max() <= 2e-5
+    pts = dms.bartlett_points(cand).cpu().numpy()
+    assert_parity(pts, ref)

@@ -1,0 +1,181 @@
+"""GPU tier: float64 GP posterior / acquisition kernels (through the C ABI) against the oracle and the sklearn goldens.
+
+Bar: acquisition values within 1e-5 relative of the float64 reference (north_star).  Both sides are float64, so
+most checks are much tighter.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp as ogp
+from oracle import optimize as oopt
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).parent / "golden"
+
+
+def make_problem(n, d, kind="matern52", noise=1e-6, seed=0):
+    rng = np.random.default_rng(seed)
+    X = torch.quasirandom.SobolEngine(d, scramble=True, seed=seed).draw(n, dtype=torch.float64).numpy()
+    y = np.sin(3.0 * X[:, 0]) + 0.5 * np.cos(4.0 * X.sum(1)) + 0.1 * rng.standard_normal(n)
+    y = (y - y.mean()) / y.std()
+    ls = np.full(d, 0.3) if d <= 3 else rng.uniform(0.4, 1.2, d)
+    from bogp_b200.gp import SingleTaskGP
+    model = SingleTaskGP(X, y, kind, lengthscale=ls, outputscale=1.0, mean=0.0, noise=noise)
+    oracle = ogp.GPState(X, y, kind, ls, 1.0, 0.0, noise)
+    return model, oracle, X, y
+
+
+@pytest.mark.parametrize("name,kind", [("m52_d2", "matern52"), ("m52_d7", "matern52"), ("rbf_d3", "rbf")])
+def test_posterior_and_acq_vs_sklearn_golden(name, kind):
+    from bogp_b200.acquisition import ExpectedImprovement, ProbabilityOfImprovement, UpperConfidenceBound
+    from bogp_b200.gp import SingleTaskGP
+    g = np.load(GOLD / "gp_sklearn.npz")
+    model = SingleTaskGP(g[f"{name}_X"], g[f"{name}_y"], kind, lengthscale=g[f"{name}_ls"],
+                         outputscale=float(g[f"{name}_s"]), noise=float(g[f"{name}_noise"]))
+    Xs = torch.as_tensor(g[f"{name}_Xs"]).unsqueeze(1)
+    post = model.posterior(Xs)
+    assert post.mean.shape == (200, 1, 1) and post.variance.shape == (200, 1, 1)
+    np.testing.assert_allclose(post.mean.reshape(-1).cpu().numpy(), g[f"{name}_mu"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(post.variance.reshape(-1).sqrt().cpu().numpy(), g[f"{name}_sd"], rtol=1e-5, atol=1e-8)
+    best = float(g[f"{name}_best"])
+    np.testing.assert_allclose(ExpectedImprovement(model, best)(Xs).cpu().numpy(), g[f"{name}_ei"], rtol=1e-4, atol=1e-10)
+    np.testing.assert_allclose(UpperConfidenceBound(model, 4.0)(Xs).cpu().numpy(), g[f"{name}_ucb"], rtol=1e-6)
+    np.testing.assert_allclose(ProbabilityOfImprovement(model, best)(Xs).cpu().numpy(), g[f"{name}_pi"], rtol=1e-4, atol=1e-10)
+
+
+@pytest.mark.parametrize("n,d,kind,b", [(128, 2, "matern52", 4096), (256, 3, "matern52", 1024), (512, 7, "matern52", 4096),
+                                        (300, 3, "rbf", 513), (33, 1, "matern52", 401), (1024, 4, "matern52", 64)])
+def test_posterior_and_all_acquisitions_vs_oracle(n, d, kind, b):
+    """BASELINE config 3 sizes (n in {128,256,512}, d in {2,3,7}, 4096 raw samples) plus ragged / extreme shapes."""
+    from bogp_b200 import acquisition as A
+    model, oracle, X, y = make_problem(n, d, kind, noise=1e-6 if kind == "matern52" else 1e-4)
+    Xs = torch.rand(b, 1, d, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    Xs[:3, 0] = torch.as_tensor(X[:3])                  # exactly on training points: variance at the noise floor
+    mu_o, var_o = ogp.posterior_mean_var(oracle, Xs)
+    post = model.posterior(Xs)
+    np.testing.assert_allclose(post.mean.reshape(-1).cpu().numpy(), mu_o.reshape(-1).numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(post.variance.reshape(-1).cpu().numpy(), var_o.reshape(-1).numpy(), rtol=1e-6, atol=1e-10)
+    noisy = model.posterior(Xs, observation_noise=True).variance.reshape(-1).cpu().numpy()
+    np.testing.assert_allclose(noisy, ogp.posterior_mean_var(oracle, Xs, True)[1].reshape(-1).numpy(), rtol=1e-6, atol=1e-10)
+    best = float(y.max())
+    for cls, kind_o, kw in ((A.ExpectedImprovement, "ei", {"best_f": best}), (A.LogExpectedImprovement, "logei", {"best_f": best}),
+                            (A.ProbabilityOfImprovement, "pi", {"best_f": best}), (A.UpperConfidenceBound, "ucb", {"beta": 4.0})):
+        got = cls(model, **kw)(Xs).cpu().numpy()
+        ref = ogp.acq_value(oracle, kind_o, Xs, best, 4.0).numpy()
+        scale = np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max())
+        assert (np.abs(got - ref) / scale).max() <= 1e-5, kind_o
+        if kind_o in ("ei", "ucb"):
+            assert int(got.argmax()) == int(ref.argmax())
+
+
+@pytest.mark.parametrize("n,d,kind", [(128, 2, "matern52"), (512, 7, "matern52"), (200, 3, "rbf")])
+def test_acquisition_gradients_vs_autograd_oracle(n, d, kind):
+    """(viii) the analytic backward the L-BFGS-B restarts use == autograd through the float64 oracle."""
+    from bogp_b200 import acquisition as A
+    model, oracle, X, y = make_problem(n, d, kind, noise=1e-4)
+    best = float(y.max())
+    for b in (64, 7, 1000):
+        Xs = torch.rand(b, 1, d, dtype=torch.float64, generator=torch.Generator().manual_seed(b))
+        for cls, kind_o, kw in ((A.ExpectedImprovement, "ei", {"best_f": best}), (A.LogExpectedImprovement, "logei", {"best_f": best}),
+                                (A.ProbabilityOfImprovement, "pi", {"best_f": best}), (A.UpperConfidenceBound, "ucb", {"beta": 2.0})):
+            Xg = Xs.clone().requires_grad_(True)
+            val = cls(model, **kw)(Xg)
+            (grad,) = torch.autograd.grad(val.sum(), Xg)
+            v_o, g_o = ogp.acq_value_and_grad(oracle, kind_o, Xs, best, 2.0)
+            scale = max(float(g_o.abs().max()), 1e-300)
+            assert float((grad.cpu() - g_o).abs().max()) / scale <= 1e-6, (kind_o, b)
+            np.testing.assert_allclose(val.detach().cpu().numpy(), v_o.numpy(), rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("q", [2, 4, 5])
+def test_joint_posterior_and_qei(q):
+    from bogp_b200 import acquisition as A
+    from bogp_b200.gp import joint_posterior
+    model, oracle, X, y = make_problem(160, 3, "matern52", noise=1e-4)
+    b = 37
+    Xs = torch.rand(b, q, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(q))
+    mu_o, cov_o = ogp.posterior(oracle, Xs)
+    post = model.posterior(Xs)
+    np.testing.assert_allclose(post.mean.squeeze(-1).cpu().numpy(), mu_o.numpy(), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(post.covariance.cpu().numpy(), cov_o.numpy(), rtol=1e-6, atol=1e-10)
+    # backward of the joint posterior against autograd through the oracle, random upstream gradients
+    Xg = Xs.clone().cuda().requires_grad_(True)
+    mean, cov = joint_posterior(model, Xg)
+    gm = torch.randn(b, q, dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    gc = torch.randn(b, q, q, dtype=torch.float64, generator=torch.Generator().manual_seed(4))
+    ((mean * gm.cuda()).sum() + (cov * gc.cuda()).sum()).backward()
+    Xo = Xs.clone().requires_grad_(True)
+    mo, co = ogp.posterior(oracle, Xo)
+    ((mo * gm).sum() + (co * gc).sum()).backward()
+    assert float((Xg.grad.cpu() - Xo.grad).abs().max()) / float(Xo.grad.abs().max()) <= 1e-7
+    # fused MC qEI value + gradient
+    base = ogp.sobol_normal_samples(q, 512, 0)
+    best = float(y.max()) - 0.5
+    acq = A.qExpectedImprovement(model, best, q=q, base_samples=base)
+    Xq = Xs.clone().requires_grad_(True)
+    val = acq(Xq)
+    (grad,) = torch.autograd.grad(val.sum(), Xq)
+    v_o, g_o = ogp.acq_value_and_grad(oracle, "qei", Xs, best, base_samples=base)
+    np.testing.assert_allclose(val.detach().cpu().numpy(), v_o.numpy(), rtol=1e-6, atol=1e-10)
+    assert float((grad.cpu() - g_o).abs().max()) / max(float(g_o.abs().max()), 1e-300) <= 1e-5
+
+
+def test_optimize_acqf_and_bo_trajectory_match_oracle(cfg1):
+    """Same orchestration, same seeds: the GPU path reproduces the oracle's BO trajectory (config 1, small budget)."""
+    from bogp_b200 import acquisition as A
+    from bogp_b200.gp import FitConfig, SingleTaskGP, fit_gp_adamw
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.optim import optimize_acqf
+    from oracle import bartlett as ob
+    m, K = cfg1["modes"], cfg1["K"]
+    lo, hi = np.array([0.57, 51.0]), np.array([1.57, 91.0])
+    dms = DeviceModeSet(m, K)
+
+    def obj_gpu(Xn):
+        phys = lo + (np.atleast_2d(Xn) + 1.0) * 0.5 * (hi - lo)
+        return -dms.bartlett_points(np.concatenate([phys, np.zeros((len(phys), 1))], 1)).cpu().numpy().astype(np.float64)
+
+    def obj_cpu(Xn):
+        phys = lo + (np.atleast_2d(Xn) + 1.0) * 0.5 * (hi - lo)
+        return -ob.bartlett_points(m, K, np.concatenate([phys, np.zeros((len(phys), 1))], 1))
+
+    budget, n_init, restarts, raw, steps = 14, 8, 6, 128, 30
+    Xo, Yo = oopt.bo_loop(obj_cpu, 2, budget, n_init, restarts, raw, seed=0, fit_cfg=ogp.FitConfig(steps=steps))
+
+    torch.manual_seed(0)
+    sob = torch.quasirandom.SobolEngine(2, scramble=True, seed=0)
+    X = 2.0 * sob.draw(n_init).to(torch.float64) - 1.0
+    Y = -torch.as_tensor(obj_gpu(X.numpy()))
+    bounds = torch.tensor([[-1.0, -1.0], [1.0, 1.0]], dtype=torch.float64)
+    while len(Y) < budget:
+        tY = (Y - Y.mean()) / Y.std()
+        model = fit_gp_adamw(SingleTaskGP(X, tY), FitConfig(steps=steps))
+        cand, _ = optimize_acqf(A.ExpectedImprovement(model, float(tY.max())), bounds, 1, restarts, raw)
+        X = torch.cat((X, cand.reshape(1, -1)))
+        Y = torch.cat((Y, -torch.as_tensor(obj_gpu(cand.numpy())).reshape(-1)))
+    # float32 objective + float64 GP on a different device: trajectories agree to optimiser tolerance
+    np.testing.assert_allclose(X.numpy(), Xo.numpy(), atol=5e-3)
+    np.testing.assert_allclose((-Y).numpy(), Yo.numpy(), atol=5e-3)
+
+
+def test_gp_edge_cases():
+    from bogp_b200 import _lib
+    from bogp_b200 import acquisition as A
+    from bogp_b200.gp import SingleTaskGP
+    model, oracle, X, y = make_problem(40, 2)
+    assert model.posterior(torch.zeros(0, 1, 2)).mean.shape == (0, 1, 1)
+    assert A.ExpectedImprovement(model, 0.0)(torch.zeros(0, 1, 2)).shape == (0,)
+    with pytest.raises(ValueError):
+        A.ExpectedImprovement(model, 0.0)(torch.zeros(3, 2, 2))
+    with pytest.raises(ValueError):
+        model.posterior(torch.zeros(3, 1, 5))
+    # duplicated training points and zero noise: needs the jitter retries, like gpytorch ("A not p.d., added jitter")
+    Xd = np.concatenate([X[:10], X[:10]])
+    dup = SingleTaskGP(Xd, np.concatenate([y[:10], y[:10]]), lengthscale=[0.3, 0.3], outputscale=1.0, noise=0.0)
+    assert dup.jitter in (1e-8, 1e-7, 1e-6)
+    assert np.isfinite(dup.posterior(torch.rand(5, 1, 2, dtype=torch.float64)).mean.cpu().numpy()).all()
+    with pytest.raises(_lib.BogpError):
+        SingleTaskGP(np.zeros((1100, 2)), np.zeros(1100)).handle()          # n above the kernel's limit
