@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: Bartlett candidate-evals/s (candidate x frequency) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine auto|simt|umma]
+
+Workload (config.workload): BASELINE.json configs[1] -- SWellEx-96-shaped 13-tonal incoherent Bartlett ambiguity
+surface over a 1000 x 1000 (range x depth) grid, 64-element VLA, synthetic Pekeris-like mode set, rank-1 covariance
+from a known truth.  One *step* = one full pass of the hot path over one rank's slab: phase/depth table generation,
+the fused modal-sum + Bartlett + multi-frequency kernel, and the final arg-max reduction (collate.py:50) -- on N > 1
+GPUs every rank evaluates its own 1000-row slab of a (1000 N)-row surface (weak scaling, no data-path collective)
+and the step ends with the NCCL all-gather of one 16-byte (max, index) record per rank.
+
+Keys of the JSON line (see the task contract): value = whole-job cand x freq evals/s with mode tables / covariance
+resident in HBM (device timed, CUDA events, max over ranks); e2e = same metric through the host-buffer C-ABI call
+(host range/depth vectors in, page-locked host surface out, copies inside the timed region); roofline = dominant
+kernel against the tensor-core peak; cpu_baseline = the float64 oracle port on this host's cores (rank 0, N = 1).
+
+``--impl reference`` times the reference's CPU path (the oracle port: the reference's arithmetic lives in un-vendored
+TritonOA, so there is no oracle/_ref build -- DESIGN.md) with a process pool over every host core.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+NR, NZ_PER_GPU = 1000, 1000
+R_KM = (0.1, 10.0)
+Z_M = (1.0, 200.0)
+TRUTH_NODE = (296, 495)        # (depth row, range column) of the synthetic source on the N=1 grid
+METRIC = "bartlett_cand_freq_evals_per_s"
+UNIT = "cand*freq/s"
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "configs[1]: 13-tonal incoherent Bartlett surface, 1000 ranges x 1000 depths per GPU, "
+                        "64-element VLA, synthetic Pekeris mode set (276 modes), rank-1 K",
+            "grid": [NZ_PER_GPU * n_gpus, NR], "tonals": 13, "receivers": 64,
+            "sharding": f"depth-row slabs over {n_gpus} rank(s), replicated mode tables",
+            "l2": "flushed between timed steps (256 MiB device memset, untimed); tables are L2-resident by design"}
+
+
+def build_inputs(n_gpus: int):
+    from bogp_b200.modes import SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    r = np.linspace(R_KM[0], R_KM[1], NR)
+    z1 = np.linspace(Z_M[0], Z_M[1], NZ_PER_GPU)
+    z = np.linspace(Z_M[0], Z_M[1], NZ_PER_GPU * n_gpus)
+    K = synthetic_covariance(modes, z1[TRUTH_NODE[0]], r[TRUTH_NODE[1]])
+    return modes, K, r, z
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, p[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU path
+def _cpu_rows(args):
+    """Worker: oracle surface rows [lo, hi) with one BLAS thread (the pool supplies the parallelism)."""
+    lo, hi, n_gpus = args
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1)
+    except Exception:   # pragma: no cover
+        import contextlib
+        ctx = contextlib.nullcontext()
+    from oracle import bartlett as ob
+    modes, K, r, z = build_inputs(n_gpus)
+    with ctx:
+        t0 = time.perf_counter()
+        ob.ambiguity_surface(modes, K, r, z[lo:hi])
+        return time.perf_counter() - t0
+
+
+def cpu_pool(cores: int):
+    """Process pool mirroring the reference's own parallelism (ProcessPoolExecutor(max_workers=8),
+    conf/data/mfp.yaml:12), one BLAS thread per worker; workers are imported and warmed before any timing."""
+    from concurrent.futures import ProcessPoolExecutor
+    ex = ProcessPoolExecutor(max_workers=cores)
+    list(ex.map(_cpu_rows, [(0, 1, 1)] * (2 * cores)))
+    return ex
+
+
+def cpu_path_rate(ex, rows: int, cores: int, n_gpus: int = 1):
+    """cand x freq evals/s of the oracle port over `rows` depth rows x 1000 ranges x 13 tonals on `cores` workers."""
+    per = max(1, rows // cores)
+    chunks = [(i * per, (i + 1) * per, n_gpus) for i in range(cores)]
+    t0 = time.perf_counter()
+    list(ex.map(_cpu_rows, chunks))
+    dt = time.perf_counter() - t0
+    evals = per * cores * NR * 13
+    return evals / dt, dt, per * cores
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    rows_per_step = min(1000, 8 * cores)
+    rates = []
+    with cpu_pool(cores) as ex:
+        for i in range(args.warmup + args.steps):
+            rate, dt, rows = cpu_path_rate(ex, rows_per_step, cores, 1)
+            if i >= args.warmup:
+                rates.append((rate, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([d for _, d in rates]) * 1e3)
+    sample = f"{rows_per_step} depth rows x {NR} ranges x 13 tonals per step ({rows_per_step * NR * 13} evals)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference CPU path = float64 oracle port of MatchedFieldProcessor/run_kraken modal sum/beamformer "
+                "(TritonOA is un-vendored and absent, so no oracle/_ref); modes precomputed on both arms"}))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+    from bogp_b200 import _lib, mfp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (bogp_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+
+    modes, K, r, z = build_inputs(world)
+    lo, hi = rank * NZ_PER_GPU, (rank + 1) * NZ_PER_GPU
+    z_slab = np.ascontiguousarray(z[lo:hi])
+    dms = mfp.DeviceModeSet(modes, K)
+    surf = torch.empty((NZ_PER_GPU, NR), dtype=torch.float32, device=dev)
+    pair = torch.zeros(2, dtype=torch.int64, device=dev)
+    pairs = torch.zeros((world, 2), dtype=torch.int64, device=dev)
+    scratch = torch.empty(8192, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    host_surf = torch.empty((NZ_PER_GPU, NR), dtype=torch.float32, pin_memory=True)
+    host_surf_np = host_surf.numpy()
+
+    def step_device():
+        dms.bartlett_grid(r, z_slab, engine=args.engine, out=surf)
+        mfp.argext_device(surf, pair, scratch, maximize=True)
+        if world > 1:
+            dist.all_gather_into_tensor(pairs.view(-1), pair)
+
+    def step_e2e():
+        out = dms.bartlett_grid_host(r, z_slab, engine=args.engine, out=host_surf_np)
+        flat = int(np.argmax(out))          # final reduction on the host copy (collate.py:50)
+        if world > 1:
+            rec = torch.tensor([lo * NR + flat, 0], dtype=torch.int64)
+            rec[1] = int(np.float32(out.reshape(-1)[flat]).view(np.int32))
+            pair.copy_(rec)
+            dist.all_gather_into_tensor(pairs.view(-1), pair)
+            pairs.cpu()
+        return flat
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness gate before timing: peak on the truth node, value ~ 1
+    step_device()
+    torch.cuda.synchronize()
+    val, pos = mfp.argmax(surf)
+    if world == 1 and not (pos == TRUTH_NODE and abs(val - 1.0) < 2e-5):
+        raise SystemExit(f"bench.py: parity gate failed: argmax {pos} value {val}")
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    _lib.timing_read()
+    _lib.timing_enable(True)
+    launches0 = _lib.kernel_launches()
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for a, b in ev:
+            flush.zero_()
+            a.record()
+            step_device()
+            b.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = _lib.kernel_launches() - launches0
+    _lib.timing_enable(False)
+    kern_ms, kern_n = _lib.timing_read()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    evals_per_step = world * NZ_PER_GPU * NR * modes.n_freq
+    value = evals_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer entry point
+    for _ in range(max(3, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = evals_per_step * args.steps / e2e_s
+    h2d = (len(r) + len(z_slab)) * 8 + (16 if world > 1 else 0)
+    d2h = NZ_PER_GPU * NR * 4 + (16 * world if world > 1 else 0)
+
+    # ---- roofline of the dominant kernel
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        bf16 = float(json.loads(peaks_path.read_text())["bf16_tflops"])
+        peak_src = "MEASURED_PEAKS.json bf16_tflops (burst)"
+    else:
+        bf16, peak_src = 1590.0, "fallback 1.59 PFLOP/s bf16 (B200_PROFILING.md)"
+    peak = bf16 / 2.0 / 3.0     # TF32 runs at half the bf16 rate; 3xTF32 spends three MMAs per product
+    flop_per_launch = dms.flops_per_candidate() * NZ_PER_GPU * NR
+    kern_avg_ms = kern_ms / max(kern_n, 1)
+    achieved = flop_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_n else None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
+                "flop_per_launch": flop_per_launch,
+                "peak_def": f"{peak_src} / 2 (TF32 rate) / 3 (3xTF32 split) of measured",
+                "algorithmic": "sum_f 4*rows_f*M_f flop per candidate (mode-space operator, DESIGN.md)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(world), engine=args.engine),
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s * 1e3 / args.steps,
+                    "api": "DeviceModeSet.bartlett_grid_host -> bogp_bartlett_grid_host (page-locked host surface)"},
+            "gpu_launches": int(launches), "roofline": roofline,
+            "wall_s_timed_region": t_wall}
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        with cpu_pool(cores) as ex:
+            rate, dt, rows = cpu_path_rate(ex, min(1000, 64 * cores), cores, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{rows} of 1000 depth rows x {NR} ranges x 13 tonals, {dt:.1f} s, "
+                                          f"{cores} processes x 1 BLAS thread"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--engine", choices=["auto", "simt", "umma"], default="auto")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

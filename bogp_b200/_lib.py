@@ -30,10 +30,13 @@ SIGNATURES = {
     "bogp_last_error": (C.c_char_p, []),
     "bogp_version": (C.c_int, []),
     "bogp_kernel_launches": (_ll, []),
+    "bogp_timing_enable": (C.c_int, [C.c_int]),
+    "bogp_timing_read": (C.c_int, [_dp, C.POINTER(_ll)]),
     "bogp_device_info": (C.c_int, [_ip, _ip, _ip]),
     "bogp_modeset_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _ip, _dp, _dp, _dp, _dp, C.c_int, C.c_double,
                                       C.c_double, _dp, _dp, _dp, C.c_double]),
     "bogp_modeset_destroy": (C.c_int, [_vp]),
+    "bogp_modeset_info": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip]),
     "bogp_covariance_set": (C.c_int, [_vp, _dp, _dp]),
     "bogp_bartlett_grid": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "bogp_bartlett_grid_host": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _vp]),
@@ -45,6 +48,7 @@ SIGNATURES = {
     "bogp_envbatch_destroy": (C.c_int, [_vp]),
     "bogp_argmax_f32": (C.c_int, [_vp, _ll, _fp, C.POINTER(_ll), _vp]),
     "bogp_argmin_f32": (C.c_int, [_vp, _ll, _fp, C.POINTER(_ll), _vp]),
+    "bogp_argext_f32_dev": (C.c_int, [_vp, _ll, C.c_int, _vp, _vp, _vp, _ll, _vp]),
     "bogp_gp_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_double, C.c_double, C.c_double]),
     "bogp_gp_destroy": (C.c_int, [_vp]),
     "bogp_gp_jitter": (C.c_int, [_vp, _dp]),
@@ -110,3 +114,18 @@ def device_info():
     sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
     call("bogp_device_info", C.byref(sm), C.byref(maj), C.byref(mnr))
     return sm.value, maj.value, mnr.value
+
+
+def kernel_launches() -> int:
+    return int(lib().bogp_kernel_launches())
+
+
+def timing_enable(on: bool) -> None:
+    call("bogp_timing_enable", 1 if on else 0)
+
+
+def timing_read():
+    """(summed dominant-kernel milliseconds, launches) since the last read; synchronises the recorded events."""
+    ms, n = C.c_double(), _ll()
+    call("bogp_timing_read", C.byref(ms), C.byref(n))
+    return ms.value, n.value

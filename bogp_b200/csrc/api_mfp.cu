@@ -46,6 +46,16 @@ int ensure_scratch(bogp_modeset_s* h, size_t bytes) {
 }
 }  // namespace bogp
 
+static int io_scratch(bogp_modeset_s* h, size_t bytes) {
+  if (h->io_scratch_bytes >= bytes) return 0;
+  if (h->io_scratch) cudaFree(h->io_scratch);
+  h->io_scratch = nullptr;
+  h->io_scratch_bytes = 0;
+  BOGP_CUDA(cudaMalloc(&h->io_scratch, bytes));
+  h->io_scratch_bytes = bytes;
+  return 0;
+}
+
 extern "C" int bogp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (int rc = require_device()) return rc;
   int dev = 0;
@@ -152,6 +162,7 @@ extern "C" int bogp_modeset_destroy(bogp_modeset_t h) {
   for (void* p : h->allocs) cudaFree(p);
   for (void* p : h->cov_allocs) cudaFree(p);
   if (h->grid_scratch) cudaFree(h->grid_scratch);
+  if (h->io_scratch) cudaFree(h->io_scratch);
   delete h;
   return 0;
 }
@@ -256,6 +267,15 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
   return 0;
 }
 
+extern "C" int bogp_modeset_info(bogp_modeset_t h, int f, int* M, int* rows, int* J) {
+  BOGP_REQUIRE(h && f >= 0 && f < h->F, "bogp_modeset_info: bad argument");
+  BOGP_REQUIRE(h->has_cov, "bogp_modeset_info: call bogp_covariance_set first");
+  if (M) *M = h->dev.t[f].M;
+  if (rows) *rows = h->dev.t[f].rows;
+  if (J) *J = h->dev.t[f].J;
+  return 0;
+}
+
 static int check_modes(int atype, int mf) {
   BOGP_REQUIRE(atype == BOGP_ATYPE_CBF || atype == BOGP_ATYPE_CBF_ML, "unknown atype %d", atype);
   BOGP_REQUIRE(mf == BOGP_MF_MEAN || mf == BOGP_MF_PRODUCT, "unknown multifreq method %d", mf);
@@ -265,11 +285,12 @@ static int check_modes(int atype, int mf) {
 extern "C" int bogp_bartlett_grid(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
                                   const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
                                   float* out_dev, void* stream) {
-  BOGP_REQUIRE(h && r_m_host && z_host && out_dev, "bogp_bartlett_grid: NULL argument");
+  BOGP_REQUIRE(h != nullptr, "bogp_bartlett_grid: NULL handle");
   BOGP_REQUIRE(h->has_cov, "bogp_bartlett_grid: call bogp_covariance_set first");
   BOGP_REQUIRE(Nr >= 0 && Nz >= 0 && Nt >= 1, "bogp_bartlett_grid: bad sizes Nr=%d Nz=%d Nt=%d", Nr, Nz, Nt);
   if (int rc = check_modes(atype, mf_method)) return rc;
-  if (Nr == 0 || Nz == 0) return 0;
+  if (Nr == 0 || Nz == 0) return 0;   // empty surface: nothing to read or write (pointers may be NULL)
+  BOGP_REQUIRE(r_m_host && z_host && out_dev, "bogp_bartlett_grid: NULL argument");
   for (int i = 0; i < Nr; ++i) BOGP_REQUIRE(r_m_host[i] > 0.0, "bogp_bartlett_grid: range[%d]=%g must be > 0", i, r_m_host[i]);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   bool tilted = false;
@@ -291,17 +312,17 @@ extern "C" int bogp_bartlett_grid_host(bogp_modeset_t h, const double* r_m_host,
                                        const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
                                        float* out_host, void* stream) {
   BOGP_REQUIRE(out_host != nullptr, "bogp_bartlett_grid_host: out is NULL");
+  BOGP_REQUIRE(h != nullptr, "bogp_bartlett_grid_host: NULL handle");
   size_t n = (size_t)std::max(Nt, 1) * Nz * Nr;
   if (n == 0) return 0;
-  float* tmp = nullptr;
-  BOGP_CUDA(cudaMalloc(&tmp, n * sizeof(float)));
+  if (int rc0 = io_scratch(h, n * sizeof(float))) return rc0;
+  float* tmp = static_cast<float*>(h->io_scratch);
   int rc = bogp_bartlett_grid(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, tmp, stream);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(out_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream));
     if (e == cudaSuccess) e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) { bogp::set_error("bogp_bartlett_grid_host: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
   }
-  cudaFree(tmp);
   return rc;
 }
 
@@ -338,11 +359,11 @@ extern "C" int bogp_bartlett_points_host(bogp_modeset_t h, const double* cand_ho
                                          int mf_method, float* out_host, void* stream) {
   BOGP_REQUIRE(C >= 0 && (C == 0 || (cand_host && out_host)), "bogp_bartlett_points_host: bad argument");
   if (C == 0) return 0;
+  BOGP_REQUIRE(h != nullptr, "bogp_bartlett_points_host: NULL handle");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  double* cd = nullptr;
-  float* od = nullptr;
-  BOGP_CUDA(cudaMalloc(&cd, (size_t)C * 3 * sizeof(double)));
-  if (cudaMalloc(&od, (size_t)C * sizeof(float)) != cudaSuccess) { cudaFree(cd); bogp::set_error("cudaMalloc failed"); return BOGP_ERR_CUDA; }
+  if (int rc0 = io_scratch(h, (size_t)C * (3 * sizeof(double) + sizeof(float)))) return rc0;
+  double* cd = static_cast<double*>(h->io_scratch);
+  float* od = reinterpret_cast<float*>(cd + (size_t)C * 3);
   int rc = 0;
   cudaError_t e = cudaMemcpyAsync(cd, cand_host, (size_t)C * 3 * sizeof(double), cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) { bogp::set_error("H2D: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
@@ -352,7 +373,5 @@ extern "C" int bogp_bartlett_points_host(bogp_modeset_t h, const double* cand_ho
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { bogp::set_error("D2H: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
   }
-  cudaFree(cd);
-  cudaFree(od);
   return rc;
 }

@@ -18,6 +18,9 @@ typedef std::complex<double> cplx;
 void set_error(const char* fmt, ...);
 // Number of kernels this library has launched (bench.py reports it as gpu_launches).
 void count_launch(int n = 1);
+// Event bracket around a dominant kernel (no-ops returning nullptr unless bogp_timing_enable(1)).
+cudaEvent_t timing_begin(cudaStream_t s);
+void timing_end(cudaEvent_t stop, cudaStream_t s);
 
 #define BOGP_CUDA(call)                                                                      \
   do {                                                                                       \
@@ -111,6 +114,9 @@ struct bogp_modeset_s {
   // scratch for the grid paths (grown on demand)
   void* grid_scratch = nullptr;
   size_t grid_scratch_bytes = 0;
+  // device staging for the *_host entry points (grown on demand)
+  void* io_scratch = nullptr;
+  size_t io_scratch_bytes = 0;
 };
 
 namespace bogp {

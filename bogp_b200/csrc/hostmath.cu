@@ -25,6 +25,23 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
+// ---------------------------------------------------------------- dominant-kernel timing (bench.py roofline)
+// When enabled, the launcher of a dominant kernel brackets it with a CUDA event pair recorded on the launching
+// stream; bogp_timing_read() synchronises the pairs, sums their elapsed times and recycles them.
+static bool g_timing = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_ev_pool, g_ev_live;
+bool timing_enabled() { return g_timing; }
+cudaEvent_t timing_begin(cudaStream_t s) {
+  if (!g_timing) return nullptr;
+  std::pair<cudaEvent_t, cudaEvent_t> pr;
+  if (!g_ev_pool.empty()) { pr = g_ev_pool.back(); g_ev_pool.pop_back(); }
+  else if (cudaEventCreate(&pr.first) != cudaSuccess || cudaEventCreate(&pr.second) != cudaSuccess) return nullptr;
+  cudaEventRecord(pr.first, s);
+  g_ev_live.push_back(pr);
+  return pr.second;
+}
+void timing_end(cudaEvent_t stop, cudaStream_t s) { if (stop) cudaEventRecord(stop, s); }
+
 int pivoted_cholesky(const std::vector<cplx>& A, int n, double tol, std::vector<cplx>& L, int& rank) {
   // Outer-product pivoted Cholesky; L is returned in ORIGINAL row order, column j = j-th pivot step.
   std::vector<double> d(n);
@@ -102,3 +119,20 @@ void invert_lower(std::vector<double>& L, int n) {
 extern "C" const char* bogp_last_error(void) { return bogp::last_error_cstr(); }
 extern "C" int bogp_version(void) { return 100; }
 extern "C" long long bogp_kernel_launches(void) { return bogp::launches(); }
+extern "C" int bogp_timing_enable(int on) { bogp::g_timing = on != 0; return 0; }
+extern "C" int bogp_timing_read(double* total_ms, long long* count) {
+  double tot = 0.0;
+  long long n = 0;
+  for (auto& pr : bogp::g_ev_live) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+    bogp::g_ev_pool.push_back(pr);
+  }
+  bogp::g_ev_live.clear();
+  if (total_ms) *total_ms = tot;
+  if (count) *count = n;
+  return 0;
+}

@@ -190,6 +190,25 @@ extern "C" int bogp_argmax_f32(const float* x_dev, long long n, float* val_host,
 extern "C" int bogp_argmin_f32(const float* x_dev, long long n, float* val_host, long long* idx_host, void* stream) {
   return bogp::argext<false>(x_dev, n, val_host, idx_host, static_cast<cudaStream_t>(stream));
 }
+extern "C" int bogp_argext_f32_dev(const float* x_dev, long long n, int maximize, float* val_dev, long long* idx_dev,
+                                   void* scratch_dev, long long scratch_bytes, void* stream) {
+  BOGP_REQUIRE(x_dev && val_dev && idx_dev && scratch_dev && n >= 1, "bogp_argext_f32_dev: bad argument");
+  BOGP_REQUIRE(scratch_bytes >= 8192, "bogp_argext_f32_dev: scratch must be >= 8192 bytes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int nb = (int)std::max<long long>(1, std::min<long long>((n + 1023) / 1024, 592));
+  long long* pi = static_cast<long long*>(scratch_dev);          // [592] int64 then [592] float
+  float* pv = reinterpret_cast<float*>(pi + 592);
+  if (maximize) {
+    bogp::argext_stage1<true><<<nb, 256, 0, s>>>(x_dev, n, pv, pi);
+    bogp::argext_stage2<true><<<1, 256, 0, s>>>(pv, pi, nb, val_dev, idx_dev);
+  } else {
+    bogp::argext_stage1<false><<<nb, 256, 0, s>>>(x_dev, n, pv, pi);
+    bogp::argext_stage2<false><<<1, 256, 0, s>>>(pv, pi, nb, val_dev, idx_dev);
+  }
+  bogp::count_launch(2);
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ env batch API
 template <typename T>

@@ -460,7 +460,9 @@ static int launch_gp(const bogp_gp_s* g, const GpArgs& a, bool grad, cudaStream_
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
   const int grid = (int)std::max<long long>(1, std::min<long long>(ctas, (long long)sms * per_sm));
+  cudaEvent_t ev = bogp::timing_begin(s);
   gp_eval_kernel<BC><<<grid, kGpThreads, smem, s>>>(dev, a);
+  bogp::timing_end(ev, s);
   bogp::count_launch();
   BOGP_CUDA(cudaGetLastError());
   return 0;

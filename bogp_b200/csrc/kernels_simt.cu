@@ -282,13 +282,17 @@ int launch_points(const bogp_modeset_s* h, const double* cand_dev, long long C, 
     const int aStride = h->max_Mp, tStride = pad_to(std::max(h->max_rows, 1), 32);
     const size_t smem = (size_t)kWarpsPerBlock * (aStride + tStride) * sizeof(float2);
     if (int rc = set_smem(points_modespace_kernel, smem)) return rc;
+    cudaEvent_t ev = timing_begin(s);
     points_modespace_kernel<<<grid_for(C, smem), kThreads, smem, s>>>(h->dev, cand_dev, C, atype, mf, out_dev, aStride, tStride);
+    timing_end(ev, s);
     bogp::count_launch();
   } else {
     const int qStride = h->max_Mp, pStride = h->N;
     const size_t smem = (size_t)kWarpsPerBlock * (qStride + pStride) * sizeof(float2);
     if (int rc = set_smem(points_tilt_kernel, smem)) return rc;
+    cudaEvent_t ev = timing_begin(s);
     points_tilt_kernel<<<grid_for(C, smem), kThreads, smem, s>>>(h->dev, cand_dev, C, atype, mf, out_dev, qStride, pStride);
+    timing_end(ev, s);
     bogp::count_launch();
   }
   BOGP_CUDA(cudaGetLastError());
@@ -319,7 +323,9 @@ int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     const int aStride = h->max_Mp, tStride = pad_to(std::max(h->max_rows, 1), 32);
     const size_t smem = (size_t)kWarpsPerBlock * (aStride + tStride) * sizeof(float2);
     if (int rc = set_smem(grid_modespace_kernel, smem)) return rc;
+    cudaEvent_t ev = timing_begin(s);
     grid_modespace_kernel<<<grid_for((long long)Nr * Nz, smem), kThreads, smem, s>>>(d, E, PZ, Nr, Nz, atype, mf, out_dev, aStride, tStride);
+    timing_end(ev, s);
     bogp::count_launch();
     BOGP_CUDA(cudaGetLastError());
     return 0;

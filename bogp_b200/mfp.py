@@ -80,6 +80,19 @@ class DeviceModeSet:
         K_im = np.ascontiguousarray(K.imag if np.iscomplexobj(K) else np.zeros_like(K_re), dtype=np.float64)
         _lib.call("bogp_covariance_set", self._h, _lib.dptr(K_re), _lib.dptr(K_im))
 
+    def tonal_info(self):
+        """Per tonal ``(M_f, rows_f, J_f)``: modes, rows of the mode-space operator, covariance rank."""
+        out = []
+        for f in range(self.modes.n_freq):
+            M, rows, J = C.c_int(), C.c_int(), C.c_int()
+            _lib.call("bogp_modeset_info", self._h, f, C.byref(M), C.byref(rows), C.byref(J))
+            out.append((M.value, rows.value, J.value))
+        return out
+
+    def flops_per_candidate(self) -> float:
+        """Algorithmic flop of one candidate over all tonals on the vertical-array path: sum_f 4 rows_f M_f."""
+        return float(sum(4 * rows * M for M, rows, _ in self.tonal_info()))
+
     # ------------------------------------------------------------------ evaluation
     def bartlett_grid(self, r_km: ArrayLike, z: ArrayLike, tilt_deg: Optional[ArrayLike] = None, *,
                       atype: str = "cbf", multifreq_method: str = "mean", engine: str = "auto",
@@ -103,14 +116,19 @@ class DeviceModeSet:
         return out
 
     def bartlett_grid_host(self, r_km: ArrayLike, z: ArrayLike, tilt_deg: Optional[ArrayLike] = None, *,
-                           atype: str = "cbf", multifreq_method: str = "mean", engine: str = "auto") -> np.ndarray:
-        """Same through the host-buffer entry point (device->host copy inside the call)."""
+                           atype: str = "cbf", multifreq_method: str = "mean", engine: str = "auto",
+                           out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Same through the host-buffer entry point (device->host copy inside the call).  ``out``: optional
+        C-contiguous float32 host array of the result shape (pass page-locked memory for a DMA copy)."""
         r_m = np.ascontiguousarray(1000.0 * np.atleast_1d(np.asarray(r_km, dtype=np.float64)))
         zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
         tt = None if tilt_deg is None else np.ascontiguousarray(np.atleast_1d(np.asarray(tilt_deg, dtype=np.float64)))
         Nt = 1 if tt is None else len(tt)
         shape = (len(zz), len(r_m)) if tt is None else (Nt, len(zz), len(r_m))
-        out = np.empty(shape, dtype=np.float32)
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        elif out.shape != shape or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous float32 array of shape {shape}")
         _lib.call("bogp_bartlett_grid_host", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz), _lib.dptr(tt),
                   Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine], _lib.fptr(out),
                   C.c_void_p(_lib.current_stream_ptr()))
@@ -146,6 +164,25 @@ def _argext(fn: str, x: torch.Tensor):
     _lib.call(fn, C.c_void_p(x.data_ptr()), x.numel(), C.byref(val), C.byref(idx),
               C.c_void_p(_lib.current_stream_ptr()))
     return val.value, tuple(int(i) for i in np.unravel_index(idx.value, tuple(x.shape)))
+
+
+def argext_device(x: torch.Tensor, pair: torch.Tensor, scratch: torch.Tensor, maximize: bool = True) -> None:
+    """Arg-max/min without a host round trip: writes ``pair[0] = flat index`` (int64, -1 if all NaN) and the float32
+    extremum into the low 4 bytes of ``pair[1]``.  ``pair``: int64[2] on the device (the 16-byte record the multi-GPU
+    final reduction all-gathers); ``scratch``: >= 8192 bytes of device memory."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        raise ValueError("expected a contiguous float32 CUDA tensor")
+    if pair.dtype != torch.int64 or pair.numel() < 2 or not pair.is_cuda:
+        raise ValueError("pair must be an int64[2] CUDA tensor")
+    _lib.call("bogp_argext_f32_dev", C.c_void_p(x.data_ptr()), x.numel(), 1 if maximize else 0,
+              C.c_void_p(pair.data_ptr() + 8), C.c_void_p(pair.data_ptr()), C.c_void_p(scratch.data_ptr()),
+              scratch.numel() * scratch.element_size(), C.c_void_p(_lib.current_stream_ptr()))
+
+
+def unpack_pairs(pairs: torch.Tensor):
+    """Host view of all-gathered ``[world, 2]`` int64 records -> (values float32[world], indices int64[world])."""
+    p = pairs.reshape(-1, 2).cpu().numpy()
+    return p[:, 1].astype(np.int64).view(np.float32)[::2].copy(), p[:, 0].copy()
 
 
 # ---------------------------------------------------------------------------------------------- tritonoa mirror

@@ -61,6 +61,11 @@ const char* bogp_last_error(void);
 int bogp_version(void);
 /* Kernels launched by this library since load (monotonic; bench.py reports the per-step difference). */
 long long bogp_kernel_launches(void);
+/* Roofline instrumentation: while enabled, each launch of a dominant kernel (the Bartlett grid/points kernels, the
+ * GP evaluation kernel) is bracketed by CUDA events on its own stream; bogp_timing_read() waits for them and returns
+ * the summed kernel time and the number of launches since the last read. */
+int bogp_timing_enable(int on);
+int bogp_timing_read(double* total_ms, long long* count);
 /* sm_count / compute capability of the current device; fails without a GPU. */
 int bogp_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
@@ -85,6 +90,11 @@ int bogp_modeset_destroy(bogp_modeset_t h);
  * (layout [F,N,N] per ref/optimization/utils.py:23-32, 42-56).  Factorises K on the host (pivoted
  * Cholesky, float64) into the projection rows the kernels consume. */
 int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, const double* K_im_host);
+
+/* Shape of tonal f after bogp_covariance_set: modes M_f, rows of the mode-space operator W_f = [R_f ; C_f]
+ * (G = Phi^H Phi = R^H R, Phi^H K Phi = C^H C; complex rows count twice) and rank J of K_f.  The algorithmic work of
+ * one candidate x tonal on the vertical-array path is 4 * rows * M flop. */
+int bogp_modeset_info(bogp_modeset_t h, int f, int* M, int* rows, int* J);
 
 /* Ambiguity surface: replaces the loop `for z in src_z: amb[zz,:] = MFP({"src_z": z, "rec_r": rvec})`
  * (mfp.py:213-214) including runner + beamformer + multifreq combine.
@@ -120,6 +130,10 @@ int bogp_envbatch_destroy(bogp_envbatch_t h);
  * first index of the maximum of x_dev[n]; NaNs are ignored. */
 int bogp_argmax_f32(const float* x_dev, long long n, float* val_host, long long* idx_host, void* stream);
 int bogp_argmin_f32(const float* x_dev, long long n, float* val_host, long long* idx_host, void* stream);
+/* Same without the host round trip (multi-GPU final reduction: the (value, index) pair stays on the device for the
+ * NCCL all-gather).  scratch_dev: >= 8192 bytes of device memory.  idx_dev gets -1 if every element is NaN. */
+int bogp_argext_f32_dev(const float* x_dev, long long n, int maximize, float* val_dev, long long* idx_dev,
+                        void* scratch_dev, long long scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------ Boundary B: GP posterior + acquisition
  * Replaces SingleTaskGP(X, Y, ...) in eval mode (ei.py:67; gpmodels.py:16-30): exact GP with constant mean,
