@@ -172,7 +172,7 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
   const int F = h->F, N = h->N;
   bogp::ModesetDev& d = h->dev;
   const double tol = 1e-13;
-  std::vector<float> W, Wt, Ckre, Ckim;
+  std::vector<float> W, Wt, Wu, Ckre, Ckim;
   h->max_rows = 0; h->max_J = 0;
   for (int f = 0; f < F; ++f) {
     bogp::TonalMeta& t = d.t[f];
@@ -244,6 +244,28 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
     Wt.resize(Wt.size() + (size_t)t.Mp * t.rowsP, 0.f);
     for (int r2 = 0; r2 < t.rows; ++r2)
       for (int m = 0; m < M; ++m) Wt[t.offWt + (size_t)m * t.rowsP + r2] = Wf[(size_t)r2 * t.Mp + m];
+    // UMMA row order (bogp_internal.h): plain | pad to even | (re, im) norm pairs | (re, im) numerator pairs | pad
+    t.u_p0 = (t.n_plain + 1) & ~1;
+    t.u_rowsP = bogp::pad_to(std::max(t.u_p0 + 2 * t.n_npair + 2 * t.n_qpair, 1), 16);
+    t.offWu = (int)Wu.size();
+    Wu.resize(Wu.size() + (size_t)t.u_rowsP * t.Mp, 0.f);
+    {
+      float* U = &Wu[t.offWu];
+      for (int j = 0; j < t.n_plain; ++j)
+        for (int m = 0; m < M; ++m) U[(size_t)j * t.Mp + m] = Wf[(size_t)j * t.Mp + m];
+      int src = t.n_plain, dst = t.u_p0;
+      for (int j = 0; j < t.n_npair; ++j, dst += 2)
+        for (int m = 0; m < M; ++m) {
+          U[(size_t)dst * t.Mp + m] = Wf[(size_t)(src + j) * t.Mp + m];
+          U[(size_t)(dst + 1) * t.Mp + m] = Wf[(size_t)(src + t.n_npair + j) * t.Mp + m];
+        }
+      src += 2 * t.n_npair;
+      for (int j = 0; j < t.n_qpair; ++j, dst += 2)
+        for (int m = 0; m < M; ++m) {
+          U[(size_t)dst * t.Mp + m] = Wf[(size_t)(src + j) * t.Mp + m];
+          U[(size_t)(dst + 1) * t.Mp + m] = Wf[(size_t)(src + t.n_qpair + j) * t.Mp + m];
+        }
+    }
     // Receiver-space factor: num = || LK^H p ||^2 ; Ck[j, n] = conj(LK[n, j]); stored transposed [N][J]
     t.J = rK;
     t.offC = (int)Ckre.size();
@@ -260,6 +282,7 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
   int rc = 0;
   rc |= upload(h, h->cov_allocs, W, &d.W);
   rc |= upload(h, h->cov_allocs, Wt, &d.Wt);
+  rc |= upload(h, h->cov_allocs, Wu, &d.Wu);
   rc |= upload(h, h->cov_allocs, Ckre, &d.CkT_re);
   rc |= upload(h, h->cov_allocs, Ckim, &d.CkT_im);
   if (rc) return BOGP_ERR_CUDA;

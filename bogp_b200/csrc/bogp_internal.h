@@ -69,6 +69,11 @@ struct TonalMeta {
   int offRec;    // offset into phi_rec (N * Mp)
   int offC;      // offset into receiver-space factor (J * N complex)
   float trK;     // trace of K_f (cbf_ml)
+  // tcgen05 (UMMA) row order of the same operator: plain rows, zero-padded to the even row u_p0, then the complex
+  // rows as ADJACENT (re, im) pairs -- norm pairs first, numerator pairs after -- zero-padded to u_rowsP (x16).
+  int u_p0;      // first pair row (even)
+  int u_rowsP;   // rows padded to a multiple of 16 (the MMA N granularity at M = 128)
+  int offWu;     // offset into Wu (u_rowsP * Mp floats, row-major [row][Mp])
 };
 
 #define BOGP_MAX_TONALS 32
@@ -95,6 +100,7 @@ struct ModesetDev {
   // set by covariance_set
   const float* W;        // [sum rows*Mp]   row-major (UMMA operand generation)
   const float* Wt;       // [sum Mp*rowsP]  transposed (SIMT kernels)
+  const float* Wu;       // [sum u_rowsP*Mp] UMMA row order
   const float* CkT_re;   // [sum N*J]       receiver-space factor, transposed [N][J]
   const float* CkT_im;
 };

@@ -1,10 +1,498 @@
-// tcgen05 (UMMA) grid kernel -- placeholder until the 3xTF32 kernel lands; the dispatcher falls back to SIMT.
+// tcgen05 (UMMA) Bartlett grid kernel for sm_100a: the separable (range x depth) ambiguity surface as a 3xTF32
+// tensor-core contraction with TMEM accumulators and a fused Bartlett epilogue.
+//
+// Math (mode space, see kernels_simt.cu): for tonal f, range r_i and source depth z_j
+//     T[row, (i,j)] = sum_m W_f[row, m] phi_m(z_j) E_f[m, i],   E_f[m, i] = e^{-i k_m r_i} / sqrt(k_m r_i)
+//     B_f(i, j)     = sum_{numerator rows} |T|^2 / sum_{norm rows} |T|^2
+// As a GEMM per (depth j, tonal f):   D[i, row] = sum_m  A[i, m] * Bop[row, m]
+//     A   = E_f^T, the 128-range tile of the phase table (re and im parts -> two accumulators), resident in shared
+//           memory for the whole depth sweep of a tonal;
+//     Bop = W_f diag(phi(z_j)), streamed per depth (several depths stacked along the MMA N dimension).
+// 3xTF32: every fp32 operand x is split x = hi + lo (hi = tf32-rounded); D = A_lo B_hi + A_hi B_lo + A_hi B_hi
+// accumulates in fp32 in TMEM (1xTF32 fails the 1e-5 bar, 3xTF32 gives ~3e-7).
+// D puts range i on TMEM lane i, so each epilogue thread owns one range and reduces over the operator rows of its
+// own lane: no cross-lane shuffles; the replica field never exists outside TMEM.
+//
+// Pipeline per CTA (persistent over (range tile, depth chunk) units), 10 warps:
+//     warp 0    bulk-copy producer: E_f tile (once per tonal) and the ring of Bop stages (cp.async.bulk + mbarrier)
+//     warp 1    MMA issuer (one lane): tcgen05.mma.kind::tf32, commits to the ring / TMEM barriers; owns TMEM
+//     warps 2-9 epilogue: tcgen05.ld -> sum of squares -> Bartlett -> multi-frequency combine in shared memory
+// Operand tables are built per call by two small kernels directly in the UMMA canonical K-major no-swizzle layout
+// ([8-row group][16-byte K chunk][8 rows][4 floats]; LBO = 128 B, SBO = 32 * Mp B), so the producer issues plain
+// 1-D bulk copies.
+//
+// Replaces the loop `for z in src_z: amb[zz,:] = MFP({"src_z": z, "rec_r": rvec})`
+// (ref/projects/swellex96_localization/data/mfp.py:213-214) for a vertical array.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
 #include "bogp_internal.h"
+#include "device_math.cuh"
 
 namespace bogp {
-bool umma_supported(const bogp_modeset_s*) { return false; }
-int launch_grid_umma(bogp_modeset_s*, const double*, int, const double*, int, int, int, float*, cudaStream_t) {
-  set_error("UMMA engine not built");
-  return BOGP_ERR_UNSUPPORTED;
+
+constexpr int kTileR = 128;            // ranges per tile = MMA M = TMEM lanes
+constexpr int kStages = 4;             // Bop ring depth
+constexpr int kAccCols = 128;          // TMEM columns per accumulator half (re | im)
+constexpr int kEpiWarps = 8;
+constexpr int kUmmaThreads = (2 + kEpiWarps) * 32;
+constexpr unsigned kSmemLimit = 227u * 1024u;
+
+struct UTonal {
+  int Mp, rowsP, p0, n1;       // n1 = p0 + 2 * n_npair: pair rows below n1 feed the norm, above it the numerator
+  int nj;                      // depths stacked per stage
+  int wait_prev;               // this tonal's E tile overlaps the previous tonal's in shared memory
+  unsigned e_bytes;            // 2048 * Mp  (re_hi | re_lo | im_hi | im_lo)
+  unsigned e_off;              // offset of the tonal inside one range tile's block of the E table
+  unsigned b_zbytes;           // rowsP * Mp * 4: one depth of one split of Bop
+  unsigned long long b_off;    // offset of the tonal inside the Bop tables
+  float trK;
+};
+
+struct UParams {
+  int F, Nr, Nz, nrt, ZC, units, atype, mf;
+  int swap_lbo_sbo;            // debug knob (BOGP_UMMA_SWAP=1)
+  unsigned e_rt_stride, e_region, stage_bytes;
+  unsigned smem_B, smem_acc, smem_bar;
+  const unsigned char* E;
+  const unsigned char* Bhi;
+  const unsigned char* Blo;
+  float* out;
+  int* err;
+  UTonal t[BOGP_MAX_TONALS];
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must trap (an error the host sees), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 1023u) == 1023u && clock64() - t0 > 3000000000LL) {
+      atomicExch(err, code + 1000 * (int)blockIdx.x);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor bit layout): start address
+// [0,14), leading byte offset [16,30), stride byte offset [32,46) -- all in 16-byte units -- version 1 at [46,48).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+// ------------------------------------------------------------------------------------------------ table kernels
+__device__ __forceinline__ float tf32_rna(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+// offset (floats) of element (row, m) inside a K-major no-swizzle block of leading dimension Mp
+__device__ __forceinline__ size_t canon_off(int row, int m, int Mp) {
+  return ((size_t)((row >> 3) * (Mp >> 2) + (m >> 2)) * 8 + (row & 7)) * 4 + (m & 3);
+}
+
+// E table: per (range tile, tonal) the four blocks re_hi | re_lo | im_hi | im_lo of E_f^T [128, Mp].
+__global__ void umma_E_table_kernel(ModesetDev ms, UParams p, const double* __restrict__ r) {
+  const int rt = blockIdx.x, f = blockIdx.y;
+  const TonalMeta& t = ms.t[f];
+  const UTonal& u = p.t[f];
+  float* base = reinterpret_cast<float*>(const_cast<unsigned char*>(p.E) + (size_t)rt * p.e_rt_stride + u.e_off);
+  const size_t blk = (size_t)kTileR * u.Mp;
+  for (int idx = threadIdx.x; idx < kTileR * u.Mp; idx += blockDim.x) {
+    // memory order: (rowgroup, kchunk, row8, k4) so that stores coalesce
+    const int k4 = idx & 3, r8 = (idx >> 2) & 7, kc = (idx >> 5) % (u.Mp >> 2), rg = (idx >> 5) / (u.Mp >> 2);
+    const int row = rg * 8 + r8, m = kc * 4 + k4, i = rt * kTileR + row;
+    double vr = 0.0, vi = 0.0;
+    if (i < p.Nr && m < t.M) {
+      const double kre = ms.k_re[t.offM + m], kim = ms.k_im[t.offM + m], rr = r[i];
+      const double ar = kre * rr, ai = kim * rr;
+      const double mag = rsqrt(sqrt(ar * ar + ai * ai));
+      const double ang = -0.5 * atan2(ai, ar);
+      double s, c, s2, c2;
+      sincos(-(kre * rr), &s, &c);
+      sincos(ang, &s2, &c2);
+      const double amp = exp(kim * rr) * mag;
+      vr = amp * (c * c2 - s * s2);
+      vi = amp * (s * c2 + c * s2);
+    }
+    const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
+    base[idx] = rh;
+    base[blk + idx] = (float)(vr - (double)rh);
+    base[2 * blk + idx] = ih;
+    base[3 * blk + idx] = (float)(vi - (double)ih);
+  }
+}
+
+// Bop tables: per (tonal, depth) the block W_f diag(phi(z_j)) [rowsP, Mp], split into hi and lo arrays.
+__global__ void umma_B_table_kernel(ModesetDev ms, UParams p, const double* __restrict__ z) {
+  const int f = blockIdx.y;
+  const TonalMeta& t = ms.t[f];
+  const UTonal& u = p.t[f];
+  const int per = u.rowsP * u.Mp;
+  const long long total = (long long)p.Nz * per;
+  const float* Wu = ms.Wu + t.offWu;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(g / per), idx = (int)(g % per);
+    const int k4 = idx & 3, r8 = (idx >> 2) & 7, kc = (idx >> 5) % (u.Mp >> 2), rg = (idx >> 5) / (u.Mp >> 2);
+    const int row = rg * 8 + r8, m = kc * 4 + k4;
+    float x = 0.f;
+    if (m < t.M) {
+      int i0; float w;
+      depth_index(z[j], ms.z0, ms.dz, ms.nz_tab, i0, w);
+      const float* tr = ms.tab_re + t.offTab + (size_t)i0 * t.Mp + m;
+      const float phi = fmaf(w, __ldg(tr + t.Mp) - __ldg(tr), __ldg(tr));
+      x = __ldg(Wu + (size_t)row * t.Mp + m) * phi;
+    }
+    const float hi = tf32_rna(x);
+    const size_t o = (size_t)(u.b_off / 4) + (size_t)j * per + idx;
+    reinterpret_cast<float*>(const_cast<unsigned char*>(p.Bhi))[o] = hi;
+    reinterpret_cast<float*>(const_cast<unsigned char*>(p.Blo))[o] = x - hi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ main kernel
+// barrier slots (8 bytes each) at smem_bar
+enum { BAR_BFULL = 0, BAR_BEMPTY = kStages, BAR_EFULL = 2 * kStages, BAR_EDONE = 2 * kStages + 2,
+       BAR_TFULL = 2 * kStages + 4, BAR_TEMPTY = 2 * kStages + 6, BAR_COUNT = 2 * kStages + 8 };
+
+__global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid_constant__ UParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t bar0 = s_base + p.smem_bar;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.smem_bar + BAR_COUNT * 8);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_BFULL + s), 1); mbar_init(bar(BAR_BEMPTY + s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(BAR_EFULL + b), 1);
+      mbar_init(bar(BAR_EDONE + b), 1);
+      mbar_init(bar(BAR_TFULL + b), 1);
+      mbar_init(bar(BAR_TEMPTY + b), kEpiWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================================================== producer
+    if (lane == 0) {
+      uint32_t sc = 0;       // global stage counter
+      int g = 0;             // global tonal counter
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        const int rt = unit % p.nrt, zc = unit / p.nrt;
+        const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
+        for (int f = 0; f < p.F; ++f, ++g) {
+          const UTonal& u = p.t[f];
+          // E tile of tonal g goes to the low end (g even) or the high end (g odd) of the E region
+          if (g >= 2) mbar_wait(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1);
+          if (g >= 1) {
+            const UTonal& up = p.t[f == 0 ? p.F - 1 : f - 1];
+            if (up.e_bytes + u.e_bytes > p.e_region)
+              mbar_wait(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2);
+          }
+          const uint32_t e_dst = s_base + ((g & 1) ? p.e_region - u.e_bytes : 0u);
+          mbar_expect_tx(bar(BAR_EFULL + (g & 1)), u.e_bytes);
+          bulk_g2s(e_dst, p.E + (size_t)rt * p.e_rt_stride + u.e_off, u.e_bytes, bar(BAR_EFULL + (g & 1)));
+          for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
+            const int njs = min(u.nj, nzu - j0);
+            const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
+            mbar_wait(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3);
+            const uint32_t bytes = (uint32_t)njs * u.b_zbytes;
+            const uint32_t dst = s_base + p.smem_B + slot * p.stage_bytes;
+            const size_t src = (size_t)u.b_off + (size_t)(z0 + j0) * u.b_zbytes;
+            mbar_expect_tx(bar(BAR_BFULL + slot), 2 * bytes);
+            bulk_g2s(dst, p.Bhi + src, bytes, bar(BAR_BFULL + slot));
+            bulk_g2s(dst + bytes, p.Blo + src, bytes, bar(BAR_BFULL + slot));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t sc = 0;
+      int g = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        const int zc = unit / p.nrt;
+        const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
+        for (int f = 0; f < p.F; ++f, ++g) {
+          const UTonal& u = p.t[f];
+          const uint32_t sbo = 32u * (uint32_t)u.Mp, lbo = 128u;
+          const uint32_t d_lbo = p.swap_lbo_sbo ? sbo : lbo, d_sbo = p.swap_lbo_sbo ? lbo : sbo;
+          const uint32_t e_src = s_base + ((g & 1) ? p.e_region - u.e_bytes : 0u);
+          const uint32_t e_blk = 512u * (uint32_t)u.Mp;      // one of re_hi | re_lo | im_hi | im_lo
+          mbar_wait(bar(BAR_EFULL + (g & 1)), (uint32_t)((g >> 1) & 1), p.err, 4);
+          for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
+            const int njs = min(u.nj, nzu - j0);
+            const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
+            const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
+            mbar_wait(bar(BAR_BFULL + slot), ph, p.err, 5);
+            mbar_wait(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6);
+            tc_fence_after();
+            const uint32_t N = (uint32_t)(njs * u.rowsP);
+            // instruction descriptor: D = f32 [4,6), A = B = tf32 [7,10) / [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((kTileR >> 4) << 24);
+            const uint32_t b_hi = s_base + p.smem_B + slot * p.stage_bytes;
+            const uint32_t b_lo = b_hi + (uint32_t)njs * u.b_zbytes;
+            const int ksteps = u.Mp >> 3;
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {
+              const uint32_t a_hi = e_src + (uint32_t)(2 * part) * e_blk, a_lo = a_hi + e_blk;
+              const uint32_t d = tmem_base + buf * (2 * kAccCols) + (uint32_t)part * kAccCols;
+#pragma unroll 1
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t ko = 256u * (uint32_t)ks;    // 8 K elements = 2 chunks of 128 B per row group
+                const uint64_t dah = make_desc(a_hi + ko, d_lbo, d_sbo), dal = make_desc(a_lo + ko, d_lbo, d_sbo);
+                const uint64_t dbh = make_desc(b_hi + ko, d_lbo, d_sbo), dbl = make_desc(b_lo + ko, d_lbo, d_sbo);
+                tc_mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+                tc_mma_tf32(d, dah, dbl, idesc, 1u);
+                tc_mma_tf32(d, dah, dbh, idesc, 1u);
+              }
+            }
+            tc_commit(bar(BAR_BEMPTY + slot));
+            tc_commit(bar(BAR_TFULL + buf));
+          }
+          tc_commit(bar(BAR_EDONE + (g & 1)));
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ============================================================== epilogue
+    const int ew = warp - 2;                 // 0..7
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;                // which depth parity this warp handles
+    const int tl = quad * 32 + lane;         // lane in the tile = range index in the tile
+    float* acc = reinterpret_cast<float*>(smem + p.smem_acc);     // [ZC][128]
+    uint32_t sc = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int rt = unit % p.nrt, zc = unit / p.nrt;
+      const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
+      for (int f = 0; f < p.F; ++f) {
+        const UTonal& u = p.t[f];
+        const int p0 = u.p0, n1 = u.n1, rowsP = u.rowsP;
+        for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
+          const int njs = min(u.nj, nzu - j0);
+          const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
+          mbar_wait(bar(BAR_TFULL + buf), tph, p.err, 7);
+          tc_fence_after();
+          for (int s = 0; s < njs; ++s) {
+            const int j = j0 + s;
+            if ((j & 1) != half) continue;
+            const uint32_t t_re = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (2 * kAccCols) + (uint32_t)(s * rowsP);
+            float norm = 0.f, num = 0.f;
+            for (int c0 = 0; c0 < rowsP; c0 += 16) {
+              float re[16], im[16];
+              tc_ld16(t_re + (uint32_t)c0, re);
+              tc_ld16(t_re + (uint32_t)(kAccCols + c0), im);
+              tc_wait_ld();
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int c = c0 + 2 * q;
+                const float r0 = re[2 * q], r1 = re[2 * q + 1], i0 = im[2 * q], i1 = im[2 * q + 1];
+                if (c < p0) {
+                  norm += r0 * r0 + i0 * i0 + r1 * r1 + i1 * i1;
+                } else {
+                  const float tr = r0 - i1, ti = i0 + r1;
+                  const float v = tr * tr + ti * ti;
+                  if (c < n1) norm += v; else num += v;
+                }
+              }
+            }
+            const float b = num / norm;
+            const float val = p.atype == BOGP_ATYPE_CBF ? b : u.trK - b;
+            float* a = acc + (size_t)j * kTileR + tl;
+            *a = (f == 0) ? val : (p.mf == BOGP_MF_MEAN ? *a + val : *a * val);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+        }
+      }
+      // this thread alone touched acc[j][tl] for its depth parity: no barrier needed before the write-out
+      const int i = rt * kTileR + tl;
+      const float scale = p.mf == BOGP_MF_MEAN ? 1.f / (float)p.F : 1.f;
+      if (i < p.Nr)
+        for (int j = half; j < nzu; j += 2) p.out[(size_t)(z0 + j) * p.Nr + i] = acc[(size_t)j * kTileR + tl] * scale;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int device_sms() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+// Fills the size-independent part of the plan; returns false when the mode set does not fit the kernel.
+static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
+  const ModesetDev& d = h->dev;
+  if (d.src_complex) return false;     // complex source tables would need a complex Bop (not built yet)
+  unsigned e_max = 0, e_off = 0;
+  for (int f = 0; f < d.F; ++f) {
+    const TonalMeta& t = d.t[f];
+    UTonal& u = p.t[f];
+    u.Mp = t.Mp; u.rowsP = t.u_rowsP; u.p0 = t.u_p0; u.n1 = t.u_p0 + 2 * t.n_npair; u.trK = t.trK;
+    if (u.rowsP > kAccCols || u.Mp > 96) return false;
+    u.e_bytes = 2048u * (unsigned)u.Mp;
+    u.e_off = e_off;
+    e_off += u.e_bytes;
+    e_max = std::max(e_max, u.e_bytes);
+    u.b_zbytes = (unsigned)(u.rowsP * u.Mp * 4);
+  }
+  p.F = d.F;
+  p.e_rt_stride = e_off;
+  p.e_region = e_max;
+  const unsigned acc_bytes = (unsigned)ZC * kTileR * 4u;
+  const unsigned bar_bytes = 256;
+  if (p.e_region + acc_bytes + bar_bytes + 4 * 4096 > kSmemLimit) return false;
+  unsigned stage = (kSmemLimit - p.e_region - acc_bytes - bar_bytes) / kStages;
+  stage = std::min(stage & ~127u, 32u * 1024u);
+  for (int f = 0; f < d.F; ++f) {
+    UTonal& u = p.t[f];
+    const unsigned per = 2u * u.b_zbytes;          // hi + lo of one depth
+    if (per > stage) return false;
+    u.nj = (int)std::min<unsigned>(std::min<unsigned>(stage / per, (unsigned)(kAccCols / u.rowsP)), 16u);
+    if (u.nj < 1) return false;
+  }
+  p.stage_bytes = stage;
+  p.smem_B = p.e_region;
+  p.smem_acc = p.smem_B + kStages * stage;
+  p.smem_bar = p.smem_acc + acc_bytes;
+  return true;
+}
+
+static int choose_zc(int Nr, int Nz, int sms) {
+  const int nrt = (Nr + kTileR - 1) / kTileR;
+  const int chunks = std::max(1, sms / nrt);
+  int zc = (Nz + chunks - 1) / chunks;
+  zc = std::max(8, std::min(64, (zc + 7) & ~7));
+  return zc;
+}
+
+bool umma_supported(const bogp_modeset_s* h) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10 || !h->has_cov) return false;
+  UParams p{};
+  return plan_tonals(h, p, 64);
+}
+
+int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype, int mf,
+                     float* out_dev, cudaStream_t s) {
+  const ModesetDev& d = h->dev;
+  const int sms = device_sms();
+  UParams p{};
+  const int ZC = choose_zc(Nr, Nz, sms);
+  if (!plan_tonals(h, p, ZC)) { set_error("UMMA engine: mode set does not fit (rows > 128, Mp > 96 or complex source table)"); return BOGP_ERR_UNSUPPORTED; }
+  p.Nr = Nr; p.Nz = Nz; p.ZC = ZC; p.atype = atype; p.mf = mf;
+  p.nrt = (Nr + kTileR - 1) / kTileR;
+  const int nzc = (Nz + ZC - 1) / ZC;
+  p.units = p.nrt * nzc;
+  const char* sw = std::getenv("BOGP_UMMA_SWAP");
+  p.swap_lbo_sbo = (sw && sw[0] == '1') ? 1 : 0;
+  unsigned long long b_off = 0;
+  for (int f = 0; f < d.F; ++f) { p.t[f].b_off = b_off; b_off += (unsigned long long)Nz * p.t[f].b_zbytes; }
+  // scratch: [r | z doubles][err int][E table][Bhi][Blo]
+  const size_t off_rz = 0, bytes_rz = ((size_t)Nr + Nz) * sizeof(double);
+  const size_t off_err = (bytes_rz + 255) & ~(size_t)255;
+  const size_t off_E = off_err + 256;
+  const size_t bytes_E = (size_t)p.nrt * p.e_rt_stride;
+  const size_t off_Bhi = (off_E + bytes_E + 255) & ~(size_t)255;
+  const size_t off_Blo = (off_Bhi + b_off + 255) & ~(size_t)255;
+  if (int rc = ensure_scratch(h, off_Blo + b_off + 256)) return rc;
+  unsigned char* base = static_cast<unsigned char*>(h->grid_scratch);
+  double* r_dev = reinterpret_cast<double*>(base + off_rz);
+  double* z_dev = r_dev + Nr;
+  p.err = reinterpret_cast<int*>(base + off_err);
+  p.E = base + off_E; p.Bhi = base + off_Bhi; p.Blo = base + off_Blo;
+  p.out = out_dev;
+  BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
+  BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  BOGP_CUDA(cudaMemsetAsync(p.err, 0, sizeof(int), s));
+  umma_E_table_kernel<<<dim3(p.nrt, d.F), 256, 0, s>>>(d, p, r_dev);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  umma_B_table_kernel<<<dim3(std::max(1, std::min(4 * sms, Nz)), d.F), 256, 0, s>>>(d, p, z_dev);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  const size_t smem = (size_t)p.smem_bar + 256;
+  BOGP_CUDA(cudaFuncSetAttribute(umma_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t ev = timing_begin(s);
+  umma_grid_kernel<<<std::min(p.units, sms), kUmmaThreads, smem, s>>>(p);
+  timing_end(ev, s);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace bogp
