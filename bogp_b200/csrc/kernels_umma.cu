@@ -41,6 +41,7 @@ constexpr unsigned kSmemLimit = 227u * 1024u;
 
 struct UTonal {
   int Mp, rowsP, p0, n1;       // n1 = p0 + 2 * n_npair: pair rows below n1 feed the norm, above it the numerator
+  int nq;                      // numerator (re, im) row pairs = rank of Phi^H K Phi
   int nj;                      // depths stacked per stage
   int wait_prev;               // this tonal's E tile overlaps the previous tonal's in shared memory
   unsigned e_bytes;            // 2048 * Mp  (re_hi | re_lo | im_hi | im_lo)
@@ -60,6 +61,7 @@ struct UParams {
   const unsigned char* Blo;
   float* out;
   int* err;
+  long long* dbg;              // optional [grid][16] cycle counters (BOGP_UMMA_DBG=1): where each role waits
   UTonal t[BOGP_MAX_TONALS];
 };
 
@@ -95,6 +97,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// One lane of a converged warp (elect.sync): the tcgen05 / bulk-copy instructions take warp-uniform operands, so the
+// issuing roles run their loops with the whole warp and predicate only the instruction itself -- issuing from inside
+// an `if (lane == 0)` region makes ptxas wrap every UTCHMMA in a per-lane waterfall loop (~90 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// mbar_wait that also accumulates the waiting time into *acc when profiling is on
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int* err, int code, long long* acc) {
+  if (acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity, err, code);
+    *acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity, err, code);
+  }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -123,6 +147,25 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
       : "r"(taddr));
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld2(uint32_t taddr, float& a, float& b) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+  a = __uint_as_float(r0);
+  b = __uint_as_float(r1);
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -235,7 +278,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
 
   if (warp == 0) {
     // ============================================================== producer
-    if (lane == 0) {
+    {
+      long long w_edone = 0, w_bempty = 0;
+      const long long t_start = clock64();
       uint32_t sc = 0;       // global stage counter
       int g = 0;             // global tonal counter
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
@@ -244,32 +289,44 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
         for (int f = 0; f < p.F; ++f, ++g) {
           const UTonal& u = p.t[f];
           // E tile of tonal g goes to the low end (g even) or the high end (g odd) of the E region
-          if (g >= 2) mbar_wait(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1);
+          if (g >= 2) mbar_wait_t(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1, p.dbg ? &w_edone : nullptr);
           if (g >= 1) {
             const UTonal& up = p.t[f == 0 ? p.F - 1 : f - 1];
             if (up.e_bytes + u.e_bytes > p.e_region)
-              mbar_wait(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2);
+              mbar_wait_t(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2, p.dbg ? &w_edone : nullptr);
           }
           const uint32_t e_dst = s_base + ((g & 1) ? p.e_region - u.e_bytes : 0u);
-          mbar_expect_tx(bar(BAR_EFULL + (g & 1)), u.e_bytes);
-          bulk_g2s(e_dst, p.E + (size_t)rt * p.e_rt_stride + u.e_off, u.e_bytes, bar(BAR_EFULL + (g & 1)));
+          if (elect_one()) {
+            mbar_expect_tx(bar(BAR_EFULL + (g & 1)), u.e_bytes);
+            bulk_g2s(e_dst, p.E + (size_t)rt * p.e_rt_stride + u.e_off, u.e_bytes, bar(BAR_EFULL + (g & 1)));
+          }
+          __syncwarp();
           for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
             const int njs = min(u.nj, nzu - j0);
             const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
-            mbar_wait(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3);
+            mbar_wait_t(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3, p.dbg ? &w_bempty : nullptr);
             const uint32_t bytes = (uint32_t)njs * u.b_zbytes;
             const uint32_t dst = s_base + p.smem_B + slot * p.stage_bytes;
             const size_t src = (size_t)u.b_off + (size_t)(z0 + j0) * u.b_zbytes;
-            mbar_expect_tx(bar(BAR_BFULL + slot), 2 * bytes);
-            bulk_g2s(dst, p.Bhi + src, bytes, bar(BAR_BFULL + slot));
-            bulk_g2s(dst + bytes, p.Blo + src, bytes, bar(BAR_BFULL + slot));
+            if (elect_one()) {
+              mbar_expect_tx(bar(BAR_BFULL + slot), 2 * bytes);
+              bulk_g2s(dst, p.Bhi + src, bytes, bar(BAR_BFULL + slot));
+              bulk_g2s(dst + bytes, p.Blo + src, bytes, bar(BAR_BFULL + slot));
+            }
+            __syncwarp();
           }
         }
+      }
+      if (p.dbg && lane == 0) {
+        long long* d = p.dbg + 16 * blockIdx.x;
+        d[0] = clock64() - t_start; d[1] = w_edone; d[2] = w_bempty;
       }
     }
   } else if (warp == 1) {
     // ============================================================== MMA issuer
-    if (lane == 0) {
+    {
+      long long w_efull = 0, w_bfull = 0, w_tempty = 0;
+      const long long t_start = clock64();
       uint32_t sc = 0;
       int g = 0;
       for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
@@ -281,13 +338,13 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           const uint32_t d_lbo = p.swap_lbo_sbo ? sbo : lbo, d_sbo = p.swap_lbo_sbo ? lbo : sbo;
           const uint32_t e_src = s_base + ((g & 1) ? p.e_region - u.e_bytes : 0u);
           const uint32_t e_blk = 512u * (uint32_t)u.Mp;      // one of re_hi | re_lo | im_hi | im_lo
-          mbar_wait(bar(BAR_EFULL + (g & 1)), (uint32_t)((g >> 1) & 1), p.err, 4);
+          mbar_wait_t(bar(BAR_EFULL + (g & 1)), (uint32_t)((g >> 1) & 1), p.err, 4, p.dbg ? &w_efull : nullptr);
           for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
             const int njs = min(u.nj, nzu - j0);
             const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
             const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
-            mbar_wait(bar(BAR_BFULL + slot), ph, p.err, 5);
-            mbar_wait(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6);
+            mbar_wait_t(bar(BAR_BFULL + slot), ph, p.err, 5, p.dbg ? &w_bfull : nullptr);
+            mbar_wait_t(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6, p.dbg ? &w_tempty : nullptr);
             tc_fence_after();
             const uint32_t N = (uint32_t)(njs * u.rowsP);
             // instruction descriptor: D = f32 [4,6), A = B = tf32 [7,10) / [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
@@ -304,16 +361,27 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
                 const uint32_t ko = 256u * (uint32_t)ks;    // 8 K elements = 2 chunks of 128 B per row group
                 const uint64_t dah = make_desc(a_hi + ko, d_lbo, d_sbo), dal = make_desc(a_lo + ko, d_lbo, d_sbo);
                 const uint64_t dbh = make_desc(b_hi + ko, d_lbo, d_sbo), dbl = make_desc(b_lo + ko, d_lbo, d_sbo);
-                tc_mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-                tc_mma_tf32(d, dah, dbl, idesc, 1u);
-                tc_mma_tf32(d, dah, dbh, idesc, 1u);
+                if (elect_one()) {
+                  tc_mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+                  tc_mma_tf32(d, dah, dbl, idesc, 1u);
+                  tc_mma_tf32(d, dah, dbh, idesc, 1u);
+                }
+                __syncwarp();
               }
             }
-            tc_commit(bar(BAR_BEMPTY + slot));
-            tc_commit(bar(BAR_TFULL + buf));
+            if (elect_one()) {
+              tc_commit(bar(BAR_BEMPTY + slot));
+              tc_commit(bar(BAR_TFULL + buf));
+            }
+            __syncwarp();
           }
-          tc_commit(bar(BAR_EDONE + (g & 1)));
+          if (elect_one()) tc_commit(bar(BAR_EDONE + (g & 1)));
+          __syncwarp();
         }
+      }
+      if (p.dbg && lane == 0) {
+        long long* d = p.dbg + 16 * blockIdx.x;
+        d[3] = clock64() - t_start; d[4] = w_efull; d[5] = w_bfull; d[6] = w_tempty; d[7] = sc;
       }
     }
     __syncwarp();
@@ -325,6 +393,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     const int tl = quad * 32 + lane;         // lane in the tile = range index in the tile
     float* acc = reinterpret_cast<float*>(smem + p.smem_acc);     // [ZC][128]
     uint32_t sc = 0;
+    long long w_tfull = 0;
+    const long long t_start = clock64();
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int rt = unit % p.nrt, zc = unit / p.nrt;
       const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
@@ -334,28 +404,77 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
         for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
           const int njs = min(u.nj, nzu - j0);
           const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
-          mbar_wait(bar(BAR_TFULL + buf), tph, p.err, 7);
+          mbar_wait_t(bar(BAR_TFULL + buf), tph, p.err, 7, p.dbg ? &w_tfull : nullptr);
           tc_fence_after();
           for (int s = 0; s < njs; ++s) {
             const int j = j0 + s;
             if ((j & 1) != half) continue;
             const uint32_t t_re = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (2 * kAccCols) + (uint32_t)(s * rowsP);
             float norm = 0.f, num = 0.f;
-            for (int c0 = 0; c0 < rowsP; c0 += 16) {
-              float re[16], im[16];
-              tc_ld16(t_re + (uint32_t)c0, re);
-              tc_ld16(t_re + (uint32_t)(kAccCols + c0), im);
-              tc_wait_ld();
+            if (n1 == p0) {
+              // Real receiver modes (KRAKEN): every |T|^2 term is a plain square except the nq numerator pairs, and
+              // (r0 - i1)^2 + (i0 + r1)^2 = r0^2 + i0^2 + r1^2 + i1^2 + 2 (i0 r1 - r0 i1).  One FFMA per value over
+              // ALL columns gives tot = norm + numsq; the numerator pairs are re-read on their own.
+              float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, numsq = 0.f;
+              int c0 = 0;
+              float nr0 = 0.f, nr1 = 0.f, ni0 = 0.f, ni1 = 0.f;
+              if (u.nq > 0) {
+                tc_ld2(t_re + (uint32_t)p0, nr0, nr1);
+                tc_ld2(t_re + (uint32_t)(kAccCols + p0), ni0, ni1);
+              }
+              for (; c0 + 32 <= rowsP; c0 += 32) {
+                float re[32], im[32];
+                tc_ld32(t_re + (uint32_t)c0, re);
+                tc_ld32(t_re + (uint32_t)(kAccCols + c0), im);
+                tc_wait_ld();
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int c = c0 + 2 * q;
-                const float r0 = re[2 * q], r1 = re[2 * q + 1], i0 = im[2 * q], i1 = im[2 * q + 1];
-                if (c < p0) {
-                  norm += r0 * r0 + i0 * i0 + r1 * r1 + i1 * i1;
-                } else {
-                  const float tr = r0 - i1, ti = i0 + r1;
-                  const float v = tr * tr + ti * ti;
-                  if (c < n1) norm += v; else num += v;
+                for (int q = 0; q < 32; q += 2) {
+                  t0 = fmaf(re[q], re[q], t0);
+                  t1 = fmaf(im[q], im[q], t1);
+                  t2 = fmaf(re[q + 1], re[q + 1], t2);
+                  t3 = fmaf(im[q + 1], im[q + 1], t3);
+                }
+              }
+              if (c0 < rowsP) {
+                float re[16], im[16];
+                tc_ld16(t_re + (uint32_t)c0, re);
+                tc_ld16(t_re + (uint32_t)(kAccCols + c0), im);
+                tc_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 16; q += 2) {
+                  t0 = fmaf(re[q], re[q], t0);
+                  t1 = fmaf(im[q], im[q], t1);
+                  t2 = fmaf(re[q + 1], re[q + 1], t2);
+                  t3 = fmaf(im[q + 1], im[q + 1], t3);
+                }
+              }
+              for (int q = 0;;) {
+                const float tr = nr0 - ni1, ti = ni0 + nr1;
+                num = fmaf(tr, tr, fmaf(ti, ti, num));
+                numsq += fmaf(nr0, nr0, ni0 * ni0) + fmaf(nr1, nr1, ni1 * ni1);
+                if (++q >= u.nq) break;
+                tc_ld2(t_re + (uint32_t)(p0 + 2 * q), nr0, nr1);
+                tc_ld2(t_re + (uint32_t)(kAccCols + p0 + 2 * q), ni0, ni1);
+                tc_wait_ld();
+              }
+              norm = ((t0 + t1) + (t2 + t3)) - numsq;
+            } else {
+              for (int c0 = 0; c0 < rowsP; c0 += 16) {
+                float re[16], im[16];
+                tc_ld16(t_re + (uint32_t)c0, re);
+                tc_ld16(t_re + (uint32_t)(kAccCols + c0), im);
+                tc_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int c = c0 + 2 * q;
+                  const float r0 = re[2 * q], r1 = re[2 * q + 1], i0 = im[2 * q], i1 = im[2 * q + 1];
+                  if (c < p0) {
+                    norm += r0 * r0 + i0 * i0 + r1 * r1 + i1 * i1;
+                  } else {
+                    const float tr = r0 - i1, ti = i0 + r1;
+                    const float v = tr * tr + ti * ti;
+                    if (c < n1) norm += v; else num += v;
+                  }
                 }
               }
             }
@@ -374,6 +493,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       const float scale = p.mf == BOGP_MF_MEAN ? 1.f / (float)p.F : 1.f;
       if (i < p.Nr)
         for (int j = half; j < nzu; j += 2) p.out[(size_t)(z0 + j) * p.Nr + i] = acc[(size_t)j * kTileR + tl] * scale;
+    }
+    if (p.dbg && lane == 0 && (ew == 0 || ew == 4)) {
+      long long* d = p.dbg + 16 * blockIdx.x + 8 + (ew >> 2) * 2;
+      d[0] = clock64() - t_start; d[1] = w_tfull;
     }
   }
   tc_fence_before();
@@ -400,7 +523,7 @@ static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
   for (int f = 0; f < d.F; ++f) {
     const TonalMeta& t = d.t[f];
     UTonal& u = p.t[f];
-    u.Mp = t.Mp; u.rowsP = t.u_rowsP; u.p0 = t.u_p0; u.n1 = t.u_p0 + 2 * t.n_npair; u.trK = t.trK;
+    u.Mp = t.Mp; u.rowsP = t.u_rowsP; u.p0 = t.u_p0; u.n1 = t.u_p0 + 2 * t.n_npair; u.nq = t.n_qpair; u.trK = t.trK;
     if (u.rowsP > kAccCols || u.Mp > 96) return false;
     u.e_bytes = 2048u * (unsigned)u.Mp;
     u.e_off = e_off;
@@ -476,6 +599,13 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   p.err = reinterpret_cast<int*>(base + off_err);
   p.E = base + off_E; p.Bhi = base + off_Bhi; p.Blo = base + off_Blo;
   p.out = out_dev;
+  const char* dbg_env = std::getenv("BOGP_UMMA_DBG");
+  static long long* dbg_dev = nullptr;
+  if (dbg_env && dbg_env[0] == '1') {
+    if (!dbg_dev) BOGP_CUDA(cudaMalloc(&dbg_dev, 256 * 16 * sizeof(long long)));
+    BOGP_CUDA(cudaMemsetAsync(dbg_dev, 0, 256 * 16 * sizeof(long long), s));
+    p.dbg = dbg_dev;
+  }
   BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
   BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
   BOGP_CUDA(cudaMemsetAsync(p.err, 0, sizeof(int), s));
@@ -492,6 +622,20 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   timing_end(ev, s);
   count_launch();
   BOGP_CUDA(cudaGetLastError());
+  if (p.dbg) {
+    std::vector<long long> hdbg(256 * 16);
+    BOGP_CUDA(cudaMemcpyAsync(hdbg.data(), dbg_dev, hdbg.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    BOGP_CUDA(cudaStreamSynchronize(s));
+    const int grid = std::min(p.units, sms);
+    const char* names[12] = {"prod_total", "prod_wait_edone", "prod_wait_bempty", "mma_total", "mma_wait_efull",
+                             "mma_wait_bfull", "mma_wait_tempty", "stages", "epi0_total", "epi0_wait_tfull",
+                             "epi4_total", "epi4_wait_tfull"};
+    for (int k = 0; k < 12; ++k) {
+      double sum = 0; long long mx = 0;
+      for (int b = 0; b < grid; ++b) { sum += (double)hdbg[b * 16 + k]; mx = std::max(mx, hdbg[b * 16 + k]); }
+      fprintf(stderr, "[umma dbg] %-18s avg %12.0f max %12lld\n", names[k], sum / grid, mx);
+    }
+  }
   return 0;
 }
 

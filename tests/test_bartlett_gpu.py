@@ -42,7 +42,7 @@ def dms2(cfg2_small):
     return DeviceModeSet(cfg2_small["modes"], cfg2_small["K"])
 
 
-@pytest.mark.parametrize("engine", ["simt", "auto"])
+@pytest.mark.parametrize("engine", ["simt", "umma", "auto"])
 def test_cfg1_surface_vs_golden(cfg1, dms1, engine):
     from bogp_b200 import mfp
     g = np.load(GOLD / "bartlett_cfg1.npz")
@@ -56,7 +56,7 @@ def test_cfg1_surface_vs_golden(cfg1, dms1, engine):
     np.testing.assert_array_equal(host, surf.cpu().numpy())
 
 
-@pytest.mark.parametrize("engine", ["simt", "auto"])
+@pytest.mark.parametrize("engine", ["simt", "umma", "auto"])
 def test_cfg2_shape_surface_vs_oracle(cfg2_small, dms2, engine):
     """13 tonals, 64 receivers (SWellEx-96 shape); identical arg-max index."""
     c = cfg2_small
@@ -64,6 +64,40 @@ def test_cfg2_shape_surface_vs_oracle(cfg2_small, dms2, engine):
     surf = dms2.bartlett_grid(c["r"], c["z"], engine=engine).cpu().numpy()
     assert_parity(surf, ref)
     assert np.unravel_index(surf.argmax(), surf.shape) == np.unravel_index(ref.argmax(), ref.shape)
+
+
+@pytest.mark.parametrize("shape", [(300, 70), (129, 9), (1, 1), (128, 64), (513, 131)])
+def test_umma_rank8_ragged_grids(shape):
+    """tcgen05 engine on grids that do not fill its 128-range tiles / 8-depth groups, rank-8 covariance (J = 8),
+    both processors: against the oracle and bit-for-bit independent of the launch decomposition."""
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    K = synthetic_covariance(modes, 60.0, 5.0, snapshots=8, seed=3)
+    dms = DeviceModeSet(modes, K)
+    nr, nz = shape
+    r, z = np.linspace(0.3, 10.0, nr), np.linspace(2.0, 199.0, nz)
+    got = dms.bartlett_grid(r, z, engine="umma").cpu().numpy()
+    simt = dms.bartlett_grid(r, z, engine="simt").cpu().numpy()
+    assert_parity(got, simt, rtol=5e-6)
+    if nr * nz <= 300 * 70:
+        assert_parity(got, ob.ambiguity_surface(modes, K, r, z))
+        ml = dms.bartlett_grid(r, z, atype="cbf_ml", multifreq_method="product", engine="umma").cpu().numpy()
+        assert_parity(ml, ob.ambiguity_surface(modes, K, r, z, atype="cbf_ml", multifreq_method="product"), floor=1.0)
+    # a sub-grid must reproduce the same numbers (tiles/chunks change, arithmetic per node does not)
+    sub = dms.bartlett_grid(r[: max(1, nr // 2)], z[: max(1, nz // 3)], engine="umma").cpu().numpy()
+    np.testing.assert_array_equal(sub, got[: max(1, nz // 3), : max(1, nr // 2)])
+
+
+def test_umma_rejects_what_it_cannot_fuse():
+    from bogp_b200 import _lib
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import INV_TONALS_3, REC_Z_21, pekeris_modes, synthetic_covariance
+    modes = pekeris_modes(INV_TONALS_3, REC_Z_21, complex_modes=True)
+    dms = DeviceModeSet(modes, synthetic_covariance(modes, 40.0, 2.2))
+    with pytest.raises(_lib.BogpError):
+        dms.bartlett_grid([1.0, 2.0], [10.0], engine="umma")          # complex source table: SIMT only
+    assert np.isfinite(dms.bartlett_grid([1.0, 2.0], [10.0], engine="auto").cpu().numpy()).all()
 
 
 def test_truth_is_one_and_ml_zero(cfg2_small, dms2):
