@@ -244,27 +244,27 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
     Wt.resize(Wt.size() + (size_t)t.Mp * t.rowsP, 0.f);
     for (int r2 = 0; r2 < t.rows; ++r2)
       for (int m = 0; m < M; ++m) Wt[t.offWt + (size_t)m * t.rowsP + r2] = Wf[(size_t)r2 * t.Mp + m];
-    // UMMA row order (bogp_internal.h): plain | pad to even | (re, im) norm pairs | (re, im) numerator pairs | pad
-    t.u_p0 = (t.n_plain + 1) & ~1;
-    t.u_rowsP = bogp::pad_to(std::max(t.u_p0 + 2 * t.n_npair + 2 * t.n_qpair, 1), 16);
+    // UMMA row order (bogp_internal.h): (re, im) numerator pairs | (re, im) norm pairs | plain rows | zero pad
+    t.u_p0 = 2 * t.n_qpair + 2 * t.n_npair;        // first plain row (even)
+    t.u_rowsP = bogp::pad_to(std::max(t.u_p0 + t.n_plain, 1), 16);
     t.offWu = (int)Wu.size();
     Wu.resize(Wu.size() + (size_t)t.u_rowsP * t.Mp, 0.f);
     {
       float* U = &Wu[t.offWu];
-      for (int j = 0; j < t.n_plain; ++j)
-        for (int m = 0; m < M; ++m) U[(size_t)j * t.Mp + m] = Wf[(size_t)j * t.Mp + m];
-      int src = t.n_plain, dst = t.u_p0;
-      for (int j = 0; j < t.n_npair; ++j, dst += 2)
-        for (int m = 0; m < M; ++m) {
-          U[(size_t)dst * t.Mp + m] = Wf[(size_t)(src + j) * t.Mp + m];
-          U[(size_t)(dst + 1) * t.Mp + m] = Wf[(size_t)(src + t.n_npair + j) * t.Mp + m];
-        }
-      src += 2 * t.n_npair;
+      const int src_np = t.n_plain, src_q = t.n_plain + 2 * t.n_npair;
+      int dst = 0;
       for (int j = 0; j < t.n_qpair; ++j, dst += 2)
         for (int m = 0; m < M; ++m) {
-          U[(size_t)dst * t.Mp + m] = Wf[(size_t)(src + j) * t.Mp + m];
-          U[(size_t)(dst + 1) * t.Mp + m] = Wf[(size_t)(src + t.n_qpair + j) * t.Mp + m];
+          U[(size_t)dst * t.Mp + m] = Wf[(size_t)(src_q + j) * t.Mp + m];
+          U[(size_t)(dst + 1) * t.Mp + m] = Wf[(size_t)(src_q + t.n_qpair + j) * t.Mp + m];
         }
+      for (int j = 0; j < t.n_npair; ++j, dst += 2)
+        for (int m = 0; m < M; ++m) {
+          U[(size_t)dst * t.Mp + m] = Wf[(size_t)(src_np + j) * t.Mp + m];
+          U[(size_t)(dst + 1) * t.Mp + m] = Wf[(size_t)(src_np + t.n_npair + j) * t.Mp + m];
+        }
+      for (int j = 0; j < t.n_plain; ++j, ++dst)
+        for (int m = 0; m < M; ++m) U[(size_t)dst * t.Mp + m] = Wf[(size_t)j * t.Mp + m];
     }
     // Receiver-space factor: num = || LK^H p ||^2 ; Ck[j, n] = conj(LK[n, j]); stored transposed [N][J]
     t.J = rK;

@@ -69,9 +69,9 @@ struct TonalMeta {
   int offRec;    // offset into phi_rec (N * Mp)
   int offC;      // offset into receiver-space factor (J * N complex)
   float trK;     // trace of K_f (cbf_ml)
-  // tcgen05 (UMMA) row order of the same operator: plain rows, zero-padded to the even row u_p0, then the complex
-  // rows as ADJACENT (re, im) pairs -- norm pairs first, numerator pairs after -- zero-padded to u_rowsP (x16).
-  int u_p0;      // first pair row (even)
+  // tcgen05 (UMMA) row order of the same operator: the complex rows as ADJACENT (re, im) pairs -- numerator pairs
+  // first, norm pairs after -- then the plain rows from the even row u_p0 on, zero-padded to u_rowsP (x16).
+  int u_p0;      // first plain row (even) = 2 n_qpair + 2 n_npair
   int u_rowsP;   // rows padded to a multiple of 16 (the MMA N granularity at M = 128)
   int offWu;     // offset into Wu (u_rowsP * Mp floats, row-major [row][Mp])
 };

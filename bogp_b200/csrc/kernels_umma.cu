@@ -5,21 +5,24 @@
 //     T[row, (i,j)] = sum_m W_f[row, m] phi_m(z_j) E_f[m, i],   E_f[m, i] = e^{-i k_m r_i} / sqrt(k_m r_i)
 //     B_f(i, j)     = sum_{numerator rows} |T|^2 / sum_{norm rows} |T|^2
 // As a GEMM per (depth j, tonal f):   D[i, row] = sum_m  A[i, m] * Bop[row, m]
-//     A   = E_f^T, the 128-range tile of the phase table (re and im parts -> two accumulators), resident in shared
-//           memory for the whole depth sweep of a tonal;
+//     A   = E_f^T, the 128-range tile of the phase table (re and im parts -> two accumulators), resident in TENSOR
+//           MEMORY for the whole depth sweep of a tonal (tcgen05.mma with A in TMEM: with K = 8 per TF32 MMA an A
+//           operand in shared memory costs 4 KB of shared-memory reads per instruction and bounds the pipe);
 //     Bop = W_f diag(phi(z_j)), streamed per depth (several depths stacked along the MMA N dimension).
 // 3xTF32: every fp32 operand x is split x = hi + lo (hi = tf32-rounded); D = A_lo B_hi + A_hi B_lo + A_hi B_hi
 // accumulates in fp32 in TMEM (1xTF32 fails the 1e-5 bar, 3xTF32 gives ~3e-7).
 // D puts range i on TMEM lane i, so each epilogue thread owns one range and reduces over the operator rows of its
 // own lane: no cross-lane shuffles; the replica field never exists outside TMEM.
 //
-// Pipeline per CTA (persistent over (range tile, depth chunk) units), 10 warps:
-//     warp 0    bulk-copy producer: E_f tile (once per tonal) and the ring of Bop stages (cp.async.bulk + mbarrier)
-//     warp 1    MMA issuer (one lane): tcgen05.mma.kind::tf32, commits to the ring / TMEM barriers; owns TMEM
-//     warps 2-9 epilogue: tcgen05.ld -> sum of squares -> Bartlett -> multi-frequency combine in shared memory
-// Operand tables are built per call by two small kernels directly in the UMMA canonical K-major no-swizzle layout
-// ([8-row group][16-byte K chunk][8 rows][4 floats]; LBO = 128 B, SBO = 32 * Mp B), so the producer issues plain
-// 1-D bulk copies.
+// Pipeline per CTA (persistent over (range tile, depth chunk) units), 14 warps:
+//     warp 0      bulk-copy producer: the ring of Bop stages (cp.async.bulk + mbarrier complete_tx)
+//     warp 1      MMA issuer: tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory), commits to the ring / TMEM
+//                 barriers; owns the TMEM allocation
+//     warps 2-9   epilogue: tcgen05.ld -> sum of squares -> Bartlett -> multi-frequency combine in shared memory
+//     warps 10-13 E loaders: global -> registers -> tcgen05.st, one tonal ahead of the MMAs
+// The Bop table is built per call directly in the UMMA canonical K-major no-swizzle layout ([8-row group][16-byte K
+// chunk][8 rows][4 floats]; LBO = 128 B, SBO = 32 * Mp B), so the producer issues plain 1-D bulk copies.
+// TMEM map (512 columns): two accumulator buffers of (re | im) x NA columns, then the A region.
 //
 // Replaces the loop `for z in src_z: amb[zz,:] = MFP({"src_z": z, "rec_r": rvec})`
 // (ref/projects/swellex96_localization/data/mfp.py:213-214) for a vertical array.
@@ -33,18 +36,19 @@
 namespace bogp {
 
 constexpr int kTileR = 128;            // ranges per tile = MMA M = TMEM lanes
-constexpr int kStages = 4;             // Bop ring depth
-constexpr int kAccCols = 128;          // TMEM columns per accumulator half (re | im)
-constexpr int kEpiWarps = 8;
-constexpr int kUmmaThreads = (2 + kEpiWarps) * 32;
+constexpr int kStages = 6;             // Bop ring depth
+constexpr int kEpiWarps = 16;          // 2 accumulator-buffer sets x 2 depth parities x 4 TMEM lane quadrants
+constexpr int kLoadWarps = 4;
+constexpr int kUmmaThreads = (2 + kEpiWarps + kLoadWarps) * 32;
 constexpr unsigned kSmemLimit = 227u * 1024u;
 
 struct UTonal {
-  int Mp, rowsP, p0, n1;       // n1 = p0 + 2 * n_npair: pair rows below n1 feed the norm, above it the numerator
-  int nq;                      // numerator (re, im) row pairs = rank of Phi^H K Phi
+  int Mp, rowsP;
+  int nq;                      // numerator (re, im) row pairs = rank of Phi^H K Phi: columns [0, 2 nq)
+  int n1;                      // 2 nq + 2 n_npair: pair columns in [2 nq, n1) feed the norm; plain columns from n1 on
   int nj;                      // depths stacked per stage
   int wait_prev;               // this tonal's E tile overlaps the previous tonal's in shared memory
-  unsigned e_bytes;            // 2048 * Mp  (re_hi | re_lo | im_hi | im_lo)
+  unsigned e_bytes;            // 2048 * Mp  (re_hi | re_lo | im_hi | im_lo) x 128 ranges
   unsigned e_off;              // offset of the tonal inside one range tile's block of the E table
   unsigned b_zbytes;           // rowsP * Mp * 4: one depth of one split of Bop
   unsigned long long b_off;    // offset of the tonal inside the Bop tables
@@ -53,9 +57,10 @@ struct UTonal {
 
 struct UParams {
   int F, Nr, Nz, nrt, ZC, units, atype, mf;
-  int swap_lbo_sbo;            // debug knob (BOGP_UMMA_SWAP=1)
-  unsigned e_rt_stride, e_region, stage_bytes;
+  unsigned e_rt_stride, stage_bytes;
   unsigned smem_B, smem_acc, smem_bar;
+  int NA;                      // TMEM columns per accumulator half; buffers at 0 and 2 NA, A region at [4 NA, 4 NA + AR)
+  int AR;                      // TMEM columns of the A region
   const unsigned char* E;
   const unsigned char* Bhi;
   const unsigned char* Blo;
@@ -138,6 +143,76 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same with the shared-memory descriptor passed as two 32-bit halves (only the low half changes between K steps).
+__device__ __forceinline__ void tc_mma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t b_desc_hi,
+                                                uint32_t idesc, bool accumulate) {
+  if (accumulate)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 d;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 d;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc)
+        : "memory");
+}
+// All MMAs of one stage, fully unrolled over the KS K-steps: per K-step D += A_lo B_hi + A_hi B_lo + A_hi B_hi for
+// the re and the im accumulator.  Called by ONE elected lane; a single warp must keep the tensor pipe fed with
+// 128 x N x 8 MMAs of only N/2 cycles each, so the instruction count per MMA matters (v1 spent ~90 cycles per MMA
+// in address arithmetic and R2UR moves).
+template <int KS>
+__device__ __forceinline__ void issue_stage(uint32_t d_re, uint32_t d_im, uint32_t a_col, uint32_t Mp, uint32_t bh_lo,
+                                            uint32_t bl_lo, uint32_t desc_hi, uint32_t idesc) {
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {
+    const uint32_t d = part ? d_im : d_re;
+    const uint32_t a_hi = a_col + (uint32_t)(2 * part) * Mp, a_lo = a_hi + Mp;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      tc_mma_tf32_ts2(d, a_lo + 8u * ks, bh_lo + 16u * ks, desc_hi, idesc, ks > 0);
+      tc_mma_tf32_ts2(d, a_hi + 8u * ks, bl_lo + 16u * ks, desc_hi, idesc, true);
+      tc_mma_tf32_ts2(d, a_hi + 8u * ks, bh_lo + 16u * ks, desc_hi, idesc, true);
+    }
+  }
+}
+// Numerator pairs live in the first 2 nq <= 16 columns: T = (r0 + i i0) + i (r1 + i i1) per (re, im) row pair.
+__device__ __forceinline__ void numerator16(const float* re, const float* im, int nq, float& num, float& numsq) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (q < nq) {
+      const float r0 = re[2 * q], r1 = re[2 * q + 1], i0 = im[2 * q], i1 = im[2 * q + 1];
+      const float tr = r0 - i1, ti = i0 + r1;
+      num = fmaf(tr, tr, fmaf(ti, ti, num));
+      numsq = fmaf(r0, r0, fmaf(i0, i0, fmaf(r1, r1, fmaf(i1, i1, numsq))));
+    }
+  }
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const float4& a, const float4& b, const float4& c, const float4& d) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(a.x)), "r"(__float_as_uint(a.y)), "r"(__float_as_uint(a.z)), "r"(__float_as_uint(a.w)),
+      "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)), "r"(__float_as_uint(b.z)), "r"(__float_as_uint(b.w)),
+      "r"(__float_as_uint(c.x)), "r"(__float_as_uint(c.y)), "r"(__float_as_uint(c.z)), "r"(__float_as_uint(c.w)),
+      "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y)), "r"(__float_as_uint(d.z)), "r"(__float_as_uint(d.w))
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -185,17 +260,15 @@ __device__ __forceinline__ size_t canon_off(int row, int m, int Mp) {
   return ((size_t)((row >> 3) * (Mp >> 2) + (m >> 2)) * 8 + (row & 7)) * 4 + (m & 3);
 }
 
-// E table: per (range tile, tonal) the four blocks re_hi | re_lo | im_hi | im_lo of E_f^T [128, Mp].
+// E table: per (range tile, tonal) the TMEM image of E_f^T: columns [re_hi (Mp) | re_lo | im_hi | im_lo] for each of the
+// 128 ranges, stored as [16-byte column chunk][range][4 floats] so that a loader warp reads coalesced float4s.
 __global__ void umma_E_table_kernel(ModesetDev ms, UParams p, const double* __restrict__ r) {
   const int rt = blockIdx.x, f = blockIdx.y;
   const TonalMeta& t = ms.t[f];
   const UTonal& u = p.t[f];
   float* base = reinterpret_cast<float*>(const_cast<unsigned char*>(p.E) + (size_t)rt * p.e_rt_stride + u.e_off);
-  const size_t blk = (size_t)kTileR * u.Mp;
   for (int idx = threadIdx.x; idx < kTileR * u.Mp; idx += blockDim.x) {
-    // memory order: (rowgroup, kchunk, row8, k4) so that stores coalesce
-    const int k4 = idx & 3, r8 = (idx >> 2) & 7, kc = (idx >> 5) % (u.Mp >> 2), rg = (idx >> 5) / (u.Mp >> 2);
-    const int row = rg * 8 + r8, m = kc * 4 + k4, i = rt * kTileR + row;
+    const int m = idx % u.Mp, row = idx / u.Mp, i = rt * kTileR + row;
     double vr = 0.0, vi = 0.0;
     if (i < p.Nr && m < t.M) {
       const double kre = ms.k_re[t.offM + m], kim = ms.k_im[t.offM + m], rr = r[i];
@@ -210,10 +283,12 @@ __global__ void umma_E_table_kernel(ModesetDev ms, UParams p, const double* __re
       vi = amp * (s * c2 + c * s2);
     }
     const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
-    base[idx] = rh;
-    base[blk + idx] = (float)(vr - (double)rh);
-    base[2 * blk + idx] = ih;
-    base[3 * blk + idx] = (float)(vi - (double)ih);
+    const float v[4] = {rh, (float)(vr - (double)rh), ih, (float)(vi - (double)ih)};
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int col = b * u.Mp + m;
+      base[((size_t)(col >> 2) * kTileR + row) * 4 + (col & 3)] = v[b];
+    }
   }
 }
 
@@ -249,6 +324,62 @@ __global__ void umma_B_table_kernel(ModesetDev ms, UParams p, const double* __re
 enum { BAR_BFULL = 0, BAR_BEMPTY = kStages, BAR_EFULL = 2 * kStages, BAR_EDONE = 2 * kStages + 2,
        BAR_TFULL = 2 * kStages + 4, BAR_TEMPTY = 2 * kStages + 6, BAR_COUNT = 2 * kStages + 8 };
 
+// TMEM column of tonal g's E image: even tonals grow from the low end of the A region, odd ones sit at the high end,
+// so tonal g+1 can be loaded while tonal g is still being multiplied whenever the two fit side by side.
+__device__ __forceinline__ uint32_t a_column(const UParams& p, int g, int Mp) {
+  return (uint32_t)(4 * p.NA) + ((g & 1) ? (uint32_t)(p.AR - 4 * Mp) : 0u);
+}
+
+struct MmaState {
+  const UParams* p;
+  uint32_t tmem_base, s_base, bar0;
+  uint32_t sc;       // global stage counter
+  int g;             // global tonal counter
+  int nzu;
+  bool dbg;
+  long long w_efull, w_bfull, w_tempty;
+};
+
+// All stages of one tonal of one unit.  Templated on the K steps so that a stage is straight-line code: two barrier
+// waits, 6 * KS tcgen05.mma, two commits.  (The per-stage scalar code runs on a single warp at ~5 cycles per dependent
+// instruction, while a 128 x 64 x 8 MMA lasts 32 cycles: anything not hoisted out of the stage loop idles the pipe.)
+template <int KS>
+__device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
+  const UParams& p = *st.p;
+  const uint32_t Mp = 8u * KS;
+  const uint32_t a_col = st.tmem_base + a_column(p, st.g, (int)Mp);
+  const uint32_t desc_hi = (uint32_t)(make_desc(0, 128u, 32u * Mp) >> 32);
+  const uint32_t desc_lo0 = (uint32_t)make_desc(0, 128u, 32u * Mp);       // LBO field; start address added per stage
+  const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((kTileR >> 4) << 24);
+  auto bar = [&](int i) { return st.bar0 + 8u * (uint32_t)i; };
+  mbar_wait_t(bar(BAR_EFULL + (st.g & 1)), (uint32_t)((st.g >> 1) & 1), p.err, 4, st.dbg ? &st.w_efull : nullptr);
+  const int nj = u.nj, nzu = st.nzu;
+  uint32_t sc = st.sc;
+#pragma unroll 1
+  for (int j0 = 0; j0 < nzu; j0 += nj, ++sc) {
+    const int njs = min(nj, nzu - j0);
+    const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
+    const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
+    mbar_wait_t(bar(BAR_BFULL + slot), ph, p.err, 5, st.dbg ? &st.w_bfull : nullptr);
+    mbar_wait_t(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6, st.dbg ? &st.w_tempty : nullptr);
+    tc_fence_after();
+    const uint32_t N = (uint32_t)(njs * u.rowsP);
+    const uint32_t idesc = idesc0 | ((N >> 3) << 17);
+    const uint32_t b_hi = st.s_base + p.smem_B + slot * p.stage_bytes;
+    const uint32_t b_lo = b_hi + (uint32_t)njs * u.b_zbytes;
+    const uint32_t d_re = st.tmem_base + buf * (uint32_t)(2 * p.NA), d_im = d_re + (uint32_t)p.NA;
+    if (elect_one()) {
+      issue_stage<KS>(d_re, d_im, a_col, Mp, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc);
+      tc_commit(bar(BAR_BEMPTY + slot));
+      tc_commit(bar(BAR_TFULL + buf));
+    }
+    __syncwarp();
+  }
+  st.sc = sc;
+  if (elect_one()) tc_commit(bar(BAR_EDONE + (st.g & 1)));
+  __syncwarp();
+}
+
 __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid_constant__ UParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -260,10 +391,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_BFULL + s), 1); mbar_init(bar(BAR_BEMPTY + s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar(BAR_EFULL + b), 1);
+      mbar_init(bar(BAR_EFULL + b), kLoadWarps);
       mbar_init(bar(BAR_EDONE + b), 1);
       mbar_init(bar(BAR_TFULL + b), 1);
-      mbar_init(bar(BAR_TEMPTY + b), kEpiWarps);
+      mbar_init(bar(BAR_TEMPTY + b), kEpiWarps / 2);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -275,171 +406,143 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long* const dbg = p.dbg ? p.dbg + 16 * blockIdx.x : nullptr;
+  const long long t_start = clock64();
 
   if (warp == 0) {
-    // ============================================================== producer
-    {
-      long long w_edone = 0, w_bempty = 0;
-      const long long t_start = clock64();
-      uint32_t sc = 0;       // global stage counter
-      int g = 0;             // global tonal counter
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        const int rt = unit % p.nrt, zc = unit / p.nrt;
-        const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
-        for (int f = 0; f < p.F; ++f, ++g) {
-          const UTonal& u = p.t[f];
-          // E tile of tonal g goes to the low end (g even) or the high end (g odd) of the E region
-          if (g >= 2) mbar_wait_t(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1, p.dbg ? &w_edone : nullptr);
-          if (g >= 1) {
-            const UTonal& up = p.t[f == 0 ? p.F - 1 : f - 1];
-            if (up.e_bytes + u.e_bytes > p.e_region)
-              mbar_wait_t(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2, p.dbg ? &w_edone : nullptr);
-          }
-          const uint32_t e_dst = s_base + ((g & 1) ? p.e_region - u.e_bytes : 0u);
+    // ============================================================== Bop producer (whole warp, one elected lane issues)
+    long long w_bempty = 0;
+    uint32_t sc = 0;       // global stage counter
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int zc = unit / p.nrt;
+      const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
+      for (int f = 0; f < p.F; ++f) {
+        const UTonal& u = p.t[f];
+        for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
+          const int njs = min(u.nj, nzu - j0);
+          const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
+          mbar_wait_t(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3, dbg ? &w_bempty : nullptr);
+          const uint32_t bytes = (uint32_t)njs * u.b_zbytes;
+          const uint32_t dst = s_base + p.smem_B + slot * p.stage_bytes;
+          const size_t src = (size_t)u.b_off + (size_t)(z0 + j0) * u.b_zbytes;
           if (elect_one()) {
-            mbar_expect_tx(bar(BAR_EFULL + (g & 1)), u.e_bytes);
-            bulk_g2s(e_dst, p.E + (size_t)rt * p.e_rt_stride + u.e_off, u.e_bytes, bar(BAR_EFULL + (g & 1)));
+            mbar_expect_tx(bar(BAR_BFULL + slot), 2 * bytes);
+            bulk_g2s(dst, p.Bhi + src, bytes, bar(BAR_BFULL + slot));
+            bulk_g2s(dst + bytes, p.Blo + src, bytes, bar(BAR_BFULL + slot));
           }
           __syncwarp();
-          for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
-            const int njs = min(u.nj, nzu - j0);
-            const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
-            mbar_wait_t(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3, p.dbg ? &w_bempty : nullptr);
-            const uint32_t bytes = (uint32_t)njs * u.b_zbytes;
-            const uint32_t dst = s_base + p.smem_B + slot * p.stage_bytes;
-            const size_t src = (size_t)u.b_off + (size_t)(z0 + j0) * u.b_zbytes;
-            if (elect_one()) {
-              mbar_expect_tx(bar(BAR_BFULL + slot), 2 * bytes);
-              bulk_g2s(dst, p.Bhi + src, bytes, bar(BAR_BFULL + slot));
-              bulk_g2s(dst + bytes, p.Blo + src, bytes, bar(BAR_BFULL + slot));
-            }
-            __syncwarp();
-          }
         }
       }
-      if (p.dbg && lane == 0) {
-        long long* d = p.dbg + 16 * blockIdx.x;
-        d[0] = clock64() - t_start; d[1] = w_edone; d[2] = w_bempty;
-      }
     }
+    (void)w_bempty;
   } else if (warp == 1) {
-    // ============================================================== MMA issuer
-    {
-      long long w_efull = 0, w_bfull = 0, w_tempty = 0;
-      const long long t_start = clock64();
-      uint32_t sc = 0;
-      int g = 0;
-      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-        const int zc = unit / p.nrt;
-        const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
-        for (int f = 0; f < p.F; ++f, ++g) {
-          const UTonal& u = p.t[f];
-          const uint32_t sbo = 32u * (uint32_t)u.Mp, lbo = 128u;
-          const uint32_t d_lbo = p.swap_lbo_sbo ? sbo : lbo, d_sbo = p.swap_lbo_sbo ? lbo : sbo;
-          const uint32_t e_src = s_base + ((g & 1) ? p.e_region - u.e_bytes : 0u);
-          const uint32_t e_blk = 512u * (uint32_t)u.Mp;      // one of re_hi | re_lo | im_hi | im_lo
-          mbar_wait_t(bar(BAR_EFULL + (g & 1)), (uint32_t)((g >> 1) & 1), p.err, 4, p.dbg ? &w_efull : nullptr);
-          for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
-            const int njs = min(u.nj, nzu - j0);
-            const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
-            const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
-            mbar_wait_t(bar(BAR_BFULL + slot), ph, p.err, 5, p.dbg ? &w_bfull : nullptr);
-            mbar_wait_t(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6, p.dbg ? &w_tempty : nullptr);
-            tc_fence_after();
-            const uint32_t N = (uint32_t)(njs * u.rowsP);
-            // instruction descriptor: D = f32 [4,6), A = B = tf32 [7,10) / [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((kTileR >> 4) << 24);
-            const uint32_t b_hi = s_base + p.smem_B + slot * p.stage_bytes;
-            const uint32_t b_lo = b_hi + (uint32_t)njs * u.b_zbytes;
-            const int ksteps = u.Mp >> 3;
-#pragma unroll 1
-            for (int part = 0; part < 2; ++part) {
-              const uint32_t a_hi = e_src + (uint32_t)(2 * part) * e_blk, a_lo = a_hi + e_blk;
-              const uint32_t d = tmem_base + buf * (2 * kAccCols) + (uint32_t)part * kAccCols;
-#pragma unroll 1
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t ko = 256u * (uint32_t)ks;    // 8 K elements = 2 chunks of 128 B per row group
-                const uint64_t dah = make_desc(a_hi + ko, d_lbo, d_sbo), dal = make_desc(a_lo + ko, d_lbo, d_sbo);
-                const uint64_t dbh = make_desc(b_hi + ko, d_lbo, d_sbo), dbl = make_desc(b_lo + ko, d_lbo, d_sbo);
-                if (elect_one()) {
-                  tc_mma_tf32(d, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-                  tc_mma_tf32(d, dah, dbl, idesc, 1u);
-                  tc_mma_tf32(d, dah, dbh, idesc, 1u);
-                }
-                __syncwarp();
-              }
-            }
-            if (elect_one()) {
-              tc_commit(bar(BAR_BEMPTY + slot));
-              tc_commit(bar(BAR_TFULL + buf));
-            }
-            __syncwarp();
-          }
-          if (elect_one()) tc_commit(bar(BAR_EDONE + (g & 1)));
-          __syncwarp();
+    // ============================================================== MMA issuer (whole warp, one elected lane issues)
+    MmaState st{};
+    st.p = &p; st.tmem_base = tmem_base; st.s_base = s_base; st.bar0 = bar0; st.dbg = dbg != nullptr;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int zc = unit / p.nrt;
+      const int z0 = zc * p.ZC;
+      st.nzu = min(p.ZC, p.Nz - z0);
+      for (int f = 0; f < p.F; ++f, ++st.g) {
+        switch (p.t[f].Mp >> 3) {
+          case 1: mma_tonal<1>(st, p.t[f]); break;
+          case 2: mma_tonal<2>(st, p.t[f]); break;
+          case 3: mma_tonal<3>(st, p.t[f]); break;
+          case 4: mma_tonal<4>(st, p.t[f]); break;
+          case 5: mma_tonal<5>(st, p.t[f]); break;
+          case 6: mma_tonal<6>(st, p.t[f]); break;
+          case 7: mma_tonal<7>(st, p.t[f]); break;
+          default: mma_tonal<8>(st, p.t[f]); break;
         }
       }
-      if (p.dbg && lane == 0) {
-        long long* d = p.dbg + 16 * blockIdx.x;
-        d[3] = clock64() - t_start; d[4] = w_efull; d[5] = w_bfull; d[6] = w_tempty; d[7] = sc;
+    }
+    if (dbg && lane == 0) { dbg[3] = clock64() - t_start; dbg[4] = st.w_efull; dbg[5] = st.w_bfull; dbg[6] = st.w_tempty; dbg[7] = st.sc; }
+  } else if (warp >= 2 + kEpiWarps) {
+    // ============================================================== E loaders: global -> registers -> TMEM
+    const int quad = warp & 3;
+    const int tl = quad * 32 + lane;
+    long long w_edone = 0;
+    int g = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int rt = unit % p.nrt;
+      for (int f = 0; f < p.F; ++f, ++g) {
+        const UTonal& u = p.t[f];
+        if (g >= 2) mbar_wait_t(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1, dbg ? &w_edone : nullptr);
+        if (g >= 1) {
+          const UTonal& up = p.t[f == 0 ? p.F - 1 : f - 1];
+          if (4 * (up.Mp + u.Mp) > p.AR)
+            mbar_wait_t(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2, dbg ? &w_edone : nullptr);
+        }
+        tc_fence_after();
+        const float4* src = reinterpret_cast<const float4*>(p.E + (size_t)rt * p.e_rt_stride + u.e_off) + tl;
+        const uint32_t dst = tmem_base + ((uint32_t)(quad * 32) << 16) + a_column(p, g, u.Mp);
+        const int n16 = u.Mp >> 2;            // 4 Mp columns in groups of 16
+        for (int c = 0; c < n16; c += 2) {
+          const float4 v0 = __ldg(src + (size_t)(4 * c + 0) * kTileR), v1 = __ldg(src + (size_t)(4 * c + 1) * kTileR);
+          const float4 v2 = __ldg(src + (size_t)(4 * c + 2) * kTileR), v3 = __ldg(src + (size_t)(4 * c + 3) * kTileR);
+          const float4 v4 = __ldg(src + (size_t)(4 * c + 4) * kTileR), v5 = __ldg(src + (size_t)(4 * c + 5) * kTileR);
+          const float4 v6 = __ldg(src + (size_t)(4 * c + 6) * kTileR), v7 = __ldg(src + (size_t)(4 * c + 7) * kTileR);
+          tc_st16(dst + (uint32_t)(16 * c), v0, v1, v2, v3);
+          tc_st16(dst + (uint32_t)(16 * c + 16), v4, v5, v6, v7);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_EFULL + (g & 1)));
       }
     }
-    __syncwarp();
+    if (dbg && lane == 0 && quad == 0) { dbg[12] = clock64() - t_start; }
   } else {
     // ============================================================== epilogue
-    const int ew = warp - 2;                 // 0..7
+    // 16 warps = 2 buffer sets x 2 depth parities x 4 TMEM lane quadrants.  Set b drains accumulator buffer b only,
+    // so the two buffers are processed concurrently by different warps, and a warp releases its buffer as soon as its
+    // last tcgen05.ld has landed in registers -- the squares, the division and the combine run after the release.
+    const int ew = warp - 2;                 // 0..15
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                // which depth parity this warp handles
+    const int set = (ew >> 2) & 1;           // accumulator buffer (= stage parity) this warp drains
+    const int sub = ew >> 3;                 // depth parity this warp handles
     const int tl = quad * 32 + lane;         // lane in the tile = range index in the tile
+    const uint32_t NA = (uint32_t)p.NA;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)set * (2 * NA);
     float* acc = reinterpret_cast<float*>(smem + p.smem_acc);     // [ZC][128]
     uint32_t sc = 0;
     long long w_tfull = 0;
-    const long long t_start = clock64();
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int rt = unit % p.nrt, zc = unit / p.nrt;
       const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
       for (int f = 0; f < p.F; ++f) {
         const UTonal& u = p.t[f];
-        const int p0 = u.p0, n1 = u.n1, rowsP = u.rowsP;
+        const int rowsP = u.rowsP, nq = u.nq;
+        const bool fast = (u.n1 == 2 * nq) && nq <= 8;
         for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
+          if ((int)(sc & 1u) != set) continue;
           const int njs = min(u.nj, nzu - j0);
-          const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
-          mbar_wait_t(bar(BAR_TFULL + buf), tph, p.err, 7, p.dbg ? &w_tfull : nullptr);
+          mbar_wait_t(bar(BAR_TFULL + set), (sc >> 1) & 1u, p.err, 7, dbg ? &w_tfull : nullptr);
           tc_fence_after();
-          for (int s = 0; s < njs; ++s) {
+          // slots of this stage owned by this warp: s = s_first, s_first + 2, ...
+          const int s_first = (sub - (j0 & 1)) & 1;
+          bool released = false;
+          for (int s = s_first; s < njs; s += 2) {
             const int j = j0 + s;
-            if ((j & 1) != half) continue;
-            const uint32_t t_re = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (2 * kAccCols) + (uint32_t)(s * rowsP);
+            const bool last_slot = s + 2 >= njs;
+            const uint32_t t_re = t_lane + (uint32_t)(s * rowsP);
             float norm = 0.f, num = 0.f;
-            if (n1 == p0) {
+            if (fast) {
               // Real receiver modes (KRAKEN): every |T|^2 term is a plain square except the nq numerator pairs, and
               // (r0 - i1)^2 + (i0 + r1)^2 = r0^2 + i0^2 + r1^2 + i1^2 + 2 (i0 r1 - r0 i1).  One FFMA per value over
-              // ALL columns gives tot = norm + numsq; the numerator pairs are re-read on their own.
+              // ALL columns gives tot = norm + numsq; the numerator pairs sit in the first columns already loaded.
               float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, numsq = 0.f;
-              int c0 = 0;
-              float nr0 = 0.f, nr1 = 0.f, ni0 = 0.f, ni1 = 0.f;
-              if (u.nq > 0) {
-                tc_ld2(t_re + (uint32_t)p0, nr0, nr1);
-                tc_ld2(t_re + (uint32_t)(kAccCols + p0), ni0, ni1);
-              }
-              for (; c0 + 32 <= rowsP; c0 += 32) {
-                float re[32], im[32];
-                tc_ld32(t_re + (uint32_t)c0, re);
-                tc_ld32(t_re + (uint32_t)(kAccCols + c0), im);
-                tc_wait_ld();
-#pragma unroll
-                for (int q = 0; q < 32; q += 2) {
-                  t0 = fmaf(re[q], re[q], t0);
-                  t1 = fmaf(im[q], im[q], t1);
-                  t2 = fmaf(re[q + 1], re[q + 1], t2);
-                  t3 = fmaf(im[q + 1], im[q + 1], t3);
-                }
-              }
-              if (c0 < rowsP) {
+              for (int c0 = 0; c0 < rowsP; c0 += 16) {
                 float re[16], im[16];
                 tc_ld16(t_re + (uint32_t)c0, re);
-                tc_ld16(t_re + (uint32_t)(kAccCols + c0), im);
+                tc_ld16(t_re + NA + (uint32_t)c0, im);
                 tc_wait_ld();
+                if (last_slot && c0 + 16 >= rowsP) {
+                  tc_fence_before();
+                  if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
+                  released = true;
+                }
+                if (c0 == 0) numerator16(re, im, nq, num, numsq);
 #pragma unroll
                 for (int q = 0; q < 16; q += 2) {
                   t0 = fmaf(re[q], re[q], t0);
@@ -448,56 +551,56 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
                   t3 = fmaf(im[q + 1], im[q + 1], t3);
                 }
               }
-              for (int q = 0;;) {
-                const float tr = nr0 - ni1, ti = ni0 + nr1;
-                num = fmaf(tr, tr, fmaf(ti, ti, num));
-                numsq += fmaf(nr0, nr0, ni0 * ni0) + fmaf(nr1, nr1, ni1 * ni1);
-                if (++q >= u.nq) break;
-                tc_ld2(t_re + (uint32_t)(p0 + 2 * q), nr0, nr1);
-                tc_ld2(t_re + (uint32_t)(kAccCols + p0 + 2 * q), ni0, ni1);
-                tc_wait_ld();
-              }
               norm = ((t0 + t1) + (t2 + t3)) - numsq;
             } else {
+              const int nq2 = 2 * nq, n1 = u.n1;
               for (int c0 = 0; c0 < rowsP; c0 += 16) {
                 float re[16], im[16];
                 tc_ld16(t_re + (uint32_t)c0, re);
-                tc_ld16(t_re + (uint32_t)(kAccCols + c0), im);
+                tc_ld16(t_re + NA + (uint32_t)c0, im);
                 tc_wait_ld();
+                if (last_slot && c0 + 16 >= rowsP) {
+                  tc_fence_before();
+                  if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
+                  released = true;
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                   const int c = c0 + 2 * q;
                   const float r0 = re[2 * q], r1 = re[2 * q + 1], i0 = im[2 * q], i1 = im[2 * q + 1];
-                  if (c < p0) {
+                  if (c >= n1) {
                     norm += r0 * r0 + i0 * i0 + r1 * r1 + i1 * i1;
                   } else {
                     const float tr = r0 - i1, ti = i0 + r1;
                     const float v = tr * tr + ti * ti;
-                    if (c < n1) norm += v; else num += v;
+                    if (c < nq2) num += v; else norm += v;
                   }
                 }
               }
             }
-            const float b = num / norm;
+            const float b = __fdividef(num, norm);
             const float val = p.atype == BOGP_ATYPE_CBF ? b : u.trK - b;
             float* a = acc + (size_t)j * kTileR + tl;
             *a = (f == 0) ? val : (p.mf == BOGP_MF_MEAN ? *a + val : *a * val);
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+          if (!released) {      // no slot of this stage belongs to this warp
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
+          }
         }
       }
-      // this thread alone touched acc[j][tl] for its depth parity: no barrier needed before the write-out
+      // acc[j][tl] is updated by the two sets' warps of this (quadrant, parity) in stage order; the buffer hand-shake
+      // orders those updates (release/acquire on the mbarriers), but the write-out below reads both sets' updates, so
+      // the warps of this quadrant meet on a named barrier first (4 warps = 128 threads per quadrant).
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(128) : "memory");
       const int i = rt * kTileR + tl;
       const float scale = p.mf == BOGP_MF_MEAN ? 1.f / (float)p.F : 1.f;
+      const int k4 = ew >> 2;                  // 0..3: this warp writes depths j = k4, k4 + 4, ...
       if (i < p.Nr)
-        for (int j = half; j < nzu; j += 2) p.out[(size_t)(z0 + j) * p.Nr + i] = acc[(size_t)j * kTileR + tl] * scale;
+        for (int j = k4; j < nzu; j += 4) p.out[(size_t)(z0 + j) * p.Nr + i] = acc[(size_t)j * kTileR + tl] * scale;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(128) : "memory");     // before the next unit overwrites acc
     }
-    if (p.dbg && lane == 0 && (ew == 0 || ew == 4)) {
-      long long* d = p.dbg + 16 * blockIdx.x + 8 + (ew >> 2) * 2;
-      d[0] = clock64() - t_start; d[1] = w_tfull;
-    }
+    if (dbg && lane == 0 && (ew == 0 || ew == 4)) { dbg[8 + (ew >> 2) * 2] = clock64() - t_start; dbg[9 + (ew >> 2) * 2] = w_tfull; }
   }
   tc_fence_before();
   __syncthreads();
@@ -519,35 +622,39 @@ static int device_sms() {
 static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
   const ModesetDev& d = h->dev;
   if (d.src_complex) return false;     // complex source tables would need a complex Bop (not built yet)
-  unsigned e_max = 0, e_off = 0;
+  unsigned e_off = 0;
+  int maxMp = 0, maxRows = 0;
   for (int f = 0; f < d.F; ++f) {
     const TonalMeta& t = d.t[f];
     UTonal& u = p.t[f];
-    u.Mp = t.Mp; u.rowsP = t.u_rowsP; u.p0 = t.u_p0; u.n1 = t.u_p0 + 2 * t.n_npair; u.nq = t.n_qpair; u.trK = t.trK;
-    if (u.rowsP > kAccCols || u.Mp > 96) return false;
+    u.Mp = t.Mp; u.rowsP = t.u_rowsP; u.n1 = t.u_p0; u.nq = t.n_qpair; u.trK = t.trK;
     u.e_bytes = 2048u * (unsigned)u.Mp;
     u.e_off = e_off;
     e_off += u.e_bytes;
-    e_max = std::max(e_max, u.e_bytes);
     u.b_zbytes = (unsigned)(u.rowsP * u.Mp * 4);
+    maxMp = std::max(maxMp, u.Mp);
+    maxRows = std::max(maxRows, u.rowsP);
   }
+  // TMEM: 4 NA accumulator columns + AR columns for the E image (two tonals side by side when they fit)
+  if (4 * maxMp > 256) return false;
+  p.AR = maxRows <= 64 ? 256 : pad_to(4 * maxMp, 32);
+  p.NA = std::min(128, ((512 - p.AR) / 4) & ~15);
+  if (maxRows > p.NA) return false;
   p.F = d.F;
   p.e_rt_stride = e_off;
-  p.e_region = e_max;
   const unsigned acc_bytes = (unsigned)ZC * kTileR * 4u;
   const unsigned bar_bytes = 256;
-  if (p.e_region + acc_bytes + bar_bytes + 4 * 4096 > kSmemLimit) return false;
-  unsigned stage = (kSmemLimit - p.e_region - acc_bytes - bar_bytes) / kStages;
+  unsigned stage = (kSmemLimit - acc_bytes - bar_bytes) / kStages;
   stage = std::min(stage & ~127u, 32u * 1024u);
   for (int f = 0; f < d.F; ++f) {
     UTonal& u = p.t[f];
     const unsigned per = 2u * u.b_zbytes;          // hi + lo of one depth
     if (per > stage) return false;
-    u.nj = (int)std::min<unsigned>(std::min<unsigned>(stage / per, (unsigned)(kAccCols / u.rowsP)), 16u);
+    u.nj = (int)std::min<unsigned>(std::min<unsigned>(stage / per, (unsigned)(p.NA / u.rowsP)), 16u);
     if (u.nj < 1) return false;
   }
   p.stage_bytes = stage;
-  p.smem_B = p.e_region;
+  p.smem_B = 0;
   p.smem_acc = p.smem_B + kStages * stage;
   p.smem_bar = p.smem_acc + acc_bytes;
   return true;
@@ -576,13 +683,11 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   const int sms = device_sms();
   UParams p{};
   const int ZC = choose_zc(Nr, Nz, sms);
-  if (!plan_tonals(h, p, ZC)) { set_error("UMMA engine: mode set does not fit (rows > 128, Mp > 96 or complex source table)"); return BOGP_ERR_UNSUPPORTED; }
+  if (!plan_tonals(h, p, ZC)) { set_error("UMMA engine: mode set does not fit (operator rows, Mp > 64 or complex source table)"); return BOGP_ERR_UNSUPPORTED; }
   p.Nr = Nr; p.Nz = Nz; p.ZC = ZC; p.atype = atype; p.mf = mf;
   p.nrt = (Nr + kTileR - 1) / kTileR;
   const int nzc = (Nz + ZC - 1) / ZC;
   p.units = p.nrt * nzc;
-  const char* sw = std::getenv("BOGP_UMMA_SWAP");
-  p.swap_lbo_sbo = (sw && sw[0] == '1') ? 1 : 0;
   unsigned long long b_off = 0;
   for (int f = 0; f < d.F; ++f) { p.t[f].b_off = b_off; b_off += (unsigned long long)Nz * p.t[f].b_zbytes; }
   // scratch: [r | z doubles][err int][E table][Bhi][Blo]
@@ -627,10 +732,10 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     BOGP_CUDA(cudaMemcpyAsync(hdbg.data(), dbg_dev, hdbg.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
     BOGP_CUDA(cudaStreamSynchronize(s));
     const int grid = std::min(p.units, sms);
-    const char* names[12] = {"prod_total", "prod_wait_edone", "prod_wait_bempty", "mma_total", "mma_wait_efull",
+    const char* names[16] = {"-", "-", "-", "mma_total", "mma_wait_efull",
                              "mma_wait_bfull", "mma_wait_tempty", "stages", "epi0_total", "epi0_wait_tfull",
-                             "epi4_total", "epi4_wait_tfull"};
-    for (int k = 0; k < 12; ++k) {
+                             "epi4_total", "epi4_wait_tfull", "load_total", "-", "-", "-"};
+    for (int k = 0; k < 16; ++k) {
       double sum = 0; long long mx = 0;
       for (int b = 0; b < grid; ++b) { sum += (double)hdbg[b * 16 + k]; mx = std::max(mx, hdbg[b * 16 + k]); }
       fprintf(stderr, "[umma dbg] %-18s avg %12.0f max %12lld\n", names[k], sum / grid, mx);
