@@ -14,12 +14,13 @@
 // D puts range i on TMEM lane i, so each epilogue thread owns one range and reduces over the operator rows of its
 // own lane: no cross-lane shuffles; the replica field never exists outside TMEM.
 //
-// Pipeline per CTA (persistent over (range tile, depth chunk) units), 14 warps:
-//     warp 0      bulk-copy producer: the ring of Bop stages (cp.async.bulk + mbarrier complete_tx)
-//     warp 1      MMA issuer: tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory), commits to the ring / TMEM
-//                 barriers; owns the TMEM allocation
-//     warps 2-9   epilogue: tcgen05.ld -> sum of squares -> Bartlett -> multi-frequency combine in shared memory
-//     warps 10-13 E loaders: global -> registers -> tcgen05.st, one tonal ahead of the MMAs
+// Pipeline per CTA (persistent over (range tile, depth chunk) units), 23 warps:
+//     warp 0       bulk-copy producer: the ring of Bop stages (cp.async.bulk + mbarrier complete_tx)
+//     warps 1, 22  MMA issuers, one per accumulator buffer (stage parity): tcgen05.mma.kind::tf32 with A from TMEM and
+//                  B from shared memory, tcgen05.commit to the ring / TMEM barriers; warp 1 owns the TMEM allocation
+//     warps 2-17   epilogue: 2 buffer sets x 2 depth parities x 4 lane quadrants; tcgen05.ld -> sum of squares ->
+//                  Bartlett -> multi-frequency combine in shared memory
+//     warps 18-21  E loaders: global -> registers -> tcgen05.st, one tonal ahead of the MMAs
 // The Bop table is built per call directly in the UMMA canonical K-major no-swizzle layout ([8-row group][16-byte K
 // chunk][8 rows][4 floats]; LBO = 128 B, SBO = 32 * Mp B), so the producer issues plain 1-D bulk copies.
 // TMEM map (512 columns): two accumulator buffers of (re | im) x NA columns, then the A region.
@@ -39,7 +40,8 @@ constexpr int kTileR = 128;            // ranges per tile = MMA M = TMEM lanes
 constexpr int kStages = 6;             // Bop ring depth
 constexpr int kEpiWarps = 16;          // 2 accumulator-buffer sets x 2 depth parities x 4 TMEM lane quadrants
 constexpr int kLoadWarps = 4;
-constexpr int kUmmaThreads = (2 + kEpiWarps + kLoadWarps) * 32;
+constexpr int kUmmaThreads = (2 + kEpiWarps + kLoadWarps + 1) * 32;   // + the second MMA issuer (last warp)
+constexpr int kMmaWarpB = 2 + kEpiWarps + kLoadWarps;
 constexpr unsigned kSmemLimit = 227u * 1024u;
 
 struct UTonal {
@@ -85,7 +87,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // Bounded wait: a protocol bug must trap (an error the host sees), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
   uint32_t ok = 0;
-  const long long t0 = clock64();
+  long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -95,6 +97,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
+    if (spin == 0) t0 = clock64();
     if ((spin & 1023u) == 1023u && clock64() - t0 > 3000000000LL) {
       atomicExch(err, code + 1000 * (int)blockIdx.x);
       __threadfence_system();
@@ -336,11 +339,14 @@ struct MmaState {
   uint32_t sc;       // global stage counter
   int g;             // global tonal counter
   int nzu;
+  int id;            // issuer 0 / 1: owns accumulator buffer `id` and the stages of that parity
   bool dbg;
   long long w_efull, w_bfull, w_tempty;
 };
 
-// All stages of one tonal of one unit.  Templated on the K steps so that a stage is straight-line code: two barrier
+// The stages of one tonal of one unit that belong to issuer st.id (stage parity = accumulator buffer = issuer: two
+// issuer warps alternate stages so that one warp's barrier waits and address set-up overlap the other's MMAs -- a
+// single issuer blocks on the MMA queue and then leaves the pipe idle while it prepares the next stage).  Templated on the K steps so that a stage is straight-line code: two barrier
 // waits, 6 * KS tcgen05.mma, two commits.  (The per-stage scalar code runs on a single warp at ~5 cycles per dependent
 // instruction, while a 128 x 64 x 8 MMA lasts 32 cycles: anything not hoisted out of the stage loop idles the pipe.)
 template <int KS>
@@ -357,6 +363,7 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
   uint32_t sc = st.sc;
 #pragma unroll 1
   for (int j0 = 0; j0 < nzu; j0 += nj, ++sc) {
+    if ((int)(sc & 1u) != st.id) continue;     // the other issuer's stage
     const int njs = min(nj, nzu - j0);
     const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
     const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_BFULL + s), 1); mbar_init(bar(BAR_BEMPTY + s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(BAR_EFULL + b), kLoadWarps);
-      mbar_init(bar(BAR_EDONE + b), 1);
+      mbar_init(bar(BAR_EDONE + b), 2);          // both MMA issuers commit
       mbar_init(bar(BAR_TFULL + b), 1);
       mbar_init(bar(BAR_TEMPTY + b), kEpiWarps / 2);
     }
@@ -435,9 +442,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       }
     }
     (void)w_bempty;
-  } else if (warp == 1) {
-    // ============================================================== MMA issuer (whole warp, one elected lane issues)
+  } else if (warp == 1 || warp == kMmaWarpB) {
+    // ============================================================== MMA issuers (whole warp, one elected lane issues)
     MmaState st{};
+    st.id = warp == 1 ? 0 : 1;
     st.p = &p; st.tmem_base = tmem_base; st.s_base = s_base; st.bar0 = bar0; st.dbg = dbg != nullptr;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int zc = unit / p.nrt;
@@ -456,8 +464,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
         }
       }
     }
-    if (dbg && lane == 0) { dbg[3] = clock64() - t_start; dbg[4] = st.w_efull; dbg[5] = st.w_bfull; dbg[6] = st.w_tempty; dbg[7] = st.sc; }
-  } else if (warp >= 2 + kEpiWarps) {
+    if (dbg && lane == 0 && st.id == 0) { dbg[3] = clock64() - t_start; dbg[4] = st.w_efull; dbg[5] = st.w_bfull; dbg[6] = st.w_tempty; dbg[7] = st.sc; }
+  } else if (warp >= 2 + kEpiWarps && warp < kMmaWarpB) {
     // ============================================================== E loaders: global -> registers -> TMEM
     const int quad = warp & 3;
     const int tl = quad * 32 + lane;
