@@ -148,6 +148,10 @@ class SingleTaskGP:
         self._invalidate()
         return self
 
+    def fit(self, cfg: Optional["FitConfig"] = None) -> "SingleTaskGP":
+        """The reference's hyper-parameter fit (100 x AdamW on -mll, ei.py:69-78); see :func:`fit_gp_adamw`."""
+        return fit_gp_adamw(self, cfg if cfg is not None else FitConfig())
+
     def eval(self):
         return self
 

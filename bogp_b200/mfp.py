@@ -334,6 +334,17 @@ class MatchedFieldProcessor:
                                 multifreq_method=self.multifreq_method)
         return out.reshape(-1).cpu().numpy().astype(np.float64)
 
+    def surface(self, rec_r: ArrayLike, src_z: ArrayLike, tilt: Optional[ArrayLike] = None, *,
+                engine: str = "auto") -> np.ndarray:
+        """The whole ambiguity surface ``[Nz, Nr]`` (``[Nt, Nz, Nr]`` with a tilt axis) in ONE launch: what the
+        reference assembles with ``for z in src_z: amb[zz, :] = MFP({"src_z": z, "rec_r": rvec})`` (mfp.py:206-214).
+        ``rec_r`` in km as at the reference boundary; float64 host array like the reference's ``amb``."""
+        if not self.runner.is_static:
+            raise ValueError("surface() needs one shared mode set (static ModeRunner)")
+        out = self._device_modes().bartlett_grid_host(rec_r, src_z, tilt, atype=self.atype,
+                                                      multifreq_method=self.multifreq_method, engine=engine)
+        return out.astype(np.float64)
+
     def _call_batch(self, plist: List[dict]) -> np.ndarray:
         merged = [self._merged(p) for p in plist]
         if not self.runner.is_static:

@@ -159,6 +159,12 @@ def test_matched_field_processor_is_drop_in(cfg1):
         assert_parity(got, ref_proc({"src_z": zs, "rec_r": rvec}))
     one = gpu_proc({"src_z": 71.11, "rec_r": 1.07})
     assert isinstance(one, float) and abs(one - 1.0) < 2e-5
+    # the reference's row loop (mfp.py:206-214) == one-launch surface()
+    zs3 = np.array([10.0, 71.11, 150.5])
+    amb = np.stack([gpu_proc({"src_z": float(z), "rec_r": rvec}) for z in zs3])
+    surf = gpu_proc.surface(rvec, zs3)
+    assert surf.shape == (3, len(rvec)) and surf.dtype == np.float64
+    assert_parity(surf, amb, rtol=2e-6)
     batch = [{"src_z": 20.0 + 3 * i, "rec_r": 0.5 + 0.2 * i, "tilt": 0.1 * i} for i in range(9)]
     got = gpu_proc(batch)
     ref = np.array([ref_proc(p) for p in batch])
