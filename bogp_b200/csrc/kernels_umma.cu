@@ -14,16 +14,15 @@
 // D puts range i on TMEM lane i, so each epilogue thread owns one range and reduces over the operator rows of its
 // own lane: no cross-lane shuffles; the replica field never exists outside TMEM.
 //
-// Pipeline per CTA (persistent over (range tile, depth chunk) units), 22 warps:
-//     warps 0, 1   MMA issuers, one per accumulator buffer (stage parity): tcgen05.mma.kind::tf32 with A from TMEM and
-//                  B from shared memory, tcgen05.commit to the ring / TMEM barriers; warp 0 owns the TMEM allocation
-//     warps 2-9    epilogue: 2 buffer sets x 4 lane quadrants; tcgen05.ld -> sum of squares -> Bartlett ->
-//                  multi-frequency combine in shared memory
-//     warps 10-13  E loaders: global -> registers -> tcgen05.st, one tonal ahead of the MMAs
-//     warps 14-21  Bop generators: W_f (registers) x phi(z_j) (shared memory) -> hi/lo split -> the ring of Bop
-//                  stages, written straight in the UMMA canonical K-major no-swizzle layout ([8-row group][16-byte K
-//                  chunk][8 rows][4 floats]; LBO = 128 B, SBO = 32 * Mp B), fence.proxy.async, mbarrier arrive.
-//                  Nothing of Bop ever exists in global memory.
+// Pipeline per CTA (persistent over (range tile, depth chunk) units), 23 warps:
+//     warp 0       bulk-copy producer: the ring of Bop stages (cp.async.bulk + mbarrier complete_tx)
+//     warps 1, 22  MMA issuers, one per accumulator buffer (stage parity): tcgen05.mma.kind::tf32 with A from TMEM and
+//                  B from shared memory, tcgen05.commit to the ring / TMEM barriers; warp 1 owns the TMEM allocation
+//     warps 2-17   epilogue: 2 buffer sets x 2 depth parities x 4 lane quadrants; tcgen05.ld -> sum of squares ->
+//                  Bartlett -> multi-frequency combine in shared memory
+//     warps 18-21  E loaders: global -> registers -> tcgen05.st, one tonal ahead of the MMAs
+// The Bop table is built per call directly in the UMMA canonical K-major no-swizzle layout ([8-row group][16-byte K
+// chunk][8 rows][4 floats]; LBO = 128 B, SBO = 32 * Mp B), so the producer issues plain 1-D bulk copies.
 // TMEM map (512 columns): two accumulator buffers of (re | im) x NA columns, then the A region.
 //
 // Replaces the loop `for z in src_z: amb[zz,:] = MFP({"src_z": z, "rec_r": rvec})`
@@ -39,15 +38,10 @@ namespace bogp {
 
 constexpr int kTileR = 128;            // ranges per tile = MMA M = TMEM lanes
 constexpr int kStages = 6;             // Bop ring depth
-constexpr int kEpiSub = 2;             // epilogue warps per (buffer set, lane quadrant): depth j goes to warp j % kEpiSub
-constexpr int kEpiWarps = 8 * kEpiSub;  // 2 accumulator-buffer sets x kEpiSub depth residues x 4 TMEM lane quadrants
-constexpr int kLoadWarps = 4;                  // E loaders (one per TMEM lane quadrant)
-constexpr int kGenWarps = 8;                   // Bop generators (latency-bound per item: two warps per scheduler)
-constexpr int kGenThreads = kGenWarps * 32;
-constexpr int kUmmaThreads = (2 + kEpiWarps + kLoadWarps + kGenWarps) * 32;
-constexpr int kLoadWarp0 = 2 + kEpiWarps;      // first E loader warp
-constexpr int kGenWarp0 = kLoadWarp0 + kLoadWarps;
-constexpr int kMaxQ = 4;                       // float4 items of W_f per generator thread: rowsP * Mp / 4 <= kGenThreads * kMaxQ
+constexpr int kEpiWarps = 16;          // 2 accumulator-buffer sets x 2 depth parities x 4 TMEM lane quadrants
+constexpr int kLoadWarps = 4;
+constexpr int kUmmaThreads = (2 + kEpiWarps + kLoadWarps + 1) * 32;   // + the second MMA issuer (last warp)
+constexpr int kMmaWarpB = 2 + kEpiWarps + kLoadWarps;
 constexpr unsigned kSmemLimit = 227u * 1024u;
 
 struct UTonal {
@@ -59,20 +53,19 @@ struct UTonal {
   unsigned e_bytes;            // 2048 * Mp  (re_hi | re_lo | im_hi | im_lo) x 128 ranges
   unsigned e_off;              // offset of the tonal inside one range tile's block of the E table
   unsigned b_zbytes;           // rowsP * Mp * 4: one depth of one split of Bop
-  unsigned w_off;              // offset (floats) of W_f [rowsP][Mp] inside ModesetDev::Wu
-  unsigned pz_off;             // offset (floats) of the tonal inside the depth table PZ [Nz][Mp]
+  unsigned long long b_off;    // offset of the tonal inside the Bop tables
   float trK;
 };
 
 struct UParams {
   int F, Nr, Nz, nrt, ZC, units, atype, mf;
   unsigned e_rt_stride, stage_bytes;
-  unsigned smem_B, smem_acc, smem_W, smem_PZ, smem_bar;
+  unsigned smem_B, smem_acc, smem_bar;
   int NA;                      // TMEM columns per accumulator half; buffers at 0 and 2 NA, A region at [4 NA, 4 NA + AR)
   int AR;                      // TMEM columns of the A region
   const unsigned char* E;
-  const float* Wu;             // mode-space operators, tcgen05 row order (ModesetDev::Wu)
-  const float* PZ;             // phi_m(z_j): per tonal [Nz][Mp]
+  const unsigned char* Bhi;
+  const unsigned char* Blo;
   float* out;
   int* err;
   long long* dbg;              // optional [grid][16] cycle counters (BOGP_UMMA_DBG=1): where each role waits
@@ -270,55 +263,112 @@ __device__ __forceinline__ size_t canon_off(int row, int m, int Mp) {
   return ((size_t)((row >> 3) * (Mp >> 2) + (m >> 2)) * 8 + (row & 7)) * 4 + (m & 3);
 }
 
+// ---- operand tables, one launch: blocks [0, nE) build the E table, blocks [nE, nE + nB) the Bop tables.
 // E table: per (range tile, tonal) the TMEM image of E_f^T: columns [re_hi (Mp) | re_lo | im_hi | im_lo] for each of the
 // 128 ranges, stored as [16-byte column chunk][range][4 floats] so that a loader warp reads coalesced float4s.
-__global__ void umma_E_table_kernel(ModesetDev ms, UParams p, const double* __restrict__ r) {
-  const int rt = blockIdx.x, f = blockIdx.y;
-  const TonalMeta& t = ms.t[f];
-  const UTonal& u = p.t[f];
-  float* base = reinterpret_cast<float*>(const_cast<unsigned char*>(p.E) + (size_t)rt * p.e_rt_stride + u.e_off);
-  for (int idx = threadIdx.x; idx < kTileR * u.Mp; idx += blockDim.x) {
-    const int m = idx % u.Mp, row = idx / u.Mp, i = rt * kTileR + row;
-    double vr = 0.0, vi = 0.0;
-    if (i < p.Nr && m < t.M) {
-      const double kre = ms.k_re[t.offM + m], kim = ms.k_im[t.offM + m], rr = r[i];
-      const double ar = kre * rr, ai = kim * rr;
-      const double mag = rsqrt(sqrt(ar * ar + ai * ai));
-      const double ang = -0.5 * atan2(ai, ar);
-      double s, c, s2, c2;
-      sincos(-(kre * rr), &s, &c);
-      sincos(ang, &s2, &c2);
-      const double amp = exp(kim * rr) * mag;
-      vr = amp * (c * c2 - s * s2);
-      vi = amp * (s * c2 + c * s2);
-    }
-    const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
-    const float v[4] = {rh, (float)(vr - (double)rh), ih, (float)(vi - (double)ih)};
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int col = b * u.Mp + m;
-      base[((size_t)(col >> 2) * kTileR + row) * 4 + (col & 3)] = v[b];
-    }
-  }
-}
+// E[m, i] = exp(-i k_m r_i) / sqrt(k_m r_i) = r^-1/2 e^{k_im r} * k^-1/2 * (cos(k_re r) - i sin(k_re r)), in float64
+// (k r reaches 1.6e4 rad), then split x = hi + lo with hi rounded to TF32.
+// Bop tables: per (tonal, depth) the block W_f diag(phi(z_j)) [rowsP, Mp] in the UMMA canonical K-major no-swizzle
+// layout, hi and lo arrays.  One block = kTabDepths depths of one tonal; the block's share of W_f stays in registers.
+constexpr int kTabThreads = 128;
+constexpr int kTabDepths = 8;
+constexpr int kTabRows = 32;          // ranges per E block
+constexpr int kTabMaxQ = 8;           // float4 items of W_f per thread: rowsP * Mp / 4 <= 1024
 
-// Depth table: PZ[f][j][m] = phi_m(z_j) (linear interpolation of the source-depth table: the data contract).
-__global__ void umma_PZ_table_kernel(ModesetDev ms, UParams p, const double* __restrict__ z) {
-  const int f = blockIdx.y;
+__global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms, UParams p, const double* __restrict__ r,
+                                                                  const double* __restrict__ z, int nE) {
+  __shared__ double2 kinv[128];       // k_m^-1/2
+  __shared__ float phi_s[2][128];
+  const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid == 0) *p.err = 0;
+  if ((int)blockIdx.x < nE) {
+    // ------------------------------------------------------------------ E table
+    const int per_f = p.nrt * (kTileR / kTabRows);
+    const int f = blockIdx.x / per_f, rem = blockIdx.x % per_f;
+    const int rt = rem / (kTileR / kTabRows), row0 = (rem % (kTileR / kTabRows)) * kTabRows;
+    const TonalMeta& t = ms.t[f];
+    const UTonal& u = p.t[f];
+    for (int m = tid; m < u.Mp; m += kTabThreads) {
+      double cr = 0.0, ci = 0.0;
+      if (m < t.M) {
+        const double kre = ms.k_re[t.offM + m], kim = ms.k_im[t.offM + m];
+        const double mag = rsqrt(sqrt(kre * kre + kim * kim)), ang = -0.5 * atan2(kim, kre);
+        sincos(ang, &ci, &cr);
+        cr *= mag; ci *= mag;
+      }
+      kinv[m] = make_double2(cr, ci);
+    }
+    __syncthreads();
+    float* base = reinterpret_cast<float*>(const_cast<unsigned char*>(p.E) + (size_t)rt * p.e_rt_stride + u.e_off);
+    for (int idx = tid; idx < kTabRows * u.Mp; idx += kTabThreads) {
+      const int m = idx % u.Mp, row = row0 + idx / u.Mp, i = rt * kTileR + row;
+      double vr = 0.0, vi = 0.0;
+      if (i < p.Nr && m < t.M) {
+        const double kre = ms.k_re[t.offM + m], kim = ms.k_im[t.offM + m], rr = r[i];
+        double s, c;
+        sincos(kre * rr, &s, &c);
+        const double amp = exp(kim * rr) * rsqrt(rr);
+        const double2 q = kinv[m];
+        vr = amp * (q.x * c + q.y * s);          // (q.x + i q.y) (c - i s)
+        vi = amp * (q.y * c - q.x * s);
+      }
+      const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
+      const float v[4] = {rh, (float)(vr - (double)rh), ih, (float)(vi - (double)ih)};
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int col = b * u.Mp + m;
+        base[((size_t)(col >> 2) * kTileR + row) * 4 + (col & 3)] = v[b];
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------------- Bop tables
+  const int nzb = (p.Nz + kTabDepths - 1) / kTabDepths;
+  const int bb = blockIdx.x - nE;
+  const int f = bb / nzb, j0 = (bb % nzb) * kTabDepths;
   const TonalMeta& t = ms.t[f];
   const UTonal& u = p.t[f];
-  const int total = p.Nz * u.Mp;
-  float* out = const_cast<float*>(p.PZ) + u.pz_off;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
-    const int j = g / u.Mp, m = g % u.Mp;
-    float v = 0.f;
-    if (m < t.M) {
-      int i0; float w;
-      depth_index(z[j], ms.z0, ms.dz, ms.nz_tab, i0, w);
-      const float* tr = ms.tab_re + t.offTab + (size_t)i0 * t.Mp + m;
-      v = fmaf(w, __ldg(tr + t.Mp) - __ldg(tr), __ldg(tr));
+  const int KC = u.Mp >> 2, n_q = u.rowsP * KC;
+  // items q = tid, tid + 128, ...: q = (row group * KC + K chunk) * 8 + row8 is the float4 index inside a depth block
+  float4 wq[kTabMaxQ];
+  int kc4[kTabMaxQ];
+#pragma unroll
+  for (int i = 0; i < kTabMaxQ; ++i) {
+    const int q = min(tid + i * kTabThreads, n_q - 1);
+    const int pc = q >> 3, kc = pc % KC, rg = pc / KC;
+    kc4[i] = kc * 4;
+    wq[i] = __ldg(reinterpret_cast<const float4*>(ms.Wu + t.offWu + (size_t)(rg * 8 + (q & 7)) * t.Mp) + kc);
+  }
+  float4* Bhi = reinterpret_cast<float4*>(const_cast<unsigned char*>(p.Bhi) + u.b_off);
+  float4* Blo = reinterpret_cast<float4*>(const_cast<unsigned char*>(p.Blo) + u.b_off);
+  const int nd = min(kTabDepths, p.Nz - j0);
+  for (int dj = 0; dj < nd; ++dj) {
+    const int j = j0 + dj;
+    float* ph = phi_s[dj & 1];
+    if (tid < u.Mp) {
+      float v = 0.f;
+      if (tid < t.M) {
+        int i0; float w;
+        depth_index(z[j], ms.z0, ms.dz, ms.nz_tab, i0, w);
+        const float* tr = ms.tab_re + t.offTab + (size_t)i0 * t.Mp + tid;
+        v = fmaf(w, __ldg(tr + t.Mp) - __ldg(tr), __ldg(tr));
+      }
+      ph[tid] = v;
     }
-    out[g] = v;
+    __syncthreads();
+    float4* hi = Bhi + (size_t)j * n_q;
+    float4* lo = Blo + (size_t)j * n_q;
+#pragma unroll
+    for (int i = 0; i < kTabMaxQ; ++i) {
+      const int q = tid + i * kTabThreads;
+      if (q < n_q) {
+        const float4 pv = *reinterpret_cast<const float4*>(ph + kc4[i]);
+        const float x0 = wq[i].x * pv.x, x1 = wq[i].y * pv.y, x2 = wq[i].z * pv.z, x3 = wq[i].w * pv.w;
+        const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
+        hi[q] = make_float4(h0, h1, h2, h3);
+        lo[q] = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
+      }
+    }
   }
 }
 
@@ -331,27 +381,6 @@ enum { BAR_BFULL = 0, BAR_BEMPTY = kStages, BAR_EFULL = 2 * kStages, BAR_EDONE =
 // so tonal g+1 can be loaded while tonal g is still being multiplied whenever the two fit side by side.
 __device__ __forceinline__ uint32_t a_column(const UParams& p, int g, int Mp) {
   return (uint32_t)(4 * p.NA) + ((g & 1) ? (uint32_t)(p.AR - 4 * Mp) : 0u);
-}
-
-// One Bop stage (njs depths) by one operand thread: CNT items per depth, branch-free so that the CNT shared-memory
-// loads and split chains overlap (one warp per scheduler: a predicated item per branch region runs at ~90 cycles each).
-// Items past the end of the block were clamped to the last one at set-up: they rewrite the same value.
-template <int CNT>
-__device__ __forceinline__ void gen_stage(const float4 (&wq)[kMaxQ], const int (&kc4)[kMaxQ], const int (&qc)[kMaxQ],
-                                          const float4* __restrict__ Ps4, int KC, int n_q, int njs, float4* hi, float4* lo) {
-#pragma unroll 1
-  for (int s = 0; s < njs; ++s) {
-    float4 ph[CNT];
-#pragma unroll
-    for (int i = 0; i < CNT; ++i) ph[i] = Ps4[s * KC + kc4[i]];
-#pragma unroll
-    for (int i = 0; i < CNT; ++i) {
-      const float x0 = wq[i].x * ph[i].x, x1 = wq[i].y * ph[i].y, x2 = wq[i].z * ph[i].z, x3 = wq[i].w * ph[i].w;
-      const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
-      hi[s * n_q + qc[i]] = make_float4(h0, h1, h2, h3);
-      lo[s * n_q + qc[i]] = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
-    }
-  }
 }
 
 struct MmaState {
@@ -416,8 +445,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.smem_bar + BAR_COUNT * 8);
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_BFULL + s), kGenWarps); mbar_init(bar(BAR_BEMPTY + s), 1); }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(BAR_BFULL + s), 1); mbar_init(bar(BAR_BEMPTY + s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(BAR_EFULL + b), kLoadWarps);
       mbar_init(bar(BAR_EDONE + b), 2);          // both MMA issuers commit
@@ -426,7 +455,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -437,10 +466,36 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
   long long* const dbg = p.dbg ? p.dbg + 16 * blockIdx.x : nullptr;
   const long long t_start = clock64();
 
-  if (warp < 2) {
+  if (warp == 0) {
+    // ============================================================== Bop producer (whole warp, one elected lane issues)
+    long long w_bempty = 0;
+    uint32_t sc = 0;       // global stage counter
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int zc = unit / p.nrt;
+      const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
+      for (int f = 0; f < p.F; ++f) {
+        const UTonal& u = p.t[f];
+        for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
+          const int njs = min(u.nj, nzu - j0);
+          const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
+          mbar_wait_t(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3, dbg ? &w_bempty : nullptr);
+          const uint32_t bytes = (uint32_t)njs * u.b_zbytes;
+          const uint32_t dst = s_base + p.smem_B + slot * p.stage_bytes;
+          const size_t src = (size_t)u.b_off + (size_t)(z0 + j0) * u.b_zbytes;
+          if (elect_one()) {
+            mbar_expect_tx(bar(BAR_BFULL + slot), 2 * bytes);
+            bulk_g2s(dst, p.Bhi + src, bytes, bar(BAR_BFULL + slot));
+            bulk_g2s(dst + bytes, p.Blo + src, bytes, bar(BAR_BFULL + slot));
+          }
+          __syncwarp();
+        }
+      }
+    }
+    (void)w_bempty;
+  } else if (warp == 1 || warp == kMmaWarpB) {
     // ============================================================== MMA issuers (whole warp, one elected lane issues)
     MmaState st{};
-    st.id = warp;
+    st.id = warp == 1 ? 0 : 1;
     st.p = &p; st.tmem_base = tmem_base; st.s_base = s_base; st.bar0 = bar0; st.dbg = dbg != nullptr;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int zc = unit / p.nrt;
@@ -460,7 +515,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       }
     }
     if (dbg && lane == 0 && st.id == 0) { dbg[3] = clock64() - t_start; dbg[4] = st.w_efull; dbg[5] = st.w_bfull; dbg[6] = st.w_tempty; dbg[7] = st.sc; }
-  } else if (warp >= kLoadWarp0 && warp < kGenWarp0) {
+  } else if (warp >= 2 + kEpiWarps && warp < kMmaWarpB) {
     // ============================================================== E loaders: global -> registers -> TMEM
     const int quad = warp & 3;
     const int tl = quad * 32 + lane;
@@ -470,8 +525,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       const int rt = unit % p.nrt;
       for (int f = 0; f < p.F; ++f, ++g) {
         const UTonal& u = p.t[f];
-        // tonal g goes to the low (g even) or high (g odd) end of the A region: wait for tonal g - 2 (same place) and,
-        // if the two do not fit side by side, for tonal g - 1 as well
         if (g >= 2) mbar_wait_t(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1, dbg ? &w_edone : nullptr);
         if (g >= 1) {
           const UTonal& up = p.t[f == 0 ? p.F - 1 : f - 1];
@@ -496,66 +549,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
         if (lane == 0) mbar_arrive(bar(BAR_EFULL + (g & 1)));
       }
     }
-    if (dbg && lane == 0 && quad == 0) { dbg[2] = clock64() - t_start; dbg[13] = w_edone; }
-  } else if (warp >= kGenWarp0) {
-    // ============================================================== Bop generators
-    const int ot = (warp - kGenWarp0) * 32 + lane;      // 0..kGenThreads-1
-    float* Ps = reinterpret_cast<float*>(smem + p.smem_PZ);      // phi_m(z_j) [nzu][Mp] of the current tonal and unit
-    long long w_bempty = 0, c_gen = 0, c_fence = 0, c_setup = 0;
-    uint32_t sc = 0;
-    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-      const int zc = unit / p.nrt;
-      const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
-      for (int f = 0; f < p.F; ++f) {
-        const UTonal& u = p.t[f];
-        const long long ts0 = dbg ? clock64() : 0;
-        const int KC = u.Mp >> 2;
-        const int n_q = u.rowsP * KC;          // float4 items of one depth: q = (row group * KC + K chunk) * 8 + row8
-        // This thread's share of W_f stays in registers for the whole tonal: items q = ot, ot + kGenThreads, ...  (q is also
-        // the float4 index inside a depth block of the canonical layout, so consecutive threads store consecutive
-        // 16-byte chunks); the depth table slice phi_m(z_j), j in this unit, goes to shared memory.
-        float4 wq[kMaxQ];
-        int kc4[kMaxQ], qc[kMaxQ];
-        const int cnt = (n_q + kGenThreads - 1) / kGenThreads;     // items per thread per depth (uniform)
-#pragma unroll
-        for (int i = 0; i < kMaxQ; ++i) {
-          const int q = min(ot + i * kGenThreads, n_q - 1);           // clamped: duplicates rewrite the same value
-          const int pc = q >> 3, kc = pc % KC, rg = pc / KC;
-          qc[i] = q;
-          kc4[i] = kc;
-          wq[i] = __ldg(reinterpret_cast<const float4*>(p.Wu + u.w_off + (size_t)(rg * 8 + (q & 7)) * u.Mp) + kc);
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(5), "r"(kGenThreads) : "memory");     // previous tonal's Ps reads done
-        {
-          const float4* psrc = reinterpret_cast<const float4*>(p.PZ + u.pz_off + (size_t)z0 * u.Mp);
-          float4* pdst = reinterpret_cast<float4*>(Ps);
-          for (int i = ot; i < nzu * KC; i += kGenThreads) pdst[i] = __ldg(psrc + i);
-        }
-        asm volatile("bar.sync %0, %1;" ::"r"(5), "r"(kGenThreads) : "memory");
-        if (dbg) c_setup += clock64() - ts0;
-        for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
-          const int njs = min(u.nj, nzu - j0);
-          const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
-          mbar_wait_t(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3, dbg ? &w_bempty : nullptr);
-          const long long tg0 = dbg ? clock64() : 0;
-          float4* hi = reinterpret_cast<float4*>(smem + p.smem_B + slot * p.stage_bytes);
-          float4* lo = hi + (size_t)njs * (u.b_zbytes >> 4);
-          const float4* Ps4 = reinterpret_cast<const float4*>(Ps) + (size_t)j0 * KC;
-          switch (cnt) {
-            case 1: gen_stage<1>(wq, kc4, qc, Ps4, KC, n_q, njs, hi, lo); break;
-            case 2: gen_stage<2>(wq, kc4, qc, Ps4, KC, n_q, njs, hi, lo); break;
-            case 3: gen_stage<3>(wq, kc4, qc, Ps4, KC, n_q, njs, hi, lo); break;
-            default: gen_stage<4>(wq, kc4, qc, Ps4, KC, n_q, njs, hi, lo); break;
-          }
-          const long long tg1 = dbg ? clock64() : 0;
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(BAR_BFULL + slot));
-          if (dbg) { c_gen += tg1 - tg0; c_fence += clock64() - tg1; }
-        }
-      }
-    }
-    if (dbg && ot == 0) { dbg[12] = clock64() - t_start; dbg[14] = w_bempty; dbg[0] = c_gen; dbg[1] = c_fence; dbg[15] = c_setup; }
+    if (dbg && lane == 0 && quad == 0) { dbg[12] = clock64() - t_start; }
   } else {
     // ============================================================== epilogue
     // 16 warps = 2 buffer sets x 2 depth parities x 4 TMEM lane quadrants.  Set b drains accumulator buffer b only,
@@ -564,7 +558,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     const int ew = warp - 2;                 // 0..15
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const int set = (ew >> 2) & 1;           // accumulator buffer (= stage parity) this warp drains
-    const int sub = ew >> 3;                 // depth residue (j % kEpiSub) this warp handles
+    const int sub = ew >> 3;                 // depth parity this warp handles
     const int tl = quad * 32 + lane;         // lane in the tile = range index in the tile
     const uint32_t NA = (uint32_t)p.NA;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)set * (2 * NA);
@@ -583,12 +577,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           const int njs = min(u.nj, nzu - j0);
           mbar_wait_t(bar(BAR_TFULL + set), (sc >> 1) & 1u, p.err, 7, dbg ? &w_tfull : nullptr);
           tc_fence_after();
-          // slots of this stage owned by this warp: s = s_first, s_first + kEpiSub, ...
-          const int s_first = (sub - j0 % kEpiSub + kEpiSub) % kEpiSub;
+          // slots of this stage owned by this warp: s = s_first, s_first + 2, ...
+          const int s_first = (sub - (j0 & 1)) & 1;
           bool released = false;
-          for (int s = s_first; s < njs; s += kEpiSub) {
+          for (int s = s_first; s < njs; s += 2) {
             const int j = j0 + s;
-            const bool last_slot = s + kEpiSub >= njs;
+            const bool last_slot = s + 2 >= njs;
             const uint32_t t_re = t_lane + (uint32_t)(s * rowsP);
             float norm = 0.f, num = 0.f;
             if (fast) {
@@ -655,21 +649,20 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       }
       // acc[j][tl] is updated by the two sets' warps of this (quadrant, parity) in stage order; the buffer hand-shake
       // orders those updates (release/acquire on the mbarriers), but the write-out below reads both sets' updates, so
-      // the warps of this quadrant meet on a named barrier first.
-      constexpr int kPerQuad = kEpiWarps / 4;      // warps sharing a lane quadrant
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(kPerQuad * 32) : "memory");
+      // the warps of this quadrant meet on a named barrier first (4 warps = 128 threads per quadrant).
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(128) : "memory");
       const int i = rt * kTileR + tl;
       const float scale = p.mf == BOGP_MF_MEAN ? 1.f / (float)p.F : 1.f;
-      const int k4 = ew >> 2;                  // this warp writes depths j = k4, k4 + kPerQuad, ...
+      const int k4 = ew >> 2;                  // 0..3: this warp writes depths j = k4, k4 + 4, ...
       if (i < p.Nr)
-        for (int j = k4; j < nzu; j += kPerQuad) p.out[(size_t)(z0 + j) * p.Nr + i] = acc[(size_t)j * kTileR + tl] * scale;
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(kPerQuad * 32) : "memory");     // before the next unit overwrites acc
+        for (int j = k4; j < nzu; j += 4) p.out[(size_t)(z0 + j) * p.Nr + i] = acc[(size_t)j * kTileR + tl] * scale;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(128) : "memory");     // before the next unit overwrites acc
     }
     if (dbg && lane == 0 && (ew == 0 || ew == 4)) { dbg[8 + (ew >> 2) * 2] = clock64() - t_start; dbg[9 + (ew >> 2) * 2] = w_tfull; }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
@@ -697,7 +690,7 @@ static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
     u.e_off = e_off;
     e_off += u.e_bytes;
     u.b_zbytes = (unsigned)(u.rowsP * u.Mp * 4);
-    u.w_off = (unsigned)t.offWu;
+    if (u.rowsP * u.Mp / 4 > kTabMaxQ * kTabThreads) return false;
     maxMp = std::max(maxMp, u.Mp);
     maxRows = std::max(maxRows, u.rowsP);
   }
@@ -710,11 +703,7 @@ static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
   p.e_rt_stride = e_off;
   const unsigned acc_bytes = (unsigned)ZC * kTileR * 4u;
   const unsigned bar_bytes = 256;
-  const unsigned w_bytes = 0;
-  for (int f = 0; f < d.F; ++f)
-    if (p.t[f].rowsP * p.t[f].Mp / 4 > kMaxQ * kGenThreads) return false;
-  const unsigned pz_bytes = (unsigned)pad_to(ZC * maxMp * 4, 128);
-  unsigned stage = (kSmemLimit - acc_bytes - bar_bytes - w_bytes - pz_bytes) / kStages;
+  unsigned stage = (kSmemLimit - acc_bytes - bar_bytes) / kStages;
   stage = std::min(stage & ~127u, 32u * 1024u);
   for (int f = 0; f < d.F; ++f) {
     UTonal& u = p.t[f];
@@ -726,9 +715,7 @@ static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
   p.stage_bytes = stage;
   p.smem_B = 0;
   p.smem_acc = p.smem_B + kStages * stage;
-  p.smem_W = p.smem_acc + acc_bytes;
-  p.smem_PZ = p.smem_W + w_bytes;
-  p.smem_bar = p.smem_PZ + pz_bytes;
+  p.smem_bar = p.smem_acc + acc_bytes;
   return true;
 }
 
@@ -760,22 +747,21 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   p.nrt = (Nr + kTileR - 1) / kTileR;
   const int nzc = (Nz + ZC - 1) / ZC;
   p.units = p.nrt * nzc;
-  unsigned pz_floats = 0;
-  for (int f = 0; f < d.F; ++f) { p.t[f].pz_off = pz_floats; pz_floats += (unsigned)Nz * (unsigned)p.t[f].Mp; }
-  // scratch: [r | z doubles][err int][E table][PZ table]
+  unsigned long long b_off = 0;
+  for (int f = 0; f < d.F; ++f) { p.t[f].b_off = b_off; b_off += (unsigned long long)Nz * p.t[f].b_zbytes; }
+  // scratch: [r | z doubles][err int][E table][Bhi][Blo]
   const size_t off_rz = 0, bytes_rz = ((size_t)Nr + Nz) * sizeof(double);
   const size_t off_err = (bytes_rz + 255) & ~(size_t)255;
   const size_t off_E = off_err + 256;
   const size_t bytes_E = (size_t)p.nrt * p.e_rt_stride;
-  const size_t off_PZ = (off_E + bytes_E + 255) & ~(size_t)255;
-  if (int rc = ensure_scratch(h, off_PZ + (size_t)pz_floats * sizeof(float) + 256)) return rc;
+  const size_t off_Bhi = (off_E + bytes_E + 255) & ~(size_t)255;
+  const size_t off_Blo = (off_Bhi + b_off + 255) & ~(size_t)255;
+  if (int rc = ensure_scratch(h, off_Blo + b_off + 256)) return rc;
   unsigned char* base = static_cast<unsigned char*>(h->grid_scratch);
   double* r_dev = reinterpret_cast<double*>(base + off_rz);
   double* z_dev = r_dev + Nr;
   p.err = reinterpret_cast<int*>(base + off_err);
-  p.E = base + off_E;
-  p.PZ = reinterpret_cast<const float*>(base + off_PZ);
-  p.Wu = d.Wu;
+  p.E = base + off_E; p.Bhi = base + off_Bhi; p.Blo = base + off_Blo;
   p.out = out_dev;
   const char* dbg_env = std::getenv("BOGP_UMMA_DBG");
   static long long* dbg_dev = nullptr;
@@ -786,11 +772,8 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   }
   BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
   BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
-  BOGP_CUDA(cudaMemsetAsync(p.err, 0, sizeof(int), s));
-  umma_E_table_kernel<<<dim3(p.nrt, d.F), 256, 0, s>>>(d, p, r_dev);
-  count_launch();
-  BOGP_CUDA(cudaGetLastError());
-  umma_PZ_table_kernel<<<dim3(std::max(1, std::min(sms, (Nz * 48 + 255) / 256)), d.F), 256, 0, s>>>(d, p, z_dev);
+  const int nE = d.F * p.nrt * (kTileR / kTabRows), nB = d.F * ((Nz + kTabDepths - 1) / kTabDepths);
+  umma_tables_kernel<<<nE + nB, kTabThreads, 0, s>>>(d, p, r_dev, z_dev, nE);
   count_launch();
   BOGP_CUDA(cudaGetLastError());
   const size_t smem = (size_t)p.smem_bar + 256;
@@ -805,9 +788,9 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     BOGP_CUDA(cudaMemcpyAsync(hdbg.data(), dbg_dev, hdbg.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
     BOGP_CUDA(cudaStreamSynchronize(s));
     const int grid = std::min(p.units, sms);
-    const char* names[16] = {"gen_gen", "gen_fence_arrive", "load_total", "mma_total", "mma_wait_efull",
+    const char* names[16] = {"-", "-", "-", "mma_total", "mma_wait_efull",
                              "mma_wait_bfull", "mma_wait_tempty", "stages", "epi0_total", "epi0_wait_tfull",
-                             "epi4_total", "epi4_wait_tfull", "gen_total", "load_wait_edone", "gen_wait_bempty", "gen_setup"};
+                             "epi4_total", "epi4_wait_tfull", "load_total", "-", "-", "-"};
     for (int k = 0; k < 16; ++k) {
       double sum = 0; long long mx = 0;
       for (int b = 0; b < grid; ++b) { sum += (double)hdbg[b * 16 + k]; mx = std::max(mx, hdbg[b * 16 + k]); }
