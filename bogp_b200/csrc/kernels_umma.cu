@@ -38,7 +38,8 @@ namespace bogp {
 
 constexpr int kTileR = 128;            // ranges per tile = MMA M = TMEM lanes
 constexpr int kStages = 6;             // Bop ring depth
-constexpr int kEpiWarps = 16;          // 2 accumulator-buffer sets x 2 depth parities x 4 TMEM lane quadrants
+constexpr int kEpiSub = 2;             // epilogue warps per (buffer set, lane quadrant): depth j goes to warp j % kEpiSub
+constexpr int kEpiWarps = 8 * kEpiSub;  // 2 accumulator-buffer sets x kEpiSub depth residues x 4 TMEM lane quadrants
 constexpr int kLoadWarps = 4;
 constexpr int kUmmaThreads = (2 + kEpiWarps + kLoadWarps + 1) * 32;   // + the second MMA issuer (last warp)
 constexpr int kMmaWarpB = 2 + kEpiWarps + kLoadWarps;
@@ -117,6 +118,29 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// Waiting flavour for the roles that run ahead of the pipeline (producer, loaders): back off between polls so the
+// spinning warp does not take issue slots from the epilogue warps on its scheduler (higher warp ids win arbitration).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* err, int code) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    __nanosleep(256);
+    if (spin == 0) t0 = clock64();
+    if ((spin & 255u) == 255u && clock64() - t0 > 3000000000LL) {
+      atomicExch(err, code + 1000 * (int)blockIdx.x);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
 // mbar_wait that also accumulates the waiting time into *acc when profiling is on
 __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, int* err, int code, long long* acc) {
   if (acc) {
@@ -193,6 +217,17 @@ __device__ __forceinline__ void issue_stage(uint32_t d_re, uint32_t d_im, uint32
       tc_mma_tf32_ts2(d, a_hi + 8u * ks, bh_lo + 16u * ks, desc_hi, idesc, true);
     }
   }
+}
+// Packed fp32x2 FMA (FFMA2 on sm_100): acc.{lo,hi} += {a,b}^2 -- halves the epilogue's dominant instruction count.
+__device__ __forceinline__ void sq_acc2(unsigned long long& acc, float a, float b) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(v));
+}
+__device__ __forceinline__ float sum2(unsigned long long acc) {
+  float x, y;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(acc));
+  return x + y;
 }
 // Numerator pairs live in the first 2 nq <= 16 columns: T = (r0 + i i0) + i (r1 + i i1) per (re, im) row pair.
 __device__ __forceinline__ void numerator16(const float* re, const float* im, int nq, float& num, float& numsq) {
@@ -409,6 +444,7 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
   const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((kTileR >> 4) << 24);
   auto bar = [&](int i) { return st.bar0 + 8u * (uint32_t)i; };
   mbar_wait_t(bar(BAR_EFULL + (st.g & 1)), (uint32_t)((st.g >> 1) & 1), p.err, 4, st.dbg ? &st.w_efull : nullptr);
+  if (st.dbg && st.id == 0 && blockIdx.x == 0 && st.g < 32 && (threadIdx.x & 31) == 0) p.dbg[16 * 200 + st.g] = clock64();
   const int nj = u.nj, nzu = st.nzu;
   uint32_t sc = st.sc;
 #pragma unroll 1
@@ -478,7 +514,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
         for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
           const int njs = min(u.nj, nzu - j0);
           const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
-          mbar_wait_t(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3, dbg ? &w_bempty : nullptr);
+          mbar_wait_relaxed(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3);
           const uint32_t bytes = (uint32_t)njs * u.b_zbytes;
           const uint32_t dst = s_base + p.smem_B + slot * p.stage_bytes;
           const size_t src = (size_t)u.b_off + (size_t)(z0 + j0) * u.b_zbytes;
@@ -525,11 +561,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       const int rt = unit % p.nrt;
       for (int f = 0; f < p.F; ++f, ++g) {
         const UTonal& u = p.t[f];
-        if (g >= 2) mbar_wait_t(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1, dbg ? &w_edone : nullptr);
+        if (g >= 2) mbar_wait_relaxed(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1);
         if (g >= 1) {
           const UTonal& up = p.t[f == 0 ? p.F - 1 : f - 1];
           if (4 * (up.Mp + u.Mp) > p.AR)
-            mbar_wait_t(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2, dbg ? &w_edone : nullptr);
+            mbar_wait_relaxed(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2);
         }
         tc_fence_after();
         const float4* src = reinterpret_cast<const float4*>(p.E + (size_t)rt * p.e_rt_stride + u.e_off) + tl;
@@ -558,7 +594,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     const int ew = warp - 2;                 // 0..15
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const int set = (ew >> 2) & 1;           // accumulator buffer (= stage parity) this warp drains
-    const int sub = ew >> 3;                 // depth parity this warp handles
+    const int sub = ew >> 3;                 // depth residue (j % kEpiSub) this warp handles
     const int tl = quad * 32 + lane;         // lane in the tile = range index in the tile
     const uint32_t NA = (uint32_t)p.NA;
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)set * (2 * NA);
@@ -576,40 +612,53 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           if ((int)(sc & 1u) != set) continue;
           const int njs = min(u.nj, nzu - j0);
           mbar_wait_t(bar(BAR_TFULL + set), (sc >> 1) & 1u, p.err, 7, dbg ? &w_tfull : nullptr);
+          const long long tw = (dbg && ew == 0 && blockIdx.x == 0) ? clock64() : 0;
           tc_fence_after();
-          // slots of this stage owned by this warp: s = s_first, s_first + 2, ...
-          const int s_first = (sub - (j0 & 1)) & 1;
+          // slots of this stage owned by this warp: s = s_first, s_first + kEpiSub, ...
+          const int s_first = (sub - j0 % kEpiSub + kEpiSub) % kEpiSub;
           bool released = false;
-          for (int s = s_first; s < njs; s += 2) {
+          for (int s = s_first; s < njs; s += kEpiSub) {
             const int j = j0 + s;
-            const bool last_slot = s + 2 >= njs;
+            const bool last_slot = s + kEpiSub >= njs;
             const uint32_t t_re = t_lane + (uint32_t)(s * rowsP);
             float norm = 0.f, num = 0.f;
             if (fast) {
               // Real receiver modes (KRAKEN): every |T|^2 term is a plain square except the nq numerator pairs, and
               // (r0 - i1)^2 + (i0 + r1)^2 = r0^2 + i0^2 + r1^2 + i1^2 + 2 (i0 r1 - r0 i1).  One FFMA per value over
               // ALL columns gives tot = norm + numsq; the numerator pairs sit in the first columns already loaded.
-              float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, numsq = 0.f;
-              for (int c0 = 0; c0 < rowsP; c0 += 16) {
+              // The epilogue is ISSUE-bound (all warps of a lane quadrant share one scheduler), so this path is kept
+              // to the bare instruction count: 2 loads + 32 FFMA per 16 columns, rank-1 numerator special-cased.
+              unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;      // packed (even, odd column) partial sums
+              float numsq = 0.f;
+              const int c_last = rowsP - 16;
+              for (int c0 = 0; c0 <= c_last; c0 += 16) {
                 float re[16], im[16];
                 tc_ld16(t_re + (uint32_t)c0, re);
                 tc_ld16(t_re + NA + (uint32_t)c0, im);
                 tc_wait_ld();
-                if (last_slot && c0 + 16 >= rowsP) {
+                if (last_slot && c0 == c_last) {
                   tc_fence_before();
                   if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
                   released = true;
                 }
-                if (c0 == 0) numerator16(re, im, nq, num, numsq);
+                if (c0 == 0) {
+                  if (nq == 1) {
+                    const float tr = re[0] - im[1], ti = im[0] + re[1];
+                    num = fmaf(tr, tr, ti * ti);
+                    numsq = fmaf(re[0], re[0], fmaf(im[0], im[0], fmaf(re[1], re[1], im[1] * im[1])));
+                  } else {
+                    numerator16(re, im, nq, num, numsq);
+                  }
+                }
 #pragma unroll
-                for (int q = 0; q < 16; q += 2) {
-                  t0 = fmaf(re[q], re[q], t0);
-                  t1 = fmaf(im[q], im[q], t1);
-                  t2 = fmaf(re[q + 1], re[q + 1], t2);
-                  t3 = fmaf(im[q + 1], im[q + 1], t3);
+                for (int q = 0; q < 16; q += 4) {
+                  sq_acc2(t0, re[q], re[q + 1]);
+                  sq_acc2(t1, im[q], im[q + 1]);
+                  sq_acc2(t2, re[q + 2], re[q + 3]);
+                  sq_acc2(t3, im[q + 2], im[q + 3]);
                 }
               }
-              norm = ((t0 + t1) + (t2 + t3)) - numsq;
+              norm = ((sum2(t0) + sum2(t1)) + (sum2(t2) + sum2(t3))) - numsq;
             } else {
               const int nq2 = 2 * nq, n1 = u.n1;
               for (int c0 = 0; c0 < rowsP; c0 += 16) {
@@ -645,18 +694,20 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
           }
+          if (tw && lane == 0 && unit == (int)blockIdx.x) { p.dbg[16 * 201 + f] += clock64() - tw; p.dbg[16 * 203 + f] += 1; }
         }
       }
       // acc[j][tl] is updated by the two sets' warps of this (quadrant, parity) in stage order; the buffer hand-shake
       // orders those updates (release/acquire on the mbarriers), but the write-out below reads both sets' updates, so
       // the warps of this quadrant meet on a named barrier first (4 warps = 128 threads per quadrant).
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(128) : "memory");
+      constexpr int kPerQuad = kEpiWarps / 4;      // warps sharing a lane quadrant
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(kPerQuad * 32) : "memory");
       const int i = rt * kTileR + tl;
       const float scale = p.mf == BOGP_MF_MEAN ? 1.f / (float)p.F : 1.f;
-      const int k4 = ew >> 2;                  // 0..3: this warp writes depths j = k4, k4 + 4, ...
+      const int k4 = ew >> 2;                  // this warp writes depths j = k4, k4 + kPerQuad, ...
       if (i < p.Nr)
-        for (int j = k4; j < nzu; j += 4) p.out[(size_t)(z0 + j) * p.Nr + i] = acc[(size_t)j * kTileR + tl] * scale;
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(128) : "memory");     // before the next unit overwrites acc
+        for (int j = k4; j < nzu; j += kPerQuad) p.out[(size_t)(z0 + j) * p.Nr + i] = acc[(size_t)j * kTileR + tl] * scale;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(kPerQuad * 32) : "memory");     // before the next unit overwrites acc
     }
     if (dbg && lane == 0 && (ew == 0 || ew == 4)) { dbg[8 + (ew >> 2) * 2] = clock64() - t_start; dbg[9 + (ew >> 2) * 2] = w_tfull; }
   }
@@ -796,6 +847,11 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
       for (int b = 0; b < grid; ++b) { sum += (double)hdbg[b * 16 + k]; mx = std::max(mx, hdbg[b * 16 + k]); }
       fprintf(stderr, "[umma dbg] %-18s avg %12.0f max %12lld\n", names[k], sum / grid, mx);
     }
+    fprintf(stderr, "[umma dbg] tonal start deltas (CTA 0, issuer 0):");
+    for (int f = 1; f < d.F && f < 32; ++f) fprintf(stderr, " %lld", hdbg[16 * 200 + f] - hdbg[16 * 200 + f - 1]);
+    fprintf(stderr, "\n[umma dbg] epilogue cycles per stage by tonal (CTA 0, warp 0):");
+    for (int f = 0; f < d.F && f < 32; ++f) fprintf(stderr, " %lld", hdbg[16 * 201 + f] / std::max<long long>(1, hdbg[16 * 203 + f]));
+    fprintf(stderr, "\n");
   }
   return 0;
 }
