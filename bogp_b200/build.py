@@ -38,10 +38,12 @@ def _digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source for sm_100a and link the shared library.  Returns its path."""
-    digest = _digest()
+    digest = _digest() + ("+dbg" if os.environ.get("BOGP_UMMA_DBG_BUILD") == "1" else "")
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    if os.environ.get("BOGP_UMMA_DBG_BUILD") == "1":      # per-role wait counters in the tcgen05 kernel (tools/umma_dbg_counters.py)
+        flags.append("-DBOGP_UMMA_DBG=1")
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
     procs = []

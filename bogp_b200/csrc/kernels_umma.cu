@@ -34,6 +34,12 @@
 #include "bogp_internal.h"
 #include "device_math.cuh"
 
+// Per-role wait counters (tools/umma_dbg_counters.py) are compiled in only with -DBOGP_UMMA_DBG=1
+// (BOGP_UMMA_DBG_BUILD=1 python -m bogp_b200.build): their 64-bit accumulators cost registers in every role.
+#ifndef BOGP_UMMA_DBG
+#define BOGP_UMMA_DBG 0
+#endif
+
 namespace bogp {
 
 constexpr int kTileR = 128;            // ranges per tile = MMA M = TMEM lanes
@@ -443,8 +449,8 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
   const uint32_t desc_lo0 = (uint32_t)make_desc(0, 128u, 32u * Mp);       // LBO field; start address added per stage
   const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((kTileR >> 4) << 24);
   auto bar = [&](int i) { return st.bar0 + 8u * (uint32_t)i; };
-  mbar_wait_t(bar(BAR_EFULL + (st.g & 1)), (uint32_t)((st.g >> 1) & 1), p.err, 4, st.dbg ? &st.w_efull : nullptr);
-  if (st.dbg && st.id == 0 && blockIdx.x == 0 && st.g < 32 && (threadIdx.x & 31) == 0) p.dbg[16 * 200 + st.g] = clock64();
+  mbar_wait_t(bar(BAR_EFULL + (st.g & 1)), (uint32_t)((st.g >> 1) & 1), p.err, 4, (BOGP_UMMA_DBG && st.dbg) ? &st.w_efull : nullptr);
+  if (BOGP_UMMA_DBG && st.dbg && st.id == 0 && blockIdx.x == 0 && st.g < 32 && (threadIdx.x & 31) == 0) p.dbg[16 * 200 + st.g] = clock64();
   const int nj = u.nj, nzu = st.nzu;
   uint32_t sc = st.sc;
 #pragma unroll 1
@@ -453,8 +459,8 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
     const int njs = min(nj, nzu - j0);
     const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
     const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
-    mbar_wait_t(bar(BAR_BFULL + slot), ph, p.err, 5, st.dbg ? &st.w_bfull : nullptr);
-    mbar_wait_t(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6, st.dbg ? &st.w_tempty : nullptr);
+    mbar_wait_t(bar(BAR_BFULL + slot), ph, p.err, 5, (BOGP_UMMA_DBG && st.dbg) ? &st.w_bfull : nullptr);
+    mbar_wait_t(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6, (BOGP_UMMA_DBG && st.dbg) ? &st.w_tempty : nullptr);
     tc_fence_after();
     const uint32_t N = (uint32_t)(njs * u.rowsP);
     const uint32_t idesc = idesc0 | ((N >> 3) << 17);
@@ -499,7 +505,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  long long* const dbg = p.dbg ? p.dbg + 16 * blockIdx.x : nullptr;
+  long long* const dbg = (BOGP_UMMA_DBG && p.dbg) ? p.dbg + 16 * blockIdx.x : nullptr;
   const long long t_start = clock64();
 
   if (warp == 0) {
@@ -814,7 +820,7 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   p.err = reinterpret_cast<int*>(base + off_err);
   p.E = base + off_E; p.Bhi = base + off_Bhi; p.Blo = base + off_Blo;
   p.out = out_dev;
-  const char* dbg_env = std::getenv("BOGP_UMMA_DBG");
+  const char* dbg_env = BOGP_UMMA_DBG ? std::getenv("BOGP_UMMA_DBG") : nullptr;
   static long long* dbg_dev = nullptr;
   if (dbg_env && dbg_env[0] == '1') {
     if (!dbg_dev) BOGP_CUDA(cudaMalloc(&dbg_dev, 256 * 16 * sizeof(long long)));
