@@ -178,6 +178,53 @@ def run_reference(args) -> None:
                 "(TritonOA is un-vendored and absent, so no oracle/_ref); modes precomputed on both arms"}))
 
 
+# ------------------------------------------------------------------------------------------------ BO iteration
+def bo_iteration(n: int = 256, d: int = 3, raw: int = 4096, restarts: int = 64, reps: int = 3, cpu: bool = True) -> dict:
+    """Second half of BASELINE.json's metric: wall time of one acquisition optimisation of a BO iteration (configs[2]:
+    SingleTaskGP Matern-5/2, EI, optimize_acqf with 4096 raw samples and 64 restarts) with the posterior/acquisition
+    evaluations on the GPU, next to the same orchestration over the float64 CPU oracle.  Fixed hyper-parameters and
+    seeds; the GPU and CPU runs must return the same candidate."""
+    import torch
+    from bogp_b200 import acquisition as A
+    from bogp_b200.gp import SingleTaskGP
+    from bogp_b200.optim import optimize_acqf
+    rng = np.random.default_rng(0)
+    X = torch.quasirandom.SobolEngine(d, scramble=True, seed=0).draw(n, dtype=torch.float64).numpy() * 2.0 - 1.0
+    y = np.sin(3.0 * X[:, 0]) * np.cos(2.0 * X[:, 1:].sum(1)) + 0.05 * rng.standard_normal(n)
+    y = (y - y.mean()) / y.std()
+    ls = [0.6] * d
+    bounds = torch.tensor([[-1.0] * d, [1.0] * d], dtype=torch.float64)
+    model = SingleTaskGP(X, y, lengthscale=ls, outputscale=1.0, noise=1e-4)
+    ei = A.ExpectedImprovement(model, float(y.max()))
+    out = {"config": f"configs[2]: n={n} d={d} Matern-5/2 EI, raw_samples={raw}, num_restarts={restarts}, L-BFGS-B maxiter 200"}
+    times, cand = [], None
+    for i in range(reps + 1):
+        torch.manual_seed(1234)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cand, val = optimize_acqf(ei, bounds, q=1, num_restarts=restarts, raw_samples=raw)
+        torch.cuda.synchronize()
+        if i:
+            times.append(time.perf_counter() - t0)
+    out["gpu_ms"] = float(np.median(times) * 1e3)
+    out["acq_value"] = float(val)
+    if cpu:
+        from oracle import gp as ogp
+        from oracle import optimize as oopt
+        g = ogp.GPState(X, y, "matern52", ls, 1.0, 0.0, 1e-4)
+        best = float(y.max())
+        torch.manual_seed(1234)
+        t0 = time.perf_counter()
+        c2, v2 = oopt.optimize_acqf(lambda Z: ogp.acq_value(g, "ei", Z, best),
+                                    lambda Z: ogp.acq_value_and_grad(g, "ei", Z, best),
+                                    bounds, 1, restarts, raw, nonneg=True)
+        out["cpu_oracle_ms"] = float((time.perf_counter() - t0) * 1e3)
+        out["cpu_threads"] = torch.get_num_threads()
+        out["same_candidate"] = bool(np.allclose(np.asarray(cand), np.asarray(c2), rtol=0, atol=1e-6))
+        out["acq_value_rel_diff"] = float(abs(float(v2) - float(val)) / max(abs(float(v2)), 1e-300))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args) -> None:
     import torch
@@ -217,11 +264,11 @@ def run_ours(args) -> None:
             dist.all_gather_into_tensor(pairs.view(-1), pair)
 
     def step_e2e():
-        out = dms.bartlett_grid_host(r, z_slab, engine=args.engine, out=host_surf_np)
-        flat = int(np.argmax(out))          # final reduction on the host copy (collate.py:50)
+        out, (val, pos) = dms.bartlett_grid_host(r, z_slab, engine=args.engine, out=host_surf_np, argext="max")
+        flat = pos[0] * NR + pos[1]          # final reduction (collate.py:50), computed on the device with the surface
         if world > 1:
             rec = torch.tensor([lo * NR + flat, 0], dtype=torch.int64)
-            rec[1] = int(np.float32(out.reshape(-1)[flat]).view(np.int32))
+            rec[1] = int(np.float32(val).view(np.int32))
             pair.copy_(rec)
             dist.all_gather_into_tensor(pairs.view(-1), pair)
             pairs.cpu()
@@ -310,10 +357,15 @@ def run_ours(args) -> None:
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3 / args.steps,
-                    "api": "DeviceModeSet.bartlett_grid_host -> bogp_bartlett_grid_host (page-locked host surface)"},
+                    "api": "DeviceModeSet.bartlett_grid_host(argext='max') -> bogp_bartlett_grid_host_argmax (page-locked host surface)"},
             "gpu_launches": int(launches), "roofline": roofline,
             "wall_s_timed_region": t_wall}
 
+    if rank == 0 and world == 1 and not args.no_bo:
+        try:
+            line["bo_iter"] = bo_iteration(cpu=not args.no_cpu)
+        except Exception as exc:   # the Bartlett line must survive a failure here
+            line["bo_iter"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         with cpu_pool(cores) as ex:
@@ -335,6 +387,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--engine", choices=["auto", "simt", "umma"], default="auto")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-bo", action="store_true", help="skip the BO-iteration (GP acquisition optimisation) timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -40,6 +40,8 @@ SIGNATURES = {
     "bogp_covariance_set": (C.c_int, [_vp, _dp, _dp]),
     "bogp_bartlett_grid": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "bogp_bartlett_grid_host": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _vp]),
+    "bogp_bartlett_grid_host_argmax": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                _fp, C.c_int, _fp, C.POINTER(_ll), _vp]),
     "bogp_bartlett_points": (C.c_int, [_vp, _vp, _ll, C.c_int, C.c_int, _vp, _vp]),
     "bogp_bartlett_points_host": (C.c_int, [_vp, _dp, _ll, C.c_int, C.c_int, _fp, _vp]),
     "bogp_envbatch_create": (C.c_int, [C.POINTER(_vp), _ll, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _fp, _dp]),

@@ -349,6 +349,36 @@ extern "C" int bogp_bartlett_grid_host(bogp_modeset_t h, const double* r_m_host,
   return rc;
 }
 
+extern "C" int bogp_bartlett_grid_host_argmax(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host,
+                                              int Nz, const double* tilt_deg_host, int Nt, int atype, int mf_method,
+                                              int engine, float* out_host, int maximize, float* val_host,
+                                              long long* idx_host, void* stream) {
+  BOGP_REQUIRE(out_host && val_host && idx_host, "bogp_bartlett_grid_host_argmax: NULL output");
+  BOGP_REQUIRE(h != nullptr, "bogp_bartlett_grid_host_argmax: NULL handle");
+  const size_t n = (size_t)std::max(Nt, 1) * Nz * Nr;
+  *val_host = 0.f;
+  *idx_host = -1;
+  if (n == 0) return 0;
+  // staging: [surface n floats][pad to 16][idx int64, val float][argext scratch 8192]
+  const size_t off_pair = (n * sizeof(float) + 15) & ~(size_t)15;
+  if (int rc0 = io_scratch(h, off_pair + 16 + 8192)) return rc0;
+  char* base = static_cast<char*>(h->io_scratch);
+  float* tmp = reinterpret_cast<float*>(base);
+  long long* idx_dev = reinterpret_cast<long long*>(base + off_pair);
+  float* val_dev = reinterpret_cast<float*>(base + off_pair + 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = bogp_bartlett_grid(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, tmp, stream);
+  if (rc == 0) rc = bogp_argext_f32_dev(tmp, (long long)n, maximize, val_dev, idx_dev, base + off_pair + 16, 8192, stream);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(idx_host, idx_dev, sizeof(long long), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(val_host, val_dev, sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { bogp::set_error("bogp_bartlett_grid_host_argmax: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
+  }
+  return rc;
+}
+
 // any(cand[:,2] != 0) on the device, so the tilt-free fast path is chosen without a host copy of cand.
 __global__ void any_tilt_kernel(const double* __restrict__ cand, long long C, int* flag) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;

@@ -117,9 +117,11 @@ class DeviceModeSet:
 
     def bartlett_grid_host(self, r_km: ArrayLike, z: ArrayLike, tilt_deg: Optional[ArrayLike] = None, *,
                            atype: str = "cbf", multifreq_method: str = "mean", engine: str = "auto",
-                           out: Optional[np.ndarray] = None) -> np.ndarray:
+                           out: Optional[np.ndarray] = None, argext: Optional[str] = None):
         """Same through the host-buffer entry point (device->host copy inside the call).  ``out``: optional
-        C-contiguous float32 host array of the result shape (pass page-locked memory for a DMA copy)."""
+        C-contiguous float32 host array of the result shape (pass page-locked memory for a DMA copy).
+        ``argext="max"|"min"`` also returns ``(value, unravelled index)`` of the extremum (collate.py:50), computed
+        on the device while the surface is still there: ``(surface, (value, index))``."""
         r_m = np.ascontiguousarray(1000.0 * np.atleast_1d(np.asarray(r_km, dtype=np.float64)))
         zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
         tt = None if tilt_deg is None else np.ascontiguousarray(np.atleast_1d(np.asarray(tilt_deg, dtype=np.float64)))
@@ -129,6 +131,16 @@ class DeviceModeSet:
             out = np.empty(shape, dtype=np.float32)
         elif out.shape != shape or out.dtype != np.float32 or not out.flags.c_contiguous:
             raise ValueError(f"out must be a C-contiguous float32 array of shape {shape}")
+        if argext is not None:
+            if argext not in ("max", "min"):
+                raise ValueError("argext must be 'max', 'min' or None")
+            val, idx = C.c_float(), C.c_longlong()
+            _lib.call("bogp_bartlett_grid_host_argmax", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
+                      _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
+                      _lib.fptr(out), 1 if argext == "max" else 0, C.byref(val), C.byref(idx),
+                      C.c_void_p(_lib.current_stream_ptr()))
+            pos = tuple(int(i) for i in np.unravel_index(idx.value, shape)) if idx.value >= 0 else tuple(-1 for _ in shape)
+            return out, (val.value, pos)
         _lib.call("bogp_bartlett_grid_host", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz), _lib.dptr(tt),
                   Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine], _lib.fptr(out),
                   C.c_void_p(_lib.current_stream_ptr()))

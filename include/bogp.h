@@ -107,6 +107,12 @@ int bogp_bartlett_grid_host(bogp_modeset_t h, const double* r_m_host, int Nr, co
                             const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
                             float* out_host, void* stream);
 
+/* Surface + its arg-max (arg-min for the minimised cbf_ml objective) in one call: what mfp.py:213-214 followed by
+ * np.unravel_index(np.argmax(surface)) (collate.py:50) produce.  One stream synchronisation for both results. */
+int bogp_bartlett_grid_host_argmax(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                                   const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                                   float* out_host, int maximize, float* val_host, long long* idx_host, void* stream);
+
 /* Scattered candidates (BO raw samples / trials): cand_dev[C, 3] float64 = (range m, depth m, tilt deg).
  * Replaces one MatchedFieldProcessor.__call__ per candidate (obj.py:28-30). */
 int bogp_bartlett_points(bogp_modeset_t h, const double* cand_dev, long long C, int atype, int mf_method,

@@ -54,6 +54,11 @@ def test_cfg1_surface_vs_golden(cfg1, dms1, engine):
     assert_parity(ml.cpu().numpy(), g["cbf_ml_product"], floor=1.0)   # product of (1 - B): absolute 1e-5 of O(1)
     host = dms1.bartlett_grid_host(cfg1["r"], cfg1["z"], engine=engine)
     np.testing.assert_array_equal(host, surf.cpu().numpy())
+    host2, (v2, pos2) = dms1.bartlett_grid_host(cfg1["r"], cfg1["z"], engine=engine, argext="max")
+    np.testing.assert_array_equal(host2, host)
+    assert pos2 == tuple(g["argmax"]) and v2 == pytest.approx(val)
+    _, (vmin, posmin) = dms1.bartlett_grid_host(cfg1["r"], cfg1["z"], engine=engine, argext="min")
+    assert posmin == tuple(int(i) for i in np.unravel_index(np.argmin(host), host.shape)) and vmin == pytest.approx(host.min())
 
 
 @pytest.mark.parametrize("engine", ["simt", "umma", "auto"])
