@@ -1,0 +1,139 @@
+"""Roofline numbers for the other kernels of the path: the GP posterior/acquisition kernel (K2),
+the scattered-candidate and tilted-array Bartlett kernels (K1-SIMT) and the per-environment kernel (K1-ENV).
+
+    python tools/bench_paths.py [gp] [points] [tilt] [env] > profiles/paths_<tag>.jsonl
+
+One JSON line per case.  Kernel time = CUDA events around the dominant kernel inside the library
+(bogp_timing_enable/read) where it is instrumented, CUDA events around the call otherwise; 3 warm-up + 10 timed calls.
+"""
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from bogp_b200 import _lib, mfp  # noqa: E402
+from bogp_b200 import acquisition as A  # noqa: E402
+from bogp_b200.gp import SingleTaskGP  # noqa: E402
+from bogp_b200.modes import (INV_TONALS_3, REC_Z_21, SWELLEX_TONALS_13, pekeris_modes, perturbed_pekeris_batch,  # noqa: E402
+                             synthetic_covariance)
+
+HBM_GBS = 6547.5
+try:
+    HBM_GBS = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, reps=10, warm=3, lib_timing=True):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    _lib.timing_read()
+    _lib.timing_enable(lib_timing)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    _lib.timing_enable(False)
+    kms, kn = _lib.timing_read()
+    return a.elapsed_time(b) / reps, (kms / kn if kn else None)
+
+
+def bench_gp():
+    rng = np.random.default_rng(0)
+    for n in (128, 256, 512):
+        for d in (2, 3, 7):
+            X = rng.uniform(-1, 1, (n, d))
+            y = np.sin(3 * X[:, 0]) + 0.3 * np.cos(2 * X.sum(1))
+            y = (y - y.mean()) / y.std()
+            model = SingleTaskGP(X, y, lengthscale=[0.5] * d, outputscale=1.0, noise=1e-4)
+            ei = A.ExpectedImprovement(model, float(y.max()))
+            b = 4096
+            Xs = torch.as_tensor(rng.uniform(-1, 1, (b, 1, d)), device="cuda")
+            with torch.no_grad():
+                call_ms, k_ms = timed(lambda: ei(Xs))
+            Xg = Xs.clone().requires_grad_(True)
+
+            def fwd_bwd():
+                v = ei(Xg)
+                torch.autograd.grad(v.sum(), Xg)
+            callg_ms, kg_ms = timed(fwd_bwd)
+            flop_f = n * (3 * d + 24) + n * n
+            flop_b = flop_f + n * n + 6 * n * d
+            print(json.dumps({"kernel": "gp_eval_kernel (K2)", "case": f"n={n} d={d} b={b} EI", "dtype": "f64",
+                              "forward_kernel_ms": k_ms, "forward_call_ms": call_ms,
+                              "forward_cand_per_s": b / (k_ms * 1e-3) if k_ms else None,
+                              "forward_tflops": b * flop_f / (k_ms * 1e-3) / 1e12 if k_ms else None,
+                              "value_grad_kernel_ms": kg_ms, "value_grad_call_ms": callg_ms,
+                              "value_grad_tflops": b * flop_b / (kg_ms * 1e-3) / 1e12 if kg_ms else None,
+                              "alg_flop_per_cand_forward": flop_f, "alg_flop_per_cand_value_grad": flop_b,
+                              "alg_bytes_per_cand": 8 * d + 8, "hbm_GBs_forward": b * (8 * d + 8) / (k_ms * 1e-3) / 1e9 if k_ms else None,
+                              "bound": "fp64 FMA (compute); HBM fraction reported for reference", "hbm_peak_GBs": HBM_GBS}), flush=True)
+
+
+def bench_points():
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    K = synthetic_covariance(modes, 60.0, 5.0)
+    dms = mfp.DeviceModeSet(modes, K)
+    rng = np.random.default_rng(1)
+    flop = dms.flops_per_candidate()
+    for C in (4096, 1_000_000):
+        cand = np.stack([rng.uniform(0.1, 10.0, C), rng.uniform(1.0, 200.0, C), np.zeros(C)], 1)
+        cd = torch.as_tensor(cand, device="cuda")
+        call_ms, k_ms = timed(lambda: dms.bartlett_points(cd))
+        print(json.dumps({"kernel": "points_modespace_kernel (K1-SIMT)", "case": f"C={C} scattered, 13 tonals, no tilt",
+                          "kernel_ms": k_ms, "call_ms": call_ms, "cand_freq_per_s": C * 13 / (k_ms * 1e-3),
+                          "alg_tflops": C * flop / (k_ms * 1e-3) / 1e12, "bound": "fp32 FMA issue + sincos (CUDA cores)"}), flush=True)
+
+
+def bench_tilt():
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    K = synthetic_covariance(modes, 60.0, 5.0, tilt_deg=1.0)
+    dms = mfp.DeviceModeSet(modes, K)
+    r, z, tilt = np.linspace(0.1, 10.0, 1000), np.linspace(1.0, 200.0, 100), np.linspace(-4.0, 4.0, 10)
+    C = len(r) * len(z) * len(tilt)
+    out = torch.empty((len(tilt), len(z), len(r)), dtype=torch.float32, device="cuda")
+    call_ms, k_ms = timed(lambda: dms.bartlett_grid(r, z, tilt, out=out), reps=3, warm=1)
+    N, sumM = 64, sum(modes.n_modes)
+    print(json.dumps({"kernel": "points_tilt_kernel (K1-SIMT, receiver space)",
+                      "case": "configs[3] at 1/10 scale: 1000 r x 100 z x 10 tilt = 1e6 candidates, 13 tonals",
+                      "kernel_ms": k_ms, "call_ms": call_ms, "cand_freq_per_s": C * 13 / (k_ms * 1e-3),
+                      "alg_tflops": C * 8.0 * N * sumM / (k_ms * 1e-3) / 1e12,
+                      "alg_flop_per_cand": 8 * N * sumM, "projected_s_for_1e7": 10 * k_ms * 1e-3,
+                      "bound": "fp32 FMA + per-(receiver, mode) sincos (CUDA cores); tensor-core path is future work"}), flush=True)
+
+
+def bench_env():
+    Cn = 10_000
+    rng = np.random.default_rng(2)
+    depths = rng.uniform(200.0, 230.0, Cn)
+    cbs = rng.uniform(1600.0, 1700.0, Cn)
+    t0 = time.time()
+    base = perturbed_pekeris_batch(INV_TONALS_3, REC_Z_21, depths[:200], cbs[:200])
+    mode_sets = [base[i % 200] for i in range(Cn)]          # 200 distinct environments tiled to 1e4 (host set-up cost)
+    ref = pekeris_modes(INV_TONALS_3, REC_Z_21)
+    K = synthetic_covariance(ref, 71.11, 1.07)
+    from bogp_b200.envbatch import EnvBatch
+    eb = EnvBatch(mode_sets, rng.uniform(0.5, 6.0, Cn), rng.uniform(10.0, 190.0, Cn), K)
+    setup_s = time.time() - t0
+    out = torch.empty(Cn, dtype=torch.float32, device="cuda")
+    call_ms, _ = timed(lambda: eb.bartlett(out=out), lib_timing=False)
+    print(json.dumps({"kernel": "envbatch_kernel (K1-ENV)", "case": f"configs[4]: {Cn} environments x 3 tonals x 21 receivers, Mmax={eb.Mmax}",
+                      "kernel_ms": call_ms, "cand_freq_per_s": Cn * 3 / (call_ms * 1e-3), "bytes_streamed": eb.bytes_streamed,
+                      "achieved_GBs": eb.bytes_streamed / (call_ms * 1e-3) / 1e9, "hbm_peak_GBs": HBM_GBS,
+                      "frac": eb.bytes_streamed / (call_ms * 1e-3) / 1e9 / HBM_GBS, "bound": "hbm", "host_setup_s": setup_s}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gp", "points", "tilt", "env"]
+    torch.cuda.set_device(0)
+    for w in which:
+        {"gp": bench_gp, "points": bench_points, "tilt": bench_tilt, "env": bench_env}[w]()
