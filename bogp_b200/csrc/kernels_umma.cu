@@ -76,6 +76,7 @@ struct UParams {
   float* out;
   int* err;
   long long* dbg;              // optional [grid][16] cycle counters (BOGP_UMMA_DBG=1): where each role waits
+  int skip;                    // debug build only: 1 = issue no MMAs, 2 = epilogue releases without reading (bottleneck bracketing)
   UTonal t[BOGP_MAX_TONALS];
 };
 
@@ -212,6 +213,11 @@ __device__ __forceinline__ void tc_mma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem
 template <int KS>
 __device__ __forceinline__ void issue_stage(uint32_t d_re, uint32_t d_im, uint32_t a_col, uint32_t Mp, uint32_t bh_lo,
                                             uint32_t bl_lo, uint32_t desc_hi, uint32_t idesc) {
+  // Opaque copies: keeps ptxas from hoisting the 4 KS derived addresses out of the stage loop into vector registers
+  // (it then re-moves every one of them to a uniform register per stage); derived here they stay in the uniform path.
+  asm volatile("mov.u32 %0, %0;" : "+r"(a_col));
+  asm volatile("mov.u32 %0, %0;" : "+r"(bh_lo));
+  asm volatile("mov.u32 %0, %0;" : "+r"(bl_lo));
 #pragma unroll
   for (int part = 0; part < 2; ++part) {
     const uint32_t d = part ? d_im : d_re;
@@ -468,7 +474,8 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
     const uint32_t b_lo = b_hi + (uint32_t)njs * u.b_zbytes;
     const uint32_t d_re = st.tmem_base + buf * (uint32_t)(2 * p.NA), d_im = d_re + (uint32_t)p.NA;
     if (elect_one()) {
-      issue_stage<KS>(d_re, d_im, a_col, Mp, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc);
+      if (!(BOGP_UMMA_DBG && p.skip == 1))
+        issue_stage<KS>(d_re, d_im, a_col, Mp, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc);
       tc_commit(bar(BAR_BEMPTY + slot));
       tc_commit(bar(BAR_TFULL + buf));
     }
@@ -504,7 +511,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // broadcast through a shuffle so that ptxas treats the TMEM base (and everything derived from it: accumulator and
+  // A-operand addresses of every MMA) as warp-uniform and keeps it in uniform registers instead of R2UR-ing per stage
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   long long* const dbg = (BOGP_UMMA_DBG && p.dbg) ? p.dbg + 16 * blockIdx.x : nullptr;
   const long long t_start = clock64();
 
@@ -623,7 +632,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           // slots of this stage owned by this warp: s = s_first, s_first + kEpiSub, ...
           const int s_first = (sub - j0 % kEpiSub + kEpiSub) % kEpiSub;
           bool released = false;
-          for (int s = s_first; s < njs; s += kEpiSub) {
+          for (int s = s_first; s < njs && !(BOGP_UMMA_DBG && p.skip == 2); s += kEpiSub) {
             const int j = j0 + s;
             const bool last_slot = s + kEpiSub >= njs;
             const uint32_t t_re = t_lane + (uint32_t)(s * rowsP);
@@ -822,6 +831,7 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   p.out = out_dev;
   const char* dbg_env = BOGP_UMMA_DBG ? std::getenv("BOGP_UMMA_DBG") : nullptr;
   static long long* dbg_dev = nullptr;
+  if (BOGP_UMMA_DBG) { const char* sk = std::getenv("BOGP_UMMA_SKIP"); p.skip = sk ? std::atoi(sk) : 0; }
   if (dbg_env && dbg_env[0] == '1') {
     if (!dbg_dev) BOGP_CUDA(cudaMalloc(&dbg_dev, 256 * 16 * sizeof(long long)));
     BOGP_CUDA(cudaMemsetAsync(dbg_dev, 0, 256 * 16 * sizeof(long long), s));
