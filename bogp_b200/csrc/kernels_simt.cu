@@ -243,6 +243,98 @@ points_tilt_kernel(ModesetDev ms, const double* __restrict__ cand, long long C, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tilted array on a (range x depth x tilt) grid (config 4).  e^{-i k_m r_n} with r_n = r - l_n sin(tau) factors into
+// e^{-i k_m r} (the range table E) and e^{+i k_m l_n sin(tau)}, which depends on the tilt only: one block works on one
+// tilt value and keeps Theta_tau[m][n] = Phi[n,m] e^{i k_m l_n sin(tau)} of the current tonal in shared memory, so the
+// per-candidate work is N x M complex multiply-adds and no transcendental (the scattered-candidate kernel above pays a
+// sincos per (receiver, mode)).  p_n = (r / r_n)^{1/2} sum_m Theta[m][n] phi_m(z) E[m, r]; one warp per candidate,
+// two receivers per lane (N <= 64).
+constexpr int kTiltChunk = 1024;     // candidates of one tilt plane per block
+
+__global__ void __launch_bounds__(kThreads)
+grid_tilt_kernel(ModesetDev ms, const float2* __restrict__ E, const float2* __restrict__ PZ, const double* __restrict__ r,
+                 const double* __restrict__ tilt, int Nr, int Nz, int atype, int mf, float* __restrict__ out, int MpMax) {
+  extern __shared__ float2 smem[];
+  float2* Th = smem;                                              // [MpMax][64]
+  float* acc = reinterpret_cast<float*>(Th + (size_t)MpMax * 64); // [kTiltChunk]
+  float2* a_all = reinterpret_cast<float2*>(acc + kTiltChunk);    // [warps][MpMax]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* a_s = a_all + (size_t)warp * MpMax;
+  const int plane = Nr * Nz;
+  const int nchunks = (plane + kTiltChunk - 1) / kTiltChunk;
+  const int t = blockIdx.x / nchunks, c0 = (blockIdx.x % nchunks) * kTiltChunk;
+  const int cn = min(kTiltChunk, plane - c0);
+  const double sin_t = sin(tilt[t] * 0.017453292519943295);
+  const int N = ms.N;
+  const int n0 = lane, n1 = lane + 32;
+  const float l0 = n0 < N ? ms.rec_lever[n0] : 0.f, l1 = n1 < N ? ms.rec_lever[n1] : 0.f;
+  const float fs = (float)sin_t;
+  for (int f = 0; f < ms.F; ++f) {
+    const TonalMeta& tm = ms.t[f];
+    __syncthreads();       // previous tonal's Theta no longer in use
+    for (int idx = threadIdx.x; idx < tm.Mp * 64; idx += blockDim.x) {
+      const int m = idx >> 6, n = idx & 63;
+      float2 v = make_float2(0.f, 0.f);
+      if (n < N && m < tm.M) {
+        const double ls = (double)ms.rec_lever[n] * sin_t;
+        const double kre = ms.k_re[tm.offM + m], kim = ms.k_im[tm.offM + m];
+        float sn, cs;
+        sincosf(reduce_phase(kre * ls), &sn, &cs);
+        const float amp = expf((float)(-kim * ls));
+        float2 ph = make_float2(ms.rec_re[tm.offRec + (size_t)n * tm.Mp + m], 0.f);
+        if (ms.rec_complex) ph.y = ms.rec_im[tm.offRec + (size_t)n * tm.Mp + m];
+        v = cmul(ph, make_float2(amp * cs, amp * sn));
+      }
+      Th[idx] = v;
+    }
+    __syncthreads();
+    const float2* Ef = E + (size_t)tm.offM * Nr;
+    const float2* Pf = PZ + (size_t)tm.offM * Nz;
+    const float* cr = ms.CkT_re + tm.offC;   // [N][J]
+    const float* ci = ms.CkT_im + tm.offC;
+    for (int cl = warp; cl < cn; cl += kWarpsPerBlock) {
+      const int c = c0 + cl, j = c / Nr, i = c - j * Nr;
+      for (int m = lane; m < tm.M; m += 32) a_s[m] = cmul(__ldg(Pf + (size_t)j * tm.Mp + m), __ldg(Ef + (size_t)i * tm.Mp + m));
+      __syncwarp();
+      float2 p0 = make_float2(0.f, 0.f), p1 = make_float2(0.f, 0.f);
+#pragma unroll 4
+      for (int m = 0; m < tm.M; ++m) {
+        const float2 a = a_s[m];
+        const float2 t0 = Th[m * 64 + n0], t1 = Th[m * 64 + n1];
+        p0.x = fmaf(t0.x, a.x, fmaf(-t0.y, a.y, p0.x));
+        p0.y = fmaf(t0.x, a.y, fmaf(t0.y, a.x, p0.y));
+        p1.x = fmaf(t1.x, a.x, fmaf(-t1.y, a.y, p1.x));
+        p1.y = fmaf(t1.x, a.y, fmaf(t1.y, a.x, p1.y));
+      }
+      __syncwarp();
+      const float rinv = 1.f / (float)r[i];
+      const float s0 = rsqrtf(1.f - l0 * fs * rinv), s1 = rsqrtf(1.f - l1 * fs * rinv);     // (r / r_n)^{1/2}
+      p0.x *= s0; p0.y *= s0; p1.x *= s1; p1.y *= s1;
+      float norm = warp_sum(p0.x * p0.x + p0.y * p0.y + p1.x * p1.x + p1.y * p1.y);
+      float num = 0.f;
+      for (int jj = 0; jj < tm.J; ++jj) {
+        float sr = 0.f, si = 0.f;
+        if (n0 < N) {
+          const float a = __ldg(cr + (size_t)n0 * tm.J + jj), b = __ldg(ci + (size_t)n0 * tm.J + jj);
+          sr += a * p0.x - b * p0.y; si += a * p0.y + b * p0.x;
+        }
+        if (n1 < N) {
+          const float a = __ldg(cr + (size_t)n1 * tm.J + jj), b = __ldg(ci + (size_t)n1 * tm.J + jj);
+          sr += a * p1.x - b * p1.y; si += a * p1.y + b * p1.x;
+        }
+        sr = warp_sum(sr); si = warp_sum(si);
+        num += sr * sr + si * si;
+      }
+      const float b = num / norm;
+      if (lane == 0) acc[cl] = combine_tonal(acc[cl], atype == BOGP_ATYPE_CBF ? b : tm.trK - b, mf, f == 0);
+    }
+  }
+  __syncthreads();
+  const float scale = mf == BOGP_MF_MEAN ? 1.f / (float)ms.F : 1.f;
+  for (int cl = threadIdx.x; cl < cn; cl += blockDim.x) out[(size_t)t * plane + c0 + cl] = acc[cl] * scale;
+}
+
 // cand[(t*Nz + j)*Nr + i] = (r_i, z_j, tilt_t)
 __global__ void make_grid_candidates_kernel(const double* __restrict__ r, int Nr, const double* __restrict__ z, int Nz,
                                             const double* __restrict__ tilt, int Nt, double* __restrict__ cand) {
@@ -325,6 +417,35 @@ int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     if (int rc = set_smem(grid_modespace_kernel, smem)) return rc;
     cudaEvent_t ev = timing_begin(s);
     grid_modespace_kernel<<<grid_for((long long)Nr * Nz, smem), kThreads, smem, s>>>(d, E, PZ, Nr, Nz, atype, mf, out_dev, aStride, tStride);
+    timing_end(ev, s);
+    bogp::count_launch();
+    BOGP_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (d.N <= 64) {
+    // tilt-plane kernel: range / depth tables as in the vertical-array grid, Theta_tau per block in shared memory
+    const size_t bytes_E = (size_t)sumMp * Nr * sizeof(float2), bytes_P = (size_t)sumMp * Nz * sizeof(float2);
+    if (int rc = ensure_scratch(h, off_tab + bytes_E + bytes_P)) return rc;
+    char* base = static_cast<char*>(h->grid_scratch);
+    double* r_dev = reinterpret_cast<double*>(base);
+    double* z_dev = r_dev + Nr;
+    double* t_dev = z_dev + Nz;
+    float2* E = reinterpret_cast<float2*>(base + off_tab);
+    float2* PZ = reinterpret_cast<float2*>(base + off_tab + bytes_E);
+    BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
+    BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
+    BOGP_CUDA(cudaMemcpyAsync(t_dev, tilt_host, Nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    dim3 tg(std::max(1, std::min(64, (int)(((long long)(Nr + Nz) * h->max_Mp + 255) / 256))), d.F);
+    grid_tables_kernel<<<tg, 256, 0, s>>>(d, r_dev, Nr, z_dev, Nz, E, PZ);
+    bogp::count_launch();
+    BOGP_CUDA(cudaGetLastError());
+    const size_t smem = ((size_t)h->max_Mp * 64 + (size_t)kWarpsPerBlock * h->max_Mp) * sizeof(float2) + kTiltChunk * sizeof(float);
+    if (int rc = set_smem(grid_tilt_kernel, smem)) return rc;
+    const long long plane = (long long)Nr * Nz;
+    const long long blocks = (long long)Nt * ((plane + kTiltChunk - 1) / kTiltChunk);
+    BOGP_REQUIRE(blocks < (1ll << 31), "bogp_bartlett_grid: tilt grid too large for one launch");
+    cudaEvent_t ev = timing_begin(s);
+    grid_tilt_kernel<<<(unsigned)blocks, kThreads, smem, s>>>(d, E, PZ, r_dev, t_dev, Nr, Nz, atype, mf, out_dev, h->max_Mp);
     timing_end(ev, s);
     bogp::count_launch();
     BOGP_CUDA(cudaGetLastError());

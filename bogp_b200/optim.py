@@ -82,7 +82,7 @@ def optimize_acqf(acq_function, bounds, q: int, num_restarts: int, raw_samples: 
         v = acq_function(X)
         loss = -v.sum()
         (g,) = torch.autograd.grad(loss, X)
-        return float(loss), g.reshape(-1).cpu().numpy().astype(np.float64)
+        return float(loss.detach()), g.reshape(-1).cpu().numpy().astype(np.float64)
 
     x0 = np.clip(X0.reshape(-1).numpy().astype(np.float64), lo, hi)
     res = minimize(f_and_g, x0, jac=True, method="L-BFGS-B", bounds=list(zip(lo, hi)),

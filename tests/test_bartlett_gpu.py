@@ -136,6 +136,33 @@ def test_grid_with_tilt_axis_matches_points(cfg1, dms1):
     assert_parity(vol, ref)
 
 
+def test_tilt_grid_kernel_rank8_and_complex_modes():
+    """Tilt-plane grid kernel (config 4 path): 13 tonals / 64 receivers / rank-8 K, and complex (KRAKENC) modes with
+    21 receivers; ragged sizes; both processors.  Oracle = one scattered-candidate evaluation per node."""
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import INV_TONALS_3, REC_Z_21, SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    K = synthetic_covariance(modes, 60.0, 5.0, tilt_deg=1.5, snapshots=8, seed=3)
+    dms = DeviceModeSet(modes, K)
+    r, z, tilt = np.linspace(0.4, 9.7, 37), np.linspace(3.0, 195.0, 5), np.array([-3.5, 0.0, 1.5, 4.0])
+    vol = dms.bartlett_grid(r, z, tilt).cpu().numpy()
+    cand = np.array([[ri, zi, ti] for ti in tilt for zi in z for ri in r])
+    assert_parity(vol, ob.bartlett_points(modes, K, cand).reshape(vol.shape))
+    # the truth (5 km, 60 m, 1.5 deg) is not a node; the tilt plane 1.5 deg must hold the volume's maximum
+    assert np.unravel_index(vol.argmax(), vol.shape)[0] == 2
+    mc = pekeris_modes(INV_TONALS_3, REC_Z_21, complex_modes=True)
+    Kc = synthetic_covariance(mc, 40.0, 2.2, tilt_deg=-2.0, snapshots=3, seed=5)
+    dmc = DeviceModeSet(mc, Kc)
+    r2, z2, t2 = np.linspace(0.5, 6.0, 19), np.linspace(5.0, 190.0, 7), np.array([-2.0, 0.5])
+    cand2 = np.array([[ri, zi, ti] for ti in t2 for zi in z2 for ri in r2])
+    for kw, floor in ((dict(), FLOOR), (dict(atype="cbf_ml", multifreq_method="product"), 1.0)):
+        got = dmc.bartlett_grid(r2, z2, t2, **kw).cpu().numpy()
+        assert_parity(got, ob.bartlett_points(mc, Kc, cand2, **kw).reshape(got.shape), floor=floor)
+    # grid kernel == scattered-candidate kernel (independent code paths on the device)
+    pts = dmc.bartlett_points(cand2).cpu().numpy().reshape(2, 7, 19)
+    assert_parity(dmc.bartlett_grid(r2, z2, t2).cpu().numpy(), pts, rtol=5e-6)
+
+
 def test_complex_modes_krakenc_layout():
     from bogp_b200.mfp import DeviceModeSet
     from bogp_b200.modes import INV_TONALS_3, REC_Z_21, pekeris_modes, synthetic_covariance

@@ -103,12 +103,12 @@ def bench_tilt():
     out = torch.empty((len(tilt), len(z), len(r)), dtype=torch.float32, device="cuda")
     call_ms, k_ms = timed(lambda: dms.bartlett_grid(r, z, tilt, out=out), reps=3, warm=1)
     N, sumM = 64, sum(modes.n_modes)
-    print(json.dumps({"kernel": "points_tilt_kernel (K1-SIMT, receiver space)",
+    print(json.dumps({"kernel": "grid_tilt_kernel (K1-SIMT, receiver space, Theta_tau in shared memory)",
                       "case": "configs[3] at 1/10 scale: 1000 r x 100 z x 10 tilt = 1e6 candidates, 13 tonals",
                       "kernel_ms": k_ms, "call_ms": call_ms, "cand_freq_per_s": C * 13 / (k_ms * 1e-3),
                       "alg_tflops": C * 8.0 * N * sumM / (k_ms * 1e-3) / 1e12,
                       "alg_flop_per_cand": 8 * N * sumM, "projected_s_for_1e7": 10 * k_ms * 1e-3,
-                      "bound": "fp32 FMA + per-(receiver, mode) sincos (CUDA cores); tensor-core path is future work"}), flush=True)
+                      "bound": "fp32 FMA + shared-memory operand loads (CUDA cores); tensor-core path is future work"}), flush=True)
 
 
 def bench_env():
