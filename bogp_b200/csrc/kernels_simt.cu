@@ -251,6 +251,7 @@ points_tilt_kernel(ModesetDev ms, const double* __restrict__ cand, long long C, 
 // sincos per (receiver, mode)).  p_n = (r / r_n)^{1/2} sum_m Theta[m][n] phi_m(z) E[m, r]; one warp per candidate,
 // two receivers per lane (N <= 64).
 constexpr int kTiltChunk = 1024;     // candidates of one tilt plane per block
+constexpr int kTiltCand = 4;         // candidates a warp evaluates together
 
 __global__ void __launch_bounds__(kThreads)
 grid_tilt_kernel(ModesetDev ms, const float2* __restrict__ E, const float2* __restrict__ PZ, const double* __restrict__ r,
@@ -260,7 +261,7 @@ grid_tilt_kernel(ModesetDev ms, const float2* __restrict__ E, const float2* __re
   float* acc = reinterpret_cast<float*>(Th + (size_t)MpMax * 64); // [kTiltChunk]
   float2* a_all = reinterpret_cast<float2*>(acc + kTiltChunk);    // [warps][MpMax]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float2* a_s = a_all + (size_t)warp * MpMax;
+  float2* a_s = a_all + (size_t)warp * kTiltCand * MpMax;
   const int plane = Nr * Nz;
   const int nchunks = (plane + kTiltChunk - 1) / kTiltChunk;
   const int t = blockIdx.x / nchunks, c0 = (blockIdx.x % nchunks) * kTiltChunk;
@@ -293,41 +294,59 @@ grid_tilt_kernel(ModesetDev ms, const float2* __restrict__ E, const float2* __re
     const float2* Pf = PZ + (size_t)tm.offM * Nz;
     const float* cr = ms.CkT_re + tm.offC;   // [N][J]
     const float* ci = ms.CkT_im + tm.offC;
-    for (int cl = warp; cl < cn; cl += kWarpsPerBlock) {
-      const int c = c0 + cl, j = c / Nr, i = c - j * Nr;
-      for (int m = lane; m < tm.M; m += 32) a_s[m] = cmul(__ldg(Pf + (size_t)j * tm.Mp + m), __ldg(Ef + (size_t)i * tm.Mp + m));
+    // kTiltCand candidates per warp at a time: every Theta element fetched from shared memory feeds kTiltCand complex
+    // multiply-adds (the loop is bound by shared-memory loads otherwise)
+    for (int cb = warp * kTiltCand; cb < cn; cb += kWarpsPerBlock * kTiltCand) {
+      int ii[kTiltCand];
+#pragma unroll
+      for (int q = 0; q < kTiltCand; ++q) {
+        const int c = c0 + min(cb + q, cn - 1), j = c / Nr, i = c - j * Nr;
+        ii[q] = i;
+        for (int m = lane; m < tm.M; m += 32)
+          a_s[q * MpMax + m] = cmul(__ldg(Pf + (size_t)j * tm.Mp + m), __ldg(Ef + (size_t)i * tm.Mp + m));
+      }
       __syncwarp();
-      float2 p0 = make_float2(0.f, 0.f), p1 = make_float2(0.f, 0.f);
-#pragma unroll 4
+      float2 p0[kTiltCand], p1[kTiltCand];
+#pragma unroll
+      for (int q = 0; q < kTiltCand; ++q) p0[q] = p1[q] = make_float2(0.f, 0.f);
+#pragma unroll 2
       for (int m = 0; m < tm.M; ++m) {
-        const float2 a = a_s[m];
         const float2 t0 = Th[m * 64 + n0], t1 = Th[m * 64 + n1];
-        p0.x = fmaf(t0.x, a.x, fmaf(-t0.y, a.y, p0.x));
-        p0.y = fmaf(t0.x, a.y, fmaf(t0.y, a.x, p0.y));
-        p1.x = fmaf(t1.x, a.x, fmaf(-t1.y, a.y, p1.x));
-        p1.y = fmaf(t1.x, a.y, fmaf(t1.y, a.x, p1.y));
+#pragma unroll
+        for (int q = 0; q < kTiltCand; ++q) {
+          const float2 a = a_s[q * MpMax + m];
+          p0[q].x = fmaf(t0.x, a.x, fmaf(-t0.y, a.y, p0[q].x));
+          p0[q].y = fmaf(t0.x, a.y, fmaf(t0.y, a.x, p0[q].y));
+          p1[q].x = fmaf(t1.x, a.x, fmaf(-t1.y, a.y, p1[q].x));
+          p1[q].y = fmaf(t1.x, a.y, fmaf(t1.y, a.x, p1[q].y));
+        }
       }
       __syncwarp();
-      const float rinv = 1.f / (float)r[i];
-      const float s0 = rsqrtf(1.f - l0 * fs * rinv), s1 = rsqrtf(1.f - l1 * fs * rinv);     // (r / r_n)^{1/2}
-      p0.x *= s0; p0.y *= s0; p1.x *= s1; p1.y *= s1;
-      float norm = warp_sum(p0.x * p0.x + p0.y * p0.y + p1.x * p1.x + p1.y * p1.y);
-      float num = 0.f;
-      for (int jj = 0; jj < tm.J; ++jj) {
-        float sr = 0.f, si = 0.f;
-        if (n0 < N) {
-          const float a = __ldg(cr + (size_t)n0 * tm.J + jj), b = __ldg(ci + (size_t)n0 * tm.J + jj);
-          sr += a * p0.x - b * p0.y; si += a * p0.y + b * p0.x;
+#pragma unroll
+      for (int q = 0; q < kTiltCand; ++q) {
+        const int cl = cb + q;
+        if (cl >= cn) break;                       // warp-uniform
+        const float rinv = 1.f / (float)r[ii[q]];
+        const float s0 = rsqrtf(1.f - l0 * fs * rinv), s1 = rsqrtf(1.f - l1 * fs * rinv);     // (r / r_n)^{1/2}
+        float2 u0 = make_float2(p0[q].x * s0, p0[q].y * s0), u1 = make_float2(p1[q].x * s1, p1[q].y * s1);
+        const float norm = warp_sum(u0.x * u0.x + u0.y * u0.y + u1.x * u1.x + u1.y * u1.y);
+        float num = 0.f;
+        for (int jj = 0; jj < tm.J; ++jj) {
+          float sr = 0.f, si = 0.f;
+          if (n0 < N) {
+            const float a = __ldg(cr + (size_t)n0 * tm.J + jj), b = __ldg(ci + (size_t)n0 * tm.J + jj);
+            sr += a * u0.x - b * u0.y; si += a * u0.y + b * u0.x;
+          }
+          if (n1 < N) {
+            const float a = __ldg(cr + (size_t)n1 * tm.J + jj), b = __ldg(ci + (size_t)n1 * tm.J + jj);
+            sr += a * u1.x - b * u1.y; si += a * u1.y + b * u1.x;
+          }
+          sr = warp_sum(sr); si = warp_sum(si);
+          num += sr * sr + si * si;
         }
-        if (n1 < N) {
-          const float a = __ldg(cr + (size_t)n1 * tm.J + jj), b = __ldg(ci + (size_t)n1 * tm.J + jj);
-          sr += a * p1.x - b * p1.y; si += a * p1.y + b * p1.x;
-        }
-        sr = warp_sum(sr); si = warp_sum(si);
-        num += sr * sr + si * si;
+        const float b = num / norm;
+        if (lane == 0) acc[cl] = combine_tonal(acc[cl], atype == BOGP_ATYPE_CBF ? b : tm.trK - b, mf, f == 0);
       }
-      const float b = num / norm;
-      if (lane == 0) acc[cl] = combine_tonal(acc[cl], atype == BOGP_ATYPE_CBF ? b : tm.trK - b, mf, f == 0);
     }
   }
   __syncthreads();
@@ -439,7 +458,7 @@ int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     grid_tables_kernel<<<tg, 256, 0, s>>>(d, r_dev, Nr, z_dev, Nz, E, PZ);
     bogp::count_launch();
     BOGP_CUDA(cudaGetLastError());
-    const size_t smem = ((size_t)h->max_Mp * 64 + (size_t)kWarpsPerBlock * h->max_Mp) * sizeof(float2) + kTiltChunk * sizeof(float);
+    const size_t smem = ((size_t)h->max_Mp * 64 + (size_t)kWarpsPerBlock * kTiltCand * h->max_Mp) * sizeof(float2) + kTiltChunk * sizeof(float);
     if (int rc = set_smem(grid_tilt_kernel, smem)) return rc;
     const long long plane = (long long)Nr * Nz;
     const long long blocks = (long long)Nt * ((plane + kTiltChunk - 1) / kTiltChunk);
