@@ -343,8 +343,13 @@ def run_ours(args) -> None:
     flop_per_launch = dms.flops_per_candidate() * NZ_PER_GPU * NR
     kern_avg_ms = kern_ms / max(kern_n, 1)
     achieved = flop_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_n else None
+    traffic = None
+    tpath = ROOT / "profiles" / "umma_traffic.json"
+    if tpath.exists() and args.engine in ("auto", "umma"):
+        tj = json.loads(tpath.read_text())
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]      # bytes per launch, from one ncu --set full capture
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
                 "flop_per_launch": flop_per_launch,
                 "peak_def": f"{peak_src} / 2 (TF32 rate) / 3 (3xTF32 split) of measured",
