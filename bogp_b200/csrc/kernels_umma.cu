@@ -420,6 +420,18 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
 }
 
 // ------------------------------------------------------------------------------------------------ main kernel
+// Debug build only: per-stage time stamps of CTA 0 in three windows of stages (one per tonal class), see launch_grid_umma.
+__device__ __forceinline__ void dbg_stamp(const UParams& p, int ev, uint32_t sc) {
+#if BOGP_UMMA_DBG
+  if (p.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    int idx = -1;
+    if (sc >= 20 && sc < 40) idx = (int)sc - 20;
+    else if (sc >= 100 && sc < 120) idx = 20 + (int)sc - 100;
+    else if (sc >= 280 && sc < 300) idx = 40 + (int)sc - 280;
+    if (idx >= 0) p.dbg[3360 + ev * 60 + idx] = clock64();
+  }
+#endif
+}
 // barrier slots (8 bytes each) at smem_bar
 enum { BAR_BFULL = 0, BAR_BEMPTY = kStages, BAR_EFULL = 2 * kStages, BAR_EDONE = 2 * kStages + 2,
        BAR_TFULL = 2 * kStages + 4, BAR_TEMPTY = 2 * kStages + 6, BAR_COUNT = 2 * kStages + 8 };
@@ -468,6 +480,7 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
     mbar_wait_t(bar(BAR_BFULL + slot), ph, p.err, 5, (BOGP_UMMA_DBG && st.dbg) ? &st.w_bfull : nullptr);
     mbar_wait_t(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6, (BOGP_UMMA_DBG && st.dbg) ? &st.w_tempty : nullptr);
     tc_fence_after();
+    dbg_stamp(p, 0, sc);
     const uint32_t N = (uint32_t)(njs * u.rowsP);
     const uint32_t idesc = idesc0 | ((N >> 3) << 17);
     const uint32_t b_hi = st.s_base + p.smem_B + slot * p.stage_bytes;
@@ -480,6 +493,7 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
       tc_commit(bar(BAR_TFULL + buf));
     }
     __syncwarp();
+    dbg_stamp(p, 1, sc);
   }
   st.sc = sc;
   if (elect_one()) tc_commit(bar(BAR_EDONE + (st.g & 1)));
@@ -629,6 +643,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           mbar_wait_t(bar(BAR_TFULL + set), (sc >> 1) & 1u, p.err, 7, dbg ? &w_tfull : nullptr);
           const long long tw = (dbg && ew == 0 && blockIdx.x == 0) ? clock64() : 0;
           tc_fence_after();
+          if (quad == 0 && sub == 0) dbg_stamp(p, 2, sc);
           // slots of this stage owned by this warp: s = s_first, s_first + kEpiSub, ...
           const int s_first = (sub - j0 % kEpiSub + kEpiSub) % kEpiSub;
           bool released = false;
@@ -655,6 +670,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
                   tc_fence_before();
                   if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
                   released = true;
+                  if (quad == 0 && sub == 0) dbg_stamp(p, 3, sc);
                 }
                 if (c0 == 0) {
                   if (nq == 1) {
@@ -685,6 +701,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
                   tc_fence_before();
                   if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
                   released = true;
+                  if (quad == 0 && sub == 0) dbg_stamp(p, 3, sc);
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -705,6 +722,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
             float* a = acc + (size_t)j * kTileR + tl;
             *a = (f == 0) ? val : (p.mf == BOGP_MF_MEAN ? *a + val : *a * val);
           }
+          if (quad == 0 && sub == 0) dbg_stamp(p, 4, sc);
           if (!released) {      // no slot of this stage belongs to this warp
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
@@ -868,6 +886,15 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     fprintf(stderr, "\n[umma dbg] epilogue cycles per stage by tonal (CTA 0, warp 0):");
     for (int f = 0; f < d.F && f < 32; ++f) fprintf(stderr, " %lld", hdbg[16 * 201 + f] / std::max<long long>(1, hdbg[16 * 203 + f]));
     fprintf(stderr, "\n");
+    for (int w = 0; w < 3; ++w) {
+      fprintf(stderr, "[umma dbg] window %d: stage | ready->issued | issued->tfull-wake | hold (wake->release) | release->done | release->next ready(same buf)\n", w);
+      for (int i = 0; i < 18; ++i) {
+        const long long* e = hdbg.data() + 3360;
+        const int k = w * 20 + i;
+        fprintf(stderr, "   %3d  %6lld %6lld %6lld %6lld %6lld   (t0 delta %lld)\n", i, e[60 + k] - e[k], e[120 + k] - e[60 + k], e[180 + k] - e[120 + k],
+                e[240 + k] - e[180 + k], e[k + 2] - e[180 + k], e[k + 1] - e[k]);
+      }
+    }
   }
   return 0;
 }
