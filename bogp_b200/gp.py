@@ -83,9 +83,13 @@ class SingleTaskGP:
     num_outputs = 1
     _num_outputs = 1       # gpmodels.py:17
 
-    def __init__(self, train_X, train_Y, covar_module: str = "matern52", *, lengthscale=None,
+    def __init__(self, train_X, train_Y, covar_module: str = "matern52", *, likelihood=None, lengthscale=None,
                  outputscale: Optional[float] = None, mean: float = 0.0, noise: Optional[float] = None,
                  noise_bounds: Tuple[float, float] = (1e-8, 1e-3)):
+        # ``likelihood=GaussianLikelihood(noise_constraint=Interval(lo, hi))`` (ei.py:66-67): only the interval matters
+        nc = getattr(likelihood, "noise_constraint", None)
+        if nc is not None and hasattr(nc, "lower_bound"):
+            noise_bounds = (float(nc.lower_bound), float(nc.upper_bound))
         if covar_module not in _lib.KERNEL:
             raise ValueError(f"covar_module must be one of {sorted(_lib.KERNEL)}")
         X = torch.as_tensor(train_X, dtype=DT)
@@ -150,7 +154,7 @@ class SingleTaskGP:
 
     def fit(self, cfg: Optional["FitConfig"] = None) -> "SingleTaskGP":
         """The reference's hyper-parameter fit (100 x AdamW on -mll, ei.py:69-78); see :func:`fit_gp_adamw`."""
-        return fit_gp_adamw(self, cfg if cfg is not None else FitConfig())
+        return fit_gp_adamw(self, cfg if cfg is not None else FitConfig(noise_bounds=self.noise_bounds))
 
     def eval(self):
         return self

@@ -204,6 +204,23 @@ def covariance(d: np.ndarray) -> np.ndarray:
     return d @ d.conj().T
 
 
+def simulate_covariance(runner: "ModeRunner", parameters: dict, freq: Sequence[float]) -> np.ndarray:
+    """``optimization.utils.simulate_covariance(runner, parameters, freq)`` (ref/optimization/utils.py:23-32):
+    ``K[F, N, N]`` with ``K_f = d d^H``, ``d = p/||p||`` the replica at the truth in ``parameters`` (``src_z``,
+    ``rec_r`` [km], optional ``tilt``).  Host float64, set-up only (one modal sum per tonal)."""
+    from .modes import synthetic_covariance
+    modes = runner.modes_for(parameters)
+    idx = []
+    for f in freq:
+        hits = [i for i, g in enumerate(modes.freq) if abs(g - float(f)) < 1e-9]
+        if not hits:
+            raise ValueError(f"mode set has no tonal at {f} Hz")
+        idx.append(hits[0])
+    sel = modes if idx == list(range(modes.n_freq)) else modes.select(idx)
+    return synthetic_covariance(sel, float(parameters["src_z"]), float(np.asarray(parameters["rec_r"])),
+                                float(parameters.get("tilt", 0.0) or 0.0))
+
+
 def beamformer(K: np.ndarray, replica: np.ndarray, atype: str = "cbf") -> np.ndarray:
     """Marker for ``tritonoa.sp.beamforming.beamformer``.
 

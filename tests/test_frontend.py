@@ -1,0 +1,202 @@
+"""the oao-compatible optimiser front-end, the strategy mirror and the dotted-path shims.
+
+CPU tier: host logic with a closed-form objective (no CUDA call).  GPU tier: a localisation job as
+ref/projects/swellex96_localization/data/run.py:22-49 runs it (Sobol warm-up -> GP/EI -> results.csv), with the
+fused matched-field objective, and a grid search that is one surface launch.
+"""
+import sys
+
+import numpy as np
+import pytest
+
+from bogp_b200 import oao, shim
+from bogp_b200.strategy import GPEIStrategy, GridSearchStrategy, SobolStrategy
+
+
+def _space():
+    bounds = oao.SearchSpaceBounds(bounds=[
+        oao.SearchParameterBounds("rec_r", -1.0, 1.0, relative=True, min_lower_bound=0.010, max_upper_bound=8.0),
+        oao.SearchParameterBounds("src_z", -40.0, 40.0, relative=True, min_lower_bound=1.0, max_upper_bound=200.0)])
+    return oao.format_search_space(bounds, {"rec_r": 1.07, "src_z": 71.11, "time_step": 250})
+
+
+def test_format_search_space_clipping_matches_reference_logic():
+    """ref/optimization/utils.py:72-98: relative bounds around the scenario, shifted (not shrunk) at the limits."""
+    sp = _space()
+    assert sp.names == ["rec_r", "src_z"]
+    np.testing.assert_allclose(sp.bounds, [[0.07, 31.11], [2.07, 111.11]])
+    b = oao.SearchSpaceBounds(bounds=[oao.SearchParameterBounds("rec_r", -1.0, 1.0, True, 0.010, 8.0),
+                                      oao.SearchParameterBounds("src_z", -40.0, 40.0, True, 1.0, 200.0),
+                                      oao.SearchParameterBounds("tilt", -4.0, 4.0)])
+    sp = oao.format_search_space(b, {"rec_r": 0.5, "src_z": 190.0})
+    np.testing.assert_allclose(sp.bounds, [[0.010, 120.0, -4.0], [2.010, 200.0, 4.0]])
+    u = np.random.default_rng(0).random((5, 3))
+    np.testing.assert_allclose(sp.to_unit(sp.from_unit(u)), u, atol=1e-14)
+
+
+def test_strategies_mirror_reference_signatures():
+    s = GPEIStrategy(warmup_trials=8, warmup_parallelism=4, num_trials=3, max_parallelism=1, seed=7)()
+    assert [st.model for st in s._steps] == [oao.Models.SOBOL, oao.Models.GPEI]
+    assert s._steps[0].model_kwargs == {"seed": 7} and s.num_trials == 11
+    assert SobolStrategy(num_trials=16, max_parallelism=4, seed=1)()._steps[0].num_trials == 16
+    g = GridSearchStrategy(num_trials=5)
+    assert g() is g and g.num_trials == 5
+
+
+def test_sobol_and_grid_loops_and_results_schema(tmp_path):
+    """Closed-form objective: trial bookkeeping, batch times, running best, the aggregate.py schema, client JSON."""
+    truth = np.array([1.3, 80.0])
+
+    def f(p):
+        return float(np.exp(-((p["rec_r"] - truth[0]) / 0.5) ** 2 - ((p["src_z"] - truth[1]) / 20.0) ** 2))
+
+    obj = oao.NoiselessFormattedObjective(f, name="bartlett", properties_kw={"minimize": False})
+    assert obj({"rec_r": 1.3, "src_z": 80.0}) == {"bartlett": (1.0, 0.0)}
+    opt = oao.QuasiRandom(obj, _space(), SobolStrategy(num_trials=40, max_parallelism=16, seed=3)())
+    client = opt.run(name="sobol")
+    assert len(client.trials) == 40 and len(opt.batch_execution_times) == 3          # 16 + 16 + 8
+    df = oao.get_results(client, opt.batch_execution_times, minimize=False)
+    assert list(df.columns) == ["generation_method", "rec_r", "src_z", "bartlett", "best_rec_r", "best_src_z",
+                                "best_value", "time"]
+    assert df.index.name == "trial_index" and (np.diff(df["best_value"]) >= 0).all()
+    i = int(df["bartlett"].values.argmax())
+    assert df["best_rec_r"].iloc[-1] == df["rec_r"].iloc[i] and df["time"].nunique() == 3
+    # same seed -> same trials (Sobol engine is seeded like Ax's Models.SOBOL(seed))
+    again = oao.QuasiRandom(obj, _space(), SobolStrategy(num_trials=40, max_parallelism=16, seed=3)()).run()
+    assert [t["parameters"] for t in again.trials] == [t["parameters"] for t in client.trials]
+    lo, hi = _space().bounds
+    X = np.array([[t["parameters"]["rec_r"], t["parameters"]["src_z"]] for t in client.trials])
+    assert (X >= lo).all() and (X <= hi).all()
+    client.save_to_json_file(tmp_path / "client.json")
+    import json
+    snap = json.loads((tmp_path / "client.json").read_text())
+    assert len(snap["trials"]) == 40 and snap["metric_name"] == "bartlett"
+    # grid: num_trials points per dimension, end points included
+    g = oao.GridSearch(obj, _space(), GridSearchStrategy(num_trials=7))
+    gc = g.run()
+    assert len(gc.trials) == 49 and len(g.batch_execution_times) == 1
+    best, val = gc.get_best_parameters()
+    assert abs(best["rec_r"] - truth[0]) < 0.35 and abs(best["src_z"] - truth[1]) < 14
+    # minimisation flips the running best
+    objm = oao.NoiselessFormattedObjective(lambda p: -f(p), name="ml", properties_kw={"minimize": True})
+    cm = oao.QuasiRandom(objm, _space(), SobolStrategy(num_trials=8, max_parallelism=8, seed=3)())
+    dfm = oao.get_results(cm.run(), cm.batch_execution_times, minimize=True)
+    assert (np.diff(dfm["best_value"]) <= 0).all()
+
+
+def test_gpei_loop_with_injected_backend():
+    """The GPEI step: UnitX / StandardizeY transforms, q per batch, seeds -- with a stand-in candidate generator."""
+    calls = []
+
+    class Backend:
+        def gp_ei_candidates(self, U, y, q, seed):
+            calls.append((U.copy(), y.copy(), q, seed))
+            return np.full((q, U.shape[1]), 0.5)
+
+    obj = oao.NoiselessFormattedObjective(lambda p: p["rec_r"] + p["src_z"], "m", {"minimize": True})
+    opt = oao.BayesianOptimization(obj, _space(), GPEIStrategy(6, 3, 5, 2, seed=11)(), backend=Backend())
+    client = opt.run()
+    assert len(client.trials) == 11 and [c[2] for c in calls] == [2, 2, 1]
+    U, y, _, _ = calls[0]
+    assert U.shape == (6, 2) and (U >= 0).all() and (U <= 1).all()
+    assert abs(y.mean()) < 1e-12 and abs(y.std(ddof=1) - 1.0) < 1e-12
+    # minimise -> the GP sees the negated, standardised objective: its arg-max is the smallest raw value
+    raw = np.array([t["value"] for t in client.trials[:6]])
+    assert int(np.argmax(y)) == int(np.argmin(raw))
+    mid = _space().from_unit(np.full((1, 2), 0.5))[0]
+    assert client.trials[-1]["parameters"] == {"rec_r": mid[0], "src_z": mid[1]}
+    assert client.trials[-1]["generation_method"] == "GPEI"
+
+
+def test_shims_resolve_reference_import_paths():
+    """The dotted paths of conf/optimization/run.py:15-21,89-99, ei.py:8-18 and strategy.py:5-7."""
+    done = shim.install()
+    try:
+        assert done["tritonoa"] and done["oao"]
+        from tritonoa.sp.mfp import MatchedFieldProcessor
+        from tritonoa.sp.beamforming import beamformer, covariance
+        from tritonoa.at.models.kraken.runner import run_kraken
+        from tritonoa.at.models.kraken.kraken import clean_up_kraken_files
+        from oao.optimizer import BayesianOptimization, GridSearch, QuasiRandom
+        from oao.results import get_results
+        from oao.space import SearchParameter, SearchSpace, SearchSpaceBounds
+        from oao.strategy import GridStrategy
+        from ax.modelbridge.generation_strategy import GenerationStep, GenerationStrategy
+        from ax.modelbridge.registry import Models
+        from botorch.models import SingleTaskGP
+        from botorch.acquisition import ExpectedImprovement, LogExpectedImprovement, UpperConfidenceBound
+        from botorch.optim import optimize_acqf
+        from gpytorch.constraints import Interval
+        from gpytorch.likelihoods import GaussianLikelihood
+        import bogp_b200.mfp as m, bogp_b200.gp as g
+        assert MatchedFieldProcessor is m.MatchedFieldProcessor and run_kraken is m.ModeRunner
+        assert SingleTaskGP is g.SingleTaskGP and BayesianOptimization is oao.BayesianOptimization
+        lik = GaussianLikelihood(noise_constraint=Interval(1e-8, 1e-3))
+        gp = SingleTaskGP(np.random.default_rng(0).random((5, 2)), np.arange(5.0), likelihood=lik)
+        assert gp.noise_bounds == (1e-8, 1e-3)
+        clean_up_kraken_files("anywhere")
+    finally:
+        shim.uninstall()
+    assert "tritonoa" not in sys.modules
+
+
+# ------------------------------------------------------------------------------------------------ GPU tier
+@pytest.mark.gpu
+def test_localisation_job_end_to_end(cfg1, tmp_path):
+    """data/run.py:22-49 with the fused objective: Sobol warm-up, GP + EI trials, results.csv, best near the truth."""
+    from functools import partial
+    from bogp_b200.mfp import MatchedFieldProcessor, ModeRunner, beamformer, simulate_covariance
+    modes, (r0, z0) = cfg1["modes"], cfg1["truth"]
+    runner = ModeRunner(modes)
+    K = simulate_covariance(runner, {"rec_r": r0, "src_z": z0}, modes.freq)
+    np.testing.assert_allclose(K, cfg1["K"], atol=1e-14)
+    mfp = MatchedFieldProcessor(runner=runner, covariance_matrix=K, freq=modes.freq, parameters={},
+                                beamformer=partial(beamformer, atype="cbf"))
+    obj = oao.NoiselessFormattedObjective(mfp, name="bartlett", properties_kw={"minimize": False})
+    space = oao.format_search_space(oao.SearchSpaceBounds(bounds=[
+        oao.SearchParameterBounds("rec_r", -1.0, 1.0, True, 0.010, 8.0),
+        oao.SearchParameterBounds("src_z", -40.0, 40.0, True, 1.0, 200.0)]), {"rec_r": r0, "src_z": z0})
+    opt = oao.BayesianOptimization(obj, space, GPEIStrategy(warmup_trials=32, warmup_parallelism=16, num_trials=10,
+                                                            max_parallelism=1, seed=2009)(), fit_steps=50)
+    client = opt.run(name="gpei")
+    df = oao.get_results(client, opt.batch_execution_times, minimize=False)
+    df.to_csv(tmp_path / "results.csv")
+    assert len(df) == 42 and (df["generation_method"].iloc[32:] == "GPEI").all()
+    # the GP trials must improve on the Sobol warm-up and close in on the truth used to simulate K
+    assert df["best_value"].iloc[-1] >= df["best_value"].iloc[31]
+    assert df["best_value"].iloc[-1] > 0.9
+    assert abs(df["best_rec_r"].iloc[-1] - r0) < 0.05 and abs(df["best_src_z"].iloc[-1] - z0) < 3.0
+    # every recorded value is the fused objective at the recorded parameters
+    i = 37
+    p = {"rec_r": df["rec_r"].iloc[i], "src_z": df["src_z"].iloc[i]}
+    assert mfp(p) == pytest.approx(df["bartlett"].iloc[i], rel=1e-6)
+    # q = 4 batches (qgpei, conf/optimization/run.py:202-208)
+    optq = oao.BayesianOptimization(obj, space, GPEIStrategy(16, 16, 8, 4, seed=2009)(), fit_steps=30, mc_samples=128,
+                                    num_restarts=8, raw_samples=256)
+    cq = optq.run()
+    assert len(cq.trials) == 24 and len(optq.batch_execution_times) == 3
+
+
+@pytest.mark.gpu
+def test_grid_search_is_one_surface_launch(cfg1):
+    from bogp_b200 import _lib
+    from bogp_b200.mfp import MatchedFieldProcessor, ModeRunner, beamformer
+    from oracle import bartlett as ob
+    modes = cfg1["modes"]
+    mfp = MatchedFieldProcessor(runner=ModeRunner(modes), covariance_matrix=cfg1["K"], freq=modes.freq, parameters={},
+                                beamformer=beamformer)
+    obj = oao.NoiselessFormattedObjective(mfp, name="bartlett", properties_kw={"minimize": False})
+    space = oao.SearchSpace([oao.SearchParameter("rec_r", "range", [0.5, 2.0]),
+                             oao.SearchParameter("src_z", "range", [40.0, 100.0])])
+    mfp.surface([1.0], [50.0])                       # build the device handle outside the counted region
+    n0 = _lib.kernel_launches()
+    g = oao.GridSearch(obj, space, GridSearchStrategy(num_trials=24))
+    client = g.run()
+    assert _lib.kernel_launches() - n0 <= 3          # operand tables + surface kernel (+ nothing per trial)
+    assert len(client.trials) == 576
+    ref = ob.ambiguity_surface(modes, cfg1["K"], np.linspace(0.5, 2.0, 24), np.linspace(40.0, 100.0, 24))
+    got = np.array([t["value"] for t in client.trials]).reshape(24, 24)
+    np.testing.assert_allclose(got, ref, atol=2e-6)
+    best, _ = client.get_best_parameters()
+    jz, jr = np.unravel_index(ref.argmax(), ref.shape)
+    assert best == {"src_z": np.linspace(40.0, 100.0, 24)[jz], "rec_r": np.linspace(0.5, 2.0, 24)[jr]}
