@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "bogp_internal.h"
 #include "device_math.cuh"
@@ -20,6 +22,10 @@ struct bogp_envbatch_s {
   float* trK = nullptr;                         // [F]
   int Jmax = 0;
   bool has_cov = false;
+  // streaming layout: one contiguous record per candidate (see envstream_kernel); null when a record cannot be
+  // double-buffered in shared memory
+  unsigned char* rec = nullptr;
+  unsigned rec_bytes = 0, off_kre = 0, off_kim = 0, off_g = 0, off_r = 0;
 };
 
 namespace bogp {
@@ -97,6 +103,141 @@ envbatch_kernel(long long C, int F, int N, int Mmax, const double* __restrict__ 
       acc = combine_tonal(acc, atype == BOGP_ATYPE_CBF ? b : trK[f] - b, mf, f == 0);
     }
     if (lane == 0) out[c] = (mf == BOGP_MF_MEAN) ? acc / (float)F : acc;
+  }
+}
+
+// ---- streaming variant (the fast path).  Each candidate is ONE contiguous record in HBM
+//   [Phi^T (F x Mmax x N float32) | k_re (F x Mmax float64) | k_im (float32) | g = phi_src * k^-1/2 (float2) | range]
+// pulled into shared memory by a single cp.async.bulk per candidate (mbarrier complete_tx), S stages per warp, so
+// the HBM stream never waits for the arithmetic: a warp computes candidate c from shared memory while the copies
+// of the next candidates (its own next stage and the other warps') are in flight.  Algorithmic bytes per
+// (candidate, tonal): 4 N M + 20 M; the record IS those bytes (plus zero padding to Mmax).
+__device__ __forceinline__ uint32_t env_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void env_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void env_fetch(uint32_t dst, const unsigned char* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+struct EnvStreamParams {
+  long long C;
+  int F, N, Mmax, Jmax, atype, mf, warps, stages;
+  unsigned rec_bytes, off_kre, off_kim, off_g, off_r, warp_bytes;
+  const unsigned char* rec;
+  const float* CkT_re;
+  const float* CkT_im;
+  const int* J;
+  const float* trK;
+  float* out;
+};
+
+constexpr int kEnvJ = 4;      // covariance ranks handled in registers by the streaming kernel
+
+__global__ void __launch_bounds__(512) envstream_kernel(const EnvStreamParams p) {
+  extern __shared__ __align__(128) unsigned char esm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* base = esm + (size_t)warp * p.warp_bytes;                 // [stages][rec_bytes] then a_s
+  float2* a_s = reinterpret_cast<float2*>(base + (size_t)p.stages * p.rec_bytes);
+  const uint32_t bar0 = env_smem_u32(esm + (size_t)p.warps * p.warp_bytes) + 16u * (uint32_t)warp;   // 2 barriers per warp
+  if (lane == 0) {
+    for (int st = 0; st < p.stages; ++st) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * st));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const long long TW = (long long)gridDim.x * p.warps;
+  long long c = (long long)blockIdx.x * p.warps + warp;
+  const int FM = p.F * p.Mmax;
+  // prologue: fill the ring
+  if (lane == 0) {
+    long long cc = c;
+    for (int st = 0; st < p.stages && cc < p.C; ++st, cc += TW)
+      env_fetch(env_smem_u32(base + (size_t)st * p.rec_bytes), p.rec + (size_t)cc * p.rec_bytes, p.rec_bytes, bar0 + 8u * st);
+  }
+  int st = 0;
+  uint32_t phase = 0;      // bit st = parity of stage st
+  for (; c < p.C; c += TW) {
+    env_wait(bar0 + 8u * st, (phase >> st) & 1u);
+    phase ^= 1u << st;
+    const unsigned char* buf = base + (size_t)st * p.rec_bytes;
+    const float* P = reinterpret_cast<const float*>(buf);
+    const double* kre = reinterpret_cast<const double*>(buf + p.off_kre);
+    const float* kim = reinterpret_cast<const float*>(buf + p.off_kim);
+    const float2* g = reinterpret_cast<const float2*>(buf + p.off_g);
+    const double r = *reinterpret_cast<const double*>(buf + p.off_r);
+    const float rf = (float)r, rs = (float)rsqrt(r);
+    for (int idx = lane; idx < FM; idx += 32) {
+      const float2 gg = g[idx];
+      float2 a = make_float2(0.f, 0.f);
+      if (gg.x != 0.f || gg.y != 0.f) {
+        float s, co;
+        sincosf(reduce_phase(kre[idx] * r), &s, &co);
+        const float amp = expf(kim[idx] * rf) * rs;
+        a = cmul(gg, make_float2(amp * co, -amp * s));
+      }
+      a_s[idx] = a;
+    }
+    __syncwarp();
+    float acc = 0.f;
+    for (int f = 0; f < p.F; ++f) {
+      const float* Pf = P + (size_t)f * p.Mmax * p.N;
+      const float2* af = a_s + f * p.Mmax;
+      const int J = p.J[f];
+      const float* cr = p.CkT_re + (size_t)f * p.N * p.Jmax;
+      const float* ci = p.CkT_im + (size_t)f * p.N * p.Jmax;
+      float norm = 0.f, sr[kEnvJ], si[kEnvJ];
+#pragma unroll
+      for (int j = 0; j < kEnvJ; ++j) sr[j] = si[j] = 0.f;
+      for (int n = lane; n < p.N; n += 32) {
+        float pr0 = 0.f, pi0 = 0.f, pr1 = 0.f, pi1 = 0.f;
+#pragma unroll 4
+        for (int m = 0; m < p.Mmax; m += 2) {          // Mmax is a multiple of 4
+          const float ph0 = Pf[(size_t)m * p.N + n], ph1 = Pf[(size_t)(m + 1) * p.N + n];
+          const float4 a2 = *reinterpret_cast<const float4*>(af + m);
+          pr0 = fmaf(ph0, a2.x, pr0); pi0 = fmaf(ph0, a2.y, pi0);
+          pr1 = fmaf(ph1, a2.z, pr1); pi1 = fmaf(ph1, a2.w, pi1);
+        }
+        const float pr = pr0 + pr1, pi = pi0 + pi1;
+        norm = fmaf(pr, pr, fmaf(pi, pi, norm));
+#pragma unroll
+        for (int j = 0; j < kEnvJ; ++j)
+          if (j < J) {
+            const float a = __ldg(cr + (size_t)n * p.Jmax + j), b = __ldg(ci + (size_t)n * p.Jmax + j);
+            sr[j] += a * pr - b * pi;
+            si[j] += a * pi + b * pr;
+          }
+      }
+      norm = warp_sum(norm);
+      float num = 0.f;
+#pragma unroll
+      for (int j = 0; j < kEnvJ; ++j)
+        if (j < J) {
+          const float x = warp_sum(sr[j]), y = warp_sum(si[j]);
+          num += x * x + y * y;
+        }
+      const float b = num / norm;
+      acc = combine_tonal(acc, p.atype == BOGP_ATYPE_CBF ? b : p.trK[f] - b, p.mf, f == 0);
+    }
+    if (lane == 0) p.out[c] = (p.mf == BOGP_MF_MEAN) ? acc / (float)p.F : acc;
+    __syncwarp();                                     // every lane is done with this stage's buffer
+    const long long cn = c + (long long)p.stages * TW;
+    if (cn < p.C && lane == 0)
+      env_fetch(env_smem_u32(base + (size_t)st * p.rec_bytes), p.rec + (size_t)cn * p.rec_bytes, p.rec_bytes, bar0 + 8u * st);
+    st = (st + 1 == p.stages) ? 0 : st + 1;
   }
 }
 
@@ -241,6 +382,36 @@ extern "C" int bogp_envbatch_create(bogp_envbatch_t* out, long long C, int F, in
   rc |= dev_copy(&h->phiT, phi_rec_T_host, nm * N);
   rc |= dev_copy(&h->range, range_m_host, (size_t)C);
   if (rc) { bogp_envbatch_destroy(h); return BOGP_ERR_CUDA; }
+  // streaming records (fast path): [Phi^T | k_re f64 | k_im f32 | g = phi_src k^-1/2 (float2) | range f64], 16-byte padded
+  if (Mmax % 4 == 0) {
+    const size_t FM = (size_t)F * Mmax;
+    const auto pad16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_kre = pad16(FM * N * 4), o_kim = o_kre + FM * 8, o_g = pad16(o_kim + FM * 4), o_r = o_g + FM * 8;
+    const size_t R = pad16(o_r + 8);
+    if (2 * R + FM * 8 + 64 <= 220 * 1024 && (unsigned long long)C * R < (1ull << 40)) {
+      std::vector<unsigned char> rec((size_t)C * R, 0);
+      for (long long c = 0; c < C; ++c) {
+        unsigned char* b = rec.data() + (size_t)c * R;
+        std::memcpy(b, phi_rec_T_host + (size_t)c * FM * N, FM * N * 4);
+        double* kr = reinterpret_cast<double*>(b + o_kre);
+        float* ki = reinterpret_cast<float*>(b + o_kim);
+        float* g = reinterpret_cast<float*>(b + o_g);
+        for (size_t i = 0; i < FM; ++i) {
+          const size_t s = (size_t)c * FM + i;
+          kr[i] = k_re_host[s];
+          ki[i] = (float)k_im_host[s];
+          const bogp::cplx amp(amp_re_host[s], amp_im_host ? amp_im_host[s] : 0.0);
+          const bogp::cplx gg = (amp == bogp::cplx(0.0, 0.0)) ? amp : amp / std::sqrt(bogp::cplx(k_re_host[s], k_im_host[s]));
+          g[2 * i] = (float)gg.real();
+          g[2 * i + 1] = (float)gg.imag();
+        }
+        *reinterpret_cast<double*>(b + o_r) = range_m_host[c];
+      }
+      if (dev_copy(&h->rec, rec.data(), rec.size())) { bogp_envbatch_destroy(h); return BOGP_ERR_CUDA; }
+      h->rec_bytes = (unsigned)R; h->off_kre = (unsigned)o_kre; h->off_kim = (unsigned)o_kim;
+      h->off_g = (unsigned)o_g; h->off_r = (unsigned)o_r;
+    }
+  }
   *out = h;
   return 0;
 }
@@ -289,12 +460,37 @@ extern "C" int bogp_envbatch_bartlett(bogp_envbatch_t h, int atype, int mf_metho
   BOGP_REQUIRE(h && out_dev, "bogp_envbatch_bartlett: NULL argument");
   BOGP_REQUIRE(h->has_cov, "bogp_envbatch_bartlett: call bogp_envbatch_set_covariance first");
   BOGP_REQUIRE((atype == 0 || atype == 1) && (mf_method == 0 || mf_method == 1), "bogp_envbatch_bartlett: bad atype/mf");
-  const size_t smem = (size_t)bogp::kEnvWarps * (h->Mmax + h->N) * sizeof(float2);
-  BOGP_REQUIRE(smem <= 227 * 1024, "bogp_envbatch_bartlett: Mmax+N too large");
-  if (smem > 48 * 1024) BOGP_CUDA(cudaFuncSetAttribute(bogp::envbatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int force_simt = std::getenv("BOGP_ENV_SIMT") ? std::atoi(std::getenv("BOGP_ENV_SIMT")) : 0;
+  if (h->rec && h->Jmax <= bogp::kEnvJ && !force_simt) {
+    // streaming kernel: as many warps as fit with `stages` record buffers each.  Measured (profiles/paths_r1b.jsonl):
+    // one stage per warp wins -- the kernel is then bound by the warps' arithmetic, not by copies in flight, and
+    // twice the warps beat a private second stage (BOGP_ENV_STAGES=2 keeps the comparison runnable)
+    const int stages_env = std::getenv("BOGP_ENV_STAGES") ? std::atoi(std::getenv("BOGP_ENV_STAGES")) : 1;
+    bogp::EnvStreamParams p{};
+    p.stages = std::min(2, std::max(1, stages_env));
+    p.warp_bytes = (unsigned)(((size_t)p.stages * h->rec_bytes + (size_t)h->F * h->Mmax * 8 + 127) & ~(size_t)127);
+    p.warps = (int)std::min<size_t>(16, (226 * 1024) / ((size_t)p.warp_bytes + 16));
+    if (p.warps >= 1) {
+      p.C = h->C; p.F = h->F; p.N = h->N; p.Mmax = h->Mmax; p.Jmax = h->Jmax; p.atype = atype; p.mf = mf_method;
+      p.rec_bytes = h->rec_bytes; p.off_kre = h->off_kre; p.off_kim = h->off_kim; p.off_g = h->off_g; p.off_r = h->off_r;
+      p.rec = h->rec; p.CkT_re = h->CkT_re; p.CkT_im = h->CkT_im; p.J = h->J; p.trK = h->trK; p.out = out_dev;
+      const size_t smem = (size_t)p.warps * p.warp_bytes + 16 * (size_t)p.warps;
+      BOGP_CUDA(cudaFuncSetAttribute(bogp::envstream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int grid = (int)std::max<long long>(1, std::min<long long>((h->C + p.warps - 1) / p.warps, (long long)sms));
+      cudaEvent_t ev = bogp::timing_begin(static_cast<cudaStream_t>(stream));
+      bogp::envstream_kernel<<<grid, p.warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+      bogp::timing_end(ev, static_cast<cudaStream_t>(stream));
+      bogp::count_launch();
+      BOGP_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
+  const size_t smem = (size_t)bogp::kEnvWarps * (h->Mmax + h->N) * sizeof(float2);
+  BOGP_REQUIRE(smem <= 227 * 1024, "bogp_envbatch_bartlett: Mmax+N too large");
+  if (smem > 48 * 1024) BOGP_CUDA(cudaFuncSetAttribute(bogp::envbatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::max<long long>(1, std::min<long long>((h->C + bogp::kEnvWarps - 1) / bogp::kEnvWarps, (long long)sms * 8));
   bogp::envbatch_kernel<<<grid, bogp::kEnvWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       h->C, h->F, h->N, h->Mmax, h->k_re, h->k_im, h->amp_re, h->amp_im, h->phiT, h->range, h->CkT_re, h->CkT_im, h->J,
@@ -307,7 +503,7 @@ extern "C" int bogp_envbatch_bartlett(bogp_envbatch_t h, int atype, int mf_metho
 extern "C" int bogp_envbatch_destroy(bogp_envbatch_t h) {
   if (!h) return 0;
   cudaFree(h->k_re); cudaFree(h->k_im); cudaFree(h->range); cudaFree(h->amp_re); cudaFree(h->amp_im);
-  cudaFree(h->phiT); cudaFree(h->CkT_re); cudaFree(h->CkT_im); cudaFree(h->J); cudaFree(h->trK);
+  cudaFree(h->phiT); cudaFree(h->rec); cudaFree(h->CkT_re); cudaFree(h->CkT_im); cudaFree(h->J); cudaFree(h->trK);
   delete h;
   return 0;
 }

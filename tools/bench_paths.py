@@ -112,24 +112,32 @@ def bench_tilt():
 
 
 def bench_env():
-    Cn = 10_000
+    import os
+    from bogp_b200.envbatch import EnvBatch
     rng = np.random.default_rng(2)
-    depths = rng.uniform(200.0, 230.0, Cn)
-    cbs = rng.uniform(1600.0, 1700.0, Cn)
-    t0 = time.time()
-    base = perturbed_pekeris_batch(INV_TONALS_3, REC_Z_21, depths[:200], cbs[:200])
-    mode_sets = [base[i % 200] for i in range(Cn)]          # 200 distinct environments tiled to 1e4 (host set-up cost)
+    base = perturbed_pekeris_batch(INV_TONALS_3, REC_Z_21, rng.uniform(200.0, 230.0, 200), rng.uniform(1600.0, 1700.0, 200))
     ref = pekeris_modes(INV_TONALS_3, REC_Z_21)
     K = synthetic_covariance(ref, 71.11, 1.07)
-    from bogp_b200.envbatch import EnvBatch
-    eb = EnvBatch(mode_sets, rng.uniform(0.5, 6.0, Cn), rng.uniform(10.0, 190.0, Cn), K)
-    setup_s = time.time() - t0
-    out = torch.empty(Cn, dtype=torch.float32, device="cuda")
-    call_ms, _ = timed(lambda: eb.bartlett(out=out), lib_timing=False)
-    print(json.dumps({"kernel": "envbatch_kernel (K1-ENV)", "case": f"configs[4]: {Cn} environments x 3 tonals x 21 receivers, Mmax={eb.Mmax}",
-                      "kernel_ms": call_ms, "cand_freq_per_s": Cn * 3 / (call_ms * 1e-3), "bytes_streamed": eb.bytes_streamed,
-                      "achieved_GBs": eb.bytes_streamed / (call_ms * 1e-3) / 1e9, "hbm_peak_GBs": HBM_GBS,
-                      "frac": eb.bytes_streamed / (call_ms * 1e-3) / 1e9 / HBM_GBS, "bound": "hbm", "host_setup_s": setup_s}), flush=True)
+    for Cn in (10_000, 40_000):
+        t0 = time.time()
+        mode_sets = [base[i % 200] for i in range(Cn)]      # 200 distinct environments tiled (host set-up cost)
+        eb = EnvBatch(mode_sets, rng.uniform(0.5, 6.0, Cn), rng.uniform(10.0, 190.0, Cn), K)
+        setup_s = time.time() - t0
+        out = torch.empty(Cn, dtype=torch.float32, device="cuda")
+        for name, env in (("envstream_kernel, 1 stage/warp", {"BOGP_ENV_STAGES": "1"}),
+                          ("envstream_kernel, 2 stages/warp", {"BOGP_ENV_STAGES": "2"}),
+                          ("envbatch_kernel (SIMT loads)", {"BOGP_ENV_SIMT": "1"})):
+            for k in ("BOGP_ENV_STAGES", "BOGP_ENV_SIMT"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            call_ms, _ = timed(lambda: eb.bartlett(out=out), lib_timing=False)
+            print(json.dumps({"kernel": f"K1-ENV {name}", "case": f"configs[4]: {Cn} environments x 3 tonals x 21 receivers, Mmax={eb.Mmax}",
+                              "kernel_ms": call_ms, "cand_freq_per_s": Cn * 3 / (call_ms * 1e-3), "bytes_streamed": eb.bytes_streamed,
+                              "achieved_GBs": eb.bytes_streamed / (call_ms * 1e-3) / 1e9, "hbm_peak_GBs": HBM_GBS,
+                              "frac": eb.bytes_streamed / (call_ms * 1e-3) / 1e9 / HBM_GBS, "bound": "hbm", "host_setup_s": setup_s}), flush=True)
+        for k in ("BOGP_ENV_STAGES", "BOGP_ENV_SIMT"):
+            os.environ.pop(k, None)
+        eb.close()
 
 
 if __name__ == "__main__":
