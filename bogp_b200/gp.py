@@ -10,8 +10,8 @@ Mirrors what the reference uses from BoTorch/GPyTorch (all external to ref/, SUR
   (ref/projects/swellex96_localization/data/demo_1d.py:141; gpmodels.py:27-30).
 
 All posterior arithmetic is float64 on the GPU (``bogp_gp_posterior*``); the n x n factorisation happens once per
-hyper-parameter setting inside ``bogp_gp_create``.  The hyper-parameter fit (a "next" row) runs
-as torch float64 ops on the device the training data lives on.
+hyper-parameter setting inside ``bogp_gp_create``.  The hyper-parameter fit is one launch of the
+persistent fit kernel ``bogp_gp_fit_adamw`` (all AdamW steps on the device).
 """
 from __future__ import annotations
 
@@ -248,13 +248,43 @@ def _gamma_logpdf(x, conc, rate):
     return conc * math.log(rate) - math.lgamma(conc) + (conc - 1.0) * torch.log(x) - rate * x
 
 
-def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), device=None) -> SingleTaskGP:
-    """The fit loop of ei.py:69-78: AdamW over the raw (unconstrained) parameters, initialised at 0.
+def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), raw_init: Optional[np.ndarray] = None,
+                 return_loss: bool = False):
+    """The fit loop of ei.py:69-78 -- ``steps`` x AdamW over the raw (unconstrained) parameters, initialised at 0 --
+    as ONE launch of the persistent fit kernel (``bogp_gp_fit_adamw``: kernel matrix, blocked Cholesky, K^-1,
+    analytic gradient of ``-ExactMarginalLogLikelihood = -(log N(y | m, K + s2 I) + sum log-priors)/n`` and the
+    AdamW update all on the device, float64).
 
-    ``-ExactMarginalLogLikelihood = -(log N(y | m, K + s2 I) + sum log-priors)/n``.  Runs as torch float64 ops on
-    ``device`` (default: the current CUDA device).  SURVEY 8(f) item 2: a hand-written batched Cholesky
-    forward/backward is the next row; this is the library-call stand-in until then.
+    ``raw_init[B, d+3]`` (raw lengthscale[d], outputscale, noise, mean) runs B independent fits concurrently and keeps
+    the one with the lowest final loss.  ``return_loss`` also returns the loss history ``[B, steps]``.
     """
+    _cuda_device()
+    X = np.ascontiguousarray(model.train_X.cpu().numpy(), dtype=np.float64)
+    y = np.ascontiguousarray(model.train_Y.cpu().numpy(), dtype=np.float64)
+    n, d = X.shape
+    raw = np.zeros((1, d + 3)) if raw_init is None else np.array(raw_init, dtype=np.float64).reshape(-1, d + 3)
+    raw = np.ascontiguousarray(raw)
+    B = raw.shape[0]
+    loss = np.zeros((B, cfg.steps))
+    lsp = None if cfg.lengthscale_prior is None else np.array(cfg.lengthscale_prior, dtype=np.float64)
+    osp = None if cfg.outputscale_prior is None else np.array(cfg.outputscale_prior, dtype=np.float64)
+    lo, hi = cfg.noise_bounds
+    _lib.call("bogp_gp_fit_adamw", n, d, _lib.dptr(X), _lib.dptr(y), _lib.KERNEL[model.kind], int(cfg.steps),
+              float(cfg.lr), float(cfg.weight_decay), float(lo), float(hi), _lib.dptr(lsp), _lib.dptr(osp), B,
+              _lib.dptr(raw), _lib.dptr(loss), C.c_void_p(_lib.current_stream_ptr()))
+    best = int(np.argmin(loss[:, -1])) if B > 1 else 0
+    r = raw[best]
+    sp = lambda v: np.where(v > 20.0, v, np.log1p(np.exp(np.minimum(v, 20.0))))     # noqa: E731
+    model.noise_bounds = (lo, hi)
+    model.set_hyperparameters(lengthscale=torch.as_tensor(sp(r[:d])), outputscale=float(sp(r[d])),
+                              mean=float(r[d + 2]), noise=float(lo + (hi - lo) / (1.0 + math.exp(-r[d + 1]))))
+    model.raw_parameters = r.copy()
+    return (model, loss) if return_loss else model
+
+
+def fit_gp_adamw_torch(model: SingleTaskGP, cfg: FitConfig = FitConfig(), device=None) -> SingleTaskGP:
+    """The same loop as torch float64 ops with autograd (cuSOLVER Cholesky per step): kept as the timing comparison
+    for the fused kernel (tools/bench_paths.py fit); not used by :meth:`SingleTaskGP.fit`."""
     dev = _cuda_device() if device is None else torch.device(device)
     X = model.train_X.to(dev)
     y = model.train_Y.to(dev)

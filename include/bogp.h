@@ -171,6 +171,19 @@ int bogp_gp_posterior_joint_backward(bogp_gp_t g, const double* Xs_dev, long lon
 int bogp_gp_qei(bogp_gp_t g, const double* Xs_dev, long long b, int q, const double* base_dev, int S,
                 double best_f, double* out_dev, double* grad_dev, void* stream);
 
+/* GP hyper-parameter fit: the loop of ref/projects/swellex96_inv/data/bo/ei.py:69-78 --
+ * `steps` x AdamW(lr, weight_decay; betas 0.9/0.999, eps 1e-8 as torch.optim.AdamW) on -mll/n over the raw GPyTorch
+ * parameters -- as ONE persistent kernel launch per call (kernel matrix, blocked Cholesky, K^-1, analytic gradient and
+ * the AdamW update all on the device, float64).  raw_inout_host[B][d+3] = raw {lengthscale[d], outputscale, noise,
+ * mean}: lengthscale = softplus(raw), outputscale = softplus(raw), noise = lo + (hi-lo) sigmoid(raw) (the
+ * Interval(lo, hi) constraint of ei.py:66), mean = raw.  B independent starting points run as B concurrent CTAs.
+ * lengthscale_prior / outputscale_prior: Gamma {concentration, rate} or NULL.  loss_host[B][steps] (optional):
+ * -mll/n before each update.  Returns BOGP_ERR_NUMERIC if K + noise I stays indefinite after jitter 1e-6. */
+int bogp_gp_fit_adamw(int n, int d, const double* X_host, const double* y_host, int kernel_kind, int steps,
+                      double lr, double weight_decay, double noise_lo, double noise_hi,
+                      const double* lengthscale_prior, const double* outputscale_prior, int B,
+                      double* raw_inout_host, double* loss_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

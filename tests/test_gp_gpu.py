@@ -179,3 +179,58 @@ def test_gp_edge_cases():
     assert np.isfinite(dup.posterior(torch.rand(5, 1, 2, dtype=torch.float64)).mean.cpu().numpy()).all()
     with pytest.raises(_lib.BogpError):
         SingleTaskGP(np.zeros((1100, 2)), np.zeros(1100)).handle()          # n above the kernel's limit
+
+
+@pytest.mark.parametrize("n,d,kind", [(24, 1, "matern52"), (64, 2, "matern52"), (100, 3, "rbf"), (144, 7, "matern52"),
+                                      (200, 2, "matern52")])
+def test_fused_fit_kernel_matches_oracle_adamw(n, d, kind):
+    """the one-launch fit (ei.py:69-78) against the oracle's torch-autograd AdamW loop, float64 both.
+    n <= ~150 keeps the matrix in shared memory, n = 200 exercises the L2-resident scratch path."""
+    from bogp_b200.gp import FitConfig, SingleTaskGP, fit_gp_adamw, fit_gp_adamw_torch
+    _, _, X, y = make_problem(n, d, kind)
+    steps = 60
+    cfg_o = ogp.FitConfig(kind=kind, steps=steps)
+    # loss history of the oracle loop
+    Xt, yt = torch.as_tensor(X), torch.as_tensor(y)
+    raw = {"lengthscale": torch.zeros(d, dtype=torch.float64, requires_grad=True),
+           "outputscale": torch.zeros((), dtype=torch.float64, requires_grad=True),
+           "noise": torch.zeros((), dtype=torch.float64, requires_grad=True),
+           "mean": torch.zeros((), dtype=torch.float64, requires_grad=True)}
+    opt = torch.optim.AdamW(list(raw.values()), lr=cfg_o.lr, weight_decay=cfg_o.weight_decay)
+    hist = []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = ogp.neg_mll(raw, Xt, yt, cfg_o)
+        loss.backward()
+        opt.step()
+        hist.append(float(loss))
+    ref = ogp.fit_adamw(X, y, cfg_o)
+    model, loss_hist = fit_gp_adamw(SingleTaskGP(X, y, kind), FitConfig(steps=steps), return_loss=True)
+    np.testing.assert_allclose(loss_hist[0], hist, rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(model.lengthscale.numpy(), ref.lengthscale.numpy(), rtol=1e-6)
+    assert model.outputscale == pytest.approx(ref.outputscale, rel=1e-6)
+    assert model.noise == pytest.approx(ref.noise, rel=1e-6)
+    assert model.mean_const == pytest.approx(ref.mean, rel=1e-5, abs=1e-9)
+    if n == 64:
+        # the torch/cuSOLVER loop kept for timing comparison agrees too, and a batch of starts keeps the best one
+        t = fit_gp_adamw_torch(SingleTaskGP(X, y, kind), FitConfig(steps=steps))
+        np.testing.assert_allclose(model.lengthscale.numpy(), t.lengthscale.numpy(), rtol=1e-6)
+        init = np.zeros((3, d + 3)); init[1, :d] = 1.0; init[2, :d] = -1.0
+        mb, lb = fit_gp_adamw(SingleTaskGP(X, y, kind), FitConfig(steps=steps), raw_init=init, return_loss=True)
+        np.testing.assert_allclose(lb[0], loss_hist[0], rtol=1e-12)
+        assert lb.shape == (3, steps) and lb[:, -1].min() == pytest.approx(
+            float(ogp.neg_mll({k: torch.as_tensor(v) for k, v in zip(("lengthscale", "outputscale", "noise", "mean"),
+                                                                  (mb.raw_parameters[:d], mb.raw_parameters[d],
+                                                                   mb.raw_parameters[d + 1], mb.raw_parameters[d + 2]))},
+                              Xt, yt, cfg_o)), rel=0.05)
+
+
+def test_fused_fit_kernel_jitter_and_errors():
+    from bogp_b200 import _lib
+    from bogp_b200.gp import FitConfig, SingleTaskGP, fit_gp_adamw
+    _, _, X, y = make_problem(30, 2)
+    Xd, yd = np.concatenate([X, X]), np.concatenate([y, y])       # duplicated rows: singular K up to the noise floor
+    m = fit_gp_adamw(SingleTaskGP(Xd, yd), FitConfig(steps=20, noise_bounds=(1e-14, 1e-13)))
+    assert np.isfinite(m.lengthscale.numpy()).all() and m.outputscale > 0
+    with pytest.raises(_lib.BogpError):
+        fit_gp_adamw(SingleTaskGP(X, y), FitConfig(steps=0))
