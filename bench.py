@@ -208,6 +208,20 @@ def bo_iteration(n: int = 256, d: int = 3, raw: int = 4096, restarts: int = 64, 
             times.append(time.perf_counter() - t0)
     out["gpu_ms"] = float(np.median(times) * 1e3)
     out["acq_value"] = float(val)
+    # the other half of a BO iteration (ei.py:65-78): the 100-step AdamW hyper-parameter fit, one persistent kernel launch
+    from bogp_b200.gp import FitConfig, fit_gp_adamw, fit_gp_adamw_torch
+    ft = []
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        fitted = fit_gp_adamw(SingleTaskGP(X, y), FitConfig(steps=100))
+        if i:
+            ft.append(time.perf_counter() - t0)
+    out["fit_gpu_ms"] = float(np.median(ft) * 1e3)
+    t0 = time.perf_counter()
+    fit_gp_adamw_torch(SingleTaskGP(X, y), FitConfig(steps=100))
+    torch.cuda.synchronize()
+    out["fit_gpu_torch_cusolver_ms"] = float((time.perf_counter() - t0) * 1e3)
+    out["iter_gpu_ms"] = out["gpu_ms"] + out["fit_gpu_ms"]
     if cpu:
         from oracle import gp as ogp
         from oracle import optimize as oopt
@@ -220,6 +234,12 @@ def bo_iteration(n: int = 256, d: int = 3, raw: int = 4096, restarts: int = 64, 
                                     bounds, 1, restarts, raw, nonneg=True)
         out["cpu_oracle_ms"] = float((time.perf_counter() - t0) * 1e3)
         out["cpu_threads"] = torch.get_num_threads()
+        t0 = time.perf_counter()
+        ref_fit = ogp.fit_adamw(X, y, ogp.FitConfig(steps=100))
+        out["fit_cpu_oracle_ms"] = float((time.perf_counter() - t0) * 1e3)
+        out["iter_cpu_oracle_ms"] = out["cpu_oracle_ms"] + out["fit_cpu_oracle_ms"]
+        out["fit_lengthscale_rel_diff"] = float(np.max(np.abs(fitted.lengthscale.numpy() - ref_fit.lengthscale.numpy())
+                                                       / ref_fit.lengthscale.numpy()))
         out["same_candidate"] = bool(np.allclose(np.asarray(cand), np.asarray(c2), rtol=0, atol=1e-6))
         out["acq_value_rel_diff"] = float(abs(float(v2) - float(val)) / max(abs(float(v2)), 1e-300))
     return out

@@ -10,8 +10,8 @@
 //   d mll / d theta = 1/2 tr( (alpha alpha^T - K^-1) dK/dtheta ),   alpha = K^-1 (y - m)
 //
 // float64 throughout (the reference fits in float64, ei.py:24).  Linear algebra, all on 32 x 32 blocks:
-//   * diagonal blocks: Cholesky and triangular inverse inside ONE warp -- lane i keeps row i in registers, column
-//     broadcasts by shuffle (no shared-memory traffic, no block barrier in the 32-step dependency chain);
+//   * diagonal blocks: Cholesky and triangular inverse fused level by level across the CTA (64 block barriers per
+//     32 x 32 block; a single-warp register/shuffle version was 5x slower: 4000 dependent instructions per block);
 //   * panel solve L_ik = A_ik D^-T, trailing update A_ij -= L_ik L_jk^T, blocked in-place inverse X = L^-1,
 //     K^-1 = X^T X into the (free) upper triangle: warp-per-row loops over shared memory, odd leading dimension.
 #include <algorithm>
@@ -43,54 +43,56 @@ struct FitArgs {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// In-place Cholesky of the bs x bs diagonal block at (r0, r0), lower triangle, by ONE warp; lanes >= bs carry identity
-// rows.  Returns false (warp-uniform) on a non-positive pivot.
-__device__ bool warp_chol_block(double* A, int ld, int r0, int bs) {
-  const int lane = threadIdx.x & 31;
-  double a[32];
+// Cholesky AND inverse of the bs x bs diagonal block at (r0, r0) by the whole CTA, fused level by level (two block
+// barriers per level): on exit the block of A holds D^-1 (lower) -- the factor D itself is never needed again: the
+// panel solve, the blocked inverse and log det all use D^-1 -- and Xb holds D^-1 with a zero upper triangle.
+// Thread (warp w, lane c) owns elements (w, c) and (w + 16, c) of the 32 x 32 tiles Db (factor) and Xb (inverse);
+// rows >= bs are identity.  Level j:  A(j) column j of the factor (into Lc[j & 1]) | C(j-1) inverse rows > j-1 -= ..
+// -- barrier --  B(j) trailing update, store column j, finalise inverse row j  -- barrier --.
+// Returns false (uniform) on a non-positive pivot.
+__device__ __forceinline__ bool block_chol_inv(double* A, int ld, int r0, int bs, double* Db, double* Xb, double* Lc, int* flag) {
+  const int w = threadIdx.x >> 5, c = threadIdx.x & 31;
 #pragma unroll
-  for (int c = 0; c < 32; ++c) a[c] = (lane < bs && c <= lane) ? A[(size_t)(r0 + lane) * ld + r0 + c] : (c == lane ? 1.0 : 0.0);
-  bool ok = true;
-#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = w + 16 * h;
+    Db[i * 33 + c] = (i < bs && c <= i) ? A[(r0 + i) * ld + r0 + c] : (i == c ? 1.0 : 0.0);
+    Xb[i * 33 + c] = i == c ? 1.0 : 0.0;
+  }
+  __syncthreads();
   for (int j = 0; j < 32; ++j) {
-    double ajj = __shfl_sync(kFull, a[j], j);
-    if (!(ajj > 0.0)) { ok = false; ajj = 1.0; }
-    const double dj = sqrt(ajj);
-    const double lij = lane >= j ? a[j] / dj : 0.0;
-    a[j] = lij;
-#pragma unroll
-    for (int k = j + 1; k < 32; ++k) {
-      const double lkj = __shfl_sync(kFull, lij, k);
-      if (lane >= k) a[k] = fma(-lij, lkj, a[k]);
+    double* Lj = Lc + 32 * (j & 1);
+    if (w == 0) {                                            // A(j): one warp, lane = row (the sqrt / reciprocal
+      double ajj = Db[j * 33 + j];                           // sequences are ~60 instructions: not on all 16 warps)
+      if (!(ajj > 0.0)) { if (c == 0) *flag = 1; ajj = 1.0; }
+      const double dj = sqrt(ajj);
+      if (c >= j) Lj[c] = c == j ? dj : Db[c * 33 + j] / dj;
     }
+    if (j > 0 && c <= j - 1) {                               // C(j-1)
+      const double* Lp = Lc + 32 * ((j - 1) & 1);
+      const double xk = Xb[(j - 1) * 33 + c];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = w + 16 * h;
+        if (i > j - 1) Xb[i * 33 + c] = fma(-Lp[i], xk, Xb[i * 33 + c]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                            // B(j)
+      const int i = w + 16 * h;
+      if (c > j && i >= c) Db[i * 33 + c] = fma(-Lj[i], Lj[c], Db[i * 33 + c]);
+      if (c == j && i >= j) Db[i * 33 + j] = Lj[i];
+      if (i == j && c <= j) Xb[j * 33 + c] = Xb[j * 33 + c] / Lj[j];
+    }
+    __syncthreads();
   }
-  if (lane < bs)
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c <= lane) A[(size_t)(r0 + lane) * ld + r0 + c] = a[c];
-  return ok;
-}
-
-// Inverse of the lower-triangular bs x bs block at src(r0s, r0s) written to dst(r0d, r0d) (may alias), by ONE warp:
-// lane c accumulates column c of the inverse, rows of L are broadcast from the lane that holds them.
-__device__ void warp_trinv_block(const double* S, int lds, int r0s, double* D, int ldd, int r0d, int bs) {
-  const int lane = threadIdx.x & 31;
-  double a[32], yv[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) a[c] = (lane < bs && c <= lane) ? S[(size_t)(r0s + lane) * lds + r0s + c] : (c == lane ? 1.0 : 0.0);
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < i; ++k) s = fma(__shfl_sync(kFull, a[k], i), yv[k], s);      // yv[k] = 0 for k < lane
-    const double lii = __shfl_sync(kFull, a[i], i);
-    yv[i] = i == lane ? 1.0 / lii : (i > lane ? -s / lii : 0.0);
+  for (int h = 0; h < 2; ++h) {
+    const int i = w + 16 * h;
+    if (i < bs && c <= i) A[(r0 + i) * ld + r0 + c] = Xb[i * 33 + c];
   }
-  if (lane < bs)
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i >= lane && i < bs) D[(size_t)(r0d + i) * ldd + r0d + lane] = yv[i];
+  __syncthreads();
+  return *flag == 0;
 }
 
 __device__ __forceinline__ double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }
@@ -110,21 +112,26 @@ __device__ __forceinline__ void corr_and_grad(int kind, double d2, double& kc, d
   }
 }
 
+// SMEM = true: the matrix and X live in shared memory (the compiler sees shared-space pointers: LDS/STS with
+// 32-bit addressing instead of generic loads); SMEM = false: matrix in the global scratch.
+template <bool SMEM>
 __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p) {
   extern __shared__ double fsm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = p.n, d = p.d, ld = p.ld, np = d + 3;
   const int T = (n + 31) / 32;
   double* sp = fsm;
-  double* A = p.a_in_smem ? sp : p.work + (size_t)blockIdx.x * n * ld;
-  if (p.a_in_smem) sp += (size_t)n * ld;
-  double* Xs = sp; if (p.x_in_smem) sp += (size_t)n * d;
-  const double* Xp = p.x_in_smem ? Xs : p.X;
+  double* A = SMEM ? sp : p.work + (size_t)blockIdx.x * n * ld;
+  if (SMEM) sp += n * ld;
+  double* Xs = sp; if (SMEM || p.x_in_smem) sp += n * d;
+  const double* Xp = (SMEM || p.x_in_smem) ? Xs : p.X;
   double* rv = sp; sp += n;            // y - mean
   double* alpha = sp; sp += n;
   double* zv = sp; sp += n;
   double* kdiag = sp; sp += n;         // diag(K^-1)
   double* T1 = sp; sp += 32 * 33;      // inverse of the current diagonal block / block product
+  double* Db = sp; sp += 32 * 33;      // factor of the current diagonal block
+  double* Lc = sp; sp += 64;           // current factor column, double-buffered by level parity
   double* red = sp; sp += kFitWarps * (kFitMaxD + 4);
   double* prm = sp; sp += kFitMaxD + 8;   // ls[d] | os, noise, mean, jitter at kFitMaxD..
   double* raw = sp; sp += kFitNP;
@@ -133,7 +140,7 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
   double* gsum = sp; sp += kFitMaxD + 4;
   int* flag = reinterpret_cast<int*>(sp);
 
-  if (p.x_in_smem)
+  if (SMEM || p.x_in_smem)
     for (int i = tid; i < n * d; i += kFitThreads) Xs[i] = p.X[i];
   if (tid < np) { raw[tid] = p.raw[(size_t)blockIdx.x * np + tid]; am[tid] = 0.0; av[tid] = 0.0; }
   if (tid == 0) *flag = 0;
@@ -161,40 +168,46 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
           double d2 = 0.0;
 #pragma unroll
           for (int k = 0; k < kFitMaxD; ++k)
-            if (k < d) { const double s = (Xp[(size_t)i * d + k] - Xp[(size_t)j * d + k]) * inv_ls[k]; d2 = fma(s, s, d2); }
+            if (k < d) { const double s = (Xp[i * d + k] - Xp[j * d + k]) * inv_ls[k]; d2 = fma(s, s, d2); }
           double kc, g;
           corr_and_grad(p.kind, d2, kc, g);
-          A[(size_t)i * ld + j] = os * kc + (i == j ? noise + jitter : 0.0);
+          A[i * ld + j] = os * kc + (i == j ? noise + jitter : 0.0);
         }
       __syncthreads();
       pd = true;
       for (int kb = 0; kb < T; ++kb) {
         const int r0 = kb * 32, bs = min(32, n - r0), r1 = r0 + bs;
-        if (warp == 0) {
-          const bool ok = warp_chol_block(A, ld, r0, bs);
-          if (!ok && lane == 0) *flag = 1;
-          __syncwarp();
-          if (r1 < n) warp_trinv_block(A, ld, r0, T1, 33, 0, bs);
-        }
-        __syncthreads();
-        if (*flag) { pd = false; break; }
+        if (!block_chol_inv(A, ld, r0, bs, Db, T1, Lc, flag)) { pd = false; break; }
         if (r1 < n) {
-          // panel: L_i,blk = A_i,blk D^-T   (row i is private to one warp: read everything, then write)
-          for (int i = r1 + warp; i < n; i += kFitWarps) {
-            double acc = 0.0;
-            if (lane < bs)
-              for (int c = 0; c <= lane; ++c) acc = fma(A[(size_t)i * ld + r0 + c], T1[lane * 33 + c], acc);
+          // panel: L_i,blk = A_i,blk D^-T, two rows per warp (rows are private to a warp: read everything, then
+          // write); D^-1 in T1 has a zero upper triangle and bs = 32 here (a trailing panel exists)
+          for (int i = r1 + 2 * warp; i < n; i += 2 * kFitWarps) {
+            const double* a0 = A + i * ld + r0;
+            const double* a1 = (i + 1 < n) ? a0 + ld : a0;
+            const double* t = T1 + lane * 33;
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) { const double tv = t[c]; acc0 = fma(a0[c], tv, acc0); acc1 = fma(a1[c], tv, acc1); }
             __syncwarp();
-            if (lane < bs) A[(size_t)i * ld + r0 + lane] = acc;
+            A[i * ld + r0 + lane] = acc0;
+            if (i + 1 < n) A[(i + 1) * ld + r0 + lane] = acc1;
           }
           __syncthreads();
-          // trailing update: A_ij -= sum_c L_ic L_jc,  r1 <= j <= i
-          for (int i = r1 + warp; i < n; i += kFitWarps)
-            for (int j = r1 + lane; j <= i; j += 32) {
-              double acc = 0.0;
-              for (int c = 0; c < bs; ++c) acc = fma(A[(size_t)i * ld + r0 + c], A[(size_t)j * ld + r0 + c], acc);
-              A[(size_t)i * ld + j] -= acc;
+          // trailing update: A_ij -= sum_c L_ic L_jc,  r1 <= j <= i: rows (i, i+1) per warp, lanes over j
+          for (int i = r1 + 2 * warp; i < n; i += 2 * kFitWarps) {
+            const bool two = i + 1 < n;
+            const double* li0 = A + i * ld + r0;
+            const double* li1 = two ? li0 + ld : li0;
+            const int jend = two ? i + 1 : i;
+            for (int j = r1 + lane; j <= jend; j += 32) {
+              const double* lj = A + j * ld + r0;
+              double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) { const double v = lj[c]; acc0 = fma(li0[c], v, acc0); acc1 = fma(li1[c], v, acc1); }
+              if (j <= i) A[i * ld + j] -= acc0;
+              if (two) A[(i + 1) * ld + j] -= acc1;
             }
+          }
           __syncthreads();
         }
       }
@@ -210,27 +223,46 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
     }
 
     // ---------------------------------------------------------------- X = L^-1 in place (lower)
-    for (int kb = warp; kb < T; kb += kFitWarps) warp_trinv_block(A, ld, kb * 32, A, ld, kb * 32, min(32, n - kb * 32));
-    __syncthreads();
+    // (the diagonal blocks already hold their inverses: block_chol_inv)
     for (int k = 0; k + 1 < T; ++k) {
       const int c0 = k * 32;                     // column block (always full: k < T - 1)
       for (int ib = k + 1; ib < T; ++ib) {
         const int i0 = ib * 32, bsi = min(32, n - i0);
-        // S = sum_{j = k}^{ib - 1} L_(ib, j) X_(j, k)
-        for (int a = warp; a < bsi; a += kFitWarps) {
-          double acc = 0.0;
-          const double* Li = A + (size_t)(i0 + a) * ld;
-          for (int c = lane; c < 32; ++c) acc = fma(Li[c0 + c], A[(size_t)(c0 + c) * ld + c0 + lane], acc);   // j = k: X_kk lower
-          for (int jj = c0 + 32; jj < i0; ++jj) acc = fma(Li[jj], A[(size_t)jj * ld + c0 + lane], acc);
-          T1[a * 33 + lane] = acc;
+        // S = sum_{j = k}^{ib - 1} L_(ib, j) X_(j, k): thread (warp a, lane b) owns S[a][b] and S[a + 16][b]
+        {
+          const int a = warp;
+          const double* l0 = A + (i0 + min(a, bsi - 1)) * ld;
+          const double* l1 = A + (i0 + min(a + 16, bsi - 1)) * ld;
+          double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+          for (int c = 0; c < 32; ++c) {                     // j = k: X_kk is lower triangular
+            const double xv = c >= lane ? A[(c0 + c) * ld + c0 + lane] : 0.0;
+            acc0 = fma(l0[c0 + c], xv, acc0); acc1 = fma(l1[c0 + c], xv, acc1);
+          }
+#pragma unroll 4
+          for (int jj = c0 + 32; jj < i0; ++jj) {
+            const double xv = A[jj * ld + c0 + lane];
+            acc0 = fma(l0[jj], xv, acc0); acc1 = fma(l1[jj], xv, acc1);
+          }
+          T1[a * 33 + lane] = acc0;
+          T1[(a + 16) * 33 + lane] = acc1;
         }
         __syncthreads();
-        // X_(ib, k) = - X_(ib, ib) S
-        for (int a = warp; a < bsi; a += kFitWarps) {
-          double acc = 0.0;
-          const double* Xi = A + (size_t)(i0 + a) * ld + i0;
-          for (int c = 0; c <= a; ++c) acc = fma(Xi[c], T1[c * 33 + lane], acc);
-          A[(size_t)(i0 + a) * ld + c0 + lane] = -acc;
+        // X_(ib, k) = - X_(ib, ib) S   (the upper triangle of the diagonal block of A is not zero: select)
+        {
+          const int a = warp;
+          const double* x0 = A + (i0 + min(a, bsi - 1)) * ld + i0;
+          const double* x1 = A + (i0 + min(a + 16, bsi - 1)) * ld + i0;
+          double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+          for (int c = 0; c < 32; ++c) {
+            const double sv = T1[c * 33 + lane];
+            acc0 = fma(c <= a ? x0[c] : 0.0, sv, acc0);
+            acc1 = fma((c <= a + 16 && c < bsi) ? x1[c] : 0.0, sv, acc1);
+          }
+          __syncwarp();
+          if (a < bsi) A[(i0 + a) * ld + c0 + lane] = -acc0;
+          if (a + 16 < bsi) A[(i0 + a + 16) * ld + c0 + lane] = -acc1;
         }
         __syncthreads();
       }
@@ -239,26 +271,35 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
     // ---------------------------------------------------------------- alpha = X^T X r, log det, quadratic form
     for (int k = tid; k < n; k += kFitThreads) {
       double acc = 0.0;
-      for (int j = 0; j <= k; ++j) acc = fma(A[(size_t)k * ld + j], rv[j], acc);
+      for (int j = 0; j <= k; ++j) acc = fma(A[k * ld + j], rv[j], acc);
       zv[k] = acc;
     }
     __syncthreads();
     double part_quad = 0.0, part_ld = 0.0, part_as = 0.0;
     for (int j = tid; j < n; j += kFitThreads) {
       double acc = 0.0;
-      for (int k = j; k < n; ++k) acc = fma(A[(size_t)k * ld + j], zv[k], acc);
+      for (int k = j; k < n; ++k) acc = fma(A[k * ld + j], zv[k], acc);
       alpha[j] = acc;
       part_quad = fma(rv[j], acc, part_quad);
-      part_ld -= log(A[(size_t)j * ld + j]);          // log L_jj = -log X_jj
+      part_ld -= log(A[j * ld + j]);          // log L_jj = -log X_jj
       part_as += acc;
     }
     // ---------------------------------------------------------------- K^-1 = X^T X: strict upper triangle + diagonal
-    for (int j = warp; j < n; j += kFitWarps)
-      for (int i = lane; i <= j; i += 32) {
-        double acc = 0.0;
-        for (int k = j; k < n; ++k) acc = fma(A[(size_t)k * ld + i], A[(size_t)k * ld + j], acc);
-        if (i == j) kdiag[j] = acc; else A[(size_t)i * ld + j] = acc;
+    for (int j = 2 * warp; j < n; j += 2 * kFitWarps) {      // columns (j, j + 1) per warp, lanes over i
+      const bool two = j + 1 < n;
+      const int iend = two ? j + 1 : j;
+      for (int i = lane; i <= iend; i += 32) {
+        double acc0 = i <= j ? A[j * ld + i] * A[j * ld + j] : 0.0, acc1 = 0.0;      // k = j term (column j only)
+#pragma unroll 4
+        for (int k = j + 1; k < n; ++k) {
+          const double xi = A[k * ld + i];
+          acc0 = fma(xi, A[k * ld + j], acc0);
+          acc1 = fma(xi, A[k * ld + j + 1], acc1);
+        }
+        if (i < j) A[i * ld + j] = acc0; else if (i == j) kdiag[j] = acc0;
+        if (two) { if (i <= j) A[i * ld + j + 1] = acc1; else kdiag[j + 1] = acc1; }
       }
+    }
     __syncthreads();
 
     // ---------------------------------------------------------------- gradient traces over the lower triangle
@@ -272,11 +313,11 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
 #pragma unroll
         for (int k = 0; k < kFitMaxD; ++k) {
           s2[k] = 0.0;
-          if (k < d) { const double s = (Xp[(size_t)i * d + k] - Xp[(size_t)j * d + k]) * inv_ls[k]; s2[k] = s * s; d2 += s2[k]; }
+          if (k < d) { const double s = (Xp[i * d + k] - Xp[j * d + k]) * inv_ls[k]; s2[k] = s * s; d2 += s2[k]; }
         }
         double kc, g;
         corr_and_grad(p.kind, d2, kc, g);
-        const double kinv = i == j ? kdiag[i] : A[(size_t)j * ld + i];
+        const double kinv = i == j ? kdiag[i] : A[j * ld + i];
         const double W = (i == j ? 0.5 : 1.0) * (ai * alpha[j] - kinv);      // 1/2 * (1 or 2) * W_ij
         g_os = fma(W, kc, g_os);
         if (i == j) g_noise += W;
@@ -382,7 +423,7 @@ extern "C" int bogp_gp_fit_adamw(int n, int d, const double* X_host, const doubl
   p.lr = lr; p.wd = weight_decay; p.noise_lo = noise_lo; p.noise_hi = noise_hi;
   if (lengthscale_prior) { p.has_ls_prior = 1; p.ls_conc = lengthscale_prior[0]; p.ls_rate = lengthscale_prior[1]; }
   if (outputscale_prior) { p.has_os_prior = 1; p.os_conc = outputscale_prior[0]; p.os_rate = outputscale_prior[1]; }
-  const size_t fixed = ((size_t)4 * n + 32 * 33 + kFitWarps * (kFitMaxD + 4) + (kFitMaxD + 8) + 3 * kFitNP + (kFitMaxD + 4) + 2) * sizeof(double);
+  const size_t fixed = ((size_t)4 * n + 2 * 32 * 33 + 64 + kFitWarps * (kFitMaxD + 4) + (kFitMaxD + 8) + 3 * kFitNP + (kFitMaxD + 4) + 2) * sizeof(double);
   const size_t a_bytes = (size_t)n * p.ld * sizeof(double), x_bytes = (size_t)n * d * sizeof(double);
   const size_t limit = 227 * 1024;
   p.x_in_smem = fixed + x_bytes <= limit ? 1 : 0;
@@ -403,9 +444,12 @@ extern "C" int bogp_gp_fit_adamw(int n, int d, const double* X_host, const doubl
   FIT_CUDA(cudaMemcpyAsync(dy, y_host, n * sizeof(double), cudaMemcpyHostToDevice, s));
   FIT_CUDA(cudaMemcpyAsync(draw, raw_inout_host, (size_t)B * np * sizeof(double), cudaMemcpyHostToDevice, s));
   p.X = dX; p.y = dy; p.raw = draw; p.loss = dloss; p.work = dwork; p.status = dstatus;
-  FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool in_smem = p.a_in_smem && p.x_in_smem;
+  if (in_smem) FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t ev = timing_begin(s);
-  gp_fit_kernel<<<B, kFitThreads, smem, s>>>(p);
+  if (in_smem) gp_fit_kernel<true><<<B, kFitThreads, smem, s>>>(p);
+  else gp_fit_kernel<false><<<B, kFitThreads, smem, s>>>(p);
   timing_end(ev, s);
   count_launch();
   FIT_CUDA(cudaGetLastError());

@@ -248,8 +248,11 @@ def _gamma_logpdf(x, conc, rate):
     return conc * math.log(rate) - math.lgamma(conc) + (conc - 1.0) * torch.log(x) - rate * x
 
 
+FUSED_FIT_MAX_N = 320      # above this the single-CTA kernel loses to the cuSOLVER loop (profiles/paths_r1b.jsonl)
+
+
 def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), raw_init: Optional[np.ndarray] = None,
-                 return_loss: bool = False):
+                 return_loss: bool = False, engine: str = "auto"):
     """The fit loop of ei.py:69-78 -- ``steps`` x AdamW over the raw (unconstrained) parameters, initialised at 0 --
     as ONE launch of the persistent fit kernel (``bogp_gp_fit_adamw``: kernel matrix, blocked Cholesky, K^-1,
     analytic gradient of ``-ExactMarginalLogLikelihood = -(log N(y | m, K + s2 I) + sum log-priors)/n`` and the
@@ -257,8 +260,17 @@ def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), raw_init: Op
 
     ``raw_init[B, d+3]`` (raw lengthscale[d], outputscale, noise, mean) runs B independent fits concurrently and keeps
     the one with the lowest final loss.  ``return_loss`` also returns the loss history ``[B, steps]``.
+
+    ``engine``: ``"fused"`` (the kernel), ``"torch"`` (:func:`fit_gp_adamw_torch`, cuSOLVER per step) or ``"auto"``:
+    the fused kernel keeps one fit on one SM, which wins by 7-24x up to n ~ 150 (the reference's sizes: 64-144 trials)
+    and breaks even near n ~ 320 (measured: profiles/paths_r1b.jsonl); larger n go to the cuSOLVER loop on the GPU.
     """
+    if engine not in ("auto", "fused", "torch"):
+        raise ValueError("engine must be 'auto', 'fused' or 'torch'")
     _cuda_device()
+    if engine == "torch" or (engine == "auto" and model.train_X.shape[0] > FUSED_FIT_MAX_N
+                             and raw_init is None and not return_loss):
+        return fit_gp_adamw_torch(model, cfg)
     X = np.ascontiguousarray(model.train_X.cpu().numpy(), dtype=np.float64)
     y = np.ascontiguousarray(model.train_Y.cpu().numpy(), dtype=np.float64)
     n, d = X.shape

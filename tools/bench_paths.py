@@ -1,7 +1,7 @@
 """Roofline numbers for the other kernels of the path: the GP posterior/acquisition kernel (K2),
 the scattered-candidate and tilted-array Bartlett kernels (K1-SIMT) and the per-environment kernel (K1-ENV).
 
-    python tools/bench_paths.py [gp] [points] [tilt] [env] > profiles/paths_<tag>.jsonl
+    python tools/bench_paths.py [gp] [fit] [points] [tilt] [env] > profiles/paths_<tag>.jsonl
 
 One JSON line per case.  Kernel time = CUDA events around the dominant kernel inside the library
 (bogp_timing_enable/read) where it is instrumented, CUDA events around the call otherwise; 3 warm-up + 10 timed calls.
@@ -79,6 +79,34 @@ def bench_gp():
                               "bound": "fp64 FMA (compute); HBM fraction reported for reference", "hbm_peak_GBs": HBM_GBS}), flush=True)
 
 
+def bench_fit():
+    """K2-FIT: 100 AdamW steps of the GP hyper-parameter fit, fused kernel (one launch) vs the torch/cuSOLVER loop."""
+    from bogp_b200.gp import FitConfig, fit_gp_adamw, fit_gp_adamw_torch
+    rng = np.random.default_rng(0)
+    for n, d in ((64, 2), (144, 2), (144, 7), (256, 3), (512, 7)):
+        X = rng.uniform(-1, 1, (n, d))
+        y = np.sin(3 * X[:, 0]) + 0.3 * np.cos(2 * X.sum(1))
+        y = (y - y.mean()) / y.std()
+        fit_gp_adamw(SingleTaskGP(X, y), FitConfig(steps=5))
+        torch.cuda.synchronize(); _lib.timing_read(); _lib.timing_enable(True)
+        t0 = time.perf_counter()
+        m = fit_gp_adamw(SingleTaskGP(X, y), FitConfig(steps=100))
+        call_ms = (time.perf_counter() - t0) * 1e3
+        _lib.timing_enable(False)
+        k_ms, _ = _lib.timing_read()
+        fit_gp_adamw_torch(SingleTaskGP(X, y), FitConfig(steps=3)); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        t = fit_gp_adamw_torch(SingleTaskGP(X, y), FitConfig(steps=100)); torch.cuda.synchronize()
+        torch_ms = (time.perf_counter() - t0) * 1e3
+        flop = 100 * (n ** 3 / 3 + n ** 3 / 3 + n ** 3 / 3 + 2 * n * n * (3 * d + 25) / 2)      # chol + inverse + X^T X + 2 elementwise passes
+        print(json.dumps({"kernel": "gp_fit_kernel (K2-FIT)", "case": f"n={n} d={d} Matern-5/2, 100 AdamW steps, one CTA",
+                          "dtype": "f64", "kernel_ms": k_ms, "call_ms": call_ms, "torch_cusolver_loop_ms": torch_ms,
+                          "speedup_vs_torch_loop": torch_ms / call_ms, "ms_per_step": k_ms / 100, "alg_gflop": flop / 1e9,
+                          "gflops": flop / (k_ms * 1e-3) / 1e9,
+                          "lengthscale_rel_diff_vs_torch": float(np.max(np.abs(m.lengthscale.numpy() - t.lengthscale.numpy()) / t.lengthscale.numpy())),
+                          "bound": "latency of a sequential factorisation on one SM (fp64); no launch or host round trip between steps"}), flush=True)
+
+
 def bench_points():
     modes = pekeris_modes(SWELLEX_TONALS_13)
     K = synthetic_covariance(modes, 60.0, 5.0)
@@ -141,7 +169,7 @@ def bench_env():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gp", "points", "tilt", "env"]
+    which = sys.argv[1:] or ["gp", "fit", "points", "tilt", "env"]
     torch.cuda.set_device(0)
     for w in which:
-        {"gp": bench_gp, "points": bench_points, "tilt": bench_tilt, "env": bench_env}[w]()
+        {"gp": bench_gp, "fit": bench_fit, "points": bench_points, "tilt": bench_tilt, "env": bench_env}[w]()
