@@ -278,8 +278,7 @@ def run_ours(args) -> None:
     host_surf_np = host_surf.numpy()
 
     def step_device():
-        dms.bartlett_grid(r, z_slab, engine=args.engine, out=surf)
-        mfp.argext_device(surf, pair, scratch, maximize=True)
+        dms.bartlett_grid(r, z_slab, engine=args.engine, out=surf, argext=(pair, scratch, True))
         if world > 1:
             dist.all_gather_into_tensor(pairs.view(-1), pair)
 

@@ -39,6 +39,8 @@ SIGNATURES = {
     "bogp_modeset_info": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip]),
     "bogp_covariance_set": (C.c_int, [_vp, _dp, _dp]),
     "bogp_bartlett_grid": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "bogp_bartlett_grid_argext": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
+                                           C.c_int, _vp, _vp, _vp, _ll, _vp]),
     "bogp_bartlett_grid_host": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _vp]),
     "bogp_bartlett_grid_host_argmax": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 _fp, C.c_int, _fp, C.POINTER(_ll), _vp]),

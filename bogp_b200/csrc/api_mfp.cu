@@ -305,9 +305,11 @@ static int check_modes(int atype, int mf) {
   return 0;
 }
 
-extern "C" int bogp_bartlett_grid(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
-                                  const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
-                                  float* out_dev, void* stream) {
+// ext_mode 0: surface only.  1 / 2: arg-max / arg-min of the surface into (ext_val_dev, ext_idx_dev) as well -- inside the
+// tcgen05 kernel when that engine runs (no extra launch), by the two arg-ext kernels otherwise.
+static int grid_impl(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                     const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine, float* out_dev,
+                     void* stream, int ext_mode, float* ext_val_dev, long long* ext_idx_dev, void* ext_scratch) {
   BOGP_REQUIRE(h != nullptr, "bogp_bartlett_grid: NULL handle");
   BOGP_REQUIRE(h->has_cov, "bogp_bartlett_grid: call bogp_covariance_set first");
   BOGP_REQUIRE(Nr >= 0 && Nz >= 0 && Nt >= 1, "bogp_bartlett_grid: bad sizes Nr=%d Nz=%d Nt=%d", Nr, Nz, Nt);
@@ -324,11 +326,32 @@ extern "C" int bogp_bartlett_grid(bogp_modeset_t h, const double* r_m_host, int 
   if (engine == BOGP_ENGINE_UMMA) {
     BOGP_REQUIRE(!tilted && Nt == 1, "bogp_bartlett_grid: the UMMA engine covers the vertical-array grid only");
     if (!bogp::umma_supported(h)) { bogp::set_error("UMMA engine unsupported for this mode set / device"); return BOGP_ERR_UNSUPPORTED; }
-    return bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s);
   }
-  if (engine == BOGP_ENGINE_AUTO && !tilted && Nt == 1 && bogp::umma_supported(h) && (long long)Nr * Nz >= 16384)
-    return bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s);
-  return bogp::launch_grid_simt(h, r_m_host, Nr, z_host, Nz, tilted ? tilt_deg_host : nullptr, Nt, atype, mf_method, out_dev, s);
+  const bool fuse_ext = (long long)Nr * Nz < (1ll << 32);
+  int rc;
+  if (engine == BOGP_ENGINE_UMMA || (engine == BOGP_ENGINE_AUTO && !tilted && Nt == 1 && bogp::umma_supported(h) && (long long)Nr * Nz >= 16384)) {
+    rc = bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
+    if (rc || !ext_mode || fuse_ext) return rc;
+  } else {
+    rc = bogp::launch_grid_simt(h, r_m_host, Nr, z_host, Nz, tilted ? tilt_deg_host : nullptr, Nt, atype, mf_method, out_dev, s);
+    if (rc || !ext_mode) return rc;
+  }
+  return bogp_argext_f32_dev(out_dev, (long long)std::max(Nt, 1) * Nz * Nr, ext_mode == 1, ext_val_dev, ext_idx_dev, ext_scratch, 8192, stream);
+}
+
+extern "C" int bogp_bartlett_grid(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                                  const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                                  float* out_dev, void* stream) {
+  return grid_impl(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, out_dev, stream, 0, nullptr, nullptr, nullptr);
+}
+
+extern "C" int bogp_bartlett_grid_argext(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                                         const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                                         float* out_dev, int maximize, float* val_dev, long long* idx_dev,
+                                         void* scratch_dev, long long scratch_bytes, void* stream) {
+  BOGP_REQUIRE(val_dev && idx_dev && scratch_dev && scratch_bytes >= 8192, "bogp_bartlett_grid_argext: val/idx/scratch (>= 8192 bytes) required");
+  if ((long long)std::max(Nt, 1) * Nz * Nr == 0) return 0;
+  return grid_impl(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, out_dev, stream, maximize ? 1 : 2, val_dev, idx_dev, scratch_dev);
 }
 
 extern "C" int bogp_bartlett_grid_host(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
@@ -367,8 +390,8 @@ extern "C" int bogp_bartlett_grid_host_argmax(bogp_modeset_t h, const double* r_
   long long* idx_dev = reinterpret_cast<long long*>(base + off_pair);
   float* val_dev = reinterpret_cast<float*>(base + off_pair + 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  int rc = bogp_bartlett_grid(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, tmp, stream);
-  if (rc == 0) rc = bogp_argext_f32_dev(tmp, (long long)n, maximize, val_dev, idx_dev, base + off_pair + 16, 8192, stream);
+  int rc = bogp_bartlett_grid_argext(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, tmp,
+                                     maximize, val_dev, idx_dev, base + off_pair + 16, 8192, stream);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(out_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(idx_host, idx_dev, sizeof(long long), cudaMemcpyDeviceToHost, s);

@@ -132,8 +132,11 @@ int launch_points(const bogp_modeset_s* h, const double* cand_dev, long long C, 
 int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz,
                      const double* tilt_host, int Nt, int atype, int mf, float* out_dev, cudaStream_t s);
 // kernels_umma.cu
+// ext_mode 1 / 2: also write arg-max / arg-min (value, flat index) to ext_val_dev / ext_idx_dev from inside the kernel;
+// returns with ext_mode ignored (caller falls back to the arg-ext kernels) only when Nr * Nz >= 2^32.
 int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype,
-                     int mf, float* out_dev, cudaStream_t s);
+                     int mf, float* out_dev, cudaStream_t s, int ext_mode = 0, float* ext_val_dev = nullptr,
+                     long long* ext_idx_dev = nullptr);
 bool umma_supported(const bogp_modeset_s* h);
 int ensure_scratch(bogp_modeset_s* h, size_t bytes);
 }  // namespace bogp

@@ -76,6 +76,13 @@ struct UParams {
   float* out;
   int* err;
   long long* dbg;              // optional [grid][16] cycle counters (BOGP_UMMA_DBG=1): where each role waits
+  // fused arg-ext (collate.py:50): the epilogue folds every value it writes into a packed (ordered value, ~index) key
+  // with one atomicMax per warp and unit; the last CTA to finish decodes it.  ext_mode: 0 off, 1 arg-max, 2 arg-min.
+  int ext_mode;
+  unsigned long long* ext_key;
+  unsigned int* ext_done;
+  float* ext_val;
+  long long* ext_idx;
   int skip;                    // debug build only: 1 = issue no MMAs, 2 = epilogue releases without reading (bottleneck bracketing)
   UTonal t[BOGP_MAX_TONALS];
 };
@@ -327,7 +334,7 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
   __shared__ double2 kinv[128];       // k_m^-1/2
   __shared__ float phi_s[2][128];
   const int tid = threadIdx.x;
-  if (blockIdx.x == 0 && tid == 0) *p.err = 0;
+  if (blockIdx.x == 0 && tid == 0) { *p.err = 0; if (p.ext_mode) { *p.ext_key = 0ull; *p.ext_done = 0u; } }
   if ((int)blockIdx.x < nE) {
     // ------------------------------------------------------------------ E table
     const int per_f = p.nrt * (kTileR / kTabRows);
@@ -738,14 +745,48 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       const int i = rt * kTileR + tl;
       const float scale = p.mf == BOGP_MF_MEAN ? 1.f / (float)p.F : 1.f;
       const int k4 = ew >> 2;                  // this warp writes depths j = k4, k4 + kPerQuad, ...
+      unsigned long long best = 0ull;
       if (i < p.Nr)
-        for (int j = k4; j < nzu; j += kPerQuad) p.out[(size_t)(z0 + j) * p.Nr + i] = acc[(size_t)j * kTileR + tl] * scale;
+        for (int j = k4; j < nzu; j += kPerQuad) {
+          const float v = acc[(size_t)j * kTileR + tl] * scale;
+          p.out[(size_t)(z0 + j) * p.Nr + i] = v;
+          if (p.ext_mode && v == v) {
+            uint32_t u = __float_as_uint(v);
+            u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);            // order-preserving map float -> uint32
+            if (p.ext_mode == 2) u = ~u;                                // arg-min: largest key = smallest value
+            const unsigned long long key = ((unsigned long long)u << 32) | (0xffffffffu - ((uint32_t)(z0 + j) * (uint32_t)p.Nr + (uint32_t)i));
+            best = key > best ? key : best;                             // ties: lowest flat index (np.argmax rule)
+          }
+        }
+      if (p.ext_mode) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+          best = other > best ? other : best;
+        }
+        if (lane == 0 && best) atomicMax(p.ext_key, best);
+      }
       asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(kPerQuad * 32) : "memory");     // before the next unit overwrites acc
     }
     if (dbg && lane == 0 && (ew == 0 || ew == 4)) { dbg[8 + (ew >> 2) * 2] = clock64() - t_start; dbg[9 + (ew >> 2) * 2] = w_tfull; }
   }
   tc_fence_before();
   __syncthreads();
+  if (p.ext_mode && threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.ext_done, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const unsigned long long key = atomicMax(p.ext_key, 0ull);
+      if (key == 0ull) { *p.ext_val = 0.f; *p.ext_idx = -1; }
+      else {
+        uint32_t u = (uint32_t)(key >> 32);
+        if (p.ext_mode == 2) u = ~u;
+        u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+        *p.ext_val = __uint_as_float(u);
+        *p.ext_idx = (long long)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
+      }
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -821,7 +862,7 @@ bool umma_supported(const bogp_modeset_s* h) {
 }
 
 int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype, int mf,
-                     float* out_dev, cudaStream_t s) {
+                     float* out_dev, cudaStream_t s, int ext_mode, float* ext_val_dev, long long* ext_idx_dev) {
   const ModesetDev& d = h->dev;
   const int sms = device_sms();
   UParams p{};
@@ -845,6 +886,12 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   double* r_dev = reinterpret_cast<double*>(base + off_rz);
   double* z_dev = r_dev + Nr;
   p.err = reinterpret_cast<int*>(base + off_err);
+  if (ext_mode && (long long)Nr * Nz < (1ll << 32)) {
+    p.ext_mode = ext_mode;
+    p.ext_key = reinterpret_cast<unsigned long long*>(base + off_err + 16);
+    p.ext_done = reinterpret_cast<unsigned int*>(base + off_err + 32);
+    p.ext_val = ext_val_dev; p.ext_idx = ext_idx_dev;
+  }
   p.E = base + off_E; p.Bhi = base + off_Bhi; p.Blo = base + off_Blo;
   p.out = out_dev;
   const char* dbg_env = BOGP_UMMA_DBG ? std::getenv("BOGP_UMMA_DBG") : nullptr;

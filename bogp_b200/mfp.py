@@ -96,10 +96,13 @@ class DeviceModeSet:
     # ------------------------------------------------------------------ evaluation
     def bartlett_grid(self, r_km: ArrayLike, z: ArrayLike, tilt_deg: Optional[ArrayLike] = None, *,
                       atype: str = "cbf", multifreq_method: str = "mean", engine: str = "auto",
-                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, argext: Optional[tuple] = None) -> torch.Tensor:
         """Ambiguity surface ``[Nz, Nr]`` (or ``[Nt, Nz, Nr]`` with a tilt axis), float32 on the device.
 
-        Replaces the row loop of ref/projects/swellex96_localization/data/mfp.py:213-214.
+        Replaces the row loop of ref/projects/swellex96_localization/data/mfp.py:213-214.  ``argext=(pair, scratch,
+        maximize)`` also writes the extremum record of :func:`argext_device` (``pair`` int64[2], ``scratch`` >= 8192
+        bytes) -- inside the surface kernel when the tcgen05 engine runs, so the final reduction of collate.py:50 costs
+        no extra launch.
         """
         r_m = np.ascontiguousarray(1000.0 * np.atleast_1d(np.asarray(r_km, dtype=np.float64)))
         zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
@@ -110,6 +113,16 @@ class DeviceModeSet:
             out = torch.empty(shape, dtype=torch.float32, device=self.device)
         elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_cuda or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
+        if argext is not None:
+            pair, scratch, maximize = argext
+            if pair.dtype != torch.int64 or pair.numel() < 2 or not pair.is_cuda:
+                raise ValueError("argext pair must be an int64[2] CUDA tensor")
+            _lib.call("bogp_bartlett_grid_argext", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
+                      _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
+                      C.c_void_p(out.data_ptr()), 1 if maximize else 0, C.c_void_p(pair.data_ptr() + 8),
+                      C.c_void_p(pair.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                      scratch.numel() * scratch.element_size(), C.c_void_p(_lib.current_stream_ptr()))
+            return out
         _lib.call("bogp_bartlett_grid", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz), _lib.dptr(tt), Nt,
                   _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
                   C.c_void_p(out.data_ptr()), C.c_void_p(_lib.current_stream_ptr()))

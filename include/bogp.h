@@ -102,6 +102,15 @@ int bogp_modeset_info(bogp_modeset_t h, int f, int* M, int* rows, int* J);
 int bogp_bartlett_grid(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
                        const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
                        float* out_dev, void* stream);
+/* Surface + the final reduction np.unravel_index(np.argmax(surface)) (collate.py:50) in one call, all on the device:
+ * val_dev / idx_dev receive the extremum and its flat index (-1 if every value is NaN).  With the tcgen05 engine the
+ * reduction happens inside the surface kernel's epilogue (packed atomicMax, last CTA decodes): no extra launch.
+ * scratch_dev: >= 8192 bytes (used only when the reduction needs the separate arg-ext kernels). */
+int bogp_bartlett_grid_argext(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                              const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                              float* out_dev, int maximize, float* val_dev, long long* idx_dev,
+                              void* scratch_dev, long long scratch_bytes, void* stream);
+
 /* Same, host output buffer (device->host copy inside; synchronises the stream). */
 int bogp_bartlett_grid_host(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
                             const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,

@@ -291,3 +291,26 @@ def test_full_size_surface_properties():
     assert np.abs(s2 - s).max() <= 2e-5
     pts = dms.bartlett_points(cand).cpu().numpy()
     assert_parity(pts, ref)
+
+
+@pytest.mark.parametrize("shape", [(100, 50), (257, 131), (1000, 300)])
+def test_fused_argext_matches_separate_reduction(cfg2_small, dms2, shape):
+    """bogp_bartlett_grid_argext: the arg-max / arg-min folded into the tcgen05 kernel's epilogue equals the separate
+    reduction kernels and numpy on the same surface (first-occurrence tie rule, collate.py:50)."""
+    from bogp_b200 import mfp
+    nr, nz = shape
+    r, z = np.linspace(0.1, 10.0, nr), np.linspace(1.0, 200.0, nz)
+    pair = torch.zeros(2, dtype=torch.int64, device="cuda")
+    scratch = torch.empty(8192, dtype=torch.uint8, device="cuda")
+    for engine in ("umma", "simt"):
+        for maximize in (True, False):
+            for atype in ("cbf", "cbf_ml"):
+                surf = dms2.bartlett_grid(r, z, engine=engine, atype=atype, argext=(pair, scratch, maximize))
+                plain = dms2.bartlett_grid(r, z, engine=engine, atype=atype)
+                torch.testing.assert_close(surf, plain, rtol=0, atol=0)
+                vals, idxs = mfp.unpack_pairs(pair.reshape(1, 2))
+                host = surf.cpu().numpy()
+                want = int(host.argmax() if maximize else host.argmin())
+                assert int(idxs[0]) == want and vals[0] == host.reshape(-1)[want]
+    out, (v, pos) = dms2.bartlett_grid_host(r, z, engine="umma", argext="max")
+    assert pos == np.unravel_index(out.argmax(), out.shape) and v == out.max()

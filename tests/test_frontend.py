@@ -201,3 +201,69 @@ def test_grid_search_is_one_surface_launch(cfg1):
     best, _ = client.get_best_parameters()
     jz, jr = np.unravel_index(ref.argmax(), ref.shape)
     assert best == {"src_z": np.linspace(40.0, 100.0, 24)[jz], "rec_r": np.linspace(0.5, 2.0, 24)[jr]}
+
+
+# ------------------------------------------------------------------------------------------------ sweep (8f row 3)
+def test_covariance_front_end_and_disk_formats(tmp_path):
+    """acoustics.py:116-124 per-snapshot covariances, the <f>Hz/covariance.npy layout and mfp.py:111-121 loader."""
+    from bogp_b200 import sweep
+    rng = np.random.default_rng(0)
+    p = rng.standard_normal((12, 5)) + 1j * rng.standard_normal((12, 5))
+    K = sweep.snapshot_covariance(p)
+    assert K.shape == (12, 5, 5)
+    d = p[3] / np.linalg.norm(p[3])
+    np.testing.assert_allclose(K[3], np.outer(d, d.conj()), atol=1e-15)
+    np.testing.assert_allclose(np.trace(K, axis1=1, axis2=2).real, 1.0, atol=1e-14)
+    K4 = sweep.snapshot_covariance(p, averaging=4)
+    assert K4.shape == (3, 5, 5)
+    np.testing.assert_allclose(K4[1], K[4:8].mean(0) / np.trace(K[4:8].mean(0)).real, atol=1e-15)
+    assert np.linalg.matrix_rank(K4[1]) == 4
+    freqs = [148.0, 235.0]
+    for f in freqs:
+        sweep.save_covariance(K * (1 + f / 1000), tmp_path, f)
+    assert (tmp_path / "148.0Hz" / "covariance.npy").exists()
+    L = sweep.load_covariance(tmp_path, freqs, num_segments=12, num_elements=5)
+    assert L.shape == (2, 12, 5, 5) and L.dtype == complex
+    np.testing.assert_allclose(L[1], K * 1.235)
+    with pytest.raises(ValueError):
+        sweep.load_covariance(tmp_path, freqs, num_segments=11)
+    # time steps are split like depth rows: contiguous, balanced, complete
+    got = [list(sweep.time_steps_of(r, 3, 350)) for r in range(3)]
+    assert sum(got, []) == list(range(350)) and {len(g) for g in got} == {116, 117}
+
+
+@pytest.mark.gpu
+def test_time_step_sweep_matches_oracle_and_reference_files(cfg1, tmp_path):
+    """mfp.py:131-216 for a short towed-source event: per-step covariances from synthetic snapshots, one fused
+    surface per step, reference file names, peaks that follow the source, two 'ranks' covering all steps."""
+    import pickle
+    from bogp_b200 import sweep
+    from bogp_b200.mfp import MatchedFieldProcessor, ModeRunner, beamformer
+    from oracle import bartlett as ob
+    from oracle import field as of
+    modes = cfg1["modes"]
+    rvec, zvec = np.linspace(0.5, 3.0, 90), np.linspace(20.0, 120.0, 41)
+    track = [(1.0 + 0.25 * t, 60.0 + 5.0 * t) for t in range(6)]                 # (range km, depth m) per time step
+    data = {f: np.stack([of.replica(modes, i, z, r)[:, 0] * np.exp(1j * t) for t, (r, z) in enumerate(track)])
+            for i, f in enumerate(modes.freq)}
+    for f in modes.freq:
+        sweep.save_covariance(sweep.snapshot_covariance(data[f]), tmp_path / "acoustic", f)
+    K = sweep.load_covariance(tmp_path / "acoustic", modes.freq)
+    assert K.shape == (3, 6, 21, 21)
+    mfp = MatchedFieldProcessor(runner=ModeRunner(modes), covariance_matrix=K[:, 0], freq=modes.freq, parameters={},
+                                beamformer=beamformer)
+    parts = [sweep.ambiguity_sweep(mfp, K, rvec, zvec, savepath=tmp_path / "mfp", rank=r, world=2) for r in range(2)]
+    assert parts[0]["timesteps"] == [0, 1, 2] and parts[1]["timesteps"] == [3, 4, 5]
+    with open(tmp_path / "mfp" / "grid_parameters.pkl", "rb") as fh:
+        grid = pickle.load(fh)
+    assert len(grid["rec_r"]) == 90 and len(grid["src_z"]) == 41
+    for part in parts:
+        for k, t in enumerate(part["timesteps"]):
+            ref = ob.ambiguity_surface(modes, K[:, t], rvec, zvec)
+            disk = np.load(tmp_path / "mfp" / f"surface_{t:03d}.npy")
+            assert disk.dtype == np.float64 and disk.shape == (41, 90)
+            np.testing.assert_allclose(disk, ref, atol=2e-6)
+            np.testing.assert_array_equal(disk.astype(np.float32), part["surfaces"][k])
+            val, (jz, jr) = part["peak"][k]
+            assert (jz, jr) == np.unravel_index(ref.argmax(), ref.shape)
+            assert abs(rvec[jr] - track[t][0]) < 0.03 and abs(zvec[jz] - track[t][1]) < 2.6
