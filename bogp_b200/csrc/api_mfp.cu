@@ -323,13 +323,19 @@ static int grid_impl(bogp_modeset_t h, const double* r_m_host, int Nr, const dou
     for (int i = 0; i < Nt; ++i) tilted |= (tilt_deg_host[i] != 0.0);
   else
     BOGP_REQUIRE(Nt == 1, "bogp_bartlett_grid: Nt must be 1 when tilt is NULL");
+  const bool tilt_axis = tilted || Nt > 1;
   if (engine == BOGP_ENGINE_UMMA) {
-    BOGP_REQUIRE(!tilted && Nt == 1, "bogp_bartlett_grid: the UMMA engine covers the vertical-array grid only");
-    if (!bogp::umma_supported(h)) { bogp::set_error("UMMA engine unsupported for this mode set / device"); return BOGP_ERR_UNSUPPORTED; }
+    const bool ok = tilt_axis ? bogp::umma_tilt_supported(h) : bogp::umma_supported(h);
+    if (!ok) { bogp::set_error("UMMA engine unsupported for this mode set / device"); return BOGP_ERR_UNSUPPORTED; }
   }
-  const bool fuse_ext = (long long)Nr * Nz < (1ll << 32);
+  const long long total = (long long)std::max(Nt, 1) * Nz * Nr;
+  const bool fuse_ext = total < (1ll << 32);
   int rc;
-  if (engine == BOGP_ENGINE_UMMA || (engine == BOGP_ENGINE_AUTO && !tilted && Nt == 1 && bogp::umma_supported(h) && (long long)Nr * Nz >= 16384)) {
+  if (tilt_axis && (engine == BOGP_ENGINE_UMMA || (engine == BOGP_ENGINE_AUTO && bogp::umma_tilt_supported(h) && total >= 65536))) {
+    // tilted array on the tensor cores (receiver-space epilogue)
+    rc = bogp::launch_grid_umma_tilt(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
+    if (rc || !ext_mode || fuse_ext) return rc;
+  } else if (!tilt_axis && (engine == BOGP_ENGINE_UMMA || (engine == BOGP_ENGINE_AUTO && bogp::umma_supported(h) && total >= 16384))) {
     rc = bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
     if (rc || !ext_mode || fuse_ext) return rc;
   } else {

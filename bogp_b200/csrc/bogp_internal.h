@@ -138,5 +138,10 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
                      int mf, float* out_dev, cudaStream_t s, int ext_mode = 0, float* ext_val_dev = nullptr,
                      long long* ext_idx_dev = nullptr);
 bool umma_supported(const bogp_modeset_s* h);
+// tilted-array grid (tilt axis) on the tensor cores: N <= 64 receivers, covariance rank <= 4, real source tables
+bool umma_tilt_supported(const bogp_modeset_s* h);
+int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz,
+                          const double* tilt_host, int Nt, int atype, int mf, float* out_dev, cudaStream_t s,
+                          int ext_mode = 0, float* ext_val_dev = nullptr, long long* ext_idx_dev = nullptr);
 int ensure_scratch(bogp_modeset_s* h, size_t bytes);
 }  // namespace bogp

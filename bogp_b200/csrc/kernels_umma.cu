@@ -62,6 +62,10 @@ struct UTonal {
   unsigned b_zbytes;           // rowsP * Mp * 4: one depth of one split of Bop
   unsigned long long b_off;    // offset of the tonal inside the Bop tables
   float trK;
+  // tilted-array mode only
+  int offM;                    // column offset of the tonal in the phi(z) table
+  int offC;                    // offset of the receiver-space covariance factor [N][J]
+  int J;
 };
 
 struct UParams {
@@ -83,6 +87,18 @@ struct UParams {
   unsigned int* ext_done;
   float* ext_val;
   long long* ext_idx;
+  // ---- tilted-array mode (umma_grid_kernel<true>): Nz counts PSEUDO-depths k = (tilt, receiver half) in stage order
+  // (k = 4q + {0,1,2,3} -> (tilt 2q, half 0), (2q+1, 0), (2q, 1), (2q+1, 1)), ZC = 2 * tilts per unit, and a unit is
+  // (range tile, real depth, tilt chunk)
+  int ntc;                     // tilt chunks per real depth
+  int Nzr, Nt;                 // real depths, real tilts
+  int N, sumMp;
+  const float* phiz;           // [Nzr][sumMp]  phi_m(z_j)
+  const float* sin_t;          // [Nz / 2]      sin(tilt), padded
+  const float* rinv;           // [Nr]          1 / r
+  const float* lever;          // [64]          z_pivot - z_n (0 beyond N)
+  const float* CkT_re;         // receiver-space covariance factor (ModesetDev::CkT_re / CkT_im)
+  const float* CkT_im;
   int skip;                    // debug build only: 1 = issue no MMAs, 2 = epilogue releases without reading (bottleneck bracketing)
   UTonal t[BOGP_MAX_TONALS];
 };
@@ -269,6 +285,12 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const float4& a, const f
       "r"(__float_as_uint(d.x)), "r"(__float_as_uint(d.y)), "r"(__float_as_uint(d.z)), "r"(__float_as_uint(d.w))
       : "memory");
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -426,6 +448,62 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
   }
 }
 
+// ---- tilted-array operand tables
+// Theta tables: per (tonal, pseudo-depth k = (tilt, receiver half) in stage order) the block [64 rows, Mp] with rows
+// (2q, 2q+1) = (Re, Im) of Theta_tau[n, m] = Phi[n, m] exp(i k_m l_n sin tau), n = 32 half + q, in the UMMA canonical
+// K-major layout, hi and lo arrays.  The phase k_m l_n sin(tau) is formed in float64.
+__global__ void __launch_bounds__(128) umma_tilt_theta_kernel(ModesetDev ms, UParams p, const double* __restrict__ tilt_deg) {
+  const int f = blockIdx.y, k = blockIdx.x;
+  const TonalMeta& t = ms.t[f];
+  const UTonal& u = p.t[f];
+  const int tau = min(2 * (k >> 2) + (k & 1), p.Nt - 1), half = (k >> 1) & 1;
+  const double st = sin(tilt_deg[tau] * 0.017453292519943295);
+  float* Bhi = reinterpret_cast<float*>(const_cast<unsigned char*>(p.Bhi) + u.b_off + (size_t)k * u.b_zbytes);
+  float* Blo = reinterpret_cast<float*>(const_cast<unsigned char*>(p.Blo) + u.b_off + (size_t)k * u.b_zbytes);
+  for (int idx = threadIdx.x; idx < 32 * u.Mp; idx += blockDim.x) {
+    const int q = idx / u.Mp, m = idx - q * u.Mp, n = 32 * half + q;
+    double vr = 0.0, vi = 0.0;
+    if (n < ms.N && m < t.M) {
+      const double ls = (double)ms.rec_lever[n] * st;
+      double sn, cs;
+      sincos(ms.k_re[t.offM + m] * ls, &sn, &cs);
+      const double amp = exp(-ms.k_im[t.offM + m] * ls);
+      const double pr = ms.rec_re[t.offRec + (size_t)n * t.Mp + m];
+      const double pi = ms.rec_complex ? (double)ms.rec_im[t.offRec + (size_t)n * t.Mp + m] : 0.0;
+      vr = amp * (pr * cs - pi * sn);
+      vi = amp * (pr * sn + pi * cs);
+    }
+    const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
+    const size_t o0 = canon_off(2 * q, m, u.Mp), o1 = canon_off(2 * q + 1, m, u.Mp);
+    Bhi[o0] = rh; Blo[o0] = (float)(vr - (double)rh);
+    Bhi[o1] = ih; Blo[o1] = (float)(vi - (double)ih);
+  }
+}
+
+// phi_m(z_j) for every real depth (source-depth table interpolation of the data contract), sin(tilt), 1 / r, levers
+__global__ void umma_tilt_aux_kernel(ModesetDev ms, UParams p, const double* __restrict__ r, const double* __restrict__ z,
+                                     const double* __restrict__ tilt_deg, float* phiz, float* sin_t, float* rinv, float* lever) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int idx = tid; idx < p.Nzr * p.sumMp; idx += nth) {
+    const int j = idx / p.sumMp, col = idx - j * p.sumMp;
+    int f = 0;
+    while (f + 1 < p.F && col >= p.t[f + 1].offM) ++f;
+    const int m = col - p.t[f].offM;
+    const TonalMeta& t = ms.t[f];
+    float v = 0.f;
+    if (m < t.M) {
+      int i0; float w;
+      depth_index(z[j], ms.z0, ms.dz, ms.nz_tab, i0, w);
+      const float* tr = ms.tab_re + t.offTab + (size_t)i0 * t.Mp + m;
+      v = fmaf(w, __ldg(tr + t.Mp) - __ldg(tr), __ldg(tr));
+    }
+    phiz[idx] = v;
+  }
+  for (int i = tid; i < p.Nz / 2; i += nth) sin_t[i] = (float)sin(tilt_deg[min(i, p.Nt - 1)] * 0.017453292519943295);
+  for (int i = tid; i < p.Nr; i += nth) rinv[i] = (float)(1.0 / r[i]);
+  for (int i = tid; i < 64; i += nth) lever[i] = i < ms.N ? ms.rec_lever[i] : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------------ main kernel
 // Debug build only: per-stage time stamps of CTA 0 in three windows of stages (one per tonal class), see launch_grid_umma.
 __device__ __forceinline__ void dbg_stamp(const UParams& p, int ev, uint32_t sc) {
@@ -447,6 +525,16 @@ enum { BAR_BFULL = 0, BAR_BEMPTY = kStages, BAR_EFULL = 2 * kStages, BAR_EDONE =
 // so tonal g+1 can be loaded while tonal g is still being multiplied whenever the two fit side by side.
 __device__ __forceinline__ uint32_t a_column(const UParams& p, int g, int Mp) {
   return (uint32_t)(4 * p.NA) + ((g & 1) ? (uint32_t)(p.AR - 4 * Mp) : 0u);
+}
+
+// unit -> (range tile, first [pseudo-]depth of the chunk, depths in the chunk, real depth (tilt mode))
+template <bool TILT>
+__device__ __forceinline__ void unit_decode(const UParams& p, int unit, int& rt, int& z0, int& nzu, int& jreal) {
+  rt = unit % p.nrt;
+  const int zc = unit / p.nrt;
+  if (TILT) { jreal = zc / p.ntc; z0 = (zc % p.ntc) * p.ZC; }
+  else { jreal = 0; z0 = zc * p.ZC; }
+  nzu = min(p.ZC, p.Nz - z0);
 }
 
 struct MmaState {
@@ -507,6 +595,7 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
   __syncwarp();
 }
 
+template <bool TILT>
 __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid_constant__ UParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -543,8 +632,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     long long w_bempty = 0;
     uint32_t sc = 0;       // global stage counter
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-      const int zc = unit / p.nrt;
-      const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
+      int rt_, z0, nzu, jr_;
+      unit_decode<TILT>(p, unit, rt_, z0, nzu, jr_);
       for (int f = 0; f < p.F; ++f) {
         const UTonal& u = p.t[f];
         for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
@@ -570,9 +659,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     st.id = warp == 1 ? 0 : 1;
     st.p = &p; st.tmem_base = tmem_base; st.s_base = s_base; st.bar0 = bar0; st.dbg = dbg != nullptr;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-      const int zc = unit / p.nrt;
-      const int z0 = zc * p.ZC;
-      st.nzu = min(p.ZC, p.Nz - z0);
+      int rt_, z0_, jr_;
+      unit_decode<TILT>(p, unit, rt_, z0_, st.nzu, jr_);
       for (int f = 0; f < p.F; ++f, ++st.g) {
         switch (p.t[f].Mp >> 3) {
           case 1: mma_tonal<1>(st, p.t[f]); break;
@@ -594,7 +682,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     long long w_edone = 0;
     int g = 0;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
-      const int rt = unit % p.nrt;
+      int rt, z0_, nzu_, jreal;
+      unit_decode<TILT>(p, unit, rt, z0_, nzu_, jreal);
       for (int f = 0; f < p.F; ++f, ++g) {
         const UTonal& u = p.t[f];
         if (g >= 2) mbar_wait_relaxed(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1);
@@ -607,6 +696,28 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
         const float4* src = reinterpret_cast<const float4*>(p.E + (size_t)rt * p.e_rt_stride + u.e_off) + tl;
         const uint32_t dst = tmem_base + ((uint32_t)(quad * 32) << 16) + a_column(p, g, u.Mp);
         const int n16 = u.Mp >> 2;            // 4 Mp columns in groups of 16
+        if (TILT) {
+          // tilted array: the depth goes into the A operand, A[i, m] = E[i, m] phi_m(z_j), because the B operand
+          // (Theta_tau = Phi e^{i k l sin tau}) is per tilt: rebuild the fp32 value from the table's (hi, lo), scale,
+          // split again.  Eight modes per step: (re | im) x (hi, lo) chunks in, two 8-column stores out per part.
+          const float* phi = p.phiz + (size_t)jreal * p.sumMp + u.offM;
+          const int mc = u.Mp >> 2;           // 16-byte chunks per block of Mp columns
+          for (int part = 0; part < 2; ++part) {
+            const int hb = 2 * part * mc, lb = hb + mc;
+            for (int q2 = 0; q2 < (u.Mp >> 3); ++q2) {
+              const float4 h0 = __ldg(src + (size_t)(hb + 2 * q2) * kTileR), h1 = __ldg(src + (size_t)(hb + 2 * q2 + 1) * kTileR);
+              const float4 l0 = __ldg(src + (size_t)(lb + 2 * q2) * kTileR), l1 = __ldg(src + (size_t)(lb + 2 * q2 + 1) * kTileR);
+              const float4 pa = __ldg(reinterpret_cast<const float4*>(phi + 8 * q2)), pb = __ldg(reinterpret_cast<const float4*>(phi + 8 * q2 + 4));
+              const float x[8] = {(h0.x + l0.x) * pa.x, (h0.y + l0.y) * pa.y, (h0.z + l0.z) * pa.z, (h0.w + l0.w) * pa.w,
+                                  (h1.x + l1.x) * pb.x, (h1.y + l1.y) * pb.y, (h1.z + l1.z) * pb.z, (h1.w + l1.w) * pb.w};
+              float hi[8], lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { hi[e] = tf32_rna(x[e]); lo[e] = x[e] - hi[e]; }
+              tc_st8(dst + (uint32_t)(2 * part * u.Mp + 8 * q2), hi);
+              tc_st8(dst + (uint32_t)((2 * part + 1) * u.Mp + 8 * q2), lo);
+            }
+          }
+        } else
         for (int c = 0; c < n16; c += 2) {
           const float4 v0 = __ldg(src + (size_t)(4 * c + 0) * kTileR), v1 = __ldg(src + (size_t)(4 * c + 1) * kTileR);
           const float4 v2 = __ldg(src + (size_t)(4 * c + 2) * kTileR), v3 = __ldg(src + (size_t)(4 * c + 3) * kTileR);
@@ -624,6 +735,123 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     if (dbg && lane == 0 && quad == 0) { dbg[12] = clock64() - t_start; }
   } else {
     // ============================================================== epilogue
+    if (TILT) {
+      // ------------------------------------------------------------ tilted array (receiver space)
+      // Stage k of a tonal holds, for one tilt and one half of the array, T_n = sum_m Theta_tau[n, m] a_m as adjacent
+      // (re-row, im-row) column pairs; p_n = s_n T_n with s_n = (r / r_n)^1/2 = (1 - l_n sin(tau) / r)^-1/2, a factor
+      // that depends on the lane's range and sits between the modes and the covariance, so the reduction over
+      // receivers happens here:  B = sum_j |sum_n conj(L_nj) s_n T_n|^2 / sum_n s_n^2 |T_n|^2.
+      // Stage order (k = 4q + {0,1,2,3} -> (tilt 2q, half 0), (2q+1, 0), (2q, 1), (2q+1, 1)) gives both halves of a
+      // tilt the same parity, i.e. the same accumulator buffer and the same warp (sub = (k >> 2) & 1), which keeps the
+      // partial sums in registers between the two stages.
+      constexpr int kTJ = 4;                  // covariance ranks handled in registers
+      const int ew = warp - 2, quad = warp & 3, set = (ew >> 2) & 1, sub = ew >> 3;
+      const int tl = quad * 32 + lane;
+      const uint32_t NA = (uint32_t)p.NA;
+      const uint32_t t_re = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)set * (2 * NA);
+      float* acc = reinterpret_cast<float*>(smem + p.smem_acc);     // [ZC / 2][128]
+      uint32_t sc = 0;
+      long long w_tfull = 0;
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        int rt, z0, nzu, jreal;
+        unit_decode<true>(p, unit, rt, z0, nzu, jreal);
+        const int i = rt * kTileR + tl;
+        const float rinv = i < p.Nr ? __ldg(p.rinv + i) : 0.f;
+        const int t0 = z0 >> 1;
+        for (int f = 0; f < p.F; ++f) {
+          const UTonal& u = p.t[f];
+          const int J = u.J;
+          const float* cr = p.CkT_re + u.offC;
+          const float* ci = p.CkT_im + u.offC;
+          float norm = 0.f, xs = 0.f, ur[kTJ], ui[kTJ];
+#pragma unroll
+          for (int j = 0; j < kTJ; ++j) ur[j] = ui[j] = 0.f;
+          for (int k = 0; k < nzu; ++k, ++sc) {
+            if ((int)(sc & 1u) != set) continue;
+            mbar_wait_t(bar(BAR_TFULL + set), (sc >> 1) & 1u, p.err, 7, dbg ? &w_tfull : nullptr);
+            tc_fence_after();
+            if (((k >> 2) & 1) != sub || (BOGP_UMMA_DBG && p.skip == 2)) {
+              tc_fence_before();
+              if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
+              continue;
+            }
+            const int half = (k >> 1) & 1, tloc = 2 * (k >> 2) + (k & 1);
+            if (half == 0) {
+              norm = 0.f;
+#pragma unroll
+              for (int j = 0; j < kTJ; ++j) ur[j] = ui[j] = 0.f;
+              xs = __ldg(p.sin_t + t0 + tloc) * rinv;
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+              float re[16], im[16];
+              tc_ld16(t_re + (uint32_t)c0, re);
+              tc_ld16(t_re + NA + (uint32_t)c0, im);
+              tc_wait_ld();
+              if (c0 == 48) {
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
+              }
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int n = 32 * half + (c0 >> 1) + q;
+                const float tr = re[2 * q] - im[2 * q + 1], ti = im[2 * q] + re[2 * q + 1];
+                const float sn = rsqrtf(fmaf(-__ldg(p.lever + n), xs, 1.f));
+                norm = fmaf(sn * sn, fmaf(tr, tr, ti * ti), norm);
+                const float a = sn * tr, b = sn * ti;
+                if (n < p.N) {
+#pragma unroll
+                  for (int j = 0; j < kTJ; ++j)
+                    if (j < J) {
+                      const float ca = __ldg(cr + n * J + j), cb = __ldg(ci + n * J + j);
+                      ur[j] = fmaf(ca, a, fmaf(-cb, b, ur[j]));
+                      ui[j] = fmaf(ca, b, fmaf(cb, a, ui[j]));
+                    }
+                }
+              }
+            }
+            if (half == 1) {
+              float num = 0.f;
+#pragma unroll
+              for (int j = 0; j < kTJ; ++j) num = fmaf(ur[j], ur[j], fmaf(ui[j], ui[j], num));
+              const float bq = __fdividef(num, norm);
+              const float val = p.atype == BOGP_ATYPE_CBF ? bq : u.trK - bq;
+              float* a = acc + (size_t)tloc * kTileR + tl;
+              *a = (f == 0) ? val : (p.mf == BOGP_MF_MEAN ? *a + val : *a * val);
+            }
+          }
+        }
+        constexpr int kPerQuad = kEpiWarps / 4;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(kPerQuad * 32) : "memory");
+        const float scale = p.mf == BOGP_MF_MEAN ? 1.f / (float)p.F : 1.f;
+        const int k4 = ew >> 2, ntu = nzu >> 1;
+        unsigned long long best = 0ull;
+        if (i < p.Nr)
+          for (int tloc = k4; tloc < ntu; tloc += kPerQuad) {
+            const int tau = t0 + tloc;
+            if (tau >= p.Nt) continue;               // padding tilt (odd Nt)
+            const float v = acc[(size_t)tloc * kTileR + tl] * scale;
+            const size_t flat = ((size_t)tau * p.Nzr + jreal) * p.Nr + i;
+            p.out[flat] = v;
+            if (p.ext_mode && v == v) {
+              uint32_t uu = __float_as_uint(v);
+              uu = (uu & 0x80000000u) ? ~uu : (uu | 0x80000000u);
+              if (p.ext_mode == 2) uu = ~uu;
+              const unsigned long long key = ((unsigned long long)uu << 32) | (0xffffffffu - (uint32_t)flat);
+              best = key > best ? key : best;
+            }
+          }
+        if (p.ext_mode) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+          }
+          if (lane == 0 && best) atomicMax(p.ext_key, best);
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(kPerQuad * 32) : "memory");
+      }
+    } else {
     // 16 warps = 2 buffer sets x 2 depth parities x 4 TMEM lane quadrants.  Set b drains accumulator buffer b only,
     // so the two buffers are processed concurrently by different warps, and a warp releases its buffer as soon as its
     // last tcgen05.ld has landed in registers -- the squares, the division and the combine run after the release.
@@ -769,7 +997,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(kPerQuad * 32) : "memory");     // before the next unit overwrites acc
     }
     if (dbg && lane == 0 && (ew == 0 || ew == 4)) { dbg[8 + (ew >> 2) * 2] = clock64() - t_start; dbg[9 + (ew >> 2) * 2] = w_tfull; }
-  }
+      }
+}
   tc_fence_before();
   __syncthreads();
   if (p.ext_mode && threadIdx.x == 0) {
@@ -909,9 +1138,9 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   count_launch();
   BOGP_CUDA(cudaGetLastError());
   const size_t smem = (size_t)p.smem_bar + 256;
-  BOGP_CUDA(cudaFuncSetAttribute(umma_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BOGP_CUDA(cudaFuncSetAttribute(umma_grid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t ev = timing_begin(s);
-  umma_grid_kernel<<<std::min(p.units, sms), kUmmaThreads, smem, s>>>(p);
+  umma_grid_kernel<false><<<std::min(p.units, sms), kUmmaThreads, smem, s>>>(p);
   timing_end(ev, s);
   count_launch();
   BOGP_CUDA(cudaGetLastError());
@@ -943,6 +1172,107 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
       }
     }
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ tilted-array engine
+bool umma_tilt_supported(const bogp_modeset_s* h) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10 || !h->has_cov) return false;
+  const ModesetDev& d = h->dev;
+  if (d.src_complex || d.N > 64 || h->max_J > 4 || h->max_Mp > 64) return false;
+  return true;
+}
+
+// Grid with a tilt axis on the tensor cores: out[Nt, Nz, Nr].  Units = (range tile, depth, chunk of tilts).
+int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz,
+                          const double* tilt_host, int Nt, int atype, int mf, float* out_dev, cudaStream_t s,
+                          int ext_mode, float* ext_val_dev, long long* ext_idx_dev) {
+  const ModesetDev& d = h->dev;
+  const int sms = device_sms();
+  UParams p{};
+  const int Ntp = (Nt + 1) & ~1;                       // tilts padded to even: both halves of a pair share a stage quad
+  int TC = std::min(Ntp, 32);                          // tilts per unit (even)
+  // balance: enough units for every SM, but as few A-operand rebuilds as possible
+  const int nrt = (Nr + kTileR - 1) / kTileR;
+  while (TC > 2 && (long long)nrt * Nz * ((Ntp + TC - 1) / TC) < 2ll * sms) TC = std::max(2, (TC / 2) & ~1);
+  p.F = d.F; p.Nr = Nr; p.Nzr = Nz; p.Nt = Nt; p.Nz = 2 * Ntp; p.ZC = 2 * TC; p.nrt = nrt;
+  p.ntc = (Ntp + TC - 1) / TC;
+  p.units = nrt * Nz * p.ntc;
+  p.atype = atype; p.mf = mf; p.N = d.N;
+  p.AR = 256; p.NA = 64;
+  unsigned e_off = 0;
+  unsigned long long b_off = 0;
+  int sumMp = 0, maxMp = 0;
+  for (int f = 0; f < d.F; ++f) {
+    const TonalMeta& t = d.t[f];
+    UTonal& u = p.t[f];
+    u.Mp = t.Mp; u.rowsP = 64; u.nj = 1; u.nq = 0; u.n1 = 0; u.trK = t.trK;
+    u.e_bytes = 2048u * (unsigned)u.Mp; u.e_off = e_off; e_off += u.e_bytes;
+    u.b_zbytes = 64u * (unsigned)u.Mp * 4u;
+    u.b_off = b_off; b_off += (unsigned long long)p.Nz * u.b_zbytes;
+    u.offM = sumMp; sumMp += t.Mp;
+    u.offC = t.offC; u.J = t.J;
+    maxMp = std::max(maxMp, t.Mp);
+  }
+  p.sumMp = sumMp;
+  p.e_rt_stride = e_off;
+  const unsigned acc_bytes = (unsigned)TC * kTileR * 4u;
+  unsigned stage = (kSmemLimit - acc_bytes - 256u) / kStages;
+  stage = std::min(stage & ~127u, 32u * 1024u);
+  if (2u * 64u * (unsigned)maxMp * 4u > stage) { set_error("UMMA tilt engine: mode set does not fit"); return BOGP_ERR_UNSUPPORTED; }
+  p.stage_bytes = stage; p.smem_B = 0; p.smem_acc = kStages * stage; p.smem_bar = p.smem_acc + acc_bytes;
+  // scratch: [r | z | tilt doubles][err][phiz][sin][rinv][lever][E table][Bhi][Blo]
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t off_err = al(((size_t)Nr + Nz + Nt) * sizeof(double));
+  const size_t off_phi = off_err + 256;
+  const size_t off_sin = al(off_phi + (size_t)Nz * sumMp * 4);
+  const size_t off_rinv = al(off_sin + (size_t)Ntp * 4);
+  const size_t off_lev = al(off_rinv + (size_t)Nr * 4);
+  const size_t off_E = al(off_lev + 64 * 4);
+  const size_t off_Bhi = al(off_E + (size_t)nrt * e_off);
+  const size_t off_Blo = al(off_Bhi + b_off);
+  if (int rc = ensure_scratch(h, off_Blo + b_off + 256)) return rc;
+  unsigned char* base = static_cast<unsigned char*>(h->grid_scratch);
+  double* r_dev = reinterpret_cast<double*>(base);
+  double* z_dev = r_dev + Nr;
+  double* t_dev = z_dev + Nz;
+  p.err = reinterpret_cast<int*>(base + off_err);
+  if (ext_mode && (long long)Nr * Nz * Nt < (1ll << 32)) {
+    p.ext_mode = ext_mode;
+    p.ext_key = reinterpret_cast<unsigned long long*>(base + off_err + 16);
+    p.ext_done = reinterpret_cast<unsigned int*>(base + off_err + 32);
+    p.ext_val = ext_val_dev; p.ext_idx = ext_idx_dev;
+  }
+  float* phiz = reinterpret_cast<float*>(base + off_phi);
+  float* sin_t = reinterpret_cast<float*>(base + off_sin);
+  float* rinv = reinterpret_cast<float*>(base + off_rinv);
+  float* lever = reinterpret_cast<float*>(base + off_lev);
+  p.phiz = phiz; p.sin_t = sin_t; p.rinv = rinv; p.lever = lever;
+  p.CkT_re = d.CkT_re; p.CkT_im = d.CkT_im;
+  p.E = base + off_E; p.Bhi = base + off_Bhi; p.Blo = base + off_Blo;
+  p.out = out_dev;
+  BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
+  BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  BOGP_CUDA(cudaMemcpyAsync(t_dev, tilt_host, Nt * sizeof(double), cudaMemcpyHostToDevice, s));
+  const int nE = d.F * nrt * (kTileR / kTabRows);
+  {
+    UParams pe = p;              // the E blocks of the shared table kernel read Nr / nrt / e offsets only
+    umma_tables_kernel<<<nE, kTabThreads, 0, s>>>(d, pe, r_dev, z_dev, nE);
+  }
+  umma_tilt_theta_kernel<<<dim3((unsigned)p.Nz, (unsigned)d.F), 128, 0, s>>>(d, p, t_dev);
+  umma_tilt_aux_kernel<<<std::max(1, std::min(296, (Nz * sumMp + 255) / 256)), 256, 0, s>>>(d, p, r_dev, z_dev, t_dev, phiz, sin_t, rinv, lever);
+  count_launch(3);
+  BOGP_CUDA(cudaGetLastError());
+  const size_t smem = (size_t)p.smem_bar + 256;
+  BOGP_CUDA(cudaFuncSetAttribute(umma_grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t ev = timing_begin(s);
+  umma_grid_kernel<true><<<std::min(p.units, sms), kUmmaThreads, smem, s>>>(p);
+  timing_end(ev, s);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
   return 0;
 }
 

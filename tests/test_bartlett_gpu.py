@@ -314,3 +314,45 @@ def test_fused_argext_matches_separate_reduction(cfg2_small, dms2, shape):
                 assert int(idxs[0]) == want and vals[0] == host.reshape(-1)[want]
     out, (v, pos) = dms2.bartlett_grid_host(r, z, engine="umma", argext="max")
     assert pos == np.unravel_index(out.argmax(), out.shape) and v == out.max()
+
+
+@pytest.mark.parametrize("case", ["swellex_rank1", "inv21_rank3", "complex_modes"])
+def test_tilt_tensor_core_engine_vs_oracle_and_simt(case):
+    """Config 4 path on the tensor cores (umma_grid_kernel<true>: Theta_tau as the B operand, receiver-space epilogue
+    with s_n = (r / r_n)^1/2): ragged sizes, odd tilt counts, rank-1 / rank-3 covariances, complex receiver modes,
+    both processors; against the oracle (one scattered evaluation per node) and the SIMT tilt-plane kernel."""
+    from bogp_b200 import mfp
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import INV_TONALS_3, REC_Z_21, SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    if case == "swellex_rank1":
+        modes = pekeris_modes(SWELLEX_TONALS_13)
+        K = synthetic_covariance(modes, 60.0, 5.0, tilt_deg=1.5)
+        r, z, tilt = np.linspace(0.4, 9.7, 150), np.linspace(3.0, 195.0, 3), np.array([-3.5, 0.0, 1.5, 4.0, 2.5])
+    elif case == "inv21_rank3":
+        modes = pekeris_modes(INV_TONALS_3, REC_Z_21)
+        K = synthetic_covariance(modes, 71.11, 1.07, tilt_deg=-1.0, snapshots=3, seed=2)
+        r, z, tilt = np.linspace(0.3, 6.0, 131), np.linspace(5.0, 190.0, 4), np.linspace(-4.0, 4.0, 7)
+    else:
+        modes = pekeris_modes(INV_TONALS_3, REC_Z_21, complex_modes=True)
+        K = synthetic_covariance(modes, 40.0, 2.2, tilt_deg=-2.0, snapshots=3, seed=5)
+        r, z, tilt = np.linspace(0.5, 6.0, 140), np.linspace(5.0, 190.0, 3), np.array([-2.0, 0.5, 3.0])
+    dms = DeviceModeSet(modes, K)
+    if case == "complex_modes":
+        # complex SOURCE tables are outside the tensor-core engines: must be refused loudly, auto falls back to SIMT
+        with pytest.raises(mfp._lib.BogpError):
+            dms.bartlett_grid(r, z, tilt, engine="umma")
+        return
+    cand = np.array([[ri, zi, ti] for ti in tilt for zi in z for ri in r])
+    for kw, floor in ((dict(), FLOOR), (dict(atype="cbf_ml", multifreq_method="product"), 1.0)):
+        ref = ob.bartlett_points(modes, K, cand, **kw).reshape(len(tilt), len(z), len(r))
+        got = dms.bartlett_grid(r, z, tilt, engine="umma", **kw).cpu().numpy()
+        assert_parity(got, ref, floor=floor)
+        simt = dms.bartlett_grid(r, z, tilt, engine="simt", **kw).cpu().numpy()
+        assert_parity(got, simt, rtol=5e-6, floor=floor)
+        assert np.unravel_index(got.argmax(), got.shape) == np.unravel_index(ref.argmax(), ref.shape)
+    # fused arg-max over the (tilt, depth, range) volume
+    pair = torch.zeros(2, dtype=torch.int64, device="cuda")
+    scratch = torch.empty(8192, dtype=torch.uint8, device="cuda")
+    vol = dms.bartlett_grid(r, z, tilt, engine="umma", argext=(pair, scratch, True)).cpu().numpy()
+    vals, idxs = mfp.unpack_pairs(pair.reshape(1, 2))
+    assert int(idxs[0]) == int(vol.argmax()) and vals[0] == vol.max()

@@ -126,17 +126,24 @@ def bench_tilt():
     modes = pekeris_modes(SWELLEX_TONALS_13)
     K = synthetic_covariance(modes, 60.0, 5.0, tilt_deg=1.0)
     dms = mfp.DeviceModeSet(modes, K)
-    r, z, tilt = np.linspace(0.1, 10.0, 1000), np.linspace(1.0, 200.0, 100), np.linspace(-4.0, 4.0, 10)
-    C = len(r) * len(z) * len(tilt)
-    out = torch.empty((len(tilt), len(z), len(r)), dtype=torch.float32, device="cuda")
-    call_ms, k_ms = timed(lambda: dms.bartlett_grid(r, z, tilt, out=out), reps=3, warm=1)
     N, sumM = 64, sum(modes.n_modes)
-    print(json.dumps({"kernel": "grid_tilt_kernel (K1-SIMT, receiver space, Theta_tau in shared memory)",
-                      "case": "configs[3] at 1/10 scale: 1000 r x 100 z x 10 tilt = 1e6 candidates, 13 tonals",
-                      "kernel_ms": k_ms, "call_ms": call_ms, "cand_freq_per_s": C * 13 / (k_ms * 1e-3),
-                      "alg_tflops": C * 8.0 * N * sumM / (k_ms * 1e-3) / 1e12,
-                      "alg_flop_per_cand": 8 * N * sumM, "projected_s_for_1e7": 10 * k_ms * 1e-3,
-                      "bound": "fp32 FMA + shared-memory operand loads (CUDA cores); tensor-core path is future work"}), flush=True)
+    r, z = np.linspace(0.1, 10.0, 1000), np.linspace(1.0, 200.0, 100)
+    for nt, engines in ((10, ("simt", "umma")), (100, ("simt", "umma"))):
+        tilt = np.linspace(-4.0, 4.0, nt)
+        C = len(r) * len(z) * len(tilt)
+        out = torch.empty((len(tilt), len(z), len(r)), dtype=torch.float32, device="cuda")
+        for engine in engines:
+            call_ms, k_ms = timed(lambda: dms.bartlett_grid(r, z, tilt, out=out, engine=engine), reps=3, warm=1)
+            name = ("grid_tilt_kernel (K1-SIMT, receiver space, Theta_tau in shared memory)" if engine == "simt" else
+                    "umma_grid_kernel<tilt> (K1-UMMA-TILT: tcgen05 3xTF32, Theta_tau as B operand, receiver-space epilogue)")
+            flop = 8.0 * N * sumM          # complex Theta x complex a: 4 real MACs per (receiver, mode)
+            print(json.dumps({"kernel": name, "engine": engine,
+                              "case": f"configs[3]: 1000 r x 100 z x {nt} tilt = {C:.0e} candidates, 13 tonals, 64 receivers",
+                              "kernel_ms": k_ms, "call_ms": call_ms, "cand_freq_per_s": C * 13 / (k_ms * 1e-3),
+                              "alg_tflops": C * flop / (k_ms * 1e-3) / 1e12, "alg_flop_per_cand": flop,
+                              "tensor_frac_of_measured_3xtf32_peak": (C * flop / (k_ms * 1e-3) / 1e12) / 278.6 if engine == "umma" else None,
+                              "bound": "tensor (3xTF32) with an fp32 receiver-space epilogue" if engine == "umma" else
+                                       "fp32 FMA + shared-memory operand loads (CUDA cores)"}), flush=True)
 
 
 def bench_env():
