@@ -71,7 +71,7 @@ struct UTonal {
 struct UParams {
   int F, Nr, Nz, nrt, ZC, units, atype, mf;
   unsigned e_rt_stride, stage_bytes;
-  unsigned smem_B, smem_acc, smem_bar;
+  unsigned smem_B, smem_acc, smem_bar, smem_aux;     // smem_aux (tilt mode): lever[64] | covariance factor [F][64][4] float2 | partial-sum exchange
   int NA;                      // TMEM columns per accumulator half; buffers at 0 and 2 NA, A region at [4 NA, 4 NA + AR)
   int AR;                      // TMEM columns of the A region
   const unsigned char* E;
@@ -618,6 +618,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
+  if (TILT) {
+    // tilt mode: the epilogue's per-receiver constants in shared memory (broadcast LDS instead of dependent __ldg)
+    float* lev_s = reinterpret_cast<float*>(smem + p.smem_aux);
+    float2* c_s = reinterpret_cast<float2*>(lev_s + 64);              // [F][64][4]
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) lev_s[i] = p.lever[i];
+    for (int i = threadIdx.x; i < p.F * 256; i += blockDim.x) {
+      const int f = i >> 8, n = (i >> 2) & 63, j = i & 3;
+      const UTonal& u = p.t[f];
+      c_s[i] = (n < p.N && j < u.J) ? make_float2(p.CkT_re[u.offC + n * u.J + j], p.CkT_im[u.offC + n * u.J + j]) : make_float2(0.f, 0.f);
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -742,8 +753,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       // that depends on the lane's range and sits between the modes and the covariance, so the reduction over
       // receivers happens here:  B = sum_j |sum_n conj(L_nj) s_n T_n|^2 / sum_n s_n^2 |T_n|^2.
       // Stage order (k = 4q + {0,1,2,3} -> (tilt 2q, half 0), (2q+1, 0), (2q, 1), (2q+1, 1)) gives both halves of a
-      // tilt the same parity, i.e. the same accumulator buffer and the same warp (sub = (k >> 2) & 1), which keeps the
-      // partial sums in registers between the two stages.
+      // tilt the same parity, i.e. the same accumulator buffer and the same pair of warps, which keep their partial
+      // sums in registers between the two stages; the pair splits every stage (16 receivers each) and meets once per
+      // tilt on a 64-thread named barrier to add the two partial sums.
       constexpr int kTJ = 4;                  // covariance ranks handled in registers
       const int ew = warp - 2, quad = warp & 3, set = (ew >> 2) & 1, sub = ew >> 3;
       const int tl = quad * 32 + lane;
@@ -761,8 +773,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
         for (int f = 0; f < p.F; ++f) {
           const UTonal& u = p.t[f];
           const int J = u.J;
-          const float* cr = p.CkT_re + u.offC;
-          const float* ci = p.CkT_im + u.offC;
+          const float* lev_s = reinterpret_cast<const float*>(smem + p.smem_aux);
+          const float2* c_f = reinterpret_cast<const float2*>(lev_s + 64) + f * 256;     // [64][4]
+          float* xch = const_cast<float*>(lev_s) + 64 + p.F * 512;                       // [2][2 sets][4 quads][9][32]
           float norm = 0.f, xs = 0.f, ur[kTJ], ui[kTJ];
 #pragma unroll
           for (int j = 0; j < kTJ; ++j) ur[j] = ui[j] = 0.f;
@@ -770,7 +783,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
             if ((int)(sc & 1u) != set) continue;
             mbar_wait_t(bar(BAR_TFULL + set), (sc >> 1) & 1u, p.err, 7, dbg ? &w_tfull : nullptr);
             tc_fence_after();
-            if (((k >> 2) & 1) != sub || (BOGP_UMMA_DBG && p.skip == 2)) {
+            if (BOGP_UMMA_DBG && p.skip == 2) {
               tc_fence_before();
               if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
               continue;
@@ -782,42 +795,57 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
               for (int j = 0; j < kTJ; ++j) ur[j] = ui[j] = 0.f;
               xs = __ldg(p.sin_t + t0 + tloc) * rinv;
             }
-#pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 16) {
-              float re[16], im[16];
-              tc_ld16(t_re + (uint32_t)c0, re);
-              tc_ld16(t_re + NA + (uint32_t)c0, im);
-              tc_wait_ld();
-              if (c0 == 48) {
-                tc_fence_before();
-                if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
-              }
+            // The two warps (sub 0 / 1) of this (buffer, quadrant) split the stage: 16 receivers = 32 columns each, all
+            // four tcgen05.ld up front, release at the single wait, then the receiver-space reduction from registers.
+            auto reduce16 = [&](const float* re, const float* im, int nb) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const int n = 32 * half + (c0 >> 1) + q;
+                const int n = nb + q;
                 const float tr = re[2 * q] - im[2 * q + 1], ti = im[2 * q] + re[2 * q + 1];
-                const float sn = rsqrtf(fmaf(-__ldg(p.lever + n), xs, 1.f));
+                const float sn = rsqrtf(fmaf(-lev_s[n], xs, 1.f));
                 norm = fmaf(sn * sn, fmaf(tr, tr, ti * ti), norm);
                 const float a = sn * tr, b = sn * ti;
-                if (n < p.N) {
 #pragma unroll
-                  for (int j = 0; j < kTJ; ++j)
-                    if (j < J) {
-                      const float ca = __ldg(cr + n * J + j), cb = __ldg(ci + n * J + j);
-                      ur[j] = fmaf(ca, a, fmaf(-cb, b, ur[j]));
-                      ui[j] = fmaf(ca, b, fmaf(cb, a, ui[j]));
-                    }
-                }
+                for (int j = 0; j < kTJ; ++j)
+                  if (j < J) {
+                    const float2 c = c_f[n * 4 + j];
+                    ur[j] = fmaf(c.x, a, fmaf(-c.y, b, ur[j]));
+                    ui[j] = fmaf(c.x, b, fmaf(c.y, a, ui[j]));
+                  }
               }
-            }
+            };
+            const uint32_t tc0 = t_re + 32u * (uint32_t)sub;
+            const int nb0 = 32 * half + 16 * sub;
+            float ar[16], ai[16], br[16], bi[16];
+            tc_ld16(tc0, ar); tc_ld16(tc0 + NA, ai);
+            tc_ld16(tc0 + 16u, br); tc_ld16(tc0 + NA + 16u, bi);
+            tc_wait_ld();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
+            reduce16(ar, ai, nb0);
+            reduce16(br, bi, nb0 + 8);
             if (half == 1) {
-              float num = 0.f;
+              // sub 1 hands its partial sums to sub 0 through shared memory (double-buffered by tilt pair)
+              float* x = xch + ((((tloc >> 1) & 1) * 2 + set) * 4 + quad) * (32 * (1 + 2 * kTJ)) + lane;
+              if (sub == 1) {
+                x[0] = norm;
 #pragma unroll
-              for (int j = 0; j < kTJ; ++j) num = fmaf(ur[j], ur[j], fmaf(ui[j], ui[j], num));
-              const float bq = __fdividef(num, norm);
-              const float val = p.atype == BOGP_ATYPE_CBF ? bq : u.trK - bq;
-              float* a = acc + (size_t)tloc * kTileR + tl;
-              *a = (f == 0) ? val : (p.mf == BOGP_MF_MEAN ? *a + val : *a * val);
+                for (int j = 0; j < kTJ; ++j) { x[32 * (1 + 2 * j)] = ur[j]; x[32 * (2 + 2 * j)] = ui[j]; }
+              }
+              asm volatile("bar.sync %0, %1;" ::"r"(5 + set * 4 + quad), "r"(64) : "memory");
+              if (sub == 0) {
+                norm += x[0];
+                float num = 0.f;
+#pragma unroll
+                for (int j = 0; j < kTJ; ++j) {
+                  const float vr = ur[j] + x[32 * (1 + 2 * j)], vi = ui[j] + x[32 * (2 + 2 * j)];
+                  num = fmaf(vr, vr, fmaf(vi, vi, num));
+                }
+                const float bq = __fdividef(num, norm);
+                const float val = p.atype == BOGP_ATYPE_CBF ? bq : u.trK - bq;
+                float* a = acc + (size_t)tloc * kTileR + tl;
+                *a = (f == 0) ? val : (p.mf == BOGP_MF_MEAN ? *a + val : *a * val);
+              }
             }
           }
         }
@@ -1220,10 +1248,12 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   p.sumMp = sumMp;
   p.e_rt_stride = e_off;
   const unsigned acc_bytes = (unsigned)TC * kTileR * 4u;
-  unsigned stage = (kSmemLimit - acc_bytes - 256u) / kStages;
+  const unsigned aux_bytes = (64u * 4u + (unsigned)d.F * 256u * 8u + 2u * 2u * 4u * 9u * 32u * 4u + 127u) & ~127u;
+  unsigned stage = (kSmemLimit - acc_bytes - aux_bytes - 256u) / kStages;
   stage = std::min(stage & ~127u, 32u * 1024u);
   if (2u * 64u * (unsigned)maxMp * 4u > stage) { set_error("UMMA tilt engine: mode set does not fit"); return BOGP_ERR_UNSUPPORTED; }
-  p.stage_bytes = stage; p.smem_B = 0; p.smem_acc = kStages * stage; p.smem_bar = p.smem_acc + acc_bytes;
+  p.stage_bytes = stage; p.smem_B = 0; p.smem_acc = kStages * stage; p.smem_aux = p.smem_acc + acc_bytes;
+  p.smem_bar = p.smem_aux + aux_bytes;
   // scratch: [r | z | tilt doubles][err][phiz][sin][rinv][lever][E table][Bhi][Blo]
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t off_err = al(((size_t)Nr + Nz + Nt) * sizeof(double));
