@@ -150,6 +150,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 // Waiting flavour for the roles that run ahead of the pipeline (producer, loaders): back off between polls so the
 // spinning warp does not take issue slots from the epilogue warps on its scheduler (higher warp ids win arbitration).
+template <unsigned kSleepNs = 256>
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int* err, int code) {
   uint32_t ok = 0;
   long long t0 = 0;
@@ -162,7 +163,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
-    __nanosleep(256);
+    __nanosleep(kSleepNs);
     if (spin == 0) t0 = clock64();
     if ((spin & 255u) == 255u && clock64() - t0 > 3000000000LL) {
       atomicExch(err, code + 1000 * (int)blockIdx.x);
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
         for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
           const int njs = min(u.nj, nzu - j0);
           const uint32_t slot = sc % kStages, ph = (sc / kStages) & 1u;
-          mbar_wait_relaxed(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3);
+          mbar_wait_relaxed<TILT ? 512 : 256>(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3);
           const uint32_t bytes = (uint32_t)njs * u.b_zbytes;
           const uint32_t dst = s_base + p.smem_B + slot * p.stage_bytes;
           const size_t src = (size_t)u.b_off + (size_t)(z0 + j0) * u.b_zbytes;
@@ -697,11 +698,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       unit_decode<TILT>(p, unit, rt, z0_, nzu_, jreal);
       for (int f = 0; f < p.F; ++f, ++g) {
         const UTonal& u = p.t[f];
-        if (g >= 2) mbar_wait_relaxed(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1);
+        // (tilt mode: a tonal lasts ~100k cycles and every poll costs issue slots the epilogue needs)
+        if (g >= 2) mbar_wait_relaxed<TILT ? 4096 : 256>(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1);
         if (g >= 1) {
           const UTonal& up = p.t[f == 0 ? p.F - 1 : f - 1];
           if (4 * (up.Mp + u.Mp) > p.AR)
-            mbar_wait_relaxed(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2);
+            mbar_wait_relaxed<TILT ? 2048 : 256>(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2);
         }
         tc_fence_after();
         const float4* src = reinterpret_cast<const float4*>(p.E + (size_t)rt * p.e_rt_stride + u.e_off) + tl;
@@ -798,6 +800,20 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
             // The two warps (sub 0 / 1) of this (buffer, quadrant) split the stage: 16 receivers = 32 columns each, all
             // four tcgen05.ld up front, release at the single wait, then the receiver-space reduction from registers.
             auto reduce16 = [&](const float* re, const float* im, int nb) {
+              if (J == 1) {                     // rank-1 covariance (K = d d^H, the reference's per-snapshot case):
+#pragma unroll                                  // no predicated work for the unused ranks (it still costs issue slots)
+                for (int q = 0; q < 8; ++q) {
+                  const int n = nb + q;
+                  const float tr = re[2 * q] - im[2 * q + 1], ti = im[2 * q] + re[2 * q + 1];
+                  const float sn = rsqrtf(fmaf(-lev_s[n], xs, 1.f));
+                  norm = fmaf(sn * sn, fmaf(tr, tr, ti * ti), norm);
+                  const float a = sn * tr, b = sn * ti;
+                  const float2 c = c_f[n * 4];
+                  ur[0] = fmaf(c.x, a, fmaf(-c.y, b, ur[0]));
+                  ui[0] = fmaf(c.x, b, fmaf(c.y, a, ui[0]));
+                }
+                return;
+              }
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 const int n = nb + q;
