@@ -217,6 +217,8 @@ def bo_iteration(n: int = 256, d: int = 3, raw: int = 4096, restarts: int = 64, 
         if i:
             ft.append(time.perf_counter() - t0)
     out["fit_gpu_ms"] = float(np.median(ft) * 1e3)
+    fit_gp_adamw_torch(SingleTaskGP(X, y), FitConfig(steps=3))          # cuSOLVER handle / workspace warm-up
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     fit_gp_adamw_torch(SingleTaskGP(X, y), FitConfig(steps=100))
     torch.cuda.synchronize()
