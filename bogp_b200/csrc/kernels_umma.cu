@@ -520,7 +520,7 @@ __device__ __forceinline__ void dbg_stamp(const UParams& p, int ev, uint32_t sc)
 }
 // barrier slots (8 bytes each) at smem_bar
 enum { BAR_BFULL = 0, BAR_BEMPTY = kStages, BAR_EFULL = 2 * kStages, BAR_EDONE = 2 * kStages + 2,
-       BAR_TFULL = 2 * kStages + 4, BAR_TEMPTY = 2 * kStages + 6, BAR_COUNT = 2 * kStages + 8 };
+       BAR_TFULL = 2 * kStages + 4, BAR_TEMPTY = 2 * kStages + 6, BAR_TURN = 2 * kStages + 8, BAR_COUNT = 2 * kStages + 10 };
 
 // TMEM column of tonal g's E image: even tonals grow from the low end of the A region, odd ones sit at the high end,
 // so tonal g+1 can be loaded while tonal g is still being multiplied whenever the two fit side by side.
@@ -575,6 +575,12 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
     const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
     mbar_wait_t(bar(BAR_BFULL + slot), ph, p.err, 5, (BOGP_UMMA_DBG && st.dbg) ? &st.w_bfull : nullptr);
     mbar_wait_t(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6, (BOGP_UMMA_DBG && st.dbg) ? &st.w_tempty : nullptr);
+    // Issue in stage order: wait until the other issuer has ISSUED stage sc - 1.  Without the turn the two issuers
+    // interleave their MMAs in the tensor pipe's queue, both stages complete together, both buffers sit in the
+    // epilogue together and the pipe idles meanwhile (measured lock-step: both issuers ready within ~150 cycles of
+    // each other, then nothing for ~2300); in order, stage sc - 1 completes one stage time earlier and its epilogue
+    // overlaps this stage's MMAs.
+    if (sc > 0) mbar_wait(bar(BAR_TURN + (st.id ^ 1)), ((sc - 1u) >> 1) & 1u, p.err, 8);
     tc_fence_after();
     dbg_stamp(p, 0, sc);
     const uint32_t N = (uint32_t)(njs * u.rowsP);
@@ -587,6 +593,7 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
         issue_stage<KS>(d_re, d_im, a_col, Mp, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc);
       tc_commit(bar(BAR_BEMPTY + slot));
       tc_commit(bar(BAR_TFULL + buf));
+      mbar_arrive(bar(BAR_TURN + st.id));
     }
     __syncwarp();
     dbg_stamp(p, 1, sc);
@@ -611,6 +618,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       mbar_init(bar(BAR_EFULL + b), kLoadWarps);
       mbar_init(bar(BAR_EDONE + b), 2);          // both MMA issuers commit
       mbar_init(bar(BAR_TFULL + b), 1);
+      mbar_init(bar(BAR_TURN + b), 1);
       mbar_init(bar(BAR_TEMPTY + b), kEpiWarps / 2);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
