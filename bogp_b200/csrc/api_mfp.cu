@@ -21,6 +21,24 @@ int upload(bogp_modeset_s* h, std::vector<void*>& owner, const std::vector<T>& v
   return 0;
 }
 
+// Covariance-dependent arrays are re-uploaded at every bogp_covariance_set (once per time step of a sweep): keep the
+// device buffer while the new contents fit instead of cudaFree + cudaMalloc (each an implicit device synchronisation).
+template <typename T>
+int upload_reuse(bogp_modeset_s* h, size_t slot, const std::vector<T>& v, const T** out) {
+  if (h->cov_allocs.size() <= slot) { h->cov_allocs.resize(slot + 1, nullptr); h->cov_capacity.resize(slot + 1, 0); }
+  const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  if (h->cov_capacity[slot] < bytes) {
+    if (h->cov_allocs[slot]) cudaFree(h->cov_allocs[slot]);
+    h->cov_allocs[slot] = nullptr; h->cov_capacity[slot] = 0;
+    const size_t cap = bytes + bytes / 4 + 256;          // head-room: the operator rows change with the covariance rank
+    BOGP_CUDA(cudaMalloc(&h->cov_allocs[slot], cap));
+    h->cov_capacity[slot] = cap;
+  }
+  if (!v.empty()) BOGP_CUDA(cudaMemcpy(h->cov_allocs[slot], v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<const T*>(h->cov_allocs[slot]);
+  return 0;
+}
+
 int require_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -188,34 +206,55 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
       }
     for (int a = 0; a < N; ++a) trK += K[(size_t)a * N + a].real();
     t.trK = (float)trK;
-    // G = Phi^H Phi, KP = K Phi, H = Phi^H K Phi   (all [M, M] / [N, M])
-    std::vector<cplx> G((size_t)M * M), KP((size_t)N * M), H((size_t)M * M);
-    for (int a = 0; a < M; ++a)
-      for (int b = a; b < M; ++b) {
-        cplx s = 0.0;
-        for (int n = 0; n < N; ++n) s += std::conj(Phi[(size_t)n * M + a]) * Phi[(size_t)n * M + b];
-        G[(size_t)a * M + b] = s;
-        G[(size_t)b * M + a] = std::conj(s);
-      }
-    for (int n = 0; n < N; ++n)
-      for (int m = 0; m < M; ++m) {
-        cplx s = 0.0;
-        for (int q = 0; q < N; ++q) s += K[(size_t)n * N + q] * Phi[(size_t)q * M + m];
-        KP[(size_t)n * M + m] = s;
-      }
-    for (int a = 0; a < M; ++a)
-      for (int b = a; b < M; ++b) {
-        cplx s = 0.0;
-        for (int n = 0; n < N; ++n) s += std::conj(Phi[(size_t)n * M + a]) * KP[(size_t)n * M + b];
-        H[(size_t)a * M + b] = s;
-        H[(size_t)b * M + a] = std::conj(s);
-      }
-    for (int a = 0; a < M; ++a) { G[(size_t)a * M + a] = G[(size_t)a * M + a].real(); H[(size_t)a * M + a] = H[(size_t)a * M + a].real(); }
-    std::vector<cplx> LG, LH, LK;
-    int rG = 0, rH = 0, rK = 0;
-    bogp::pivoted_cholesky(G, M, tol, LG, rG);
-    bogp::pivoted_cholesky(H, M, tol, LH, rH);
+    // G = Phi^H Phi does not depend on the covariance: its pivoted Cholesky factor is computed once per handle.
+    if ((int)h->LG_cache.size() != F) { h->LG_cache.assign(F, {}); h->rG_cache.assign(F, -1); }
+    if (h->rG_cache[f] < 0) {
+      std::vector<cplx> G((size_t)M * M);
+      for (int a = 0; a < M; ++a)
+        for (int b = a; b < M; ++b) {
+          cplx s = 0.0;
+          for (int n = 0; n < N; ++n) s += std::conj(Phi[(size_t)n * M + a]) * Phi[(size_t)n * M + b];
+          G[(size_t)a * M + b] = s;
+          G[(size_t)b * M + a] = std::conj(s);
+        }
+      for (int a = 0; a < M; ++a) G[(size_t)a * M + a] = G[(size_t)a * M + a].real();
+      bogp::pivoted_cholesky(G, M, tol, h->LG_cache[f], h->rG_cache[f]);
+    }
+    const std::vector<cplx>& LG = h->LG_cache[f];
+    const int rG = h->rG_cache[f];
+    std::vector<cplx> LH, LK;
+    int rH = 0, rK = 0;
     bogp::pivoted_cholesky(K, N, tol, LK, rK);
+    if (rK <= M) {
+      // K = LK LK^H  =>  H = Phi^H K Phi = C^H C with C = LK^H Phi (rK x M): the numerator rows directly, no N^2 M
+      // product and no second factorisation (rank-1 K = d d^H, the per-snapshot case, costs N M)
+      rH = rK;
+      LH.assign((size_t)M * M, cplx(0.0, 0.0));
+      for (int j = 0; j < rK; ++j)
+        for (int m = 0; m < M; ++m) {
+          cplx s = 0.0;
+          for (int n = 0; n < N; ++n) s += std::conj(LK[(size_t)n * N + j]) * Phi[(size_t)n * M + m];
+          LH[(size_t)m * M + j] = std::conj(s);          // LH^H = C
+        }
+    } else {
+      // rank K > M: factor the M x M mode-space matrix instead (at most M numerator rows)
+      std::vector<cplx> KP((size_t)N * M), H((size_t)M * M);
+      for (int n = 0; n < N; ++n)
+        for (int m = 0; m < M; ++m) {
+          cplx s = 0.0;
+          for (int q = 0; q < N; ++q) s += K[(size_t)n * N + q] * Phi[(size_t)q * M + m];
+          KP[(size_t)n * M + m] = s;
+        }
+      for (int a = 0; a < M; ++a)
+        for (int b = a; b < M; ++b) {
+          cplx s = 0.0;
+          for (int n = 0; n < N; ++n) s += std::conj(Phi[(size_t)n * M + a]) * KP[(size_t)n * M + b];
+          H[(size_t)a * M + b] = s;
+          H[(size_t)b * M + a] = std::conj(s);
+        }
+      for (int a = 0; a < M; ++a) H[(size_t)a * M + a] = H[(size_t)a * M + a].real();
+      bogp::pivoted_cholesky(H, M, tol, LH, rH);
+    }
     // Mode-space operator W: rows = R = LG^H (rG x M) then C = LH^H (rH x M); T = W a.
     t.n_plain = d.rec_complex ? 0 : rG;
     t.n_npair = d.rec_complex ? rG : 0;
@@ -277,14 +316,14 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
     h->max_rows = std::max(h->max_rows, t.rows);
     h->max_J = std::max(h->max_J, t.J);
   }
-  for (void* p : h->cov_allocs) cudaFree(p);
-  h->cov_allocs.clear();
+  // kernels of a previous call may still be reading the arrays that are overwritten in place below
+  BOGP_CUDA(cudaDeviceSynchronize());
   int rc = 0;
-  rc |= upload(h, h->cov_allocs, W, &d.W);
-  rc |= upload(h, h->cov_allocs, Wt, &d.Wt);
-  rc |= upload(h, h->cov_allocs, Wu, &d.Wu);
-  rc |= upload(h, h->cov_allocs, Ckre, &d.CkT_re);
-  rc |= upload(h, h->cov_allocs, Ckim, &d.CkT_im);
+  rc |= upload_reuse(h, 0, W, &d.W);
+  rc |= upload_reuse(h, 1, Wt, &d.Wt);
+  rc |= upload_reuse(h, 2, Wu, &d.Wu);
+  rc |= upload_reuse(h, 3, Ckre, &d.CkT_re);
+  rc |= upload_reuse(h, 4, Ckim, &d.CkT_im);
   if (rc) return BOGP_ERR_CUDA;
   h->has_cov = true;
   return 0;

@@ -110,7 +110,11 @@ struct ModesetDev {
 struct bogp_modeset_s {
   bogp::ModesetDev dev;           // device pointers + metadata (passed by value to kernels)
   std::vector<void*> allocs;      // every cudaMalloc owned by this handle
-  std::vector<void*> cov_allocs;  // allocations replaced at each covariance_set
+  std::vector<void*> cov_allocs;  // the five covariance-dependent device arrays (W, Wt, Wu, Ck re/im), reused while they fit
+  std::vector<size_t> cov_capacity;
+  // covariance-independent half of bogp_covariance_set, cached: pivoted Cholesky factor of G_f = Phi_f^H Phi_f
+  std::vector<std::vector<bogp::cplx>> LG_cache;
+  std::vector<int> rG_cache;
   // host copies (float64) kept for covariance_set
   int F = 0, N = 0;
   std::vector<int> M;
