@@ -322,6 +322,12 @@ __device__ __forceinline__ void tc_ld2(uint32_t taddr, float& a, float& b) {
   a = __uint_as_float(r0);
   b = __uint_as_float(r1);
 }
+// MUFU.RSQ alone: rsqrtf() adds a denormal-range rescue (FSETP + two predicated FMULs) that 1 - l sin(tau) / r ~ 1 never needs
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor bit layout): start address
@@ -813,9 +819,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
                 for (int q = 0; q < 8; ++q) {
                   const int n = nb + q;
                   const float tr = re[2 * q] - im[2 * q + 1], ti = im[2 * q] + re[2 * q + 1];
-                  const float sn = rsqrtf(fmaf(-lev_s[n], xs, 1.f));
-                  norm = fmaf(sn * sn, fmaf(tr, tr, ti * ti), norm);
-                  const float a = sn * tr, b = sn * ti;
+                  const float sn = rsqrt_fast(fmaf(-lev_s[n], xs, 1.f));
+                  const float a = sn * tr, b = sn * ti;                    // p_n = s_n T_n
+                  norm = fmaf(a, a, fmaf(b, b, norm));
                   const float2 c = c_f[n * 4];
                   ur[0] = fmaf(c.x, a, fmaf(-c.y, b, ur[0]));
                   ui[0] = fmaf(c.x, b, fmaf(c.y, a, ui[0]));
@@ -826,9 +832,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
               for (int q = 0; q < 8; ++q) {
                 const int n = nb + q;
                 const float tr = re[2 * q] - im[2 * q + 1], ti = im[2 * q] + re[2 * q + 1];
-                const float sn = rsqrtf(fmaf(-lev_s[n], xs, 1.f));
-                norm = fmaf(sn * sn, fmaf(tr, tr, ti * ti), norm);
+                const float sn = rsqrt_fast(fmaf(-lev_s[n], xs, 1.f));
                 const float a = sn * tr, b = sn * ti;
+                norm = fmaf(a, a, fmaf(b, b, norm));
 #pragma unroll
                 for (int j = 0; j < kTJ; ++j)
                   if (j < J) {
