@@ -56,6 +56,8 @@ SIGNATURES = {
     "bogp_gp_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _dp, _dp, C.c_int, _dp, C.c_double, C.c_double, C.c_double]),
     "bogp_gp_destroy": (C.c_int, [_vp]),
     "bogp_gp_jitter": (C.c_int, [_vp, _dp]),
+    "bogp_gp_acq_host": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _dp, _ll, _dp, _dp, _vp]),
+    "bogp_gp_qei_host": (C.c_int, [_vp, _dp, _ll, C.c_int, _vp, C.c_int, C.c_double, _dp, _dp, _vp]),
     "bogp_gp_fit_adamw": (C.c_int, [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                     C.c_double, _dp, _dp, C.c_int, _dp, _dp, _vp]),
     "bogp_gp_posterior": (C.c_int, [_vp, _vp, _ll, C.c_int, _vp, _vp, _vp]),

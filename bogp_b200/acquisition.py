@@ -104,6 +104,21 @@ class _Analytic(AcquisitionFunction):
         return _AnalyticAcq.apply(X, self.model, self.kind, self.best_f, self.beta)
 
 
+    def value_and_grad_host(self, X: "np.ndarray", need_grad: bool = True):
+        """``X[b, 1, d]`` float64 host array -> ``(values[b], grad[b, 1, d] or None)`` as host arrays through ONE call of
+        ``bogp_gp_acq_host`` (what :func:`bogp_b200.optim.optimize_acqf` uses inside L-BFGS-B)."""
+        import numpy as np
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        b = X.shape[0]
+        if X.ndim != 3 or X.shape[1] != 1:
+            raise ValueError("analytic acquisition functions expect q = 1 (X[b, 1, d])")
+        out = np.empty(b)
+        grad = np.empty_like(X) if need_grad else None
+        _lib.call("bogp_gp_acq_host", self.model.handle(), _lib.ACQ[self.kind], self.best_f, self.beta, _lib.dptr(X), b,
+                  _lib.dptr(out), _lib.dptr(grad), C.c_void_p(_lib.current_stream_ptr()))
+        return out, grad
+
+
 class ExpectedImprovement(_Analytic):
     kind, nonneg = "ei", True
 
@@ -159,3 +174,17 @@ class qExpectedImprovement(AcquisitionFunction):
         if X.shape[-2] != self.q:
             raise ValueError(f"expected X[b, q={self.q}, d]")
         return _QEI.apply(X, self.model, self.base_samples, self.best_f)
+
+    def value_and_grad_host(self, X: "np.ndarray", need_grad: bool = True):
+        """Host-array variant (``bogp_gp_qei_host``), see :meth:`_Analytic.value_and_grad_host`."""
+        import numpy as np
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        if X.ndim != 3 or X.shape[1] != self.q:
+            raise ValueError(f"expected X[b, q={self.q}, d]")
+        b = X.shape[0]
+        out = np.empty(b)
+        grad = np.empty_like(X) if need_grad else None
+        _lib.call("bogp_gp_qei_host", self.model.handle(), _lib.dptr(X), b, self.q, C.c_void_p(self.base_samples.data_ptr()),
+                  self.base_samples.shape[0], self.best_f, _lib.dptr(out), _lib.dptr(grad),
+                  C.c_void_p(_lib.current_stream_ptr()))
+        return out, grad

@@ -446,7 +446,13 @@ extern "C" int bogp_gp_fit_adamw(int n, int d, const double* X_host, const doubl
   p.X = dX; p.y = dy; p.raw = draw; p.loss = dloss; p.work = dwork; p.status = dstatus;
   const bool in_smem = p.a_in_smem && p.x_in_smem;
   if (in_smem) FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else {
+    FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // matrix in the global scratch: leave the rest of the SM's 256 KB to L1 -- the factorisation re-reads every panel
+    // many times and is bound by L2 latency otherwise
+    const int pct = (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1);
+    FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  }
   cudaEvent_t ev = timing_begin(s);
   if (in_smem) gp_fit_kernel<true><<<B, kFitThreads, smem, s>>>(p);
   else gp_fit_kernel<false><<<B, kFitThreads, smem, s>>>(p);

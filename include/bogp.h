@@ -180,6 +180,15 @@ int bogp_gp_posterior_joint_backward(bogp_gp_t g, const double* Xs_dev, long lon
 int bogp_gp_qei(bogp_gp_t g, const double* Xs_dev, long long b, int q, const double* base_dev, int S,
                 double best_f, double* out_dev, double* grad_dev, void* stream);
 
+/* Host-buffer variants of bogp_gp_acq / bogp_gp_qei for the optimiser loop of optimize_acqf (ei.py:81-92): L-BFGS-B calls
+ * value + gradient hundreds of times per BO iteration on a handful of restarts; one C call with page-locked staging
+ * replaces the framework round trip.  Xs_host[b,(q,)d], out_host[b], grad_host[b,(q,)d] or NULL; base_dev stays on the
+ * device.  Synchronises the stream. */
+int bogp_gp_acq_host(bogp_gp_t g, int acq_kind, double best_f, double beta, const double* Xs_host, long long b,
+                     double* out_host, double* grad_host, void* stream);
+int bogp_gp_qei_host(bogp_gp_t g, const double* Xs_host, long long b, int q, const double* base_dev, int S,
+                     double best_f, double* out_host, double* grad_host, void* stream);
+
 /* GP hyper-parameter fit: the loop of ref/projects/swellex96_inv/data/bo/ei.py:69-78 --
  * `steps` x AdamW(lr, weight_decay; betas 0.9/0.999, eps 1e-8 as torch.optim.AdamW) on -mll/n over the raw GPyTorch
  * parameters -- as ONE persistent kernel launch per call (kernel matrix, blocked Cholesky, K^-1, analytic gradient and

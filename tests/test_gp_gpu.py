@@ -234,3 +234,29 @@ def test_fused_fit_kernel_jitter_and_errors():
     assert np.isfinite(m.lengthscale.numpy()).all() and m.outputscale > 0
     with pytest.raises(_lib.BogpError):
         fit_gp_adamw(SingleTaskGP(X, y), FitConfig(steps=0))
+
+
+def test_host_buffer_acquisition_entry_points_match_device_path():
+    """bogp_gp_acq_host / bogp_gp_qei_host (what optimize_acqf's L-BFGS-B loop calls) == the device-pointer path."""
+    from bogp_b200 import acquisition as A
+    model, oracle, X, y = make_problem(96, 3)
+    rng = np.random.default_rng(5)
+    Xs = rng.random((40, 1, 3))
+    for acq in (A.ExpectedImprovement(model, float(y.max())), A.LogExpectedImprovement(model, float(y.max())),
+                A.UpperConfidenceBound(model, 2.0)):
+        Xt = torch.as_tensor(Xs).requires_grad_(True)
+        v = acq(Xt)
+        (g,) = torch.autograd.grad(v.sum(), Xt)
+        vh, gh = acq.value_and_grad_host(Xs)
+        np.testing.assert_array_equal(vh, v.detach().cpu().numpy())
+        np.testing.assert_array_equal(gh, g.cpu().numpy())
+        assert acq.value_and_grad_host(Xs, need_grad=False)[1] is None
+    q = 3
+    qei = A.qExpectedImprovement(model, float(y.max()), q=q, mc_samples=64, seed=1)
+    Xq = rng.random((10, q, 3))
+    Xt = torch.as_tensor(Xq).requires_grad_(True)
+    v = qei(Xt)
+    (g,) = torch.autograd.grad(v.sum(), Xt)
+    vh, gh = qei.value_and_grad_host(Xq)
+    np.testing.assert_array_equal(vh, v.detach().cpu().numpy())
+    np.testing.assert_array_equal(gh, g.cpu().numpy())
