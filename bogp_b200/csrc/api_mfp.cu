@@ -1,5 +1,6 @@
 // C-ABI entry points of Boundary A (matched-field objective): set-up and dispatch.
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 
@@ -399,6 +400,27 @@ extern "C" int bogp_bartlett_grid_argext(bogp_modeset_t h, const double* r_m_hos
   return grid_impl(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, out_dev, stream, maximize ? 1 : 2, val_dev, idx_dev, scratch_dev);
 }
 
+// Same choice as grid_impl: does this call run on a tcgen05 engine (where the arg-ext is fused into the surface kernel)?
+static bool picks_tensor_engine(bogp_modeset_t h, int engine, const double* tilt_deg_host, int Nt, long long total) {
+  if (!h || !h->has_cov || engine == BOGP_ENGINE_SIMT) return false;
+  bool tilted = Nt > 1;
+  if (tilt_deg_host)
+    for (int i = 0; i < Nt; ++i) tilted |= (tilt_deg_host[i] != 0.0);
+  if (tilted) return bogp::umma_tilt_supported(h) && (engine == BOGP_ENGINE_UMMA || total >= 65536);
+  return bogp::umma_supported(h) && (engine == BOGP_ENGINE_UMMA || total >= 16384);
+}
+
+// Page-locked, device-mapped host memory (cudaHostAlloc / torch pin_memory): the kernels can write the surface straight
+// into it -- the posted PCIe writes of the epilogue overlap the computation and the separate device -> host copy of the
+// finished surface disappears from the call.  Returns the device alias of `host`, or nullptr for pageable memory.
+static float* mapped_alias(float* host) {
+  if (const char* off = std::getenv("BOGP_NO_ZEROCOPY")) { if (off[0] == '1') return nullptr; }
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+  return static_cast<float*>(at.devicePointer);
+}
+
 extern "C" int bogp_bartlett_grid_host(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
                                        const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
                                        float* out_host, void* stream) {
@@ -406,6 +428,14 @@ extern "C" int bogp_bartlett_grid_host(bogp_modeset_t h, const double* r_m_host,
   BOGP_REQUIRE(h != nullptr, "bogp_bartlett_grid_host: NULL handle");
   size_t n = (size_t)std::max(Nt, 1) * Nz * Nr;
   if (n == 0) return 0;
+  if (float* alias = mapped_alias(out_host)) {
+    int rc = bogp_bartlett_grid(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, alias, stream);
+    if (rc == 0 && cudaStreamSynchronize(static_cast<cudaStream_t>(stream)) != cudaSuccess) {
+      bogp::set_error("bogp_bartlett_grid_host: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = BOGP_ERR_CUDA;
+    }
+    return rc;
+  }
   if (int rc0 = io_scratch(h, n * sizeof(float))) return rc0;
   float* tmp = static_cast<float*>(h->io_scratch);
   int rc = bogp_bartlett_grid(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, tmp, stream);
@@ -431,14 +461,17 @@ extern "C" int bogp_bartlett_grid_host_argmax(bogp_modeset_t h, const double* r_
   const size_t off_pair = (n * sizeof(float) + 15) & ~(size_t)15;
   if (int rc0 = io_scratch(h, off_pair + 16 + 8192)) return rc0;
   char* base = static_cast<char*>(h->io_scratch);
-  float* tmp = reinterpret_cast<float*>(base);
+  // mapped host memory: the kernel writes it directly (only where the reduction is fused: the separate arg-ext
+  // kernels would re-read the surface over PCIe)
+  float* alias = picks_tensor_engine(h, engine, tilt_deg_host, Nt, (long long)n) ? mapped_alias(out_host) : nullptr;
+  float* tmp = alias ? alias : reinterpret_cast<float*>(base);
   long long* idx_dev = reinterpret_cast<long long*>(base + off_pair);
   float* val_dev = reinterpret_cast<float*>(base + off_pair + 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc = bogp_bartlett_grid_argext(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, tmp,
                                      maximize, val_dev, idx_dev, base + off_pair + 16, 8192, stream);
   if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(out_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, s);
+    cudaError_t e = alias ? cudaSuccess : cudaMemcpyAsync(out_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(idx_host, idx_dev, sizeof(long long), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(val_host, val_dev, sizeof(float), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);

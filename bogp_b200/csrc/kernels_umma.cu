@@ -586,7 +586,6 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
     // epilogue together and the pipe idles meanwhile (measured lock-step: both issuers ready within ~150 cycles of
     // each other, then nothing for ~2300); in order, stage sc - 1 completes one stage time earlier and its epilogue
     // overlaps this stage's MMAs.
-    if (sc > 0) mbar_wait(bar(BAR_TURN + (st.id ^ 1)), ((sc - 1u) >> 1) & 1u, p.err, 8);
     tc_fence_after();
     dbg_stamp(p, 0, sc);
     const uint32_t N = (uint32_t)(njs * u.rowsP);
@@ -594,12 +593,15 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
     const uint32_t b_hi = st.s_base + p.smem_B + slot * p.stage_bytes;
     const uint32_t b_lo = b_hi + (uint32_t)njs * u.b_zbytes;
     const uint32_t d_re = st.tmem_base + buf * (uint32_t)(2 * p.NA), d_im = d_re + (uint32_t)p.NA;
+    // (the turn is taken as late and passed on as early as possible: only the MMA instructions themselves are
+    // serialised between the issuers, ~20 cycles each; barrier waits, address set-up and commits overlap)
+    if (sc > 0) mbar_wait(bar(BAR_TURN + (st.id ^ 1)), ((sc - 1u) >> 1) & 1u, p.err, 8);
     if (elect_one()) {
       if (!(BOGP_UMMA_DBG && p.skip == 1))
         issue_stage<KS>(d_re, d_im, a_col, Mp, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc);
+      mbar_arrive(bar(BAR_TURN + st.id));
       tc_commit(bar(BAR_BEMPTY + slot));
       tc_commit(bar(BAR_TFULL + buf));
-      mbar_arrive(bar(BAR_TURN + st.id));
     }
     __syncwarp();
     dbg_stamp(p, 1, sc);
