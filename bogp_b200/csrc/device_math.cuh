@@ -17,6 +17,26 @@ __device__ __forceinline__ float reduce_phase(double theta) {
   return (float)r;
 }
 
+// sin / cos of a LARGE float64 phase for kernels that are bound by instruction issue: reduction modulo pi/2 in
+// float64 (quadrant = n mod 4), then the cephes single-precision kernels on |r| <= pi/4 (~1e-7 absolute) -- about
+// half the instructions of reduce_phase + sincosf, which reduces a second time in float32.
+__device__ __forceinline__ void sincos_big(double theta, float& s, float& c) {
+  const double two_over_pi = 0.63661977236758134308;
+  const double pio2_hi = 1.57079632679489655800;       // fl(pi/2)
+  const double pio2_lo = 6.12323399573676603587e-17;   // pi/2 - pio2_hi
+  const double n = rint(theta * two_over_pi);
+  double r = fma(-n, pio2_hi, theta);
+  r = fma(-n, pio2_lo, r);
+  const int q = (int)(long long)n & 3;
+  const float x = (float)r, z = x * x;
+  const float sr = fmaf(fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, x, x);
+  const float cr = fmaf(fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f) * z, z,
+                        fmaf(-0.5f, z, 1.0f));
+  const float a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;      // sin, cos before the sign
+  s = (q & 2) ? -a : a;
+  c = ((q + 1) & 2) ? -b : b;
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(512) envstream_kernel(const EnvStreamParams p)
       float2 a = make_float2(0.f, 0.f);
       if (gg.x != 0.f || gg.y != 0.f) {
         float s, co;
-        sincosf(reduce_phase(kre[idx] * r), &s, &co);
+        sincos_big(kre[idx] * r, s, co);
         const float amp = expf(kim[idx] * rf) * rs;
         a = cmul(gg, make_float2(amp * co, -amp * s));
       }
@@ -203,15 +203,21 @@ __global__ void __launch_bounds__(512) envstream_kernel(const EnvStreamParams p)
 #pragma unroll
       for (int j = 0; j < kEnvJ; ++j) sr[j] = si[j] = 0.f;
       for (int n = lane; n < p.N; n += 32) {
-        float pr0 = 0.f, pi0 = 0.f, pr1 = 0.f, pi1 = 0.f;
+        // four modes per step, eight independent accumulators: the loop is bound by shared-memory load latency
+        // (12 warps per SM), so the loads of a whole unrolled body are issued before its FMAs
+        float pr0 = 0.f, pi0 = 0.f, pr1 = 0.f, pi1 = 0.f, pr2 = 0.f, pi2 = 0.f, pr3 = 0.f, pi3 = 0.f;
+        const float* pn = Pf + n;
+        const int N = p.N;
 #pragma unroll 4
-        for (int m = 0; m < p.Mmax; m += 2) {          // Mmax is a multiple of 4
-          const float ph0 = Pf[(size_t)m * p.N + n], ph1 = Pf[(size_t)(m + 1) * p.N + n];
-          const float4 a2 = *reinterpret_cast<const float4*>(af + m);
-          pr0 = fmaf(ph0, a2.x, pr0); pi0 = fmaf(ph0, a2.y, pi0);
-          pr1 = fmaf(ph1, a2.z, pr1); pi1 = fmaf(ph1, a2.w, pi1);
+        for (int m = 0; m < p.Mmax; m += 4) {          // Mmax is a multiple of 4
+          const float ph0 = pn[m * N], ph1 = pn[(m + 1) * N], ph2 = pn[(m + 2) * N], ph3 = pn[(m + 3) * N];
+          const float4 a01 = *reinterpret_cast<const float4*>(af + m), a23 = *reinterpret_cast<const float4*>(af + m + 2);
+          pr0 = fmaf(ph0, a01.x, pr0); pi0 = fmaf(ph0, a01.y, pi0);
+          pr1 = fmaf(ph1, a01.z, pr1); pi1 = fmaf(ph1, a01.w, pi1);
+          pr2 = fmaf(ph2, a23.x, pr2); pi2 = fmaf(ph2, a23.y, pi2);
+          pr3 = fmaf(ph3, a23.z, pr3); pi3 = fmaf(ph3, a23.w, pi3);
         }
-        const float pr = pr0 + pr1, pi = pi0 + pi1;
+        const float pr = (pr0 + pr1) + (pr2 + pr3), pi = (pi0 + pi1) + (pi2 + pi3);
         norm = fmaf(pr, pr, fmaf(pi, pi, norm));
 #pragma unroll
         for (int j = 0; j < kEnvJ; ++j)
