@@ -356,3 +356,37 @@ def test_tilt_tensor_core_engine_vs_oracle_and_simt(case):
     vol = dms.bartlett_grid(r, z, tilt, engine="umma", argext=(pair, scratch, True)).cpu().numpy()
     vals, idxs = mfp.unpack_pairs(pair.reshape(1, 2))
     assert int(idxs[0]) == int(vol.argmax()) and vals[0] == vol.max()
+
+
+def test_full_size_tilt_volume_properties():
+    """BASELINE config 4 shape at 1/10 of its tilt axis (1000 r x 100 z x 11 tilt x 13 tonals = 1.1e6 candidates) on
+    the tensor-core tilt engine: size-independent properties.  (a) the peak sits on the node nearest the truth
+    (range, depth, tilt) with value ~1; (b) 0 <= B <= 1; (c) the zero-tilt plane equals the vertical-array surface
+    computed by the other tensor-core kernel (mode space vs receiver space: independent code paths); (d) a random
+    sample of nodes matches the oracle; (e) the SIMT tilt-plane kernel agrees; (f) host entry point into page-locked
+    memory (the kernel writes it directly) returns the same volume and extremum."""
+    from bogp_b200 import mfp
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    r, z, tilt = np.linspace(0.1, 10.0, 1000), np.linspace(1.0, 200.0, 100), np.linspace(-4.0, 4.0, 11)
+    ti, zi, ri = 7, 30, 495                              # tilt 1.6 deg, depth 61.3 m, range 5.005 km
+    K = synthetic_covariance(modes, z[zi], r[ri], tilt_deg=tilt[ti])
+    dms = DeviceModeSet(modes, K)
+    vol_t = dms.bartlett_grid(r, z, tilt, engine="umma")
+    val, pos = mfp.argmax(vol_t)
+    assert pos == (ti, zi, ri) and abs(val - 1.0) < 3e-5
+    vol = vol_t.cpu().numpy()
+    assert vol.min() >= 0.0 and vol.max() <= 1.0 + 3e-5
+    flat = dms.bartlett_grid(r, z, engine="umma").cpu().numpy()          # vertical array, mode-space kernel
+    assert_parity(vol[5], flat, rtol=5e-6)                               # tilt[5] == 0
+    rng = np.random.default_rng(11)
+    tt, jj, ii = rng.integers(0, 11, 200), rng.integers(0, 100, 200), rng.integers(0, 1000, 200)
+    ref = ob.bartlett_points(modes, K, np.stack([r[ii], z[jj], tilt[tt]], 1))
+    assert_parity(vol[tt, jj, ii], ref)
+    simt = dms.bartlett_grid(r, z, tilt, engine="simt").cpu().numpy()
+    assert np.abs(simt - vol).max() <= 2e-5
+    pinned = torch.empty(vol.shape, dtype=torch.float32, pin_memory=True)
+    out, (v2, pos2) = dms.bartlett_grid_host(r, z, tilt, engine="umma", out=pinned.numpy(), argext="max")
+    np.testing.assert_array_equal(out, vol)
+    assert pos2 == pos and v2 == pytest.approx(val)
