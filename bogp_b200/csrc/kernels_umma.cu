@@ -24,9 +24,17 @@
 // The Bop table is built per call directly in the UMMA canonical K-major no-swizzle layout ([8-row group][16-byte K
 // chunk][8 rows][4 floats]; LBO = 128 B, SBO = 32 * Mp B), so the producer issues plain 1-D bulk copies.
 // TMEM map (512 columns): two accumulator buffers of (re | im) x NA columns, then the A region.
+// The two issuers take turns (BAR_TURN): stages enter the tensor pipe in order, so that a stage's epilogue overlaps the
+// next stage's MMAs instead of both buffers sitting in the epilogue together.  The arg-max / arg-min of the surface is
+// folded into the write-out (packed atomicMax, last CTA decodes): bogp_bartlett_grid_argext.
+//
+// Template parameter TILT = true is the tilted-array engine (config 4): same pipeline, B operand = Theta_tau =
+// Phi exp(i k l sin tau) per (tilt, receiver half), A operand = E_f phi(z_j) rebuilt in TMEM per (unit, tonal), epilogue
+// in receiver space with s_n = (r / r_n)^1/2 -- see the comments at `if (TILT)` in the loader and epilogue roles.
 //
 // Replaces the loop `for z in src_z: amb[zz,:] = MFP({"src_z": z, "rec_r": rvec})`
-// (ref/projects/swellex96_localization/data/mfp.py:213-214) for a vertical array.
+// (ref/projects/swellex96_localization/data/mfp.py:213-214) for a vertical array, and the same sweep with a `tilt`
+// key (ref/projects/swellex96_loc_tilt/data/mfp.py:196-230, ref/projects/swellex96_loc_tilt/data/env.py:73-74).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
