@@ -404,7 +404,9 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
         vi = amp * (q.y * c - q.x * s);
       }
       const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
-      const float v[4] = {rh, (float)(vr - (double)rh), ih, (float)(vi - (double)ih)};
+      // the low parts are rounded to TF32 here: the tensor core would otherwise TRUNCATE them (biased towards zero,
+      // twice the error, and the bias adds up coherently over the modes)
+      const float v[4] = {rh, tf32_rna((float)(vr - (double)rh)), ih, tf32_rna((float)(vi - (double)ih))};
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int col = b * u.Mp + m;
@@ -457,7 +459,7 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
         const float x0 = wq[i].x * pv.x, x1 = wq[i].y * pv.y, x2 = wq[i].z * pv.z, x3 = wq[i].w * pv.w;
         const float h0 = tf32_rna(x0), h1 = tf32_rna(x1), h2 = tf32_rna(x2), h3 = tf32_rna(x3);
         hi[q] = make_float4(h0, h1, h2, h3);
-        lo[q] = make_float4(x0 - h0, x1 - h1, x2 - h2, x3 - h3);
+        lo[q] = make_float4(tf32_rna(x0 - h0), tf32_rna(x1 - h1), tf32_rna(x2 - h2), tf32_rna(x3 - h3));
       }
     }
   }
@@ -490,8 +492,8 @@ __global__ void __launch_bounds__(128) umma_tilt_theta_kernel(ModesetDev ms, UPa
     }
     const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
     const size_t o0 = canon_off(2 * q, m, u.Mp), o1 = canon_off(2 * q + 1, m, u.Mp);
-    Bhi[o0] = rh; Blo[o0] = (float)(vr - (double)rh);
-    Bhi[o1] = ih; Blo[o1] = (float)(vi - (double)ih);
+    Bhi[o0] = rh; Blo[o0] = tf32_rna((float)(vr - (double)rh));
+    Bhi[o1] = ih; Blo[o1] = tf32_rna((float)(vi - (double)ih));
   }
 }
 
@@ -749,7 +751,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
                                   (h1.x + l1.x) * pb.x, (h1.y + l1.y) * pb.y, (h1.z + l1.z) * pb.z, (h1.w + l1.w) * pb.w};
               float hi[8], lo[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) { hi[e] = tf32_rna(x[e]); lo[e] = x[e] - hi[e]; }
+              for (int e = 0; e < 8; ++e) { hi[e] = tf32_rna(x[e]); lo[e] = tf32_rna(x[e] - hi[e]); }
               tc_st8(dst + (uint32_t)(2 * part * u.Mp + 8 * q2), hi);
               tc_st8(dst + (uint32_t)((2 * part + 1) * u.Mp + 8 * q2), lo);
             }
