@@ -133,3 +133,19 @@ def ambiguity_sweep(mfp, K: np.ndarray, rec_r: Sequence[float], src_z: Sequence[
             np.save(savepath / f"surface_{t:03d}.npy", out.astype(np.float64))
     mfp.covariance_matrix = np.ascontiguousarray(K[:, steps[-1]]) if steps else mfp.covariance_matrix
     return {"timesteps": steps, "surfaces": surfaces, "peak": peaks}
+
+
+def gather_peaks(result: Dict[str, object], group=None) -> Dict[int, Tuple[float, Tuple[int, int]]]:
+    """Merge the per-rank ``ambiguity_sweep`` results into ``{time step: (value, (jz, jr))}`` on every rank: the one
+    exchange of the multi-GPU sweep (a few bytes per time step; ``torch.distributed.all_gather_object`` over NCCL or
+    gloo).  Single-process runs return the local dictionary."""
+    import torch.distributed as dist
+    local = list(zip(result["timesteps"], result["peak"]))
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dict(local)
+    parts: List[object] = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, local, group=group)
+    merged: Dict[int, Tuple[float, Tuple[int, int]]] = {}
+    for part in parts:
+        merged.update(dict(part))
+    return dict(sorted(merged.items()))

@@ -232,6 +232,19 @@ def test_envbatch_geoacoustic_scoring():
             got = eb.bartlett(atype=atype, multifreq_method=mf).cpu().numpy()
         assert_parity(got, ref, floor=1.0 if atype == "cbf_ml" else FLOOR)
     assert abs(got[0]) < 2e-5                        # the true environment scores 0 under cbf_ml
+    # the three kernel variants (streaming records with one / two stages per warp, per-lane loads for records that do
+    # not fit shared memory) and a rank-3 covariance agree with the oracle
+    import os
+    K3 = synthetic_covariance(truth, 71.11, 1.07, snapshots=3, seed=7)
+    ref3 = ob.bartlett_envbatch(sets, K3, cand)
+    for env in ({"BOGP_ENV_STAGES": "1"}, {"BOGP_ENV_STAGES": "2"}, {"BOGP_ENV_SIMT": "1"}):
+        try:
+            os.environ.update(env)
+            with EnvBatch(sets, r, zs, K3) as eb:
+                assert_parity(eb.bartlett().cpu().numpy(), ref3)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
 
     # the objective protocol with a per-candidate mode provider (obj.py:73-83)
     def provider(p):

@@ -103,3 +103,35 @@ def test_sharded_argmax_gloo(world):
     assert all(p.exitcode == 0 for p in procs)
     for rank, val, pos, same in res:
         assert val == 2.0 and pos == (3, 4) and same
+
+
+def _sweep_worker(rank, world, port, n_steps, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bogp_b200 import sweep
+        steps = list(sweep.time_steps_of(rank, world, n_steps))
+        # stand-in for the per-rank ambiguity_sweep result: the peak of step t is (t / 10, (t, 2 t))
+        local = {"timesteps": steps, "peak": [(t / 10.0, (t, 2 * t)) for t in steps]}
+        q.put((rank, steps, sweep.gather_peaks(local)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_step_sweep_partition_and_gather_gloo():
+    """The sweep's multi-GPU axis on CPU (world 2, gloo): contiguous blocks of time steps per rank, one all-gather of
+    the per-step peaks, the same merged dictionary on every rank (ref: the pool over time steps, mfp.py:166-177)."""
+    world, n_steps = 2, 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sweep_worker, args=(r, world, port, n_steps, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    res.sort()
+    assert res[0][1] == [0, 1, 2, 3] and res[1][1] == [4, 5, 6]
+    want = {t: (t / 10.0, (t, 2 * t)) for t in range(n_steps)}
+    for _, _, merged in res:
+        assert merged == want and list(merged) == sorted(merged)
