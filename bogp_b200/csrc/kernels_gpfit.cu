@@ -114,7 +114,9 @@ __device__ __forceinline__ void corr_and_grad(int kind, double d2, double& kc, d
 
 // SMEM = true: the matrix and X live in shared memory (the compiler sees shared-space pointers: LDS/STS with
 // 32-bit addressing instead of generic loads); SMEM = false: matrix in the global scratch.
-template <bool SMEM>
+// DL: compile-time bound of the loops over input dimensions (4, 8 or 16 >= d): the per-pair loops are predicated, and
+// predicated-off iterations still take issue slots.
+template <bool SMEM, int DL>
 __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p) {
   extern __shared__ double fsm[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -154,9 +156,9 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
     if (tid == 34) prm[kFitMaxD + 2] = raw[d + 2];
     __syncthreads();
     const double os = prm[kFitMaxD], noise = prm[kFitMaxD + 1], mean = prm[kFitMaxD + 2];
-    double inv_ls[kFitMaxD];
+    double inv_ls[DL];
 #pragma unroll
-    for (int k = 0; k < kFitMaxD; ++k) inv_ls[k] = k < d ? 1.0 / prm[k] : 0.0;
+    for (int k = 0; k < DL; ++k) inv_ls[k] = k < d ? 1.0 / prm[k] : 0.0;
     for (int i = tid; i < n; i += kFitThreads) rv[i] = p.y[i] - mean;
 
     // ---------------------------------------------------------------- K (lower) and its Cholesky, jitter retries
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
         for (int j = lane; j <= i; j += 32) {
           double d2 = 0.0;
 #pragma unroll
-          for (int k = 0; k < kFitMaxD; ++k)
+          for (int k = 0; k < DL; ++k)
             if (k < d) { const double s = (Xp[i * d + k] - Xp[j * d + k]) * inv_ls[k]; d2 = fma(s, s, d2); }
           double kc, g;
           corr_and_grad(p.kind, d2, kc, g);
@@ -303,15 +305,15 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
     __syncthreads();
 
     // ---------------------------------------------------------------- gradient traces over the lower triangle
-    double g_ls[kFitMaxD], g_os = 0.0, g_noise = 0.0;
+    double g_ls[DL], g_os = 0.0, g_noise = 0.0;
 #pragma unroll
-    for (int k = 0; k < kFitMaxD; ++k) g_ls[k] = 0.0;
+    for (int k = 0; k < DL; ++k) g_ls[k] = 0.0;
     for (int i = warp; i < n; i += kFitWarps) {
       const double ai = alpha[i];
       for (int j = lane; j <= i; j += 32) {
-        double s2[kFitMaxD], d2 = 0.0;
+        double s2[DL], d2 = 0.0;
 #pragma unroll
-        for (int k = 0; k < kFitMaxD; ++k) {
+        for (int k = 0; k < DL; ++k) {
           s2[k] = 0.0;
           if (k < d) { const double s = (Xp[i * d + k] - Xp[j * d + k]) * inv_ls[k]; s2[k] = s * s; d2 += s2[k]; }
         }
@@ -323,21 +325,24 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
         if (i == j) g_noise += W;
         const double wg = W * os * g;
 #pragma unroll
-        for (int k = 0; k < kFitMaxD; ++k)
+        for (int k = 0; k < DL; ++k)
           if (k < d) g_ls[k] = fma(wg, s2[k] * inv_ls[k], g_ls[k]);
       }
     }
     // block reduction of d + 5 sums (fixed order: deterministic)
-    double vals[kFitMaxD + 4];
+    // block reduction of d + 4 sums (fixed order: deterministic); slot q < kFitMaxD: length-scale q, then os, noise, ...
+    {
+      double vals[DL + 4];
 #pragma unroll
-    for (int k = 0; k < kFitMaxD; ++k) vals[k] = g_ls[k];
-    vals[kFitMaxD] = g_os; vals[kFitMaxD + 1] = g_noise; vals[kFitMaxD + 2] = part_quad; vals[kFitMaxD + 3] = part_ld;
+      for (int k = 0; k < DL; ++k) vals[k] = g_ls[k];
+      vals[DL] = g_os; vals[DL + 1] = g_noise; vals[DL + 2] = part_quad; vals[DL + 3] = part_ld;
 #pragma unroll
-    for (int q = 0; q < kFitMaxD + 4; ++q) {
-      double v = vals[q];
+      for (int q = 0; q < DL + 4; ++q) {
+        double v = vals[q];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-      if (lane == 0) red[warp * (kFitMaxD + 4) + q] = v;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (lane == 0) red[warp * (kFitMaxD + 4) + (q < DL ? q : kFitMaxD + q - DL)] = v;
+      }
     }
     {
       double v = part_as;
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
       part_as = v;
     }
     __syncthreads();
-    if (tid < kFitMaxD + 4) {
+    if (tid < kFitMaxD + 4 && (tid < DL || tid >= kFitMaxD)) {
       double v = 0.0;
       for (int w = 0; w < kFitWarps; ++w) v += red[w * (kFitMaxD + 4) + tid];
       gsum[tid] = v;
@@ -445,18 +450,17 @@ extern "C" int bogp_gp_fit_adamw(int n, int d, const double* X_host, const doubl
   FIT_CUDA(cudaMemcpyAsync(draw, raw_inout_host, (size_t)B * np * sizeof(double), cudaMemcpyHostToDevice, s));
   p.X = dX; p.y = dy; p.raw = draw; p.loss = dloss; p.work = dwork; p.status = dstatus;
   const bool in_smem = p.a_in_smem && p.x_in_smem;
-  if (in_smem) FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  else {
-    FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // matrix in the global scratch: leave the rest of the SM's 256 KB to L1 -- the factorisation re-reads every panel
-    // many times and is bound by L2 latency otherwise
-    const int pct = (int)std::min<size_t>(100, (smem + 1024) * 100 / (228 * 1024) + 1);
-    FIT_CUDA(cudaFuncSetAttribute(gp_fit_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-  }
-  cudaEvent_t ev = timing_begin(s);
-  if (in_smem) gp_fit_kernel<true><<<B, kFitThreads, smem, s>>>(p);
-  else gp_fit_kernel<false><<<B, kFitThreads, smem, s>>>(p);
-  timing_end(ev, s);
+  const int dl = d <= 4 ? 4 : (d <= 8 ? 8 : 16);
+  auto launch = [&](auto kern) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaEvent_t ev = timing_begin(s);
+    kern<<<B, kFitThreads, smem, s>>>(p);
+    timing_end(ev, s);
+    return cudaGetLastError();
+  };
+  if (in_smem) FIT_CUDA(dl == 4 ? launch(gp_fit_kernel<true, 4>) : dl == 8 ? launch(gp_fit_kernel<true, 8>) : launch(gp_fit_kernel<true, 16>));
+  else FIT_CUDA(dl == 4 ? launch(gp_fit_kernel<false, 4>) : dl == 8 ? launch(gp_fit_kernel<false, 8>) : launch(gp_fit_kernel<false, 16>));
   count_launch();
   FIT_CUDA(cudaGetLastError());
   std::vector<int> status(B);
