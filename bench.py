@@ -247,6 +247,79 @@ def bo_iteration(n: int = 256, d: int = 3, raw: int = 4096, restarts: int = 64, 
     return out
 
 
+# ------------------------------------------------------------------------------------------------ other kernels
+def other_paths(hbm_gbs: float, tf32x3_peak: float) -> dict:
+    """The other kernels of the hot path at BASELINE's shapes, a few launches each (details: tools/bench_paths.py,
+    profiles/paths_*.jsonl): configs[3] tilted-array volume at 1/10 of its tilt axis on the tensor-core tilt engine,
+    configs[4] per-environment scoring (HBM-bound), the GP acquisition kernel and the fused hyper-parameter fit."""
+    import torch
+    from bogp_b200 import _lib, mfp
+    from bogp_b200 import acquisition as A
+    from bogp_b200.envbatch import EnvBatch
+    from bogp_b200.gp import FitConfig, SingleTaskGP, fit_gp_adamw
+    from bogp_b200.modes import (INV_TONALS_3, REC_Z_21, SWELLEX_TONALS_13, pekeris_modes, perturbed_pekeris_batch,
+                                 synthetic_covariance)
+
+    def kernel_ms(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        _lib.timing_read()
+        _lib.timing_enable(True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        _lib.timing_enable(False)
+        ms, n = _lib.timing_read()
+        return (ms / n) if n else a.elapsed_time(b) / reps
+
+    out = {}
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    dms = mfp.DeviceModeSet(modes, synthetic_covariance(modes, 60.0, 5.0, tilt_deg=1.0))
+    r, z, tilt = np.linspace(0.1, 10.0, 1000), np.linspace(1.0, 200.0, 100), np.linspace(-4.0, 4.0, 10)
+    vol = torch.empty((10, 100, 1000), dtype=torch.float32, device="cuda")
+    ms = kernel_ms(lambda: dms.bartlett_grid(r, z, tilt, out=vol, engine="umma"))
+    flop = 8.0 * 64 * sum(modes.n_modes)
+    out["tilt"] = {"workload": "configs[3] at 1/10 of the tilt axis: 1000 r x 100 z x 10 tilt x 13 tonals, 64 receivers",
+                   "kernel": "umma_grid_kernel<tilt>", "kernel_ms": ms, "cand_freq_per_s": 1e6 * 13 / (ms * 1e-3),
+                   "roofline": {"bound": "tensor", "achieved": 1e6 * flop / (ms * 1e-3) / 1e12, "peak": tf32x3_peak,
+                                "unit": "TFLOP/s", "frac": 1e6 * flop / (ms * 1e-3) / 1e12 / tf32x3_peak}}
+    rng = np.random.default_rng(2)
+    base = perturbed_pekeris_batch(INV_TONALS_3, REC_Z_21, rng.uniform(200.0, 230.0, 100), rng.uniform(1600.0, 1700.0, 100))
+    ref = pekeris_modes(INV_TONALS_3, REC_Z_21)
+    Cn = 10_000
+    eb = EnvBatch([base[i % 100] for i in range(Cn)], rng.uniform(0.5, 6.0, Cn), rng.uniform(10.0, 190.0, Cn),
+                  synthetic_covariance(ref, 71.11, 1.07))
+    sc = torch.empty(Cn, dtype=torch.float32, device="cuda")
+    ms = kernel_ms(lambda: eb.bartlett(out=sc))
+    out["env"] = {"workload": f"configs[4]: {Cn} environments x 3 tonals x 21 receivers (own mode set per candidate)",
+                  "kernel": "envstream_kernel", "kernel_ms": ms, "cand_freq_per_s": Cn * 3 / (ms * 1e-3),
+                  "roofline": {"bound": "hbm", "achieved": eb.bytes_streamed / (ms * 1e-3) / 1e9, "peak": hbm_gbs,
+                               "unit": "GB/s", "frac": eb.bytes_streamed / (ms * 1e-3) / 1e9 / hbm_gbs}}
+    eb.close()
+    X = rng.uniform(-1, 1, (256, 3))
+    y = np.sin(3 * X[:, 0]) + 0.3 * np.cos(2 * X.sum(1))
+    y = (y - y.mean()) / y.std()
+    model = SingleTaskGP(X, y, lengthscale=[0.5] * 3, outputscale=1.0, noise=1e-4)
+    ei = A.ExpectedImprovement(model, float(y.max()))
+    Xs = torch.as_tensor(rng.uniform(-1, 1, (4096, 1, 3)), device="cuda")
+    with torch.no_grad():
+        ms = kernel_ms(lambda: ei(Xs))
+    out["gp_acq"] = {"workload": "configs[2]: EI over 4096 raw samples, n=256 d=3 Matern-5/2, float64", "kernel": "gp_eval_kernel",
+                     "kernel_ms": ms, "cand_per_s": 4096 / (ms * 1e-3), "fp64_tflops": 4096 * (256 * 33 + 256 * 256) / (ms * 1e-3) / 1e12}
+    Xf = X[:144]
+    yf = (y[:144] - y[:144].mean()) / y[:144].std()
+    fit_gp_adamw(SingleTaskGP(Xf, yf), FitConfig(steps=5), engine="fused")
+    t0 = time.perf_counter()
+    fit_gp_adamw(SingleTaskGP(Xf, yf), FitConfig(steps=100), engine="fused")
+    out["gp_fit"] = {"workload": "100 AdamW steps of -mll, n=144 d=3 (ei.py:69-78), one kernel launch", "kernel": "gp_fit_kernel",
+                     "call_ms": (time.perf_counter() - t0) * 1e3}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args) -> None:
     import torch
@@ -353,8 +426,11 @@ def run_ours(args) -> None:
 
     # ---- roofline of the dominant kernel
     peaks_path = ROOT / "MEASURED_PEAKS.json"
+    peaks_hbm = 6547.5
     if peaks_path.exists():
-        bf16 = float(json.loads(peaks_path.read_text())["bf16_tflops"])
+        pk = json.loads(peaks_path.read_text())
+        bf16 = float(pk["bf16_tflops"])
+        peaks_hbm = float(pk.get("hbm_gbs", peaks_hbm))
         peak_src = "MEASURED_PEAKS.json bf16_tflops (burst)"
     else:
         bf16, peak_src = 1590.0, "fallback 1.59 PFLOP/s bf16 (B200_PROFILING.md)"
@@ -390,6 +466,11 @@ def run_ours(args) -> None:
             line["bo_iter"] = bo_iteration(cpu=not args.no_cpu)
         except Exception as exc:   # the Bartlett line must survive a failure here
             line["bo_iter"] = {"error": repr(exc)}
+    if rank == 0 and world == 1 and not args.no_paths:
+        try:
+            line["paths"] = other_paths(peaks_hbm, peak)
+        except Exception as exc:
+            line["paths"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         with cpu_pool(cores) as ex:
@@ -412,6 +493,7 @@ def main() -> None:
     ap.add_argument("--engine", choices=["auto", "simt", "umma"], default="auto")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-bo", action="store_true", help="skip the BO-iteration (GP acquisition optimisation) timing")
+    ap.add_argument("--no-paths", action="store_true", help="skip the other kernels of the path (tilt, env batch, GP)")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner on communicator creation,
     # whatever NCCL_DEBUG says) are sent to stderr for the whole run, and the line goes to the saved descriptor.
