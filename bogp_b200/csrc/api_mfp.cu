@@ -363,7 +363,11 @@ static int grid_impl(bogp_modeset_t h, const double* r_m_host, int Nr, const dou
     for (int i = 0; i < Nt; ++i) tilted |= (tilt_deg_host[i] != 0.0);
   else
     BOGP_REQUIRE(Nt == 1, "bogp_bartlett_grid: Nt must be 1 when tilt is NULL");
-  const bool tilt_axis = tilted || Nt > 1;
+  // The receiver-space tensor-core engine also covers complex source mode shapes (KRAKENC) on an untilted array: the
+  // depth dependence sits in its A operand, where a complex phi(z) costs nothing extra (tilt = 0, one plane).
+  static const double zero_tilt = 0.0;
+  const bool tilt_axis = tilted || Nt > 1 || h->dev.src_complex;
+  const double* tilt_arg = tilt_deg_host ? tilt_deg_host : &zero_tilt;
   if (engine == BOGP_ENGINE_UMMA) {
     const bool ok = tilt_axis ? bogp::umma_tilt_supported(h) : bogp::umma_supported(h);
     if (!ok) { bogp::set_error("UMMA engine unsupported for this mode set / device"); return BOGP_ERR_UNSUPPORTED; }
@@ -373,7 +377,7 @@ static int grid_impl(bogp_modeset_t h, const double* r_m_host, int Nr, const dou
   int rc;
   if (tilt_axis && (engine == BOGP_ENGINE_UMMA || (engine == BOGP_ENGINE_AUTO && bogp::umma_tilt_supported(h) && total >= 65536))) {
     // tilted array on the tensor cores (receiver-space epilogue)
-    rc = bogp::launch_grid_umma_tilt(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
+    rc = bogp::launch_grid_umma_tilt(h, r_m_host, Nr, z_host, Nz, tilt_arg, Nt, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
     if (rc || !ext_mode || fuse_ext) return rc;
   } else if (!tilt_axis && (engine == BOGP_ENGINE_UMMA || (engine == BOGP_ENGINE_AUTO && bogp::umma_supported(h) && total >= 16384))) {
     rc = bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
@@ -403,7 +407,7 @@ extern "C" int bogp_bartlett_grid_argext(bogp_modeset_t h, const double* r_m_hos
 // Same choice as grid_impl: does this call run on a tcgen05 engine (where the arg-ext is fused into the surface kernel)?
 static bool picks_tensor_engine(bogp_modeset_t h, int engine, const double* tilt_deg_host, int Nt, long long total) {
   if (!h || !h->has_cov || engine == BOGP_ENGINE_SIMT) return false;
-  bool tilted = Nt > 1;
+  bool tilted = Nt > 1 || h->dev.src_complex;
   if (tilt_deg_host)
     for (int i = 0; i < Nt; ++i) tilted |= (tilt_deg_host[i] != 0.0);
   if (tilted) return bogp::umma_tilt_supported(h) && (engine == BOGP_ENGINE_UMMA || total >= 65536);

@@ -102,6 +102,7 @@ struct UParams {
   int Nzr, Nt;                 // real depths, real tilts
   int N, sumMp;
   const float* phiz;           // [Nzr][sumMp]  phi_m(z_j)
+  const float* phiz_im;        // imaginary part for complex (KRAKENC) source tables, else null
   const float* sin_t;          // [Nz / 2]      sin(tilt), padded
   const float* rinv;           // [Nr]          1 / r
   const float* lever;          // [64]          z_pivot - z_n (0 beyond N)
@@ -499,7 +500,8 @@ __global__ void __launch_bounds__(128) umma_tilt_theta_kernel(ModesetDev ms, UPa
 
 // phi_m(z_j) for every real depth (source-depth table interpolation of the data contract), sin(tilt), 1 / r, levers
 __global__ void umma_tilt_aux_kernel(ModesetDev ms, UParams p, const double* __restrict__ r, const double* __restrict__ z,
-                                     const double* __restrict__ tilt_deg, float* phiz, float* sin_t, float* rinv, float* lever) {
+                                     const double* __restrict__ tilt_deg, float* phiz, float* phiz_im, float* sin_t,
+                                     float* rinv, float* lever) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int idx = tid; idx < p.Nzr * p.sumMp; idx += nth) {
     const int j = idx / p.sumMp, col = idx - j * p.sumMp;
@@ -513,6 +515,12 @@ __global__ void umma_tilt_aux_kernel(ModesetDev ms, UParams p, const double* __r
       depth_index(z[j], ms.z0, ms.dz, ms.nz_tab, i0, w);
       const float* tr = ms.tab_re + t.offTab + (size_t)i0 * t.Mp + m;
       v = fmaf(w, __ldg(tr + t.Mp) - __ldg(tr), __ldg(tr));
+      if (phiz_im) {
+        const float* ti = ms.tab_im + t.offTab + (size_t)i0 * t.Mp + m;
+        phiz_im[idx] = fmaf(w, __ldg(ti + t.Mp) - __ldg(ti), __ldg(ti));
+      }
+    } else if (phiz_im) {
+      phiz_im[idx] = 0.f;
     }
     phiz[idx] = v;
   }
@@ -741,6 +749,32 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           // split again.  Eight modes per step: (re | im) x (hi, lo) chunks in, two 8-column stores out per part.
           const float* phi = p.phiz + (size_t)jreal * p.sumMp + u.offM;
           const int mc = u.Mp >> 2;           // 16-byte chunks per block of Mp columns
+          if (p.phiz_im) {
+            // complex source mode shapes (KRAKENC): a = (E_re + i E_im)(phi_re + i phi_im), both parts per 8 modes
+            const float* phj = p.phiz_im + (size_t)jreal * p.sumMp + u.offM;
+            for (int q2 = 0; q2 < (u.Mp >> 3); ++q2) {
+              float er[8], ei[8], pr[8], pi[8];
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const float4 rh = __ldg(src + (size_t)(0 * mc + 2 * q2 + h2) * kTileR), rl = __ldg(src + (size_t)(1 * mc + 2 * q2 + h2) * kTileR);
+                const float4 ih = __ldg(src + (size_t)(2 * mc + 2 * q2 + h2) * kTileR), il = __ldg(src + (size_t)(3 * mc + 2 * q2 + h2) * kTileR);
+                const float4 a = __ldg(reinterpret_cast<const float4*>(phi + 8 * q2 + 4 * h2)), b = __ldg(reinterpret_cast<const float4*>(phj + 8 * q2 + 4 * h2));
+                er[4 * h2 + 0] = rh.x + rl.x; er[4 * h2 + 1] = rh.y + rl.y; er[4 * h2 + 2] = rh.z + rl.z; er[4 * h2 + 3] = rh.w + rl.w;
+                ei[4 * h2 + 0] = ih.x + il.x; ei[4 * h2 + 1] = ih.y + il.y; ei[4 * h2 + 2] = ih.z + il.z; ei[4 * h2 + 3] = ih.w + il.w;
+                pr[4 * h2 + 0] = a.x; pr[4 * h2 + 1] = a.y; pr[4 * h2 + 2] = a.z; pr[4 * h2 + 3] = a.w;
+                pi[4 * h2 + 0] = b.x; pi[4 * h2 + 1] = b.y; pi[4 * h2 + 2] = b.z; pi[4 * h2 + 3] = b.w;
+              }
+              float hi[8], lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { const float x = fmaf(er[e], pr[e], -ei[e] * pi[e]); hi[e] = tf32_rna(x); lo[e] = tf32_rna(x - hi[e]); }
+              tc_st8(dst + (uint32_t)(8 * q2), hi);
+              tc_st8(dst + (uint32_t)(u.Mp + 8 * q2), lo);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { const float x = fmaf(er[e], pi[e], ei[e] * pr[e]); hi[e] = tf32_rna(x); lo[e] = tf32_rna(x - hi[e]); }
+              tc_st8(dst + (uint32_t)(2 * u.Mp + 8 * q2), hi);
+              tc_st8(dst + (uint32_t)(3 * u.Mp + 8 * q2), lo);
+            }
+          } else
           for (int part = 0; part < 2; ++part) {
             const int hb = 2 * part * mc, lb = hb + mc;
             for (int q2 = 0; q2 < (u.Mp >> 3); ++q2) {
@@ -1252,7 +1286,7 @@ bool umma_tilt_supported(const bogp_modeset_s* h) {
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (major != 10 || !h->has_cov) return false;
   const ModesetDev& d = h->dev;
-  if (d.src_complex || d.N > 64 || h->max_J > 4 || h->max_Mp > 64) return false;
+  if (d.N > 64 || h->max_J > 4 || h->max_Mp > 64) return false;
   return true;
 }
 
@@ -1300,7 +1334,8 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t off_err = al(((size_t)Nr + Nz + Nt) * sizeof(double));
   const size_t off_phi = off_err + 256;
-  const size_t off_sin = al(off_phi + (size_t)Nz * sumMp * 4);
+  const size_t off_phi_im = al(off_phi + (size_t)Nz * sumMp * 4);
+  const size_t off_sin = al(off_phi_im + (d.src_complex ? (size_t)Nz * sumMp * 4 : 0));
   const size_t off_rinv = al(off_sin + (size_t)Ntp * 4);
   const size_t off_lev = al(off_rinv + (size_t)Nr * 4);
   const size_t off_E = al(off_lev + 64 * 4);
@@ -1322,7 +1357,8 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   float* sin_t = reinterpret_cast<float*>(base + off_sin);
   float* rinv = reinterpret_cast<float*>(base + off_rinv);
   float* lever = reinterpret_cast<float*>(base + off_lev);
-  p.phiz = phiz; p.sin_t = sin_t; p.rinv = rinv; p.lever = lever;
+  float* phiz_im = d.src_complex ? reinterpret_cast<float*>(base + off_phi_im) : nullptr;
+  p.phiz = phiz; p.phiz_im = phiz_im; p.sin_t = sin_t; p.rinv = rinv; p.lever = lever;
   p.CkT_re = d.CkT_re; p.CkT_im = d.CkT_im;
   p.E = base + off_E; p.Bhi = base + off_Bhi; p.Blo = base + off_Blo;
   p.out = out_dev;
@@ -1335,7 +1371,7 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
     umma_tables_kernel<<<nE, kTabThreads, 0, s>>>(d, pe, r_dev, z_dev, nE);
   }
   umma_tilt_theta_kernel<<<dim3((unsigned)p.Nz, (unsigned)d.F), 128, 0, s>>>(d, p, t_dev);
-  umma_tilt_aux_kernel<<<std::max(1, std::min(296, (Nz * sumMp + 255) / 256)), 256, 0, s>>>(d, p, r_dev, z_dev, t_dev, phiz, sin_t, rinv, lever);
+  umma_tilt_aux_kernel<<<std::max(1, std::min(296, (Nz * sumMp + 255) / 256)), 256, 0, s>>>(d, p, r_dev, z_dev, t_dev, phiz, phiz_im, sin_t, rinv, lever);
   count_launch(3);
   BOGP_CUDA(cudaGetLastError());
   const size_t smem = (size_t)p.smem_bar + 256;

@@ -95,14 +95,28 @@ def test_umma_rank8_ragged_grids(shape):
 
 
 def test_umma_rejects_what_it_cannot_fuse():
+    """The tcgen05 engines refuse loudly what they do not cover (no silent fallback under engine="umma"); "auto" falls
+    back to the CUDA-core kernels.  Covered since r1b: complex source tables (KRAKENC) run on the receiver-space
+    tensor-core engine.  Not covered: a tilt axis with covariance rank > 4."""
     from bogp_b200 import _lib
     from bogp_b200.mfp import DeviceModeSet
     from bogp_b200.modes import INV_TONALS_3, REC_Z_21, pekeris_modes, synthetic_covariance
-    modes = pekeris_modes(INV_TONALS_3, REC_Z_21, complex_modes=True)
-    dms = DeviceModeSet(modes, synthetic_covariance(modes, 40.0, 2.2))
+    modes = pekeris_modes(INV_TONALS_3, REC_Z_21)
+    dms = DeviceModeSet(modes, synthetic_covariance(modes, 40.0, 2.2, snapshots=8, seed=1))
+    r, z, tilt = np.linspace(1.0, 2.0, 40), np.linspace(10.0, 60.0, 6), np.array([0.0, 1.0])
     with pytest.raises(_lib.BogpError):
-        dms.bartlett_grid([1.0, 2.0], [10.0], engine="umma")          # complex source table: SIMT only
-    assert np.isfinite(dms.bartlett_grid([1.0, 2.0], [10.0], engine="auto").cpu().numpy()).all()
+        dms.bartlett_grid(r, z, tilt, engine="umma")                   # rank 8 > 4 on the tilt engine
+    assert np.isfinite(dms.bartlett_grid(r, z, tilt, engine="auto").cpu().numpy()).all()
+    # complex (KRAKENC) source and receiver mode shapes on the tensor cores, vertical array
+    mc = pekeris_modes(INV_TONALS_3, REC_Z_21, complex_modes=True)
+    Kc = synthetic_covariance(mc, 40.0, 2.2)
+    dmc = DeviceModeSet(mc, Kc)
+    r2, z2 = np.linspace(0.5, 6.0, 140), np.linspace(5.0, 190.0, 9)
+    ref = ob.ambiguity_surface(mc, Kc, r2, z2)
+    got = dmc.bartlett_grid(r2, z2, engine="umma").cpu().numpy()
+    assert got.shape == ref.shape
+    assert_parity(got, ref)
+    assert_parity(dmc.bartlett_grid(r2, z2, engine="simt").cpu().numpy(), ref)
 
 
 def test_truth_is_one_and_ml_zero(cfg2_small, dms2):
@@ -332,7 +346,8 @@ def test_fused_argext_matches_separate_reduction(cfg2_small, dms2, shape):
 @pytest.mark.parametrize("case", ["swellex_rank1", "inv21_rank3", "complex_modes"])
 def test_tilt_tensor_core_engine_vs_oracle_and_simt(case):
     """Config 4 path on the tensor cores (umma_grid_kernel<true>: Theta_tau as the B operand, receiver-space epilogue
-    with s_n = (r / r_n)^1/2): ragged sizes, odd tilt counts, rank-1 / rank-3 covariances, complex receiver modes,
+    with s_n = (r / r_n)^1/2): ragged sizes, odd tilt counts, rank-1 / rank-3 covariances, complex (KRAKENC) source and
+    receiver mode shapes,
     both processors; against the oracle (one scattered evaluation per node) and the SIMT tilt-plane kernel."""
     from bogp_b200 import mfp
     from bogp_b200.mfp import DeviceModeSet
@@ -350,11 +365,6 @@ def test_tilt_tensor_core_engine_vs_oracle_and_simt(case):
         K = synthetic_covariance(modes, 40.0, 2.2, tilt_deg=-2.0, snapshots=3, seed=5)
         r, z, tilt = np.linspace(0.5, 6.0, 140), np.linspace(5.0, 190.0, 3), np.array([-2.0, 0.5, 3.0])
     dms = DeviceModeSet(modes, K)
-    if case == "complex_modes":
-        # complex SOURCE tables are outside the tensor-core engines: must be refused loudly, auto falls back to SIMT
-        with pytest.raises(mfp._lib.BogpError):
-            dms.bartlett_grid(r, z, tilt, engine="umma")
-        return
     cand = np.array([[ri, zi, ti] for ti in tilt for zi in z for ri in r])
     for kw, floor in ((dict(), FLOOR), (dict(atype="cbf_ml", multifreq_method="product"), 1.0)):
         ref = ob.bartlett_points(modes, K, cand, **kw).reshape(len(tilt), len(z), len(r))
