@@ -413,3 +413,38 @@ def test_full_size_tilt_volume_properties():
     out, (v2, pos2) = dms.bartlett_grid_host(r, z, tilt, engine="umma", out=pinned.numpy(), argext="max")
     np.testing.assert_array_equal(out, vol)
     assert pos2 == pos and v2 == pytest.approx(val)
+
+
+def test_full_size_envbatch_properties():
+    """BASELINE config 5 at full size (1e4 candidate environments x 3 tonals x 21 receivers, own mode set each):
+    (a) 0 <= B <= 1; (b) the streaming kernel and the per-lane-load kernel agree; (c) a random sample matches the
+    oracle; (d) candidates that share environment, range and depth score identically (the batch is 100 distinct
+    environments tiled); (e) the candidate placed at the truth scores ~1 and is the arg-max."""
+    import os
+    from bogp_b200.envbatch import EnvBatch
+    from bogp_b200.modes import INV_TONALS_3, REC_Z_21, pekeris_modes, perturbed_pekeris_batch, synthetic_covariance
+    rng = np.random.default_rng(21)
+    truth = pekeris_modes(INV_TONALS_3, REC_Z_21)
+    K = synthetic_covariance(truth, 71.11, 1.07)
+    depths = np.r_[217.0, rng.uniform(205.0, 230.0, 99)]
+    cbs = np.r_[1650.0, rng.uniform(1600.0, 1700.0, 99)]
+    base = perturbed_pekeris_batch(INV_TONALS_3, REC_Z_21, depths, cbs)
+    C = 10_000
+    env = np.arange(C) % 100
+    r = np.where(np.arange(C) < 100, 1.07, rng.uniform(0.5, 6.0, C))
+    zs = np.where(np.arange(C) < 100, 71.11, rng.uniform(10.0, 190.0, C))
+    r[5000:5100], zs[5000:5100] = r[100:200], zs[100:200]            # duplicates of candidates 100..199 (same env index)
+    with EnvBatch([base[e] for e in env], r, zs, K) as eb:
+        got = eb.bartlett().cpu().numpy()
+        try:
+            os.environ["BOGP_ENV_SIMT"] = "1"
+            simt = eb.bartlett().cpu().numpy()
+        finally:
+            os.environ.pop("BOGP_ENV_SIMT", None)
+    assert got.min() >= 0.0 and got.max() <= 1.0 + 2e-5
+    assert np.abs(got - simt).max() <= 2e-6
+    np.testing.assert_array_equal(got[5000:5100], got[100:200])
+    assert int(got.argmax()) == 0 and abs(got[0] - 1.0) < 2e-5
+    pick = rng.choice(C, 40, replace=False)
+    ref = ob.bartlett_envbatch([base[env[c]] for c in pick], K, np.stack([r[pick], zs[pick], np.zeros(40)], 1))
+    assert_parity(got[pick], ref)
