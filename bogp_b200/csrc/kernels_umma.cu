@@ -38,6 +38,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "bogp_internal.h"
 #include "device_math.cuh"
@@ -331,6 +332,15 @@ __device__ __forceinline__ void tc_ld2(uint32_t taddr, float& a, float& b) {
   a = __uint_as_float(r0);
   b = __uint_as_float(r1);
 }
+// Packed fp32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): two receivers per instruction in the tilt epilogue.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 v; asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi)); return v; }
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
 // MUFU.RSQ alone: rsqrtf() adds a denormal-range rescue (FSETP + two predicated FMULs) that 1 - l sin(tau) / r ~ 1 never needs
 __device__ __forceinline__ float rsqrt_fast(float x) {
   float y;
@@ -467,8 +477,8 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
 }
 
 // ---- tilted-array operand tables
-// Theta tables: per (tonal, pseudo-depth k = (tilt, receiver half) in stage order) the block [64 rows, Mp] with rows
-// (2q, 2q+1) = (Re, Im) of Theta_tau[n, m] = Phi[n, m] exp(i k_m l_n sin tau), n = 32 half + q, in the UMMA canonical
+// Theta tables: per (tonal, pseudo-depth k = (tilt, receiver half) in stage order) the block [64 rows, Mp]; receiver
+// pair (q, q+1) occupies rows 2q .. 2q+3 = (Re q, Re q+1, Im q, Im q+1) of Theta_tau[n, m] = Phi[n, m] exp(i k_m l_n sin tau), n = 32 half + q, in the UMMA canonical
 // K-major layout, hi and lo arrays.  The phase k_m l_n sin(tau) is formed in float64.
 __global__ void __launch_bounds__(128) umma_tilt_theta_kernel(ModesetDev ms, UParams p, const double* __restrict__ tilt_deg) {
   const int f = blockIdx.y, k = blockIdx.x;
@@ -492,7 +502,10 @@ __global__ void __launch_bounds__(128) umma_tilt_theta_kernel(ModesetDev ms, UPa
       vi = amp * (pr * sn + pi * cs);
     }
     const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
-    const size_t o0 = canon_off(2 * q, m, u.Mp), o1 = canon_off(2 * q + 1, m, u.Mp);
+    // rows of a receiver pair (q even, q + 1): Re q, Re q+1, Im q, Im q+1 -- the epilogue then forms T of both
+    // receivers with packed fp32x2 instructions on adjacent accumulator columns
+    const int row_re = 4 * (q >> 1) + (q & 1);
+    const size_t o0 = canon_off(row_re, m, u.Mp), o1 = canon_off(row_re + 2, m, u.Mp);
     Bhi[o0] = rh; Blo[o0] = tf32_rna((float)(vr - (double)rh));
     Bhi[o1] = ih; Blo[o1] = tf32_rna((float)(vi - (double)ih));
   }
@@ -658,6 +671,15 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     float* lev_s = reinterpret_cast<float*>(smem + p.smem_aux);
     float2* c_s = reinterpret_cast<float2*>(lev_s + 64);              // [F][64][4]
     for (int i = threadIdx.x; i < 64; i += blockDim.x) lev_s[i] = p.lever[i];
+    float4* cp_s = reinterpret_cast<float4*>(lev_s + 64 + p.F * 512 + 2 * 2 * 4 * 9 * 32);      // [F][32 receiver pairs]: (cx0, cx1, cy0, cy1), rank 1
+    for (int i = threadIdx.x; i < p.F * 32; i += blockDim.x) {
+      const int f = i >> 5, n0 = 2 * (i & 31);
+      const UTonal& u = p.t[f];
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 < p.N) { v.x = p.CkT_re[u.offC + n0 * u.J]; v.z = p.CkT_im[u.offC + n0 * u.J]; }
+      if (n0 + 1 < p.N) { v.y = p.CkT_re[u.offC + (n0 + 1) * u.J]; v.w = p.CkT_im[u.offC + (n0 + 1) * u.J]; }
+      cp_s[i] = v;
+    }
     for (int i = threadIdx.x; i < p.F * 256; i += blockDim.x) {
       const int f = i >> 8, n = (i >> 2) & 63, j = i & 3;
       const UTonal& u = p.t[f];
@@ -838,9 +860,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           const float* lev_s = reinterpret_cast<const float*>(smem + p.smem_aux);
           const float2* c_f = reinterpret_cast<const float2*>(lev_s + 64) + f * 256;     // [64][4]
           float* xch = const_cast<float*>(lev_s) + 64 + p.F * 512;                       // [2][2 sets][4 quads][9][32]
+          // the rank-1 (packed) and general (scalar) reductions keep different state: two instantiations of the tonal's
+          // stage loop, so that neither carries the other's registers
+          auto tonal_loop = [&](auto rank1_tag) {
+          constexpr bool R1 = decltype(rank1_tag)::value;
           float norm = 0.f, xs = 0.f, ur[kTJ], ui[kTJ];
 #pragma unroll
           for (int j = 0; j < kTJ; ++j) ur[j] = ui[j] = 0.f;
+          f32x2 norm2 = 0ull, u1 = 0ull, w1 = 0ull, v1 = 0ull, v2 = 0ull, nxs2 = 0ull;      // rank-1 path: packed over receiver pairs
+          const f32x2 one2 = pk(1.f, 1.f);
+          const f32x2* lev2 = reinterpret_cast<const f32x2*>(lev_s);
+          const ulonglong2* cp_f = reinterpret_cast<const ulonglong2*>(lev_s + 64 + p.F * 512 + 2 * 2 * 4 * 9 * 32) + f * 32;
           for (int k = 0; k < nzu; ++k, ++sc) {
             if ((int)(sc & 1u) != set) continue;
             mbar_wait_t(bar(BAR_TFULL + set), (sc >> 1) & 1u, p.err, 7, dbg ? &w_tfull : nullptr);
@@ -856,28 +886,38 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
 #pragma unroll
               for (int j = 0; j < kTJ; ++j) ur[j] = ui[j] = 0.f;
               xs = __ldg(p.sin_t + t0 + tloc) * rinv;
+              norm2 = u1 = w1 = v1 = v2 = 0ull;
+              nxs2 = pk(-xs, -xs);
             }
             // The two warps (sub 0 / 1) of this (buffer, quadrant) split the stage: 16 receivers = 32 columns each, all
             // four tcgen05.ld up front, release at the single wait, then the receiver-space reduction from registers.
             auto reduce16 = [&](const float* re, const float* im, int nb) {
-              if (J == 1) {                     // rank-1 covariance (K = d d^H, the reference's per-snapshot case):
-#pragma unroll                                  // no predicated work for the unused ranks (it still costs issue slots)
-                for (int q = 0; q < 8; ++q) {
-                  const int n = nb + q;
-                  const float tr = re[2 * q] - im[2 * q + 1], ti = im[2 * q] + re[2 * q + 1];
-                  const float sn = rsqrt_fast(fmaf(-lev_s[n], xs, 1.f));
-                  const float a = sn * tr, b = sn * ti;                    // p_n = s_n T_n
-                  norm = fmaf(a, a, fmaf(b, b, norm));
-                  const float2 c = c_f[n * 4];
-                  ur[0] = fmaf(c.x, a, fmaf(-c.y, b, ur[0]));
-                  ui[0] = fmaf(c.x, b, fmaf(c.y, a, ui[0]));
+              if (R1) {
+                // rank-1 covariance (K = d d^H, the reference's per-snapshot case), two receivers per instruction:
+                // columns 4p .. 4p+3 of a chunk are (Re n, Re n+1, Im n, Im n+1) of receiver pair p
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                  const f32x2 r01 = pk(re[4 * pp], re[4 * pp + 1]), r23 = pk(re[4 * pp + 2], re[4 * pp + 3]);
+                  const f32x2 i01 = pk(im[4 * pp], im[4 * pp + 1]), i23 = pk(im[4 * pp + 2], im[4 * pp + 3]);
+                  const f32x2 tr = sub2(r01, i23), ti = add2(i01, r23);
+                  const int pr = (nb >> 1) + pp;
+                  const f32x2 dd = fma2(lev2[pr], nxs2, one2);                    // 1 - l_n sin(tau) / r
+                  float d0, d1;
+                  upk(dd, d0, d1);
+                  const f32x2 sn = pk(rsqrt_fast(d0), rsqrt_fast(d1));
+                  const f32x2 a = mul2(sn, tr), b = mul2(sn, ti);                 // p_n = s_n T_n
+                  norm2 = fma2(a, a, norm2);
+                  norm2 = fma2(b, b, norm2);
+                  const ulonglong2 c = cp_f[pr];                                  // (cx0, cx1), (cy0, cy1)
+                  u1 = fma2(c.x, a, u1); w1 = fma2(c.y, b, w1);                   // Re u = sum cx a - cy b
+                  v1 = fma2(c.x, b, v1); v2 = fma2(c.y, a, v2);                   // Im u = sum cx b + cy a
                 }
                 return;
               }
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const int n = nb + q;
-                const float tr = re[2 * q] - im[2 * q + 1], ti = im[2 * q] + re[2 * q + 1];
+                const int n = nb + q, c0 = 4 * (q >> 1) + (q & 1);
+                const float tr = re[c0] - im[c0 + 2], ti = im[c0] + re[c0 + 2];
                 const float sn = rsqrt_fast(fmaf(-lev_s[n], xs, 1.f));
                 const float a = sn * tr, b = sn * ti;
                 norm = fmaf(a, a, fmaf(b, b, norm));
@@ -901,6 +941,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
             reduce16(ar, ai, nb0);
             reduce16(br, bi, nb0 + 8);
             if (half == 1) {
+              if (R1) {
+                float x0, x1, y0, y1;
+                upk(norm2, x0, x1); norm = x0 + x1;
+                upk(u1, x0, x1); upk(w1, y0, y1); ur[0] = (x0 + x1) - (y0 + y1);
+                upk(v1, x0, x1); upk(v2, y0, y1); ui[0] = (x0 + x1) + (y0 + y1);
+              }
               // sub 1 hands its partial sums to sub 0 through shared memory (double-buffered by tilt pair)
               float* x = xch + ((((tloc >> 1) & 1) * 2 + set) * 4 + quad) * (32 * (1 + 2 * kTJ)) + lane;
               if (sub == 1) {
@@ -924,6 +970,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
               }
             }
           }
+          };
+          if (J == 1) tonal_loop(std::true_type{}); else tonal_loop(std::false_type{});
         }
         constexpr int kPerQuad = kEpiWarps / 4;
         asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(kPerQuad * 32) : "memory");
@@ -1324,7 +1372,7 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   p.sumMp = sumMp;
   p.e_rt_stride = e_off;
   const unsigned acc_bytes = (unsigned)TC * kTileR * 4u;
-  const unsigned aux_bytes = (64u * 4u + (unsigned)d.F * 256u * 8u + 2u * 2u * 4u * 9u * 32u * 4u + 127u) & ~127u;
+  const unsigned aux_bytes = (64u * 4u + (unsigned)d.F * 256u * 8u + 2u * 2u * 4u * 9u * 32u * 4u + (unsigned)d.F * 32u * 16u + 127u) & ~127u;
   unsigned stage = (kSmemLimit - acc_bytes - aux_bytes - 256u) / kStages;
   stage = std::min(stage & ~127u, 32u * 1024u);
   if (2u * 64u * (unsigned)maxMp * 4u > stage) { set_error("UMMA tilt engine: mode set does not fit"); return BOGP_ERR_UNSUPPORTED; }
