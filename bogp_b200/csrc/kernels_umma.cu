@@ -864,30 +864,28 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           // stage loop, so that neither carries the other's registers
           auto tonal_loop = [&](auto rank1_tag) {
           constexpr bool R1 = decltype(rank1_tag)::value;
-          float norm = 0.f, xs = 0.f, ur[kTJ], ui[kTJ];
-#pragma unroll
-          for (int j = 0; j < kTJ; ++j) ur[j] = ui[j] = 0.f;
-          f32x2 norm2 = 0ull, u1 = 0ull, w1 = 0ull, v1 = 0ull, v2 = 0ull, nxs2 = 0ull;      // rank-1 path: packed over receiver pairs
           const f32x2 one2 = pk(1.f, 1.f);
           const f32x2* lev2 = reinterpret_cast<const f32x2*>(lev_s);
           const ulonglong2* cp_f = reinterpret_cast<const ulonglong2*>(lev_s + 64 + p.F * 512 + 2 * 2 * 4 * 9 * 32) + f * 32;
-          for (int k = 0; k < nzu; ++k, ++sc) {
-            if ((int)(sc & 1u) != set) continue;
-            mbar_wait_t(bar(BAR_TFULL + set), (sc >> 1) & 1u, p.err, 7, dbg ? &w_tfull : nullptr);
+          // sc is even at the start of every tonal (nzu is a multiple of 4), so this set's stages are k = 4q + set
+          // (half 0) and 4q + 2 + set (half 1) of tilt 2q + set: iterate over the tilts, both halves unrolled
+          for (int k4 = 0; k4 < nzu; k4 += 4) {
+            const int tloc = (k4 >> 1) + set;
+            const float xs = __ldg(p.sin_t + t0 + tloc) * rinv;
+            float norm = 0.f, ur[kTJ], ui[kTJ];
+#pragma unroll
+            for (int j = 0; j < kTJ; ++j) ur[j] = ui[j] = 0.f;
+            f32x2 norm2 = 0ull, u1 = 0ull, w1 = 0ull, v1 = 0ull, v2 = 0ull;      // rank-1 path: packed over receiver pairs
+            const f32x2 nxs2 = pk(-xs, -xs);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+            const uint32_t s_own = sc + (uint32_t)(k4 + 2 * half + set);
+            mbar_wait_t(bar(BAR_TFULL + set), (s_own >> 1) & 1u, p.err, 7, dbg ? &w_tfull : nullptr);
             tc_fence_after();
             if (BOGP_UMMA_DBG && p.skip == 2) {
               tc_fence_before();
               if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
               continue;
-            }
-            const int half = (k >> 1) & 1, tloc = 2 * (k >> 2) + (k & 1);
-            if (half == 0) {
-              norm = 0.f;
-#pragma unroll
-              for (int j = 0; j < kTJ; ++j) ur[j] = ui[j] = 0.f;
-              xs = __ldg(p.sin_t + t0 + tloc) * rinv;
-              norm2 = u1 = w1 = v1 = v2 = 0ull;
-              nxs2 = pk(-xs, -xs);
             }
             // The two warps (sub 0 / 1) of this (buffer, quadrant) split the stage: 16 receivers = 32 columns each, all
             // four tcgen05.ld up front, release at the single wait, then the receiver-space reduction from registers.
@@ -940,7 +938,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
             if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
             reduce16(ar, ai, nb0);
             reduce16(br, bi, nb0 + 8);
-            if (half == 1) {
+            }
+            {
               if (R1) {
                 float x0, x1, y0, y1;
                 upk(norm2, x0, x1); norm = x0 + x1;
@@ -970,6 +969,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
               }
             }
           }
+          sc += (uint32_t)nzu;
           };
           if (J == 1) tonal_loop(std::true_type{}); else tonal_loop(std::false_type{});
         }
