@@ -14,13 +14,15 @@
 // D puts range i on TMEM lane i, so each epilogue thread owns one range and reduces over the operator rows of its
 // own lane: no cross-lane shuffles; the replica field never exists outside TMEM.
 //
-// Pipeline per CTA (persistent over (range tile, depth chunk) units), 23 warps:
-//     warp 0       bulk-copy producer: the ring of Bop stages (cp.async.bulk + mbarrier complete_tx)
-//     warps 1, 22  MMA issuers, one per accumulator buffer (stage parity): tcgen05.mma.kind::tf32 with A from TMEM and
-//                  B from shared memory, tcgen05.commit to the ring / TMEM barriers; warp 1 owns the TMEM allocation
-//     warps 2-17   epilogue: 2 buffer sets x 2 depth parities x 4 lane quadrants; tcgen05.ld -> sum of squares ->
+// Pipeline per CTA (persistent over (range tile, depth chunk) units), 24 warps, roles aligned to warpgroups so that
+// setmaxnreg moves registers from the data-movement roles to the epilogue (kEpiRegs / kAuxRegs):
+//     warps 0-15   epilogue: 2 buffer sets x 2 depth parities x 4 lane quadrants; tcgen05.ld -> sum of squares ->
 //                  Bartlett -> multi-frequency combine in shared memory
-//     warps 18-21  E loaders: global -> registers -> tcgen05.st, one tonal ahead of the MMAs
+//     warps 16-19  E loaders: global -> registers -> tcgen05.st, one tonal ahead of the MMAs
+//     warp 20      bulk-copy producer: the ring of Bop stages (cp.async.bulk + mbarrier complete_tx)
+//     warps 21, 22 MMA issuers, one per accumulator buffer (stage parity): tcgen05.mma.kind::tf32 with A from TMEM and
+//                  B from shared memory, tcgen05.commit to the ring / TMEM barriers; warp 21 owns the TMEM allocation
+//     warp 23      idle (fills the last warpgroup)
 // The Bop table is built per call directly in the UMMA canonical K-major no-swizzle layout ([8-row group][16-byte K
 // chunk][8 rows][4 floats]; LBO = 128 B, SBO = 32 * Mp B), so the producer issues plain 1-D bulk copies.
 // TMEM map (512 columns): two accumulator buffers of (re | im) x NA columns, then the A region.
@@ -53,11 +55,23 @@ namespace bogp {
 
 constexpr int kTileR = 128;            // ranges per tile = MMA M = TMEM lanes
 constexpr int kStages = 6;             // Bop ring depth
+#ifndef BOGP_EPI_REGS
+#define BOGP_EPI_REGS 96
+#define BOGP_LOAD_REGS 56
+#define BOGP_CTL_REGS 40
+#endif
 constexpr int kEpiSub = 2;             // epilogue warps per (buffer set, lane quadrant): depth j goes to warp j % kEpiSub
 constexpr int kEpiWarps = 8 * kEpiSub;  // 2 accumulator-buffer sets x kEpiSub depth residues x 4 TMEM lane quadrants
 constexpr int kLoadWarps = 4;
-constexpr int kUmmaThreads = (2 + kEpiWarps + kLoadWarps + 1) * 32;   // + the second MMA issuer (last warp)
-constexpr int kMmaWarpB = 2 + kEpiWarps + kLoadWarps;
+// Warp roles, laid out by warpgroup (4 aligned warps) so that setmaxnreg can move registers from the data-movement
+// roles to the epilogue: warps 0..15 epilogue, 16..19 A-operand loaders, 20 Bop producer, 21 / 22 MMA issuers, 23 idle.
+constexpr int kLoadWarp0 = kEpiWarps;
+constexpr int kProdWarp = kEpiWarps + kLoadWarps;
+constexpr int kMmaWarpA = kProdWarp + 1;
+constexpr int kMmaWarpB = kProdWarp + 2;
+constexpr int kUmmaThreads = (kProdWarp + 4) * 32;
+constexpr int kEpiRegs = BOGP_EPI_REGS, kLoadRegs = BOGP_LOAD_REGS, kCtlRegs = BOGP_CTL_REGS;
+static_assert(16 * kEpiRegs + 4 * kLoadRegs + 4 * kCtlRegs <= 24 * 80, "register pool of the CTA (24 warps launched at 80)");
 constexpr unsigned kSmemLimit = 227u * 1024u;
 
 struct UTonal {
@@ -662,7 +676,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == kMmaWarpA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -695,7 +709,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
   long long* const dbg = (BOGP_UMMA_DBG && p.dbg) ? p.dbg + 16 * blockIdx.x : nullptr;
   const long long t_start = clock64();
 
-  if (warp == 0) {
+  if (warp >= kProdWarp) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtlRegs));
+  if (warp == kProdWarp) {
     // ============================================================== Bop producer (whole warp, one elected lane issues)
     long long w_bempty = 0;
     uint32_t sc = 0;       // global stage counter
@@ -721,10 +737,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       }
     }
     (void)w_bempty;
-  } else if (warp == 1 || warp == kMmaWarpB) {
+  } else if (warp == kMmaWarpA || warp == kMmaWarpB) {
     // ============================================================== MMA issuers (whole warp, one elected lane issues)
     MmaState st{};
-    st.id = warp == 1 ? 0 : 1;
+    st.id = warp == kMmaWarpA ? 0 : 1;
     st.p = &p; st.tmem_base = tmem_base; st.s_base = s_base; st.bar0 = bar0; st.dbg = dbg != nullptr;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       int rt_, z0_, jr_;
@@ -743,7 +759,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       }
     }
     if (dbg && lane == 0 && st.id == 0) { dbg[3] = clock64() - t_start; dbg[4] = st.w_efull; dbg[5] = st.w_bfull; dbg[6] = st.w_tempty; dbg[7] = st.sc; }
-  } else if (warp >= 2 + kEpiWarps && warp < kMmaWarpB) {
+  }
+  } else if (warp >= kLoadWarp0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kLoadRegs));
     // ============================================================== E loaders: global -> registers -> TMEM
     const int quad = warp & 3;
     const int tl = quad * 32 + lane;
@@ -830,6 +848,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     if (dbg && lane == 0 && quad == 0) { dbg[12] = clock64() - t_start; }
   } else {
     // ============================================================== epilogue
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
     if (TILT) {
       // ------------------------------------------------------------ tilted array (receiver space)
       // Stage k of a tonal holds, for one tilt and one half of the array, T_n = sum_m Theta_tau[n, m] a_m as adjacent
@@ -841,7 +860,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       // sums in registers between the two stages; the pair splits every stage (16 receivers each) and meets once per
       // tilt on a 64-thread named barrier to add the two partial sums.
       constexpr int kTJ = 4;                  // covariance ranks handled in registers
-      const int ew = warp - 2, quad = warp & 3, set = (ew >> 2) & 1, sub = ew >> 3;
+      const int ew = warp, quad = warp & 3, set = (ew >> 2) & 1, sub = ew >> 3;
       const int tl = quad * 32 + lane;
       const uint32_t NA = (uint32_t)p.NA;
       const uint32_t t_re = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)set * (2 * NA);
@@ -1007,7 +1026,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     // 16 warps = 2 buffer sets x 2 depth parities x 4 TMEM lane quadrants.  Set b drains accumulator buffer b only,
     // so the two buffers are processed concurrently by different warps, and a warp releases its buffer as soon as its
     // last tcgen05.ld has landed in registers -- the squares, the division and the combine run after the release.
-    const int ew = warp - 2;                 // 0..15
+    const int ew = warp;                     // 0..15
     const int quad = warp & 3;               // TMEM lane quadrant this warp may read
     const int set = (ew >> 2) & 1;           // accumulator buffer (= stage parity) this warp drains
     const int sub = ew >> 3;                 // depth residue (j % kEpiSub) this warp handles
@@ -1168,7 +1187,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       }
     }
   }
-  if (warp == 1) {
+  if (warp == kMmaWarpA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
