@@ -149,3 +149,20 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
                           int ext_mode = 0, float* ext_val_dev = nullptr, long long* ext_idx_dev = nullptr);
 int ensure_scratch(bogp_modeset_s* h, size_t bytes);
 }  // namespace bogp
+
+// GP posterior handle (kernels_gp.cu creates it; kernels_ts.cu samples from it)
+struct bogp_gp_s {
+  int n = 0, d = 0, kind = 0;
+  double outputscale = 1.0, mean = 0.0, noise = 0.0, jitter = 0.0;
+  double *X = nullptr, *inv_ls = nullptr, *alpha = nullptr, *Linv = nullptr, *LinvT = nullptr;
+  // staging of the *_host entry points (grown on demand): device [Xs | out | grad], page-locked host mirror
+  double* io_dev = nullptr;
+  double* io_pin = nullptr;
+  size_t io_doubles = 0;
+  // workspace of bogp_gp_thompson (grown on demand)
+  void* ts_ws = nullptr;
+  size_t ts_bytes = 0;
+};
+namespace bogp {
+constexpr int kGpMaxDim = 256;      // input dimensions a model may have (the acquisition kernels take <= 16 of them)
+}

@@ -22,16 +22,6 @@
 
 #include "bogp_internal.h"
 
-struct bogp_gp_s {
-  int n = 0, d = 0, kind = 0;
-  double outputscale = 1.0, mean = 0.0, noise = 0.0, jitter = 0.0;
-  double *X = nullptr, *inv_ls = nullptr, *alpha = nullptr, *Linv = nullptr, *LinvT = nullptr;
-  // staging of the *_host entry points (grown on demand): device [Xs | out | grad], page-locked host mirror
-  double* io_dev = nullptr;
-  double* io_pin = nullptr;
-  size_t io_doubles = 0;
-};
-
 namespace bogp {
 
 constexpr int kGpThreads = 256;
@@ -485,6 +475,8 @@ static int pick_bc(const bogp_gp_s* g, long long b, bool grad) {
 }
 
 static int dispatch_gp(const bogp_gp_s* g, const GpArgs& a, int bc, bool grad, cudaStream_t s) {
+  BOGP_REQUIRE(g->d <= kGpMaxD, "posterior / acquisition kernels take d <= %d input dimensions (model has %d); only "
+               "bogp_gp_thompson accepts more", kGpMaxD, g->d);
   switch (bc) {
     case 1: return launch_gp<1>(g, a, grad, s);
     case 2: return launch_gp<2>(g, a, grad, s);
@@ -502,7 +494,7 @@ extern "C" int bogp_gp_create(bogp_gp_t* out, int n, int d, const double* X_host
   BOGP_REQUIRE(out, "bogp_gp_create: out is NULL");
   *out = nullptr;
   BOGP_REQUIRE(n >= 1 && n <= bogp::kGpMaxN, "bogp_gp_create: n=%d outside [1,%d]", n, bogp::kGpMaxN);
-  BOGP_REQUIRE(d >= 1 && d <= bogp::kGpMaxD, "bogp_gp_create: d=%d outside [1,%d]", d, bogp::kGpMaxD);
+  BOGP_REQUIRE(d >= 1 && d <= bogp::kGpMaxDim, "bogp_gp_create: d=%d outside [1,%d]", d, bogp::kGpMaxDim);
   BOGP_REQUIRE(X_host && y_host && lengthscale_host, "bogp_gp_create: NULL input");
   BOGP_REQUIRE(kernel_kind == BOGP_KERNEL_MATERN52 || kernel_kind == BOGP_KERNEL_RBF, "bogp_gp_create: unknown kernel %d", kernel_kind);
   BOGP_REQUIRE(outputscale > 0.0 && noise >= 0.0, "bogp_gp_create: outputscale must be > 0 and noise >= 0");
@@ -584,6 +576,7 @@ extern "C" int bogp_gp_destroy(bogp_gp_t g) {
   cudaFree(g->X); cudaFree(g->inv_ls); cudaFree(g->alpha); cudaFree(g->Linv); cudaFree(g->LinvT);
   if (g->io_dev) cudaFree(g->io_dev);
   if (g->io_pin) cudaFreeHost(g->io_pin);
+  if (g->ts_ws) cudaFree(g->ts_ws);
   delete g;
   return 0;
 }

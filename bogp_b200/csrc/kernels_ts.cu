@@ -1,0 +1,381 @@
+// Thompson sampling over a candidate set: one joint draw f ~ N(mu, Sigma) of the GP posterior at b candidates and its
+// arg-max.  This is what BAxUS's create_candidate does through botorch's MaxPosteriorSampling
+// (reference: projects/swellex96_inv/data/bo/baxus.py:121-141, n_candidates = min(5000, max(2000, 200 d)) :45):
+//     mu    = m + K_*^T K^-1 (y - m),     Sigma = K_** - K_*^T K^-1 K_*        (noise-free posterior, float64)
+//     L L^T = Sigma (+ jitter 1e-8, 1e-7, 1e-6 only if the factorisation fails: gpytorch psd_safe_cholesky [recalled])
+//     f     = mu + L z,  z ~ N(0, I) supplied by the caller;  X_next = X_cand[argmax f]
+// Everything is float64 CUDA-core work (B200 runs FP64 FMA and FP64 MMA at the same rate, so DFMA register tiles):
+//     ts_kernel_matrix   K_*^T [b][n] and K_** [b][b] (lower tiles), 64 x 64 tiles, input dimensions streamed through smem
+//     ts_gemm_nt         C (-)= A B^T, 64 x 64 tile / CTA, 4 x 4 per thread: whitening V^T = K_*^T Linv^T (triangular K
+//                        range), Sigma -= V^T V (lower tiles), and the two level-3 steps of the blocked Cholesky
+//     ts_diag_kernel     64 x 64 diagonal block: Cholesky + inverse in shared memory (one CTA), failure flag
+//     ts_mean / ts_sample / ts_argmax   mu, f = mu + L z (warp per row), arg-max without replacement over samples
+// All matrices are padded (b to 64, n to 64) with zeros / an identity diagonal, so no kernel has edge predicates.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "bogp_internal.h"
+
+namespace bogp {
+
+constexpr int kTsT = 64;          // tile edge = Cholesky panel width
+constexpr int kTsKC = 16;         // K chunk of the GEMM
+constexpr int kTsThreads = 256;
+constexpr int kTsMaxB = 16384;
+constexpr int kTsMaxS = 64;
+
+__device__ __forceinline__ double ts_kernel_value(int kind, double os, double d2) {
+  if (kind == BOGP_KERNEL_RBF) return os * exp(-0.5 * d2);
+  const double sqrt5 = 2.23606797749978969641;
+  const double r = sqrt(fmax(d2, 1e-30));
+  return os * (1.0 + sqrt5 * r + (5.0 / 3.0) * d2) * exp(-sqrt5 * r);
+}
+
+// lower-triangular tile index t -> (ti, tj), tj <= ti
+__device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
+  int i = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while ((long long)(i + 1) * (i + 2) / 2 <= t) ++i;
+  while ((long long)i * (i + 1) / 2 > t) --i;
+  ti = i;
+  tj = t - (int)((long long)i * (i + 1) / 2);
+}
+
+// out[i][j] = k(P_i, Q_j); rows i >= Pvalid / columns j >= Qvalid are padding: 0, or (lower mode) 1 on the diagonal.
+// lower: P == Q, only tiles tj <= ti are written, `diag_add` is added to the diagonal (jitter).
+struct KmArgs {
+  const double *P, *Q, *inv_ls;
+  double* out;
+  int ldo, d, Pvalid, Qvalid, kind, lower, tiles_n;
+  double os, diag_add;
+};
+
+__global__ void __launch_bounds__(kTsThreads) ts_kernel_matrix(KmArgs a) {
+  __shared__ double Ps[kTsKC][kTsT], Qs[kTsKC][kTsT];
+  int ti, tj;
+  if (a.lower) tri_decode(blockIdx.x, ti, tj);
+  else { ti = blockIdx.x / a.tiles_n; tj = blockIdx.x % a.tiles_n; }
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lr = tid & 63, lk = (tid >> 6) * 4;          // loader: row lr of the tile, dimensions lk .. lk+3 of the chunk
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  const int pi = ti * kTsT + lr, qj = tj * kTsT + lr;
+  for (int a0 = 0; a0 < a.d; a0 += kTsKC) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int dim = a0 + lk + e;
+      const double w = dim < a.d ? __ldg(a.inv_ls + dim) : 0.0;
+      Ps[lk + e][lr] = (dim < a.d && pi < a.Pvalid) ? __ldg(a.P + (size_t)pi * a.d + dim) * w : 0.0;
+      Qs[lk + e][lr] = (dim < a.d && qj < a.Qvalid) ? __ldg(a.Q + (size_t)qj * a.d + dim) * w : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTsKC; ++k) {
+      double p[4], q[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { p[i] = Ps[k][ty * 4 + i]; q[i] = Qs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const double df = p[i] - q[j]; acc[i][j] = fma(df, df, acc[i][j]); }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gi = ti * kTsT + ty * 4 + i;
+    double v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gj = tj * kTsT + tx * 4 + j;
+      const bool valid = gi < a.Pvalid && gj < a.Qvalid;
+      v[j] = valid ? ts_kernel_value(a.kind, a.os, acc[i][j]) : 0.0;
+      if (a.lower && gi == gj) v[j] = valid ? v[j] + a.diag_add : 1.0;
+    }
+    double2* o = reinterpret_cast<double2*>(a.out + (size_t)gi * a.ldo + tj * kTsT + tx * 4);
+    o[0] = make_double2(v[0], v[1]);
+    o[1] = make_double2(v[2], v[3]);
+  }
+}
+
+// C[i][j] = A B^T (accumulate 0) or C[i][j] -= A B^T (accumulate 1); A [M][K], B [N][K], all dimensions padded:
+// M, N multiples of 64, K of 16.  lower: square problem, tiles tj <= ti only.  ktri: B is lower triangular with
+// K == N: the K loop of tile column tj stops after its last row.  A may alias C when N == 64 (a CTA owns whole rows
+// and has read all of A before it writes).
+struct GemmArgs {
+  const double *A, *B;
+  double* C;
+  int lda, ldb, ldc, K, tiles_n, lower, accumulate, ktri;
+};
+
+__global__ void __launch_bounds__(kTsThreads) ts_gemm_nt(GemmArgs g) {
+  __shared__ __align__(16) double As[2][kTsKC][kTsT], Bs[2][kTsKC][kTsT];
+  int ti, tj;
+  if (g.lower) tri_decode(blockIdx.x, ti, tj);
+  else { ti = blockIdx.x / g.tiles_n; tj = blockIdx.x % g.tiles_n; }
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lr = tid & 63, lk = (tid >> 6) * 4;
+  const double* Ap = g.A + (size_t)(ti * kTsT + lr) * g.lda + lk;
+  const double* Bp = g.B + (size_t)(tj * kTsT + lr) * g.ldb + lk;
+  const int K = g.ktri ? min(g.K, (tj + 1) * kTsT) : g.K;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  double2 a0 = *reinterpret_cast<const double2*>(Ap), a1 = *reinterpret_cast<const double2*>(Ap + 2);
+  double2 b0 = *reinterpret_cast<const double2*>(Bp), b1 = *reinterpret_cast<const double2*>(Bp + 2);
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += kTsKC) {
+    As[buf][lk][lr] = a0.x; As[buf][lk + 1][lr] = a0.y; As[buf][lk + 2][lr] = a1.x; As[buf][lk + 3][lr] = a1.y;
+    Bs[buf][lk][lr] = b0.x; Bs[buf][lk + 1][lr] = b0.y; Bs[buf][lk + 2][lr] = b1.x; Bs[buf][lk + 3][lr] = b1.y;
+    __syncthreads();
+    if (k0 + kTsKC < K) {      // next chunk in flight while this one is multiplied
+      a0 = *reinterpret_cast<const double2*>(Ap + k0 + kTsKC); a1 = *reinterpret_cast<const double2*>(Ap + k0 + kTsKC + 2);
+      b0 = *reinterpret_cast<const double2*>(Bp + k0 + kTsKC); b1 = *reinterpret_cast<const double2*>(Bp + k0 + kTsKC + 2);
+    }
+#pragma unroll
+    for (int k = 0; k < kTsKC; ++k) {
+      const double2 p0 = *reinterpret_cast<const double2*>(&As[buf][k][ty * 4]), p1 = *reinterpret_cast<const double2*>(&As[buf][k][ty * 4 + 2]);
+      const double2 q0 = *reinterpret_cast<const double2*>(&Bs[buf][k][tx * 4]), q1 = *reinterpret_cast<const double2*>(&Bs[buf][k][tx * 4 + 2]);
+      const double p[4] = {p0.x, p0.y, p1.x, p1.y}, q[4] = {q0.x, q0.y, q1.x, q1.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(p[i], q[j], acc[i][j]);
+    }
+    buf ^= 1;      // the other buffer was last read before the barrier above: safe to fill without a second barrier
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double2* c = reinterpret_cast<double2*>(g.C + (size_t)(ti * kTsT + ty * 4 + i) * g.ldc + tj * kTsT + tx * 4);
+    if (g.accumulate) {
+      const double2 c0 = c[0], c1 = c[1];
+      c[0] = make_double2(c0.x - acc[i][0], c0.y - acc[i][1]);
+      c[1] = make_double2(c1.x - acc[i][2], c1.y - acc[i][3]);
+    } else {
+      c[0] = make_double2(acc[i][0], acc[i][1]);
+      c[1] = make_double2(acc[i][2], acc[i][3]);
+    }
+  }
+}
+
+// Diagonal block of panel k: D = L L^T in place (lower), Tinv = L^-1 (dense 64 x 64, zero upper) for the panel solve.
+__global__ void __launch_bounds__(kTsThreads) ts_diag_kernel(double* S, int ld, int k, double* Tinv, int* flag) {
+  __shared__ double D[kTsT][kTsT + 1];      // lower: the block / its factor; strictly upper: (L^-1)^T as it is built
+  const int tid = threadIdx.x;
+  double* base = S + (size_t)k * kTsT * ld + (size_t)k * kTsT;
+  for (int e = tid; e < kTsT * kTsT; e += kTsThreads) D[e >> 6][e & 63] = base[(size_t)(e >> 6) * ld + (e & 63)];
+  __syncthreads();
+  // right-looking, one barrier per column: every thread derives the pivot itself and applies the rank-1 update with
+  // the unscaled column (D[r][c] -= D[r][j] D[c][j] / pivot); column j is scaled after the barrier, when nobody reads
+  // it any more (step j + 1 touches columns > j only).  Four lanes share a row.
+  {
+    const int r = tid >> 2, cp = tid & 3;
+    for (int j = 0; j < kTsT; ++j) {
+      double piv = D[j][j];
+      const bool bad = !(piv > 0.0) || !isfinite(piv);
+      if (bad) piv = 1.0;
+      const double rj = r > j ? D[r][j] : 0.0, w = -rj / piv;
+      for (int c = j + 1 + cp; c <= r; c += 4) D[r][c] = fma(w, D[c][j], D[r][c]);
+      __syncthreads();
+      if (cp == 0) {
+        const double dj = sqrt(piv);
+        if (r > j) D[r][j] = rj / dj;
+        if (r == j) { D[j][j] = dj; if (bad) *flag = 1; }
+      }
+    }
+    __syncthreads();
+  }
+  // inverse by forward substitution, X = L^-1 kept transposed in the strictly upper triangle (X[i][c] at D[c][i],
+  // X[c][c] = 1 / D[c][c]): four lanes share a column c (partial dot products, two shuffles)
+  {
+    const int c = tid >> 2, part = tid & 3;
+    const double xcc = 1.0 / D[c][c];
+    for (int i = 1; i < kTsT; ++i) {
+      double s = 0.0;
+      if (i > c) {
+        if (part == 0) s = D[i][c] * xcc;
+        for (int kk = c + 1 + part; kk < i; kk += 4) s = fma(D[i][kk], D[c][kk], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0 && i > c) D[c][i] = -s / D[i][i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < kTsT * kTsT; e += kTsThreads) {
+    const int r = e >> 6, c = e & 63;
+    if (c <= r) base[(size_t)r * ld + c] = D[r][c];
+    Tinv[e] = c < r ? D[c][r] : (c == r ? 1.0 / D[r][r] : 0.0);
+  }
+}
+
+// Linv / alpha of the model into the padded workspace
+__global__ void ts_pad_kernel(const double* Linv, const double* alpha, int n, int np, double* Linvp, double* alphap) {
+  const size_t total = (size_t)np * np;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / np), j = (int)(e % np);
+    Linvp[e] = (i < n && j < n) ? Linv[(size_t)i * n + j] : 0.0;
+    if (j == 0) alphap[i] = i < n ? alpha[i] : 0.0;
+  }
+}
+
+// mu_c = m + Kt[c] . alpha   (warp per candidate)
+__global__ void ts_mean_kernel(const double* Kt, int np, const double* alphap, double mean, int b, double* mu) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= b) return;
+  double s = 0.0;
+  for (int j = lane; j < np; j += 32) s = fma(Kt[(size_t)w * np + j], alphap[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) mu[w] = mean + s;
+}
+
+// f[s][c] = mu_c + sum_{j <= c} L[c][j] z[s][j]   (warp per candidate row)
+__global__ void ts_sample_kernel(const double* L, int ld, const double* mu, const double* z, int b, int S, double* f) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= b) return;
+  for (int s = 0; s < S; ++s) {
+    double acc = 0.0;
+    for (int j = lane; j <= w; j += 32) acc = fma(L[(size_t)w * ld + j], z[(size_t)s * b + j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) f[(size_t)s * b + w] = mu[w] + acc;
+  }
+}
+
+// arg-max of each sample in turn; a candidate picked by an earlier sample is excluded (replacement = False)
+__global__ void __launch_bounds__(1024) ts_argmax_kernel(const double* f, int b, int S, long long* idx, double* val) {
+  __shared__ double sv[32];
+  __shared__ int si[32];
+  __shared__ int chosen[kTsMaxS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int s = 0; s < S; ++s) {
+    double bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = tid; c < b; c += blockDim.x) {
+      bool taken = false;
+      for (int t = 0; t < s; ++t) taken |= chosen[t] == c;
+      const double v = f[(size_t)s * b + c];
+      if (!taken && (v > bv || (v == bv && c < bi))) { bv = v; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = sv[lane]; bi = si[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) { chosen[s] = bi; idx[s] = bi; val[s] = bv; }
+    }
+    __syncthreads();
+  }
+}
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace bogp
+
+using namespace bogp;
+
+extern "C" int bogp_gp_thompson(bogp_gp_t g, const double* Xc_dev, int b, const double* z_dev, int S,
+                                long long* idx_dev, double* val_dev, double* samples_dev, double* mean_dev,
+                                double* jitter_out, void* stream) {
+  BOGP_REQUIRE(g && Xc_dev && z_dev && idx_dev && val_dev, "bogp_gp_thompson: NULL argument");
+  BOGP_REQUIRE(b >= 1 && b <= kTsMaxB, "bogp_gp_thompson: b=%d outside [1,%d]", b, kTsMaxB);
+  BOGP_REQUIRE(S >= 1 && S <= kTsMaxS && S <= b, "bogp_gp_thompson: num_samples=%d outside [1,min(%d,b)]", S, kTsMaxS);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n = g->n, d = g->d;
+  const int bp = (b + kTsT - 1) / kTsT * kTsT, np = (n + kTsT - 1) / kTsT * kTsT;
+  const int tb = bp / kTsT, tn = np / kTsT;
+  // workspace
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off = al256(off + bytes); return o; };
+  const size_t o_kt = take((size_t)bp * np * 8), o_vt = take((size_t)bp * np * 8), o_li = take((size_t)np * np * 8);
+  const size_t o_al = take((size_t)np * 8), o_sg = take((size_t)bp * bp * 8), o_ti = take((size_t)kTsT * kTsT * 8);
+  const size_t o_mu = take((size_t)bp * 8), o_f = take((size_t)S * b * 8), o_flag = take(256);
+  if (g->ts_bytes < off) {
+    if (g->ts_ws) cudaFree(g->ts_ws);
+    g->ts_ws = nullptr; g->ts_bytes = 0;
+    BOGP_CUDA(cudaMalloc(&g->ts_ws, off));
+    g->ts_bytes = off;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(g->ts_ws);
+  double *Kt = (double*)(ws + o_kt), *Vt = (double*)(ws + o_vt), *Li = (double*)(ws + o_li), *al = (double*)(ws + o_al);
+  double *Sg = (double*)(ws + o_sg), *Ti = (double*)(ws + o_ti), *mu = (double*)(ws + o_mu);
+  double* f = samples_dev ? samples_dev : (double*)(ws + o_f);
+  int* flag = (int*)(ws + o_flag);
+
+  ts_pad_kernel<<<std::min(1184, (np * np + 255) / 256), 256, 0, s>>>(g->Linv, g->alpha, n, np, Li, al);
+  KmArgs km{};
+  km.P = Xc_dev; km.Q = g->X; km.inv_ls = g->inv_ls; km.out = Kt; km.ldo = np; km.d = d; km.Pvalid = b; km.Qvalid = n;
+  km.kind = g->kind; km.lower = 0; km.tiles_n = tn; km.os = g->outputscale; km.diag_add = 0.0;
+  ts_kernel_matrix<<<tb * tn, kTsThreads, 0, s>>>(km);
+  GemmArgs wh{};
+  wh.A = Kt; wh.lda = np; wh.B = Li; wh.ldb = np; wh.C = Vt; wh.ldc = np; wh.K = np; wh.tiles_n = tn; wh.ktri = 1;
+  ts_gemm_nt<<<tb * tn, kTsThreads, 0, s>>>(wh);
+  ts_mean_kernel<<<(b * 32 + 255) / 256, 256, 0, s>>>(Kt, np, al, g->mean, b, mu);
+  count_launch(4);
+
+  const int tri = tb * (tb + 1) / 2;
+  double jitter = 0.0;
+  bool ok = false;
+  cudaEvent_t ev = timing_begin(s);
+  for (int attempt = 0; attempt < 4 && !ok; ++attempt) {
+    jitter = attempt == 0 ? 0.0 : 1e-8 * std::pow(10.0, attempt - 1);
+    BOGP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), s));
+    KmArgs kk = km;
+    kk.Q = Xc_dev; kk.Qvalid = b; kk.out = Sg; kk.ldo = bp; kk.lower = 1; kk.diag_add = jitter;
+    ts_kernel_matrix<<<tri, kTsThreads, 0, s>>>(kk);
+    GemmArgs sy{};
+    sy.A = Vt; sy.lda = np; sy.B = Vt; sy.ldb = np; sy.C = Sg; sy.ldc = bp; sy.K = np; sy.lower = 1; sy.accumulate = 1;
+    ts_gemm_nt<<<tri, kTsThreads, 0, s>>>(sy);
+    count_launch(2);
+    for (int k = 0; k < tb; ++k) {
+      ts_diag_kernel<<<1, kTsThreads, 0, s>>>(Sg, bp, k, Ti, flag);
+      count_launch(1);
+      const int rem = tb - 1 - k;
+      if (rem == 0) break;
+      double* panel = Sg + (size_t)(k + 1) * kTsT * bp + (size_t)k * kTsT;
+      GemmArgs tr{};
+      tr.A = panel; tr.lda = bp; tr.B = Ti; tr.ldb = kTsT; tr.C = panel; tr.ldc = bp; tr.K = kTsT; tr.tiles_n = 1;
+      ts_gemm_nt<<<rem, kTsThreads, 0, s>>>(tr);
+      GemmArgs up{};
+      up.A = panel; up.lda = bp; up.B = panel; up.ldb = bp; up.C = Sg + (size_t)(k + 1) * kTsT * bp + (size_t)(k + 1) * kTsT;
+      up.ldc = bp; up.K = kTsT; up.lower = 1; up.accumulate = 1;
+      ts_gemm_nt<<<rem * (rem + 1) / 2, kTsThreads, 0, s>>>(up);
+      count_launch(2);
+    }
+    int hflag = 0;
+    BOGP_CUDA(cudaMemcpyAsync(&hflag, flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    BOGP_CUDA(cudaStreamSynchronize(s));
+    ok = hflag == 0;
+  }
+  timing_end(ev, s);
+  if (!ok) {
+    set_error("bogp_gp_thompson: posterior covariance not positive definite after jitter 1e-6");
+    return BOGP_ERR_NUMERIC;
+  }
+  ts_sample_kernel<<<(b * 32 + 255) / 256, 256, 0, s>>>(Sg, bp, mu, z_dev, b, S, f);
+  ts_argmax_kernel<<<1, 1024, 0, s>>>(f, b, S, idx_dev, val_dev);
+  count_launch(2);
+  if (mean_dev) BOGP_CUDA(cudaMemcpyAsync(mean_dev, mu, (size_t)b * 8, cudaMemcpyDeviceToDevice, s));
+  BOGP_CUDA(cudaGetLastError());
+  if (jitter_out) *jitter_out = jitter;
+  return 0;
+}

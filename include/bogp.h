@@ -180,6 +180,18 @@ int bogp_gp_posterior_joint_backward(bogp_gp_t g, const double* Xs_dev, long lon
 int bogp_gp_qei(bogp_gp_t g, const double* Xs_dev, long long b, int q, const double* base_dev, int S,
                 double best_f, double* out_dev, double* grad_dev, void* stream);
 
+/* Thompson sampling over a candidate set (BAxUS create_candidate, projects/swellex96_inv/data/bo/baxus.py:121-141:
+ * botorch MaxPosteriorSampling(model, replacement=False)(X_cand, num_samples)).  One joint posterior draw per sample
+ * at the b candidates, f = mu + chol(Sigma) z with the noise-free posterior (mu, Sigma) in float64 and the standard
+ * normal base samples z_dev[S][b] supplied by the caller; sample s picks the arg-max among the candidates no earlier
+ * sample picked.  idx_dev[S] / val_dev[S]: index into Xc and sampled value.  samples_dev[S][b] and mean_dev[b] are
+ * optional outputs (NULL to skip).  jitter_out (host, optional): diagonal jitter the factorisation needed (0, or 1e-8 /
+ * 1e-7 / 1e-6 after a failed attempt: gpytorch psd_safe_cholesky); BOGP_ERR_NUMERIC if 1e-6 is not enough.
+ * Unlike the acquisition entry points this one accepts models with up to 256 input dimensions (BAxUS grows its
+ * target space).  b <= 16384, S <= 64.  Synchronises the stream once per factorisation attempt. */
+int bogp_gp_thompson(bogp_gp_t g, const double* Xc_dev, int b, const double* z_dev, int S, long long* idx_dev,
+                     double* val_dev, double* samples_dev, double* mean_dev, double* jitter_out, void* stream);
+
 /* Host-buffer variants of bogp_gp_acq / bogp_gp_qei for the optimiser loop of optimize_acqf (ei.py:81-92): L-BFGS-B calls
  * value + gradient hundreds of times per BO iteration on a handful of restarts; one C call with page-locked staging
  * replaces the framework round trip.  Xs_host[b,(q,)d], out_host[b], grad_host[b,(q,)d] or NULL; base_dev stays on the

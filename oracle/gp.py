@@ -108,6 +108,38 @@ def posterior(gp: GPState, Xs: torch.Tensor, observation_noise: bool = False):
     return mu, cov
 
 
+def thompson_sample(gp: GPState, X_cand, z):
+    """Joint posterior draw(s) over a candidate set and their arg-max without replacement.
+
+    BAxUS ``create_candidate(acqf="ts")`` (ref/projects/swellex96_inv/data/bo/baxus.py:121-141): botorch
+    ``MaxPosteriorSampling(model, replacement=False)(X_cand, num_samples)`` = ``posterior.rsample`` = ``mu + L z`` with
+    ``L = psd_safe_cholesky(Sigma)`` of the noise-free posterior [recalled], then per sample the arg-max over the
+    candidates not yet picked.  ``z[S, b]`` standard-normal base samples.  Returns ``(idx[S], f[S, b], jitter)``.
+    """
+    X_cand = _t(X_cand)
+    z = _t(z).reshape(-1, X_cand.shape[0])
+    mu, cov = posterior(gp, X_cand)
+    cov = 0.5 * (cov + cov.T)
+    L, info = torch.linalg.cholesky_ex(cov)
+    jitter = 0.0
+    if bool(info.any()):
+        for i in range(3):
+            jitter = 1e-8 * 10 ** i
+            L, info = torch.linalg.cholesky_ex(cov + jitter * torch.eye(cov.shape[0], dtype=DT))
+            if not bool(info.any()):
+                break
+        else:
+            raise np.linalg.LinAlgError("posterior covariance not positive definite after jitter 1e-6")
+    f = mu.unsqueeze(0) + z @ L.T
+    picked = []
+    for s in range(z.shape[0]):
+        fs = f[s].clone()
+        if picked:
+            fs[torch.tensor(picked)] = -math.inf
+        picked.append(int(torch.argmax(fs)))
+    return np.asarray(picked, dtype=np.int64), f, jitter
+
+
 def posterior_mean_var(gp: GPState, Xs: torch.Tensor, observation_noise: bool = False):
     """Marginals: ``(mean[..., q], var[..., q])`` with ``var = clamp_min(k** - ||v||^2, 1e-10)``."""
     Xs = _t(Xs)
