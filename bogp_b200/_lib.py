@@ -60,6 +60,8 @@ SIGNATURES = {
     "bogp_gp_qei_host": (C.c_int, [_vp, _dp, _ll, C.c_int, _vp, C.c_int, C.c_double, _dp, _dp, _vp]),
     "bogp_gp_fit_adamw": (C.c_int, [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                     C.c_double, _dp, _dp, C.c_int, _dp, _dp, _vp]),
+    "bogp_gp_fit_adamw_bounded": (C.c_int, [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                            C.c_double, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _vp]),
     "bogp_gp_thompson": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _dp, _vp]),
     "bogp_gp_posterior": (C.c_int, [_vp, _vp, _ll, C.c_int, _vp, _vp, _vp]),
     "bogp_gp_acq": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp, _ll, _vp, _vp, _vp]),

@@ -31,6 +31,7 @@ constexpr int kFitNP = kFitMaxD + 3;        // raw parameters: lengthscale[d], o
 struct FitArgs {
   int n, d, kind, steps, ld, a_in_smem, x_in_smem;
   double lr, wd, noise_lo, noise_hi;
+  double ls_lo, ls_hi, os_lo, os_hi;      // Interval constraints (hi > lo) instead of softplus (baxus.py:310-319)
   int has_ls_prior, has_os_prior;
   double ls_conc, ls_rate, os_conc, os_rate;
   const double* X;       // [n, d]
@@ -150,8 +151,8 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
 
   for (int step = 1; step <= p.steps; ++step) {
     // ---------------------------------------------------------------- constrained parameters
-    if (tid < d) prm[tid] = softplus_d(raw[tid]);
-    if (tid == 32) prm[kFitMaxD + 0] = softplus_d(raw[d]);
+    if (tid < d) prm[tid] = p.ls_hi > p.ls_lo ? p.ls_lo + (p.ls_hi - p.ls_lo) * sigmoid_d(raw[tid]) : softplus_d(raw[tid]);
+    if (tid == 32) prm[kFitMaxD + 0] = p.os_hi > p.os_lo ? p.os_lo + (p.os_hi - p.os_lo) * sigmoid_d(raw[d]) : softplus_d(raw[d]);
     if (tid == 33) prm[kFitMaxD + 1] = p.noise_lo + (p.noise_hi - p.noise_lo) * sigmoid_d(raw[d + 1]);
     if (tid == 34) prm[kFitMaxD + 2] = raw[d + 2];
     __syncthreads();
@@ -374,7 +375,8 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
           ll += p.ls_conc * log(p.ls_rate) - lgamma(p.ls_conc) + (p.ls_conc - 1.0) * log(ls) - p.ls_rate * ls;
           gl += (p.ls_conc - 1.0) / ls - p.ls_rate;
         }
-        grad[k] = -gl * sigmoid_d(raw[k]) / nn;
+        const double sk = sigmoid_d(raw[k]);
+        grad[k] = -gl * (p.ls_hi > p.ls_lo ? (p.ls_hi - p.ls_lo) * sk * (1.0 - sk) : sk) / nn;
       }
       {
         double go = gsum[kFitMaxD];
@@ -382,7 +384,8 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
           ll += p.os_conc * log(p.os_rate) - lgamma(p.os_conc) + (p.os_conc - 1.0) * log(os) - p.os_rate * os;
           go += (p.os_conc - 1.0) / os - p.os_rate;
         }
-        grad[d] = -go * sigmoid_d(raw[d]) / nn;
+        const double so = sigmoid_d(raw[d]);
+        grad[d] = -go * (p.os_hi > p.os_lo ? (p.os_hi - p.os_lo) * so * (1.0 - so) : so) / nn;
         const double sg = sigmoid_d(raw[d + 1]);
         grad[d + 1] = -gsum[kFitMaxD + 1] * (p.noise_hi - p.noise_lo) * sg * (1.0 - sg) / nn;
         grad[d + 2] = -sum_alpha / nn;
@@ -410,7 +413,21 @@ extern "C" int bogp_gp_fit_adamw(int n, int d, const double* X_host, const doubl
                                  double lr, double weight_decay, double noise_lo, double noise_hi,
                                  const double* lengthscale_prior, const double* outputscale_prior, int B,
                                  double* raw_inout_host, double* loss_host, void* stream) {
+  return bogp_gp_fit_adamw_bounded(n, d, X_host, y_host, kernel_kind, steps, lr, weight_decay, noise_lo, noise_hi,
+                                   lengthscale_prior, outputscale_prior, nullptr, nullptr, B, raw_inout_host, loss_host,
+                                   stream);
+}
+
+extern "C" int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, const double* y_host, int kernel_kind,
+                                         int steps, double lr, double weight_decay, double noise_lo, double noise_hi,
+                                         const double* lengthscale_prior, const double* outputscale_prior,
+                                         const double* lengthscale_bounds, const double* outputscale_bounds, int B,
+                                         double* raw_inout_host, double* loss_host, void* stream) {
   using namespace bogp;
+  BOGP_REQUIRE(!lengthscale_bounds || (lengthscale_bounds[0] > 0.0 && lengthscale_bounds[1] > lengthscale_bounds[0]),
+               "bogp_gp_fit_adamw: bad lengthscale bounds");
+  BOGP_REQUIRE(!outputscale_bounds || (outputscale_bounds[0] > 0.0 && outputscale_bounds[1] > outputscale_bounds[0]),
+               "bogp_gp_fit_adamw: bad outputscale bounds");
   BOGP_REQUIRE(n >= 1 && n <= kFitMaxN, "bogp_gp_fit_adamw: n=%d outside [1,%d]", n, kFitMaxN);
   BOGP_REQUIRE(d >= 1 && d <= kFitMaxD, "bogp_gp_fit_adamw: d=%d outside [1,%d]", d, kFitMaxD);
   BOGP_REQUIRE(X_host && y_host && raw_inout_host, "bogp_gp_fit_adamw: NULL input");
@@ -426,6 +443,8 @@ extern "C" int bogp_gp_fit_adamw(int n, int d, const double* X_host, const doubl
   FitArgs p{};
   p.n = n; p.d = d; p.kind = kernel_kind; p.steps = steps; p.ld = n | 1;
   p.lr = lr; p.wd = weight_decay; p.noise_lo = noise_lo; p.noise_hi = noise_hi;
+  if (lengthscale_bounds) { p.ls_lo = lengthscale_bounds[0]; p.ls_hi = lengthscale_bounds[1]; }
+  if (outputscale_bounds) { p.os_lo = outputscale_bounds[0]; p.os_hi = outputscale_bounds[1]; }
   if (lengthscale_prior) { p.has_ls_prior = 1; p.ls_conc = lengthscale_prior[0]; p.ls_rate = lengthscale_prior[1]; }
   if (outputscale_prior) { p.has_os_prior = 1; p.os_conc = outputscale_prior[0]; p.os_rate = outputscale_prior[1]; }
   const size_t fixed = ((size_t)4 * n + 2 * 32 * 33 + 64 + kFitWarps * (kFitMaxD + 4) + (kFitMaxD + 8) + 3 * kFitNP + (kFitMaxD + 4) + 2) * sizeof(double);

@@ -44,6 +44,10 @@ class FitConfig:
     lengthscale_prior: Optional[Tuple[float, float]] = (3.0, 6.0)    # Gamma(concentration, rate)
     outputscale_prior: Optional[Tuple[float, float]] = (2.0, 0.15)
     weight_decay: float = 1e-2                                       # torch.optim.AdamW default
+    # Interval constraints (value = lo + (hi - lo) sigmoid(raw)) instead of softplus: the explicit kernel of
+    # baxus.py:310-319 uses Interval(0.005, 10) on the length scales and Interval(0.05, 10) on the output scale
+    lengthscale_bounds: Optional[Tuple[float, float]] = None
+    outputscale_bounds: Optional[Tuple[float, float]] = None
 
 
 class GPPosterior:
@@ -248,6 +252,7 @@ def _gamma_logpdf(x, conc, rate):
     return conc * math.log(rate) - math.lgamma(conc) + (conc - 1.0) * torch.log(x) - rate * x
 
 
+FUSED_FIT_MAX_D = 16       # input dimensions the fused kernel takes (kFitMaxD)
 FUSED_FIT_MAX_N = 320      # above this the single-CTA kernel loses to the cuSOLVER loop (profiles/paths_r1b.jsonl)
 
 
@@ -268,8 +273,8 @@ def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), raw_init: Op
     if engine not in ("auto", "fused", "torch"):
         raise ValueError("engine must be 'auto', 'fused' or 'torch'")
     _cuda_device()
-    if engine == "torch" or (engine == "auto" and model.train_X.shape[0] > FUSED_FIT_MAX_N
-                             and raw_init is None and not return_loss):
+    if engine == "torch" or (engine == "auto" and raw_init is None and not return_loss
+                             and (model.train_X.shape[0] > FUSED_FIT_MAX_N or model.train_X.shape[1] > FUSED_FIT_MAX_D)):
         return fit_gp_adamw_torch(model, cfg)
     X = np.ascontiguousarray(model.train_X.cpu().numpy(), dtype=np.float64)
     y = np.ascontiguousarray(model.train_Y.cpu().numpy(), dtype=np.float64)
@@ -281,14 +286,19 @@ def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), raw_init: Op
     lsp = None if cfg.lengthscale_prior is None else np.array(cfg.lengthscale_prior, dtype=np.float64)
     osp = None if cfg.outputscale_prior is None else np.array(cfg.outputscale_prior, dtype=np.float64)
     lo, hi = cfg.noise_bounds
-    _lib.call("bogp_gp_fit_adamw", n, d, _lib.dptr(X), _lib.dptr(y), _lib.KERNEL[model.kind], int(cfg.steps),
-              float(cfg.lr), float(cfg.weight_decay), float(lo), float(hi), _lib.dptr(lsp), _lib.dptr(osp), B,
-              _lib.dptr(raw), _lib.dptr(loss), C.c_void_p(_lib.current_stream_ptr()))
+    lsb = None if cfg.lengthscale_bounds is None else np.array(cfg.lengthscale_bounds, dtype=np.float64)
+    osb = None if cfg.outputscale_bounds is None else np.array(cfg.outputscale_bounds, dtype=np.float64)
+    _lib.call("bogp_gp_fit_adamw_bounded", n, d, _lib.dptr(X), _lib.dptr(y), _lib.KERNEL[model.kind], int(cfg.steps),
+              float(cfg.lr), float(cfg.weight_decay), float(lo), float(hi), _lib.dptr(lsp), _lib.dptr(osp),
+              _lib.dptr(lsb), _lib.dptr(osb), B, _lib.dptr(raw), _lib.dptr(loss), C.c_void_p(_lib.current_stream_ptr()))
     best = int(np.argmin(loss[:, -1])) if B > 1 else 0
     r = raw[best]
     sp = lambda v: np.where(v > 20.0, v, np.log1p(np.exp(np.minimum(v, 20.0))))     # noqa: E731
+    iv = lambda v, b: b[0] + (b[1] - b[0]) / (1.0 + np.exp(-v))                      # noqa: E731
+    ls_v = sp(r[:d]) if lsb is None else iv(r[:d], lsb)
+    os_v = sp(r[d]) if osb is None else iv(r[d], osb)
     model.noise_bounds = (lo, hi)
-    model.set_hyperparameters(lengthscale=torch.as_tensor(sp(r[:d])), outputscale=float(sp(r[d])),
+    model.set_hyperparameters(lengthscale=torch.as_tensor(ls_v), outputscale=float(os_v),
                               mean=float(r[d + 2]), noise=float(lo + (hi - lo) / (1.0 + math.exp(-r[d + 1]))))
     model.raw_parameters = r.copy()
     return (model, loss) if return_loss else model
@@ -307,9 +317,12 @@ def fit_gp_adamw_torch(model: SingleTaskGP, cfg: FitConfig = FitConfig(), device
     opt = torch.optim.AdamW(list(raw.values()), lr=cfg.lr, weight_decay=cfg.weight_decay)
     eye = torch.eye(n, dtype=DT, device=dev)
     sp = torch.nn.functional.softplus
+    lsb, osb = cfg.lengthscale_bounds, cfg.outputscale_bounds
+    f_ls = (lambda v: sp(v)) if lsb is None else (lambda v: lsb[0] + (lsb[1] - lsb[0]) * torch.sigmoid(v))
+    f_os = (lambda v: sp(v)) if osb is None else (lambda v: osb[0] + (osb[1] - osb[0]) * torch.sigmoid(v))
     for _ in range(cfg.steps):
         opt.zero_grad()
-        ls, os_ = sp(raw["lengthscale"]), sp(raw["outputscale"])
+        ls, os_ = f_ls(raw["lengthscale"]), f_os(raw["outputscale"])
         noise = lo + (hi - lo) * torch.sigmoid(raw["noise"])
         Kxx = _kernel_matrix(model.kind, X, ls, os_) + noise * eye
         L, info = torch.linalg.cholesky_ex(Kxx)
@@ -328,6 +341,6 @@ def fit_gp_adamw_torch(model: SingleTaskGP, cfg: FitConfig = FitConfig(), device
         opt.step()
     with torch.no_grad():
         model.noise_bounds = (lo, hi)
-        model.set_hyperparameters(lengthscale=sp(raw["lengthscale"]).cpu(), outputscale=float(sp(raw["outputscale"])),
+        model.set_hyperparameters(lengthscale=f_ls(raw["lengthscale"]).cpu(), outputscale=float(f_os(raw["outputscale"])),
                                   mean=float(raw["mean"]), noise=float(lo + (hi - lo) * torch.sigmoid(raw["noise"])))
     return model

@@ -213,6 +213,14 @@ int bogp_gp_fit_adamw(int n, int d, const double* X_host, const double* y_host, 
                       double lr, double weight_decay, double noise_lo, double noise_hi,
                       const double* lengthscale_prior, const double* outputscale_prior, int B,
                       double* raw_inout_host, double* loss_host, void* stream);
+/* The same with Interval constraints on the length scales / output scale instead of softplus (the explicit
+ * ScaleKernel(MaternKernel(lengthscale_constraint=Interval(0.005, 10)), outputscale_constraint=Interval(0.05, 10)) of
+ * baxus.py:310-319): value = lo + (hi - lo) sigmoid(raw).  lengthscale_bounds / outputscale_bounds: {lo, hi} or NULL. */
+int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, const double* y_host, int kernel_kind, int steps,
+                              double lr, double weight_decay, double noise_lo, double noise_hi,
+                              const double* lengthscale_prior, const double* outputscale_prior,
+                              const double* lengthscale_bounds, const double* outputscale_bounds, int B,
+                              double* raw_inout_host, double* loss_host, void* stream);
 
 #ifdef __cplusplus
 }

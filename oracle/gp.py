@@ -255,13 +255,22 @@ class FitConfig:
     lengthscale_prior: Optional[tuple] = (3.0, 6.0)     # Gamma(concentration, rate)
     outputscale_prior: Optional[tuple] = (2.0, 0.15)
     weight_decay: float = 1e-2                           # torch.optim.AdamW default
+    # Interval(lo, hi) constraints instead of Positive/softplus: baxus.py:310-319 (0.005, 10) / (0.05, 10)
+    lengthscale_bounds: Optional[tuple] = None
+    outputscale_bounds: Optional[tuple] = None
+
+
+def _constrained(raw: dict, cfg: "FitConfig"):
+    """raw -> (lengthscale, outputscale): softplus (GPyTorch ``Positive``) or ``lo + (hi - lo) sigmoid`` (``Interval``)."""
+    def tr(v, b):
+        return torch.nn.functional.softplus(v) if b is None else b[0] + (b[1] - b[0]) * torch.sigmoid(v)
+    return tr(raw["lengthscale"], cfg.lengthscale_bounds), tr(raw["outputscale"], cfg.outputscale_bounds)
 
 
 def neg_mll(raw: dict, X: torch.Tensor, y: torch.Tensor, cfg: FitConfig) -> torch.Tensor:
     """``-ExactMarginalLogLikelihood`` = ``-(log N(y | m, K + s2 I) + sum log-priors) / n``."""
     n = X.shape[0]
-    ls = torch.nn.functional.softplus(raw["lengthscale"])
-    os_ = torch.nn.functional.softplus(raw["outputscale"])
+    ls, os_ = _constrained(raw, cfg)
     lo, hi = cfg.noise_bounds
     noise = lo + (hi - lo) * torch.sigmoid(raw["noise"])
     Kxx = kernel_matrix(cfg.kind, X, X, ls, os_) + noise * torch.eye(n, dtype=DT)
@@ -293,8 +302,9 @@ def fit_adamw(X, y, cfg: FitConfig = FitConfig()) -> GPState:
         opt.step()
     lo, hi = cfg.noise_bounds
     with torch.no_grad():
+        ls, os_ = _constrained(raw, cfg)
         return GPState(X, y, cfg.kind,
-                       torch.nn.functional.softplus(raw["lengthscale"]).clone(),
-                       float(torch.nn.functional.softplus(raw["outputscale"])),
+                       ls.clone(),
+                       float(os_),
                        float(raw["mean"]),
                        float(lo + (hi - lo) * torch.sigmoid(raw["noise"])))
