@@ -4,9 +4,9 @@
 //     mu    = m + K_*^T K^-1 (y - m),     Sigma = K_** - K_*^T K^-1 K_*        (noise-free posterior, float64)
 //     L L^T = Sigma (+ jitter 1e-8, 1e-7, 1e-6 only if the factorisation fails: gpytorch psd_safe_cholesky [recalled])
 //     f     = mu + L z,  z ~ N(0, I) supplied by the caller;  X_next = X_cand[argmax f]
-// Everything is float64 CUDA-core work (B200 runs FP64 FMA and FP64 MMA at the same rate, so DFMA register tiles):
+// Everything is float64; the level-3 work runs on the FP64 tensor cores:
 //     ts_kernel_matrix   K_*^T [b][n] and K_** [b][b] (lower tiles), 64 x 64 tiles, input dimensions streamed through smem
-//     ts_gemm_nt         C (-)= A B^T, 64 x 64 tile / CTA, 4 x 4 per thread: whitening V^T = K_*^T Linv^T (triangular K
+//     ts_gemm_nt         C (-)= A B^T, 64 x 64 tile / CTA on the FP64 tensor cores (mma.sync m8n8k4): whitening V^T = K_*^T Linv^T (triangular K
 //                        range), Sigma -= V^T V (lower tiles), and the two level-3 steps of the blocked Cholesky
 //     ts_diag_kernel     64 x 64 diagonal block: Cholesky + inverse in shared memory (one CTA), failure flag
 //     ts_mean / ts_sample / ts_argmax   mu, f = mu + L z (warp per row), arg-max without replacement over samples
@@ -112,21 +112,33 @@ struct GemmArgs {
   int lda, ldb, ldc, K, tiles_n, lower, accumulate, ktri;
 };
 
+// FP64 tensor-core MMA (DMMA): D[8x8] += A[8x4] B[4x8]; lane (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g] and
+// D[g][2t], D[g][2t + 1].  Measured on B200 (tools/micro/fp64_peak.cu): 37.1 TFLOP/s against 33.9 for DFMA, and -- what
+// matters here -- operand fragments are spread over the warp instead of broadcast, so a k-step costs 6 LDS.64 per
+// 2048 FMA where the 4 x 4 DFMA register tile needed 4 LDS.128 per 512 (shared-memory bound at half the DFMA peak).
+__device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+constexpr int kTsLd = 68;      // shared-memory row stride in doubles: the fragment loads (4 k x 8 rows) hit 32 distinct banks
+
 __global__ void __launch_bounds__(kTsThreads) ts_gemm_nt(GemmArgs g) {
-  __shared__ __align__(16) double As[2][kTsKC][kTsT], Bs[2][kTsKC][kTsT];
+  __shared__ __align__(16) double As[2][kTsKC][kTsLd], Bs[2][kTsKC][kTsLd];
   int ti, tj;
   if (g.lower) tri_decode(blockIdx.x, ti, tj);
   else { ti = blockIdx.x / g.tiles_n; tj = blockIdx.x % g.tiles_n; }
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tq = lane & 3, wm = (warp >> 2) * 32, wn = (warp & 3) * 16;    // warp tile 32 x 16
   const int lr = tid & 63, lk = (tid >> 6) * 4;
   const double* Ap = g.A + (size_t)(ti * kTsT + lr) * g.lda + lk;
   const double* Bp = g.B + (size_t)(tj * kTsT + lr) * g.ldb + lk;
   const int K = g.ktri ? min(g.K, (tj + 1) * kTsT) : g.K;
-  double acc[4][4];
+  double acc[4][2][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   double2 a0 = *reinterpret_cast<const double2*>(Ap), a1 = *reinterpret_cast<const double2*>(Ap + 2);
   double2 b0 = *reinterpret_cast<const double2*>(Bp), b1 = *reinterpret_cast<const double2*>(Bp + 2);
   int buf = 0;
@@ -139,72 +151,96 @@ __global__ void __launch_bounds__(kTsThreads) ts_gemm_nt(GemmArgs g) {
       b0 = *reinterpret_cast<const double2*>(Bp + k0 + kTsKC); b1 = *reinterpret_cast<const double2*>(Bp + k0 + kTsKC + 2);
     }
 #pragma unroll
-    for (int k = 0; k < kTsKC; ++k) {
-      const double2 p0 = *reinterpret_cast<const double2*>(&As[buf][k][ty * 4]), p1 = *reinterpret_cast<const double2*>(&As[buf][k][ty * 4 + 2]);
-      const double2 q0 = *reinterpret_cast<const double2*>(&Bs[buf][k][tx * 4]), q1 = *reinterpret_cast<const double2*>(&Bs[buf][k][tx * 4 + 2]);
-      const double p[4] = {p0.x, p0.y, p1.x, p1.y}, q[4] = {q0.x, q0.y, q1.x, q1.y};
+    for (int k4 = 0; k4 < kTsKC; k4 += 4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[buf][k4 + tq][wm + 8 * i + gq];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = Bs[buf][k4 + tq][wn + 8 * j + gq];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(p[i], q[j], acc[i][j]);
+        for (int j = 0; j < 2; ++j) dmma884(acc[i][j], a[i], b[j]);
     }
     buf ^= 1;      // the other buffer was last read before the barrier above: safe to fill without a second barrier
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double2* c = reinterpret_cast<double2*>(g.C + (size_t)(ti * kTsT + ty * 4 + i) * g.ldc + tj * kTsT + tx * 4);
-    if (g.accumulate) {
-      const double2 c0 = c[0], c1 = c[1];
-      c[0] = make_double2(c0.x - acc[i][0], c0.y - acc[i][1]);
-      c[1] = make_double2(c1.x - acc[i][2], c1.y - acc[i][3]);
-    } else {
-      c[0] = make_double2(acc[i][0], acc[i][1]);
-      c[1] = make_double2(acc[i][2], acc[i][3]);
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double2* c = reinterpret_cast<double2*>(g.C + (size_t)(ti * kTsT + wm + 8 * i + gq) * g.ldc + tj * kTsT + wn + 8 * j + 2 * tq);
+      if (g.accumulate) {
+        const double2 c0 = *c;
+        *c = make_double2(c0.x - acc[i][j][0], c0.y - acc[i][j][1]);
+      } else {
+        *c = make_double2(acc[i][j][0], acc[i][j][1]);
+      }
     }
-  }
+}
+
+// 1 / sqrt(x) in float64 from the float approximation and two Newton steps (a dependent DDIV + DSQRT per column costs
+// more than the column's whole rank-1 update)
+__device__ __forceinline__ double rsqrt_d(double x) {
+  if (!(x > 1e-30 && x < 1e30)) return 1.0 / sqrt(x);
+  double y = (double)rsqrtf((float)x);
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  return y;
 }
 
 // Diagonal block of panel k: D = L L^T in place (lower), Tinv = L^-1 (dense 64 x 64, zero upper) for the panel solve.
 __global__ void __launch_bounds__(kTsThreads) ts_diag_kernel(double* S, int ld, int k, double* Tinv, int* flag) {
   __shared__ double D[kTsT][kTsT + 1];      // lower: the block / its factor; strictly upper: (L^-1)^T as it is built
+  __shared__ double invd[kTsT];             // 1 / L[j][j]
   const int tid = threadIdx.x;
   double* base = S + (size_t)k * kTsT * ld + (size_t)k * kTsT;
   for (int e = tid; e < kTsT * kTsT; e += kTsThreads) D[e >> 6][e & 63] = base[(size_t)(e >> 6) * ld + (e & 63)];
   __syncthreads();
   // right-looking, one barrier per column: every thread derives the pivot itself and applies the rank-1 update with
   // the unscaled column (D[r][c] -= D[r][j] D[c][j] / pivot); column j is scaled after the barrier, when nobody reads
-  // it any more (step j + 1 touches columns > j only).  Four lanes share a row.
+  // it any more (step j + 1 touches columns > j only).  Four lanes share a row; the 16 column slots of a lane are
+  // unrolled and predicated so that their loads overlap.
   {
     const int r = tid >> 2, cp = tid & 3;
     for (int j = 0; j < kTsT; ++j) {
       double piv = D[j][j];
       const bool bad = !(piv > 0.0) || !isfinite(piv);
       if (bad) piv = 1.0;
-      const double rj = r > j ? D[r][j] : 0.0, w = -rj / piv;
-      for (int c = j + 1 + cp; c <= r; c += 4) D[r][c] = fma(w, D[c][j], D[r][c]);
+      const double rs = rsqrt_d(piv);
+      const double rj = r > j ? D[r][j] : 0.0, w = -rj * rs * rs;
+#pragma unroll
+      for (int m = 0; m < 16; ++m) {
+        const int c = j + 1 + cp + 4 * m;
+        if (c <= r) D[r][c] = fma(w, D[c][j], D[r][c]);
+      }
       __syncthreads();
       if (cp == 0) {
-        const double dj = sqrt(piv);
-        if (r > j) D[r][j] = rj / dj;
-        if (r == j) { D[j][j] = dj; if (bad) *flag = 1; }
+        if (r > j) D[r][j] = rj * rs;
+        if (r == j) { D[j][j] = piv * rs; invd[j] = rs; if (bad) *flag = 1; }
       }
     }
     __syncthreads();
   }
   // inverse by forward substitution, X = L^-1 kept transposed in the strictly upper triangle (X[i][c] at D[c][i],
-  // X[c][c] = 1 / D[c][c]): four lanes share a column c (partial dot products, two shuffles)
+  // X[c][c] = 1 / D[c][c]): four lanes share a column c (partial dot products in two chains, two shuffles)
   {
     const int c = tid >> 2, part = tid & 3;
-    const double xcc = 1.0 / D[c][c];
+    const double xcc = invd[c];
     for (int i = 1; i < kTsT; ++i) {
-      double s = 0.0;
+      double s0 = 0.0, s1 = 0.0;
       if (i > c) {
-        if (part == 0) s = D[i][c] * xcc;
-        for (int kk = c + 1 + part; kk < i; kk += 4) s = fma(D[i][kk], D[c][kk], s);
+        if (part == 0) s0 = D[i][c] * xcc;
+#pragma unroll
+        for (int m = 0; m < 16; m += 2) {
+          const int ka = c + 1 + part + 4 * m, kb = ka + 4;
+          if (ka < i) s0 = fma(D[i][ka], D[c][ka], s0);
+          if (kb < i) s1 = fma(D[i][kb], D[c][kb], s1);
+        }
       }
+      double s = s0 + s1;
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (part == 0 && i > c) D[c][i] = -s / D[i][i];
+      if (part == 0 && i > c) D[c][i] = -s * invd[i];
       __syncwarp();
     }
   }
@@ -212,7 +248,7 @@ __global__ void __launch_bounds__(kTsThreads) ts_diag_kernel(double* S, int ld, 
   for (int e = tid; e < kTsT * kTsT; e += kTsThreads) {
     const int r = e >> 6, c = e & 63;
     if (c <= r) base[(size_t)r * ld + c] = D[r][c];
-    Tinv[e] = c < r ? D[c][r] : (c == r ? 1.0 / D[r][r] : 0.0);
+    Tinv[e] = c < r ? D[c][r] : (c == r ? invd[r] : 0.0);
   }
 }
 
