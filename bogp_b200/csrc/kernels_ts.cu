@@ -8,7 +8,8 @@
 //     ts_kernel_matrix   K_*^T [b][n] and K_** [b][b] (lower tiles), 64 x 64 tiles, input dimensions streamed through smem
 //     ts_gemm_nt         C (-)= A B^T, 64 x 64 tile / CTA on the FP64 tensor cores (mma.sync m8n8k4): whitening V^T = K_*^T Linv^T (triangular K
 //                        range), Sigma -= V^T V (lower tiles), and the two level-3 steps of the blocked Cholesky
-//     ts_diag_kernel     64 x 64 diagonal block: Cholesky + inverse in shared memory (one CTA), failure flag
+//     (diagonal blocks)  64 x 64 Cholesky + inverse in shared memory, by the CTA that has just updated the block (the
+//                        factorisation of block k+1 hides behind the rest of trailing update k), failure flag
 //     ts_mean / ts_sample / ts_argmax   mu, f = mu + L z (warp per row), arg-max without replacement over samples
 // All matrices are padded (b to 64, n to 64) with zeros / an identity diagonal, so no kernel has edge predicates.
 #include <cuda_runtime.h>
@@ -102,6 +103,101 @@ __global__ void __launch_bounds__(kTsThreads) ts_kernel_matrix(KmArgs a) {
   }
 }
 
+// 1 / sqrt(x) in float64 from the float approximation and two Newton steps (a dependent DDIV + DSQRT per column costs
+// more than the column's whole rank-1 update)
+__device__ __forceinline__ double rsqrt_d(double x) {
+  if (!(x > 1e-30 && x < 1e30)) return 1.0 / sqrt(x);
+  double y = (double)rsqrtf((float)x);
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  y = y * fma(-0.5 * x, y * y, 1.5);
+  return y;
+}
+
+// Diagonal block of a panel: D = L L^T in place (lower), Tinv = L^-1 (dense 64 x 64, zero upper) for the panel solve.
+// Blocked in shared memory (16-wide sub-blocks): the factorisation is a chain of dependent column steps, so the work per
+// step is kept to the sub-block (<= 4 predicated slots per thread) and everything else is done as small matrix products
+// between barriers -- 64 short column steps + 3 trailing updates, then 15 substitution steps on the four diagonal
+// sub-blocks at once + 3 x 2 product phases for the off-diagonal blocks of the inverse.
+constexpr int kDiagLd = kTsT + 1;
+
+__device__ __forceinline__ void diag_factor_invert(double (*D)[kDiagLd], double (*X)[kDiagLd], double* invd,
+                                                   double (*Tm)[16][17], int tid, int* flag) {
+  const int r = tid >> 2, cp = tid & 3;
+  for (int e = tid; e < kTsT * kTsT; e += kTsThreads) X[e >> 6][e & 63] = 0.0;
+  for (int sb = 0; sb < 4; ++sb) {
+    const int j0 = 16 * sb, j1 = j0 + 16;
+    // right-looking inside the sub-block, one barrier per column: every thread derives the pivot itself and applies
+    // the rank-1 update with the unscaled column; column j is scaled after the barrier, when nobody reads it any more
+    for (int j = j0; j < j1; ++j) {
+      double piv = D[j][j];
+      const bool bad = !(piv > 0.0) || !isfinite(piv);
+      if (bad) piv = 1.0;
+      const double rs = rsqrt_d(piv);
+      const double rj = r > j ? D[r][j] : 0.0, w = -rj * rs * rs;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int c = j + 1 + cp + 4 * m;
+        if (c < j1 && c <= r) D[r][c] = fma(w, D[c][j], D[r][c]);
+      }
+      __syncthreads();
+      if (cp == 0) {
+        if (r > j) D[r][j] = rj * rs;
+        if (r == j) { D[j][j] = piv * rs; invd[j] = rs; if (bad) *flag = 1; }
+      }
+    }
+    __syncthreads();
+    if (j1 < kTsT) {      // trailing update of the columns right of the sub-block
+      for (int c = j1 + cp; c <= r; c += 4) {
+        double acc = D[r][c];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc = fma(-D[r][j0 + j], D[c][j0 + j], acc);
+        D[r][c] = acc;
+      }
+      __syncthreads();
+    }
+  }
+  // X = L^-1.  Diagonal sub-blocks: forward substitution, 4 blocks x 16 columns x 4 lanes at once
+  {
+    const int b0 = 16 * (tid >> 6), cc = b0 + ((tid >> 2) & 15), part = tid & 3;
+    if (part == 0) X[cc][cc] = invd[cc];
+    __syncwarp();
+    for (int i = 1; i < 16; ++i) {
+      const int gi = b0 + i;
+      double sum = 0.0;
+      if (gi > cc) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const int kk = cc + part + 4 * m;
+          if (kk < gi) sum = fma(D[gi][kk], X[kk][cc], sum);
+        }
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      if (part == 0 && gi > cc) X[gi][cc] = -sum * invd[gi];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // off-diagonal blocks by distance from the diagonal: X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj)
+  for (int dd = 1; dd < 4; ++dd) {
+    const int nblk = 4 - dd;
+    for (int e = tid; e < nblk * 256; e += kTsThreads) {
+      const int bj = e >> 8, bi = bj + dd, pp = (e >> 4) & 15, q = e & 15;
+      double acc = 0.0;
+      for (int kk = 16 * bj + q; kk < 16 * bi; ++kk) acc = fma(D[16 * bi + pp][kk], X[kk][16 * bj + q], acc);
+      Tm[bj][pp][q] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < nblk * 256; e += kTsThreads) {
+      const int bj = e >> 8, bi = bj + dd, pp = (e >> 4) & 15, q = e & 15;
+      double acc = 0.0;
+      for (int m = 0; m <= pp; ++m) acc = fma(X[16 * bi + pp][16 * bi + m], Tm[bj][m][q], acc);
+      X[16 * bi + pp][16 * bj + q] = -acc;
+    }
+    __syncthreads();
+  }
+}
+
 // C[i][j] = A B^T (accumulate 0) or C[i][j] -= A B^T (accumulate 1); A [M][K], B [N][K], all dimensions padded:
 // M, N multiples of 64, K of 16.  lower: square problem, tiles tj <= ti only.  ktri: B is lower triangular with
 // K == N: the K loop of tile column tj stops after its last row.  A may alias C when N == 64 (a CTA owns whole rows
@@ -110,6 +206,11 @@ struct GemmArgs {
   const double *A, *B;
   double* C;
   int lda, ldb, ldc, K, tiles_n, lower, accumulate, ktri;
+  // fuse_diag: the CTA of tile (0, 0) -- the next diagonal block of the blocked Cholesky -- factors and inverts it
+  // right after updating it, while the other CTAs are still on the rest of the trailing matrix
+  int fuse_diag;
+  double* Tinv;
+  int* flag;
 };
 
 // FP64 tensor-core MMA (DMMA): D[8x8] += A[8x4] B[4x8]; lane (g = lane / 4, t = lane % 4) holds A[g][t], B[t][g] and
@@ -121,10 +222,16 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
                : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
+constexpr int kGemmSmemDoubles = 2 * 2 * kTsKC * 68;      // As | Bs, double-buffered
+constexpr size_t kGemmSmem = kGemmSmemDoubles * sizeof(double);
+constexpr size_t kGemmDiagSmem = kGemmSmem + (size_t)(kTsT * kDiagLd + kTsT + 3 * 16 * 17) * sizeof(double);
+static_assert(kTsT * kDiagLd <= kGemmSmemDoubles, "the diagonal block aliases the operand buffers");
 constexpr int kTsLd = 68;      // shared-memory row stride in doubles: the fragment loads (4 k x 8 rows) hit 32 distinct banks
 
 __global__ void __launch_bounds__(kTsThreads) ts_gemm_nt(GemmArgs g) {
-  __shared__ __align__(16) double As[2][kTsKC][kTsLd], Bs[2][kTsKC][kTsLd];
+  extern __shared__ __align__(16) double ts_smem[];
+  double (*As)[kTsKC][kTsLd] = reinterpret_cast<double (*)[kTsKC][kTsLd]>(ts_smem);
+  double (*Bs)[kTsKC][kTsLd] = As + 2;
   int ti, tj;
   if (g.lower) tri_decode(blockIdx.x, ti, tj);
   else { ti = blockIdx.x / g.tiles_n; tj = blockIdx.x % g.tiles_n; }
@@ -176,79 +283,20 @@ __global__ void __launch_bounds__(kTsThreads) ts_gemm_nt(GemmArgs g) {
         *c = make_double2(acc[i][j][0], acc[i][j][1]);
       }
     }
-}
-
-// 1 / sqrt(x) in float64 from the float approximation and two Newton steps (a dependent DDIV + DSQRT per column costs
-// more than the column's whole rank-1 update)
-__device__ __forceinline__ double rsqrt_d(double x) {
-  if (!(x > 1e-30 && x < 1e30)) return 1.0 / sqrt(x);
-  double y = (double)rsqrtf((float)x);
-  y = y * fma(-0.5 * x, y * y, 1.5);
-  y = y * fma(-0.5 * x, y * y, 1.5);
-  return y;
-}
-
-// Diagonal block of panel k: D = L L^T in place (lower), Tinv = L^-1 (dense 64 x 64, zero upper) for the panel solve.
-__global__ void __launch_bounds__(kTsThreads) ts_diag_kernel(double* S, int ld, int k, double* Tinv, int* flag) {
-  __shared__ double D[kTsT][kTsT + 1];      // lower: the block / its factor; strictly upper: (L^-1)^T as it is built
-  __shared__ double invd[kTsT];             // 1 / L[j][j]
-  const int tid = threadIdx.x;
-  double* base = S + (size_t)k * kTsT * ld + (size_t)k * kTsT;
-  for (int e = tid; e < kTsT * kTsT; e += kTsThreads) D[e >> 6][e & 63] = base[(size_t)(e >> 6) * ld + (e & 63)];
-  __syncthreads();
-  // right-looking, one barrier per column: every thread derives the pivot itself and applies the rank-1 update with
-  // the unscaled column (D[r][c] -= D[r][j] D[c][j] / pivot); column j is scaled after the barrier, when nobody reads
-  // it any more (step j + 1 touches columns > j only).  Four lanes share a row; the 16 column slots of a lane are
-  // unrolled and predicated so that their loads overlap.
-  {
-    const int r = tid >> 2, cp = tid & 3;
-    for (int j = 0; j < kTsT; ++j) {
-      double piv = D[j][j];
-      const bool bad = !(piv > 0.0) || !isfinite(piv);
-      if (bad) piv = 1.0;
-      const double rs = rsqrt_d(piv);
-      const double rj = r > j ? D[r][j] : 0.0, w = -rj * rs * rs;
-#pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        const int c = j + 1 + cp + 4 * m;
-        if (c <= r) D[r][c] = fma(w, D[c][j], D[r][c]);
-      }
-      __syncthreads();
-      if (cp == 0) {
-        if (r > j) D[r][j] = rj * rs;
-        if (r == j) { D[j][j] = piv * rs; invd[j] = rs; if (bad) *flag = 1; }
-      }
-    }
+  if (g.fuse_diag && blockIdx.x == 0) {
+    __syncthreads();      // the tile is complete in global memory and the operand buffers are free
+    double (*D)[kDiagLd] = reinterpret_cast<double (*)[kDiagLd]>(ts_smem);            // aliases As / Bs
+    double (*X)[kDiagLd] = reinterpret_cast<double (*)[kDiagLd]>(ts_smem + kGemmSmemDoubles);
+    double* invd = reinterpret_cast<double*>(X + kTsT);
+    double (*Tm)[16][17] = reinterpret_cast<double (*)[16][17]>(invd + kTsT);
+    for (int e = tid; e < kTsT * kTsT; e += kTsThreads) D[e >> 6][e & 63] = g.C[(size_t)(e >> 6) * g.ldc + (e & 63)];
     __syncthreads();
-  }
-  // inverse by forward substitution, X = L^-1 kept transposed in the strictly upper triangle (X[i][c] at D[c][i],
-  // X[c][c] = 1 / D[c][c]): four lanes share a column c (partial dot products in two chains, two shuffles)
-  {
-    const int c = tid >> 2, part = tid & 3;
-    const double xcc = invd[c];
-    for (int i = 1; i < kTsT; ++i) {
-      double s0 = 0.0, s1 = 0.0;
-      if (i > c) {
-        if (part == 0) s0 = D[i][c] * xcc;
-#pragma unroll
-        for (int m = 0; m < 16; m += 2) {
-          const int ka = c + 1 + part + 4 * m, kb = ka + 4;
-          if (ka < i) s0 = fma(D[i][ka], D[c][ka], s0);
-          if (kb < i) s1 = fma(D[i][kb], D[c][kb], s1);
-        }
-      }
-      double s = s0 + s1;
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (part == 0 && i > c) D[c][i] = -s * invd[i];
-      __syncwarp();
+    diag_factor_invert(D, X, invd, Tm, tid, g.flag);
+    for (int e = tid; e < kTsT * kTsT; e += kTsThreads) {
+      const int r = e >> 6, c = e & 63;
+      if (c <= r) g.C[(size_t)r * g.ldc + c] = D[r][c];
+      g.Tinv[e] = c <= r ? X[r][c] : 0.0;
     }
-  }
-  __syncthreads();
-  for (int e = tid; e < kTsT * kTsT; e += kTsThreads) {
-    const int r = e >> 6, c = e & 63;
-    if (c <= r) base[(size_t)r * ld + c] = D[r][c];
-    Tinv[e] = c < r ? D[c][r] : (c == r ? invd[r] : 0.0);
   }
 }
 
@@ -364,10 +412,11 @@ extern "C" int bogp_gp_thompson(bogp_gp_t g, const double* Xc_dev, int b, const 
   ts_kernel_matrix<<<tb * tn, kTsThreads, 0, s>>>(km);
   GemmArgs wh{};
   wh.A = Kt; wh.lda = np; wh.B = Li; wh.ldb = np; wh.C = Vt; wh.ldc = np; wh.K = np; wh.tiles_n = tn; wh.ktri = 1;
-  ts_gemm_nt<<<tb * tn, kTsThreads, 0, s>>>(wh);
+  ts_gemm_nt<<<tb * tn, kTsThreads, kGemmSmem, s>>>(wh);
   ts_mean_kernel<<<(b * 32 + 255) / 256, 256, 0, s>>>(Kt, np, al, g->mean, b, mu);
   count_launch(4);
 
+  BOGP_CUDA(cudaFuncSetAttribute(ts_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmDiagSmem));
   const int tri = tb * (tb + 1) / 2;
   double jitter = 0.0;
   bool ok = false;
@@ -380,21 +429,20 @@ extern "C" int bogp_gp_thompson(bogp_gp_t g, const double* Xc_dev, int b, const 
     ts_kernel_matrix<<<tri, kTsThreads, 0, s>>>(kk);
     GemmArgs sy{};
     sy.A = Vt; sy.lda = np; sy.B = Vt; sy.ldb = np; sy.C = Sg; sy.ldc = bp; sy.K = np; sy.lower = 1; sy.accumulate = 1;
-    ts_gemm_nt<<<tri, kTsThreads, 0, s>>>(sy);
+    sy.fuse_diag = 1; sy.Tinv = Ti; sy.flag = flag;      // + diagonal block 0
+    ts_gemm_nt<<<tri, kTsThreads, kGemmDiagSmem, s>>>(sy);
     count_launch(2);
-    for (int k = 0; k < tb; ++k) {
-      ts_diag_kernel<<<1, kTsThreads, 0, s>>>(Sg, bp, k, Ti, flag);
-      count_launch(1);
+    for (int k = 0; k + 1 < tb; ++k) {
       const int rem = tb - 1 - k;
-      if (rem == 0) break;
       double* panel = Sg + (size_t)(k + 1) * kTsT * bp + (size_t)k * kTsT;
       GemmArgs tr{};
       tr.A = panel; tr.lda = bp; tr.B = Ti; tr.ldb = kTsT; tr.C = panel; tr.ldc = bp; tr.K = kTsT; tr.tiles_n = 1;
-      ts_gemm_nt<<<rem, kTsThreads, 0, s>>>(tr);
+      ts_gemm_nt<<<rem, kTsThreads, kGemmSmem, s>>>(tr);
       GemmArgs up{};
       up.A = panel; up.lda = bp; up.B = panel; up.ldb = bp; up.C = Sg + (size_t)(k + 1) * kTsT * bp + (size_t)(k + 1) * kTsT;
       up.ldc = bp; up.K = kTsT; up.lower = 1; up.accumulate = 1;
-      ts_gemm_nt<<<rem * (rem + 1) / 2, kTsThreads, 0, s>>>(up);
+      up.fuse_diag = 1; up.Tinv = Ti; up.flag = flag;    // + diagonal block k + 1, needed by the next panel solve
+      ts_gemm_nt<<<rem * (rem + 1) / 2, kTsThreads, kGemmDiagSmem, s>>>(up);
       count_launch(2);
     }
     int hflag = 0;
