@@ -121,41 +121,82 @@ __device__ __forceinline__ double rsqrt_d(double x) {
 constexpr int kDiagLd = kTsT + 1;
 
 __device__ __forceinline__ void diag_factor_invert(double (*D)[kDiagLd], double (*X)[kDiagLd], double* invd,
-                                                   double (*Tm)[16][17], int tid, int* flag) {
+                                                   double (*Tm)[16][17], int tid, int* flag,
+                                                   long long* stamps = nullptr) {
+#define TS_STAMP(i) do { if (stamps && tid == 0) stamps[i] = clock64(); } while (0)
+  TS_STAMP(0);
+  // A dependent FP64 operation costs ~40 cycles here (measured: tools/micro/diag_time.cu), so the column chain is kept
+  // to: pivot -> float reciprocal seed -> one cubic correction (3 DFMA) -> rank-1 update.  Scaling the columns by
+  // 1 / sqrt(pivot) is off that chain (one parallel pass per sub-block), and everything that is a sum runs as several
+  // independent accumulators.
   const int r = tid >> 2, cp = tid & 3;
+  double* pivs = &Tm[0][0][0];                 // pivots of the current sub-block (Tm is free until the inversion)
   for (int e = tid; e < kTsT * kTsT; e += kTsThreads) X[e >> 6][e & 63] = 0.0;
   for (int sb = 0; sb < 4; ++sb) {
     const int j0 = 16 * sb, j1 = j0 + 16;
-    // right-looking inside the sub-block, one barrier per column: every thread derives the pivot itself and applies
-    // the rank-1 update with the unscaled column; column j is scaled after the barrier, when nobody reads it any more
+    TS_STAMP(4 + 4 * sb);
     for (int j = j0; j < j1; ++j) {
       double piv = D[j][j];
       const bool bad = !(piv > 0.0) || !isfinite(piv);
       if (bad) piv = 1.0;
-      const double rs = rsqrt_d(piv);
-      const double rj = r > j ? D[r][j] : 0.0, w = -rj * rs * rs;
+      const double rj = r > j ? D[r][j] : 0.0;
+      double w;
+      if (piv > 1e-30 && piv < 1e30) {
+        const double y0 = (double)__frcp_rn((float)piv);       // 1 / piv to ~1e-7
+        const double w0 = -rj * y0;
+        const double err = fma(-piv, y0, 1.0);                 // 1 / piv = y0 (1 + err + err^2 + ...)
+        w = fma(w0, fma(err, err, err), w0);
+      } else {
+        w = -rj / piv;
+      }
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const int c = j + 1 + cp + 4 * m;
         if (c < j1 && c <= r) D[r][c] = fma(w, D[c][j], D[r][c]);
       }
+      if (r == j && cp == 0) { pivs[j - j0] = piv; if (bad) *flag = 1; }
       __syncthreads();
-      if (cp == 0) {
-        if (r > j) D[r][j] = rj * rs;
-        if (r == j) { D[j][j] = piv * rs; invd[j] = rs; if (bad) *flag = 1; }
-      }
+    }
+    TS_STAMP(5 + 4 * sb);
+    // scale the sub-block's columns: L[r][j] = D[r][j] / sqrt(piv_j)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int j = j0 + cp + 4 * m;
+      const double pv = pivs[j - j0], rs = rsqrt_d(pv);
+      if (r > j) D[r][j] *= rs;
+      if (r == j) { D[j][j] = pv * rs; invd[j] = rs; }
     }
     __syncthreads();
-    if (j1 < kTsT) {      // trailing update of the columns right of the sub-block
-      for (int c = j1 + cp; c <= r; c += 4) {
-        double acc = D[r][c];
+    TS_STAMP(6 + 4 * sb);
+    if (j1 < kTsT) {      // trailing update of the lower triangle right of the sub-block, <= 5 elements per thread at once
+      const int nt = kTsT - j1, total = nt * (nt + 1) / 2;
+      int rr[5], cc[5];
+      double acc[5];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc = fma(-D[r][j0 + j], D[c][j0 + j], acc);
-        D[r][c] = acc;
+      for (int m = 0; m < 5; ++m) {
+        // triangle folded into an (nt / 2) x (nt + 1) rectangle: row p of the rectangle = row p of the triangle
+        // (p + 1 elements) followed by row nt - 1 - p (nt - p elements)
+        const int e = tid + kTsThreads * m;
+        int a = 0, bq = 0;
+        if (e < total) {
+          const int p = nt == 48 ? e / 49 : (nt == 32 ? e / 33 : e / 17), q = e - p * (nt + 1);
+          if (q <= p) { a = p; bq = q; } else { a = nt - 1 - p; bq = q - (p + 1); }
+        }
+        rr[m] = j1 + a; cc[m] = j1 + bq;
+        acc[m] = D[rr[m]][cc[m]];
       }
+#pragma unroll 4
+      for (int j = 0; j < 16; ++j) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m) acc[m] = fma(-D[rr[m]][j0 + j], D[cc[m]][j0 + j], acc[m]);
+      }
+#pragma unroll
+      for (int m = 0; m < 5; ++m)
+        if (tid + kTsThreads * m < total) D[rr[m]][cc[m]] = acc[m];
       __syncthreads();
     }
   }
+  TS_STAMP(1);
   // X = L^-1.  Diagonal sub-blocks: forward substitution, 4 blocks x 16 columns x 4 lanes at once
   {
     const int b0 = 16 * (tid >> 6), cc = b0 + ((tid >> 2) & 15), part = tid & 3;
@@ -163,14 +204,15 @@ __device__ __forceinline__ void diag_factor_invert(double (*D)[kDiagLd], double 
     __syncwarp();
     for (int i = 1; i < 16; ++i) {
       const int gi = b0 + i;
-      double sum = 0.0;
+      double s0 = 0.0, s1 = 0.0;
       if (gi > cc) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int kk = cc + part + 4 * m;
-          if (kk < gi) sum = fma(D[gi][kk], X[kk][cc], sum);
-        }
+        const int kk = cc + part;
+        if (kk < gi) s0 = D[gi][kk] * X[kk][cc];
+        if (kk + 4 < gi) s1 = D[gi][kk + 4] * X[kk + 4][cc];
+        if (kk + 8 < gi) s0 = fma(D[gi][kk + 8], X[kk + 8][cc], s0);
+        if (kk + 12 < gi) s1 = fma(D[gi][kk + 12], X[kk + 12][cc], s1);
       }
+      double sum = s0 + s1;
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
       if (part == 0 && gi > cc) X[gi][cc] = -sum * invd[gi];
@@ -178,24 +220,39 @@ __device__ __forceinline__ void diag_factor_invert(double (*D)[kDiagLd], double 
     }
   }
   __syncthreads();
-  // off-diagonal blocks by distance from the diagonal: X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj)
+  TS_STAMP(2);
+  // off-diagonal blocks by distance from the diagonal: X_ij = -X_ii (sum_{k=j}^{i-1} L_ik X_kj); X is zero above its
+  // diagonal, so the sums run over whole 16-blocks in four independent accumulators
   for (int dd = 1; dd < 4; ++dd) {
     const int nblk = 4 - dd;
     for (int e = tid; e < nblk * 256; e += kTsThreads) {
       const int bj = e >> 8, bi = bj + dd, pp = (e >> 4) & 15, q = e & 15;
-      double acc = 0.0;
-      for (int kk = 16 * bj + q; kk < 16 * bi; ++kk) acc = fma(D[16 * bi + pp][kk], X[kk][16 * bj + q], acc);
-      Tm[bj][pp][q] = acc;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for (int kk = 16 * bj; kk < 16 * bi; kk += 4) {
+        a0 = fma(D[16 * bi + pp][kk], X[kk][16 * bj + q], a0);
+        a1 = fma(D[16 * bi + pp][kk + 1], X[kk + 1][16 * bj + q], a1);
+        a2 = fma(D[16 * bi + pp][kk + 2], X[kk + 2][16 * bj + q], a2);
+        a3 = fma(D[16 * bi + pp][kk + 3], X[kk + 3][16 * bj + q], a3);
+      }
+      Tm[bj][pp][q] = (a0 + a1) + (a2 + a3);
     }
     __syncthreads();
     for (int e = tid; e < nblk * 256; e += kTsThreads) {
       const int bj = e >> 8, bi = bj + dd, pp = (e >> 4) & 15, q = e & 15;
-      double acc = 0.0;
-      for (int m = 0; m <= pp; ++m) acc = fma(X[16 * bi + pp][16 * bi + m], Tm[bj][m][q], acc);
-      X[16 * bi + pp][16 * bj + q] = -acc;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int m = 0; m < 16; m += 4) {       // X_ii is zero above its diagonal
+        a0 = fma(X[16 * bi + pp][16 * bi + m], Tm[bj][m][q], a0);
+        a1 = fma(X[16 * bi + pp][16 * bi + m + 1], Tm[bj][m + 1][q], a1);
+        a2 = fma(X[16 * bi + pp][16 * bi + m + 2], Tm[bj][m + 2][q], a2);
+        a3 = fma(X[16 * bi + pp][16 * bi + m + 3], Tm[bj][m + 3][q], a3);
+      }
+      X[16 * bi + pp][16 * bj + q] = -((a0 + a1) + (a2 + a3));
     }
     __syncthreads();
   }
+  TS_STAMP(3);
+#undef TS_STAMP
 }
 
 // C[i][j] = A B^T (accumulate 0) or C[i][j] -= A B^T (accumulate 1); A [M][K], B [N][K], all dimensions padded:
