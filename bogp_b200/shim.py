@@ -66,7 +66,7 @@ class _GaussianLikelihood:
 
 def install(force: bool = False) -> Dict[str, bool]:
     """Registers the shims; returns ``{top-level package: shimmed?}``."""
-    from . import acquisition, gp, mfp, oao, optim, strategy
+    from . import acquisition, generation, gp, mfp, oao, optim, strategy
 
     done = {}
     if force or not _present("tritonoa"):
@@ -109,6 +109,7 @@ def install(force: bool = False) -> Dict[str, bool]:
                 ProbabilityOfImprovement=acquisition.ProbabilityOfImprovement,
                 UpperConfidenceBound=acquisition.UpperConfidenceBound)
         _module("botorch.optim", optimize_acqf=optim.optimize_acqf)
+        _module("botorch.generation", MaxPosteriorSampling=generation.MaxPosteriorSampling)
         done["botorch"] = True
     else:
         done["botorch"] = False

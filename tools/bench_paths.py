@@ -1,7 +1,7 @@
 """Roofline numbers for the other kernels of the path: the GP posterior/acquisition kernel (K2),
 the scattered-candidate and tilted-array Bartlett kernels (K1-SIMT) and the per-environment kernel (K1-ENV).
 
-    python tools/bench_paths.py [gp] [fit] [points] [tilt] [env] > profiles/paths_<tag>.jsonl
+    python tools/bench_paths.py [gp] [fit] [points] [tilt] [env] [ts] > profiles/paths_<tag>.jsonl
 
 One JSON line per case.  Kernel time = CUDA events around the dominant kernel inside the library
 (bogp_timing_enable/read) where it is instrumented, CUDA events around the call otherwise; 3 warm-up + 10 timed calls.
@@ -175,8 +175,39 @@ def bench_env():
         eb.close()
 
 
+def bench_ts():
+    """K2-TS: one joint posterior draw over the BAxUS candidate set (baxus.py:45: 2000-5000 candidates) and its arg-max."""
+    from bogp_b200.generation import MaxPosteriorSampling
+    from oracle import gp as ogp
+    rng = np.random.default_rng(0)
+    for b, n, d in ((2000, 100, 3), (5000, 200, 12), (5000, 500, 12), (5000, 500, 48)):
+        X = rng.uniform(-1, 1, (n, d))
+        y = np.sin(3 * X[:, 0]) + 0.3 * np.cos(2 * X.sum(1))
+        y = (y - y.mean()) / y.std()
+        ls = rng.uniform(0.3, 1.5, d) * (1.0 if d <= 12 else 2.5)
+        model = SingleTaskGP(X, y, lengthscale=ls, outputscale=1.3, noise=1e-4)
+        ts = MaxPosteriorSampling(model)
+        Xc = rng.uniform(-1, 1, (b, d))
+        z = rng.standard_normal((1, b))
+        call_ms, k_ms = timed(lambda: ts(Xc, base_samples=z), reps=5, warm=2)
+        t0 = time.perf_counter()
+        idx, f, jit = ogp.thompson_sample(ogp.GPState(X, y, "matern52", ls, 1.3, 0.0, 1e-4), Xc, z)
+        cpu_ms = (time.perf_counter() - t0) * 1e3
+        flop = 2.0 * (b ** 3 / 3.0 + b * b * n / 2.0)
+        print(json.dumps({"kernel": "ts_gemm_nt chain (K2-TS: posterior covariance + blocked Cholesky, FP64 tensor cores)",
+                          "case": f"b={b} candidates, n={n} observations, d={d}", "dtype": "f64",
+                          "covariance_factorisation_ms": k_ms, "call_ms": call_ms,
+                          "alg_gflop": flop / 1e9, "tflops": flop / (k_ms * 1e-3) / 1e12, "fp64_mma_peak_tflops": 37.1,
+                          "frac_of_fp64_mma_peak": flop / (k_ms * 1e-3) / 1e12 / 37.1,
+                          "oracle_torch_cpu_ms": cpu_ms, "cpu_threads": torch.get_num_threads(),
+                          "same_pick_as_oracle": bool(int(ts.last_indices[0]) == int(idx[0])), "jitter": ts.last_jitter,
+                          "bound": "FP64 tensor (mma.sync m8n8k4, measured peak tools/micro/fp64_peak.cu) early, the "
+                                   "dependent column chain of the 64 x 64 diagonal blocks (~600 cycles per column) late"}),
+              flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gp", "fit", "points", "tilt", "env"]
+    which = sys.argv[1:] or ["gp", "fit", "points", "tilt", "env", "ts"]
     torch.cuda.set_device(0)
     for w in which:
-        {"gp": bench_gp, "fit": bench_fit, "points": bench_points, "tilt": bench_tilt, "env": bench_env}[w]()
+        {"gp": bench_gp, "fit": bench_fit, "points": bench_points, "tilt": bench_tilt, "env": bench_env, "ts": bench_ts}[w]()
