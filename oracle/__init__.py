@@ -13,7 +13,9 @@ reference's call sites (cited per function), (iii) the in-repo formula
 restatements (ref/projects/swellex96_inv/visualization/bo_examples.py:61-124),
 and is cross-checked against independent implementations that *are* installed
 (scikit-learn Matern-5/2 GP, SciPy normal cdf/pdf) plus the simulation-mode
-invariants of SURVEY 8(c).
+invariants of SURVEY 8(c).  Pinned by executing the reference's own source: the
+EI / UCB formulas (tools/make_golden_acq.py -> tests/golden/acq_reference.npz)
+and, for the host logic, BaxusState / update_state (tools/make_golden_baxus.py).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
 ``--impl reference`` legs of ``bench.py`` may import this package.  Nothing under

@@ -77,6 +77,24 @@ def test_gp_posterior_and_acq_match_sklearn_scipy(name, kind):
     np.testing.assert_allclose(logei[ok], np.log(g[f"{name}_ei"][ok]), rtol=1e-6, atol=1e-8)
 
 
+def test_acquisition_formulas_match_reference_code():
+    """EI / UCB against the outputs of the reference's OWN numpy functions (bo_examples.py:61-84, :107-124), executed
+    from its source by tools/make_golden_acq.py -- these two rows of the oracle are pinned, not recalled."""
+    g = np.load(GOLD / "acq_reference.npz")
+    mu, sigma, best_f = torch.as_tensor(g["mu"]), torch.as_tensor(g["sigma"]), float(g["best_f"])
+    ei = ogp.analytic_acq("ei", mu, sigma ** 2, best_f)
+    assert float((ei - torch.as_tensor(g["ei"])).abs().max()) <= 1e-14
+    ei_xi = ogp.analytic_acq("ei", mu, sigma ** 2, best_f + 0.05)              # xi shifts the incumbent
+    assert float((ei_xi - torch.as_tensor(g["ei_xi005"])).abs().max()) <= 1e-14
+    for kappa in (0.5, 1.0, 2.0):
+        ucb = ogp.analytic_acq("ucb", mu, sigma ** 2, beta=kappa ** 2)          # botorch: mu + sqrt(beta) sigma
+        assert float((ucb - torch.as_tensor(g[f"ucb_kappa_{kappa}"])).abs().max()) <= 1e-14
+    # LogEI is the log of the same quantity wherever EI is representable
+    ok = torch.as_tensor(g["ei"]) > 1e-200
+    assert torch.allclose(ogp.analytic_acq("logei", mu, sigma ** 2, best_f)[ok], torch.log(torch.as_tensor(g["ei"]))[ok],
+                          rtol=1e-9, atol=1e-9)
+
+
 def test_gp_interpolates_and_grad_matches_fd():
     """(vii) posterior interpolates as noise -> 0, variance >= 0, EI >= 0; (viii) d acq/dX vs finite differences."""
     rng = np.random.default_rng(0)
