@@ -65,6 +65,21 @@ int ensure_scratch(bogp_modeset_s* h, size_t bytes) {
 }
 }  // namespace bogp
 
+namespace bogp {
+int ensure_pinned(bogp_modeset_s* h, size_t bytes) {
+  if (h->pin_bytes >= bytes) return 0;
+  if (h->pin_host) cudaFreeHost(h->pin_host);
+  h->pin_host = h->pin_dev = nullptr; h->pin_bytes = 0;
+  const size_t cap = std::max<size_t>(bytes, 4096);
+  void* hp = nullptr; void* dp = nullptr;
+  BOGP_CUDA(cudaHostAlloc(&hp, cap, cudaHostAllocMapped));
+  BOGP_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+  h->pin_host = static_cast<unsigned char*>(hp); h->pin_dev = static_cast<unsigned char*>(dp); h->pin_bytes = cap;
+  return 0;
+}
+
+}  // namespace bogp
+
 static int io_scratch(bogp_modeset_s* h, size_t bytes) {
   if (h->io_scratch_bytes >= bytes) return 0;
   if (h->io_scratch) cudaFree(h->io_scratch);
@@ -182,6 +197,7 @@ extern "C" int bogp_modeset_destroy(bogp_modeset_t h) {
   for (void* p : h->cov_allocs) cudaFree(p);
   if (h->grid_scratch) cudaFree(h->grid_scratch);
   if (h->io_scratch) cudaFree(h->io_scratch);
+  if (h->pin_host) cudaFreeHost(h->pin_host);
   delete h;
   return 0;
 }
@@ -469,17 +485,22 @@ extern "C" int bogp_bartlett_grid_host_argmax(bogp_modeset_t h, const double* r_
   // kernels would re-read the surface over PCIe)
   float* alias = picks_tensor_engine(h, engine, tilt_deg_host, Nt, (long long)n) ? mapped_alias(out_host) : nullptr;
   float* tmp = alias ? alias : reinterpret_cast<float*>(base);
-  long long* idx_dev = reinterpret_cast<long long*>(base + off_pair);
-  float* val_dev = reinterpret_cast<float*>(base + off_pair + 8);
+  // the (index, value) record lands in mapped page-locked memory: written by the kernel, read after the one
+  // synchronisation below -- no device -> host copies for it
+  if (int rc1 = bogp::ensure_pinned(h, 64)) return rc1;
+  long long* idx_dev = reinterpret_cast<long long*>(h->pin_dev);
+  float* val_dev = reinterpret_cast<float*>(h->pin_dev + 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc = bogp_bartlett_grid_argext(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, tmp,
                                      maximize, val_dev, idx_dev, base + off_pair + 16, 8192, stream);
   if (rc == 0) {
     cudaError_t e = alias ? cudaSuccess : cudaMemcpyAsync(out_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(idx_host, idx_dev, sizeof(long long), cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(val_host, val_dev, sizeof(float), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { bogp::set_error("bogp_bartlett_grid_host_argmax: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
+    else {
+      *idx_host = *reinterpret_cast<volatile long long*>(h->pin_host);
+      *val_host = *reinterpret_cast<volatile float*>(h->pin_host + 8);
+    }
   }
   return rc;
 }

@@ -127,9 +127,16 @@ struct bogp_modeset_s {
   // device staging for the *_host entry points (grown on demand)
   void* io_scratch = nullptr;
   size_t io_scratch_bytes = 0;
+  // small page-locked, device-mapped host block: the arg-ext record (index, value) of the *_host_argmax entry point is
+  // written into it by the kernel itself and read after the call's one synchronisation (no device -> host copies)
+  unsigned char* pin_host = nullptr;
+  unsigned char* pin_dev = nullptr;
+  size_t pin_bytes = 0;
 };
 
 namespace bogp {
+// api_mfp.cu
+int ensure_pinned(bogp_modeset_s* h, size_t bytes);
 // kernels_simt.cu
 int launch_points(const bogp_modeset_s* h, const double* cand_dev, long long C, int atype, int mf, bool any_tilt,
                   float* out_dev, cudaStream_t s);

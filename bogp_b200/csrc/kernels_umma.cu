@@ -1302,6 +1302,8 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     BOGP_CUDA(cudaMemsetAsync(dbg_dev, 0, 256 * 16 * sizeof(long long), s));
     p.dbg = dbg_dev;
   }
+  // two small pageable copies: the driver sends them inline with the command stream, which costs less GPU time than
+  // one DMA from page-locked staging (measured: 8 us per step)
   BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
   BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
   const int nE = d.F * p.nrt * (kTileR / kTabRows), nB = d.F * ((Nz + kTabDepths - 1) / kTabDepths);
