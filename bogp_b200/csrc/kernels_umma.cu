@@ -106,6 +106,7 @@ struct UParams {
   // fused arg-ext (collate.py:50): the epilogue folds every value it writes into a packed (ordered value, ~index) key
   // with one atomicMax per warp and unit; the last CTA to finish decodes it.  ext_mode: 0 off, 1 arg-max, 2 arg-min.
   int ext_mode;
+  int two_slot;                // epilogue: both depth slots of a small tonal loaded at once (A/B knob BOGP_UMMA_TWO_SLOT)
   unsigned long long* ext_key;
   unsigned int* ext_done;
   float* ext_val;
@@ -1053,6 +1054,42 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           // slots of this stage owned by this warp: s = s_first, s_first + kEpiSub, ...
           const int s_first = (sub - j0 % kEpiSub + kEpiSub) % kEpiSub;
           bool released = false;
+          if (p.two_slot && fast && rowsP == 16 && nq == 1 && s_first + kEpiSub < njs && s_first + 2 * kEpiSub >= njs &&
+              !(BOGP_UMMA_DBG && p.skip == 2)) {
+            // small tonals (one 16-column chunk per depth slot, two slots for this warp): both slots' loads in flight
+            // at once, one wait, release, then the arithmetic -- the per-stage cost of these tonals is TMEM-load
+            // latency, not tensor work
+            const int sA = s_first, sB = s_first + kEpiSub;
+            float reA[16], imA[16], reB[16], imB[16];
+            const uint32_t tA = t_lane + (uint32_t)(sA * 16), tB = t_lane + (uint32_t)(sB * 16);
+            tc_ld16(tA, reA); tc_ld16(tA + NA, imA);
+            tc_ld16(tB, reB); tc_ld16(tB + NA, imB);
+            tc_wait_ld();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
+            released = true;
+            if (quad == 0 && sub == 0) dbg_stamp(p, 3, sc);
+            auto slot = [&](const float* re, const float* im, int sidx) {
+              const float tr = re[0] - im[1], ti = im[0] + re[1];
+              const float num = fmaf(tr, tr, ti * ti);
+              const float numsq = fmaf(re[0], re[0], fmaf(im[0], im[0], fmaf(re[1], re[1], im[1] * im[1])));
+              unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
+#pragma unroll
+              for (int q = 0; q < 16; q += 4) {
+                sq_acc2(t0, re[q], re[q + 1]);
+                sq_acc2(t1, im[q], im[q + 1]);
+                sq_acc2(t2, re[q + 2], re[q + 3]);
+                sq_acc2(t3, im[q + 2], im[q + 3]);
+              }
+              const float norm = ((sum2(t0) + sum2(t1)) + (sum2(t2) + sum2(t3))) - numsq;
+              const float b = __fdividef(num, norm);
+              const float val = p.atype == BOGP_ATYPE_CBF ? b : u.trK - b;
+              float* a = acc + (size_t)(j0 + sidx) * kTileR + tl;
+              *a = (f == 0) ? val : (p.mf == BOGP_MF_MEAN ? *a + val : *a * val);
+            };
+            slot(reA, imA, sA);
+            slot(reB, imB, sB);
+          } else
           for (int s = s_first; s < njs && !(BOGP_UMMA_DBG && p.skip == 2); s += kEpiSub) {
             const int j = j0 + s;
             const bool last_slot = s + kEpiSub >= njs;
@@ -1269,6 +1306,7 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   const int ZC = choose_zc(Nr, Nz, sms);
   if (!plan_tonals(h, p, ZC)) { set_error("UMMA engine: mode set does not fit (operator rows, Mp > 64 or complex source table)"); return BOGP_ERR_UNSUPPORTED; }
   p.Nr = Nr; p.Nz = Nz; p.ZC = ZC; p.atype = atype; p.mf = mf;
+  { const char* e = std::getenv("BOGP_UMMA_TWO_SLOT"); p.two_slot = e ? std::atoi(e) : 1; }
   p.nrt = (Nr + kTileR - 1) / kTileR;
   const int nzc = (Nz + ZC - 1) / ZC;
   p.units = p.nrt * nzc;
