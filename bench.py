@@ -435,7 +435,7 @@ def run_ours(args) -> None:
     else:
         bf16, peak_src = 1590.0, "fallback 1.59 PFLOP/s bf16 (B200_PROFILING.md)"
     peak = bf16 / 2.0 / 3.0     # TF32 runs at half the bf16 rate; 3xTF32 spends three MMAs per product
-    flop_per_launch = dms.flops_per_candidate() * NZ_PER_GPU * NR
+    flop_per_launch = dms.flops_per_candidate("umma" if args.engine in ("auto", "umma") else "simt") * NZ_PER_GPU * NR
     kern_avg_ms = kern_ms / max(kern_n, 1)
     achieved = flop_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_n else None
     traffic = None
@@ -448,7 +448,7 @@ def run_ours(args) -> None:
                 "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
                 "flop_per_launch": flop_per_launch,
                 "peak_def": f"{peak_src} / 2 (TF32 rate) / 3 (3xTF32 split) of measured",
-                "algorithmic": "sum_f 4*rows_f*M_f flop per candidate (mode-space operator, DESIGN.md)"}
+                "algorithmic": "sum_f 4*rows_f*M_f flop per candidate (mode-space operator of the engine that ran: rows_f = rank(G_f) with the rank-1 numerator folded into the norm rows on the tcgen05 engine, rank(G_f) + 2 otherwise; DESIGN.md)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,

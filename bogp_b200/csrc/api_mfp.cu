@@ -300,7 +300,142 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
     Wt.resize(Wt.size() + (size_t)t.Mp * t.rowsP, 0.f);
     for (int r2 = 0; r2 < t.rows; ++r2)
       for (int m = 0; m < M; ++m) Wt[t.offWt + (size_t)m * t.rowsP + r2] = Wf[(size_t)r2 * t.Mp + m];
+    // Folded UMMA operator (bogp_internal.h): rank-1 numerator carried by the first two rows of the rotated norm rows.
+    // Phi = U R with U = Phi R^T (R R^T)^-1 (cached per handle: covariance-independent), so the numerator row
+    // C = l^H Phi (l = the rank-1 factor of K) is g^T R with g = U^T conj(l); two Householder reflections Q = H2 H1
+    // take Re/Im of g to span(e0, e1), and R' = Q R replaces R.
+    t.u_fold = 0; t.u_c[0] = t.u_c[1] = t.u_c[2] = t.u_c[3] = 0.f;
+    {
+      const char* nf = std::getenv("BOGP_NO_FOLD");
+      if (!d.rec_complex && rK == 1 && rH == 1 && rG >= 1 && !(nf && nf[0] == '1')) {
+        if ((int)h->Rm_cache.size() != F) { h->Rm_cache.assign(F, {}); h->U_cache.assign(F, {}); }
+        std::vector<double>& Rm = h->Rm_cache[f];
+        std::vector<double>& U = h->U_cache[f];
+        bool ok = true;
+        if (Rm.empty()) {
+          Rm.assign((size_t)rG * M, 0.0);
+          for (int j = 0; j < rG; ++j)
+            for (int m = 0; m < M; ++m) Rm[(size_t)j * M + m] = LG[(size_t)m * M + j].real();
+          std::vector<double> A((size_t)rG * rG);
+          for (int a2 = 0; a2 < rG; ++a2)
+            for (int b2 = 0; b2 <= a2; ++b2) {
+              double sacc = 0.0;
+              for (int m = 0; m < M; ++m) sacc += Rm[(size_t)a2 * M + m] * Rm[(size_t)b2 * M + m];
+              A[(size_t)a2 * rG + b2] = A[(size_t)b2 * rG + a2] = sacc;
+            }
+          U.assign((size_t)N * rG, 0.0);
+          if (bogp::cholesky_lower(A, rG)) {
+            for (int n = 0; n < N; ++n) {           // row n of U solves (R R^T) u = R phi_n
+              double* u = &U[(size_t)n * rG];
+              for (int a2 = 0; a2 < rG; ++a2) {
+                double sacc = 0.0;
+                for (int m = 0; m < M; ++m) sacc += Rm[(size_t)a2 * M + m] * Phi[(size_t)n * M + m].real();
+                u[a2] = sacc;
+              }
+              for (int i = 0; i < rG; ++i) {
+                double sacc = u[i];
+                for (int k = 0; k < i; ++k) sacc -= A[(size_t)i * rG + k] * u[k];
+                u[i] = sacc / A[(size_t)i * rG + i];
+              }
+              for (int i = rG - 1; i >= 0; --i) {
+                double sacc = u[i];
+                for (int k = i + 1; k < rG; ++k) sacc -= A[(size_t)k * rG + i] * u[k];
+                u[i] = sacc / A[(size_t)i * rG + i];
+              }
+            }
+          } else {
+            U.clear();      // marks "no fold" for this tonal
+          }
+        }
+        ok = !U.empty();
+        if (ok) {
+          std::vector<double> gr(rG, 0.0), gi(rG, 0.0);
+          for (int n = 0; n < N; ++n) {
+            const double lr = LK[(size_t)n * N].real(), li = -LK[(size_t)n * N].imag();     // conj(l)
+            const double* u = &U[(size_t)n * rG];
+            for (int j = 0; j < rG; ++j) { gr[j] += lr * u[j]; gi[j] += li * u[j]; }
+          }
+          // check C = g^T R against the numerator row built above
+          double res = 0.0, cmax = 0.0;
+          for (int m = 0; m < M; ++m) {
+            double er = -LH[(size_t)m * M].real(), ei = LH[(size_t)m * M].imag();
+            for (int j = 0; j < rG; ++j) { er += gr[j] * Rm[(size_t)j * M + m]; ei += gi[j] * Rm[(size_t)j * M + m]; }
+            res = std::max(res, std::max(std::fabs(er), std::fabs(ei)));
+            cmax = std::max(cmax, std::max(std::fabs(LH[(size_t)m * M].real()), std::fabs(LH[(size_t)m * M].imag())));
+          }
+          ok = res <= 1e-9 * std::max(cmax, 1e-300);
+          if (ok) {
+            double nr = 0.0, ni = 0.0;
+            for (int j = 0; j < rG; ++j) { nr += gr[j] * gr[j]; ni += gi[j] * gi[j]; }
+            const bool r_first = nr >= ni;
+            std::vector<double> x = r_first ? gr : gi, y = r_first ? gi : gr;
+            std::vector<double> Rp(Rm);
+            // reflection across v (I - 2 v v^T / v^T v) applied to a vector / to the rows of Rp, rows [from, rG)
+            auto reflect_vec = [&](const std::vector<double>& v, double vv, std::vector<double>& w, int from) {
+              double dot = 0.0;
+              for (int j = from; j < rG; ++j) dot += v[j] * w[j];
+              const double sc = 2.0 * dot / vv;
+              for (int j = from; j < rG; ++j) w[j] -= sc * v[j];
+            };
+            auto reflect_rows = [&](const std::vector<double>& v, double vv, int from) {
+              for (int m = 0; m < M; ++m) {
+                double dot = 0.0;
+                for (int j = from; j < rG; ++j) dot += v[j] * Rp[(size_t)j * M + m];
+                const double sc = 2.0 * dot / vv;
+                for (int j = from; j < rG; ++j) Rp[(size_t)j * M + m] -= sc * v[j];
+              }
+            };
+            double alpha = 0.0, s0 = 0.0, beta = 0.0;
+            {
+              double nx = 0.0;
+              for (int j = 0; j < rG; ++j) nx += x[j] * x[j];
+              nx = std::sqrt(nx);
+              if (nx > 0.0) {
+                alpha = x[0] > 0.0 ? -nx : nx;
+                std::vector<double> v(x);
+                v[0] -= alpha;
+                double vv = 0.0;
+                for (int j = 0; j < rG; ++j) vv += v[j] * v[j];
+                if (vv > 0.0) { reflect_vec(v, vv, y, 0); reflect_rows(v, vv, 0); }
+                else alpha = x[0];
+              }
+              s0 = y[0];
+              if (rG >= 2) {
+                double ny = 0.0;
+                for (int j = 1; j < rG; ++j) ny += y[j] * y[j];
+                ny = std::sqrt(ny);
+                if (ny > 0.0) {
+                  beta = y[1] > 0.0 ? -ny : ny;
+                  std::vector<double> v(y);
+                  v[0] = 0.0;
+                  v[1] -= beta;
+                  double vv = 0.0;
+                  for (int j = 1; j < rG; ++j) vv += v[j] * v[j];
+                  if (vv > 0.0) reflect_rows(v, vv, 1);
+                  else beta = y[1];
+                }
+              }
+            }
+            if (ok) {
+              // Q g_first = alpha e0, Q g_second = s0 e0 + beta e1
+              if (r_first) { t.u_c[0] = (float)alpha; t.u_c[1] = (float)s0; t.u_c[2] = 0.f; t.u_c[3] = (float)beta; }
+              else { t.u_c[0] = (float)s0; t.u_c[1] = (float)alpha; t.u_c[2] = (float)beta; t.u_c[3] = 0.f; }
+              t.u_fold = 1;
+              t.u_p0 = 0;
+              t.u_rows = rG;
+              t.u_rowsP = bogp::pad_to(std::max(rG, 1), 16);
+              t.offWu = (int)Wu.size();
+              Wu.resize(Wu.size() + (size_t)t.u_rowsP * t.Mp, 0.f);
+              float* Uo = &Wu[t.offWu];
+              for (int k = 0; k < rG; ++k)
+                for (int m = 0; m < M; ++m) Uo[(size_t)k * t.Mp + m] = (float)Rp[(size_t)k * M + m];
+            }
+          }
+        }
+      }
+    }
     // UMMA row order (bogp_internal.h): (re, im) numerator pairs | (re, im) norm pairs | plain rows | zero pad
+    if (!t.u_fold) {
     t.u_p0 = 2 * t.n_qpair + 2 * t.n_npair;        // first plain row (even)
     t.u_rowsP = bogp::pad_to(std::max(t.u_p0 + t.n_plain, 1), 16);
     t.offWu = (int)Wu.size();
@@ -321,6 +456,8 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
         }
       for (int j = 0; j < t.n_plain; ++j, ++dst)
         for (int m = 0; m < M; ++m) U[(size_t)dst * t.Mp + m] = Wf[(size_t)j * t.Mp + m];
+    }
+    t.u_rows = t.u_p0 + t.n_plain;
     }
     // Receiver-space factor: num = || LK^H p ||^2 ; Ck[j, n] = conj(LK[n, j]); stored transposed [N][J]
     t.J = rK;
@@ -352,6 +489,15 @@ extern "C" int bogp_modeset_info(bogp_modeset_t h, int f, int* M, int* rows, int
   if (M) *M = h->dev.t[f].M;
   if (rows) *rows = h->dev.t[f].rows;
   if (J) *J = h->dev.t[f].J;
+  return 0;
+}
+
+extern "C" int bogp_modeset_info_umma(bogp_modeset_t h, int f, int* rows, int* rows_padded, int* folded) {
+  BOGP_REQUIRE(h && f >= 0 && f < h->F, "bogp_modeset_info_umma: bad argument");
+  BOGP_REQUIRE(h->has_cov, "bogp_modeset_info_umma: call bogp_covariance_set first");
+  if (rows) *rows = h->dev.t[f].u_rows;
+  if (rows_padded) *rows_padded = h->dev.t[f].u_rowsP;
+  if (folded) *folded = h->dev.t[f].u_fold;
   return 0;
 }
 

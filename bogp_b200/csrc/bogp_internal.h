@@ -74,6 +74,12 @@ struct TonalMeta {
   int u_p0;      // first plain row (even) = 2 n_qpair + 2 n_npair
   int u_rowsP;   // rows padded to a multiple of 16 (the MMA N granularity at M = 128)
   int offWu;     // offset into Wu (u_rowsP * Mp floats, row-major [row][Mp])
+  // Folded operator (real receiver modes, rank-1 covariance): the norm rows R are rotated by an orthogonal Q whose first
+  // two rows span Re/Im of the numerator row written in R's row space (C = g^T R): ||Q R a|| = ||R a|| and
+  // C a = u_c1 (Q R a)_0 + u_c2 (Q R a)_1, so the numerator costs no operator rows of its own (u_p0 = 0, rank(G) rows).
+  int u_fold;
+  float u_c[4];  // c1 (re, im), c2 (re, im)
+  int u_rows;    // operator rows the tcgen05 engine multiplies by (before padding): the algorithmic row count
 };
 
 #define BOGP_MAX_TONALS 32
@@ -115,6 +121,8 @@ struct bogp_modeset_s {
   // covariance-independent half of bogp_covariance_set, cached: pivoted Cholesky factor of G_f = Phi_f^H Phi_f
   std::vector<std::vector<bogp::cplx>> LG_cache;
   std::vector<int> rG_cache;
+  // folded tcgen05 operator: R_f = LG_f^H (rG x M) and U_f = Phi_f R_f^+ (N x rG), both covariance-independent
+  std::vector<std::vector<double>> Rm_cache, U_cache;
   // host copies (float64) kept for covariance_set
   int F = 0, N = 0;
   std::vector<int> M;

@@ -85,6 +85,8 @@ struct UTonal {
   unsigned b_zbytes;           // rowsP * Mp * 4: one depth of one split of Bop
   unsigned long long b_off;    // offset of the tonal inside the Bop tables
   float trK;
+  int fold;                    // folded operator: numerator = |c1 y0 + c2 y1|^2 from the first two columns, norm = all columns
+  float c1r, c1i, c2r, c2i;
   // tilted-array mode only
   int offM;                    // column offset of the tonal in the phi(z) table
   int offC;                    // offset of the receiver-space covariance factor [N][J]
@@ -1054,7 +1056,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           // slots of this stage owned by this warp: s = s_first, s_first + kEpiSub, ...
           const int s_first = (sub - j0 % kEpiSub + kEpiSub) % kEpiSub;
           bool released = false;
-          if (p.two_slot && fast && rowsP == 16 && nq == 1 && s_first + kEpiSub < njs && s_first + 2 * kEpiSub >= njs &&
+          if (p.two_slot && fast && rowsP == 16 && (nq == 1 || u.fold) && s_first + kEpiSub < njs && s_first + 2 * kEpiSub >= njs &&
               !(BOGP_UMMA_DBG && p.skip == 2)) {
             // small tonals (one 16-column chunk per depth slot, two slots for this warp): both slots' loads in flight
             // at once, one wait, release, then the arithmetic -- the per-stage cost of these tonals is TMEM-load
@@ -1070,9 +1072,17 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
             released = true;
             if (quad == 0 && sub == 0) dbg_stamp(p, 3, sc);
             auto slot = [&](const float* re, const float* im, int sidx) {
-              const float tr = re[0] - im[1], ti = im[0] + re[1];
-              const float num = fmaf(tr, tr, ti * ti);
-              const float numsq = fmaf(re[0], re[0], fmaf(im[0], im[0], fmaf(re[1], re[1], im[1] * im[1])));
+              float num, numsq;
+              if (u.fold) {
+                const float tr = fmaf(u.c1r, re[0], fmaf(-u.c1i, im[0], fmaf(u.c2r, re[1], -u.c2i * im[1])));
+                const float ti = fmaf(u.c1r, im[0], fmaf(u.c1i, re[0], fmaf(u.c2r, im[1], u.c2i * re[1])));
+                num = fmaf(tr, tr, ti * ti);
+                numsq = 0.f;
+              } else {
+                const float tr = re[0] - im[1], ti = im[0] + re[1];
+                num = fmaf(tr, tr, ti * ti);
+                numsq = fmaf(re[0], re[0], fmaf(im[0], im[0], fmaf(re[1], re[1], im[1] * im[1])));
+              }
               unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
 #pragma unroll
               for (int q = 0; q < 16; q += 4) {
@@ -1116,7 +1126,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
                   if (quad == 0 && sub == 0) dbg_stamp(p, 3, sc);
                 }
                 if (c0 == 0) {
-                  if (nq == 1) {
+                  if (u.fold) {
+                    const float tr = fmaf(u.c1r, re[0], fmaf(-u.c1i, im[0], fmaf(u.c2r, re[1], -u.c2i * im[1])));
+                    const float ti = fmaf(u.c1r, im[0], fmaf(u.c1i, re[0], fmaf(u.c2r, im[1], u.c2i * re[1])));
+                    num = fmaf(tr, tr, ti * ti);
+                  } else if (nq == 1) {
                     const float tr = re[0] - im[1], ti = im[0] + re[1];
                     num = fmaf(tr, tr, ti * ti);
                     numsq = fmaf(re[0], re[0], fmaf(im[0], im[0], fmaf(re[1], re[1], im[1] * im[1])));
@@ -1247,7 +1261,8 @@ static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
   for (int f = 0; f < d.F; ++f) {
     const TonalMeta& t = d.t[f];
     UTonal& u = p.t[f];
-    u.Mp = t.Mp; u.rowsP = t.u_rowsP; u.n1 = t.u_p0; u.nq = t.n_qpair; u.trK = t.trK;
+    u.Mp = t.Mp; u.rowsP = t.u_rowsP; u.n1 = t.u_p0; u.nq = t.u_fold ? 0 : t.n_qpair; u.trK = t.trK;
+    u.fold = t.u_fold; u.c1r = t.u_c[0]; u.c1i = t.u_c[1]; u.c2r = t.u_c[2]; u.c2i = t.u_c[3];
     u.e_bytes = 2048u * (unsigned)u.Mp;
     u.e_off = e_off;
     e_off += u.e_bytes;

@@ -89,8 +89,21 @@ class DeviceModeSet:
             out.append((M.value, rows.value, J.value))
         return out
 
-    def flops_per_candidate(self) -> float:
-        """Algorithmic flop of one candidate over all tonals on the vertical-array path: sum_f 4 rows_f M_f."""
+    def tonal_info_umma(self):
+        """Per tonal ``(M_f, rows_f, rows_padded_f, folded_f)`` of the operator the tcgen05 engine multiplies by."""
+        out = []
+        for f, (M, _, _) in enumerate(self.tonal_info()):
+            rows, rp, fold = C.c_int(), C.c_int(), C.c_int()
+            _lib.call("bogp_modeset_info_umma", self._h, f, C.byref(rows), C.byref(rp), C.byref(fold))
+            out.append((M, rows.value, rp.value, bool(fold.value)))
+        return out
+
+    def flops_per_candidate(self, engine: str = "simt") -> float:
+        """Algorithmic flop of one candidate over all tonals on the vertical-array path: sum_f 4 rows_f M_f, with the
+        row count of the operator the engine actually needs (the tcgen05 engine folds a rank-1 numerator into the norm
+        rows: rank(G) rows instead of rank(G) + 2)."""
+        if engine == "umma":
+            return float(sum(4 * rows * M for M, rows, _, _ in self.tonal_info_umma()))
         return float(sum(4 * rows * M for M, rows, _ in self.tonal_info()))
 
     # ------------------------------------------------------------------ evaluation

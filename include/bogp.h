@@ -95,6 +95,11 @@ int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, const double*
  * (G = Phi^H Phi = R^H R, Phi^H K Phi = C^H C; complex rows count twice) and rank J of K_f.  The algorithmic work of
  * one candidate x tonal on the vertical-array path is 4 * rows * M flop. */
 int bogp_modeset_info(bogp_modeset_t h, int f, int* M, int* rows, int* J);
+/* Operator of tonal f as the tcgen05 engine multiplies by it: rows before / after padding to the MMA granularity, and
+ * whether the rank-1 numerator is folded into the norm rows (real receiver modes, rank-1 covariance: an orthogonal
+ * rotation of R puts the numerator row into the span of its first two rows, so the operator has rank(G) rows instead
+ * of rank(G) + 2).  Valid after bogp_covariance_set. */
+int bogp_modeset_info_umma(bogp_modeset_t h, int f, int* rows, int* rows_padded, int* folded);
 
 /* Ambiguity surface: replaces the loop `for z in src_z: amb[zz,:] = MFP({"src_z": z, "rec_r": rvec})`
  * (mfp.py:213-214) including runner + beamformer + multifreq combine.

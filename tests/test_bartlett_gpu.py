@@ -71,6 +71,35 @@ def test_cfg2_shape_surface_vs_oracle(cfg2_small, dms2, engine):
     assert np.unravel_index(surf.argmax(), surf.shape) == np.unravel_index(ref.argmax(), ref.shape)
 
 
+def test_folded_operator_matches_unfolded(cfg2_small, monkeypatch):
+    """Rank-1 covariance, real receiver modes: the tcgen05 engine folds the numerator row into the (rotated) norm rows
+    -- rank(G) operator rows instead of rank(G) + 2.  Same surface as the unfolded operator (BOGP_NO_FOLD=1) and as the
+    oracle, both processors; the rank-8 covariance of the other tests keeps the unfolded layout."""
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import synthetic_covariance
+    c = cfg2_small
+    folded = DeviceModeSet(c["modes"], c["K"])
+    info = folded.tonal_info_umma()
+    assert all(fold for _, _, _, fold in info)
+    assert [rows for _, rows, _, _ in info] == [rows - 2 for _, rows, _ in folded.tonal_info()]
+    assert folded.flops_per_candidate("umma") < folded.flops_per_candidate("simt")
+    monkeypatch.setenv("BOGP_NO_FOLD", "1")
+    plain = DeviceModeSet(c["modes"], c["K"])
+    monkeypatch.delenv("BOGP_NO_FOLD")
+    assert not any(fold for _, _, _, fold in plain.tonal_info_umma())
+    ref = ob.ambiguity_surface(c["modes"], c["K"], c["r"], c["z"])
+    a = folded.bartlett_grid(c["r"], c["z"], engine="umma").cpu().numpy()
+    b = plain.bartlett_grid(c["r"], c["z"], engine="umma").cpu().numpy()
+    assert_parity(a, ref)
+    assert_parity(b, ref)
+    assert np.unravel_index(a.argmax(), a.shape) == np.unravel_index(ref.argmax(), ref.shape)
+    ml_ref = ob.ambiguity_surface(c["modes"], c["K"], c["r"], c["z"], atype="cbf_ml", multifreq_method="product")
+    ml = folded.bartlett_grid(c["r"], c["z"], atype="cbf_ml", multifreq_method="product", engine="umma").cpu().numpy()
+    assert_parity(ml, ml_ref, floor=1.0)
+    K8 = synthetic_covariance(c["modes"], 60.0, 5.0, snapshots=8, seed=3)
+    assert not any(fold for _, _, _, fold in DeviceModeSet(c["modes"], K8).tonal_info_umma())
+
+
 @pytest.mark.parametrize("shape", [(300, 70), (129, 9), (1, 1), (128, 64), (513, 131)])
 def test_umma_rank8_ragged_grids(shape):
     """tcgen05 engine on grids that do not fill its 128-range tiles / 8-depth groups, rank-8 covariance (J = 8),
