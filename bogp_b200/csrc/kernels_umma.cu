@@ -1056,7 +1056,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           // slots of this stage owned by this warp: s = s_first, s_first + kEpiSub, ...
           const int s_first = (sub - j0 % kEpiSub + kEpiSub) % kEpiSub;
           bool released = false;
-          if (p.two_slot && fast && rowsP == 16 && (nq == 1 || u.fold) && s_first + kEpiSub < njs && s_first + 2 * kEpiSub >= njs &&
+          if ((p.two_slot & 1) && fast && rowsP == 16 && (nq == 1 || u.fold) && s_first + kEpiSub < njs && s_first + 2 * kEpiSub >= njs &&
               !(BOGP_UMMA_DBG && p.skip == 2)) {
             // small tonals (one 16-column chunk per depth slot, two slots for this warp): both slots' loads in flight
             // at once, one wait, release, then the arithmetic -- the per-stage cost of these tonals is TMEM-load
@@ -1099,6 +1099,49 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
             };
             slot(reA, imA, sA);
             slot(reB, imB, sB);
+          } else if ((p.two_slot & 2) && fast && rowsP == 32 && (nq == 1 || u.fold) && s_first < njs && s_first + kEpiSub >= njs &&
+                     !(BOGP_UMMA_DBG && p.skip == 2)) {
+            // one slot of two 16-column chunks: all four loads in flight, one wait
+            float reA[16], imA[16], reB[16], imB[16];
+            const uint32_t tA = t_lane + (uint32_t)(s_first * 32);
+            tc_ld16(tA, reA); tc_ld16(tA + NA, imA);
+            tc_ld16(tA + 16u, reB); tc_ld16(tA + NA + 16u, imB);
+            tc_wait_ld();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + set));
+            released = true;
+            if (quad == 0 && sub == 0) dbg_stamp(p, 3, sc);
+            float num, numsq;
+            if (u.fold) {
+              const float tr = fmaf(u.c1r, reA[0], fmaf(-u.c1i, imA[0], fmaf(u.c2r, reA[1], -u.c2i * imA[1])));
+              const float ti = fmaf(u.c1r, imA[0], fmaf(u.c1i, reA[0], fmaf(u.c2r, imA[1], u.c2i * reA[1])));
+              num = fmaf(tr, tr, ti * ti);
+              numsq = 0.f;
+            } else {
+              const float tr = reA[0] - imA[1], ti = imA[0] + reA[1];
+              num = fmaf(tr, tr, ti * ti);
+              numsq = fmaf(reA[0], reA[0], fmaf(imA[0], imA[0], fmaf(reA[1], reA[1], imA[1] * imA[1])));
+            }
+            unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+              sq_acc2(t0, reA[q], reA[q + 1]);
+              sq_acc2(t1, imA[q], imA[q + 1]);
+              sq_acc2(t2, reA[q + 2], reA[q + 3]);
+              sq_acc2(t3, imA[q + 2], imA[q + 3]);
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+              sq_acc2(t0, reB[q], reB[q + 1]);
+              sq_acc2(t1, imB[q], imB[q + 1]);
+              sq_acc2(t2, reB[q + 2], reB[q + 3]);
+              sq_acc2(t3, imB[q + 2], imB[q + 3]);
+            }
+            const float norm = ((sum2(t0) + sum2(t1)) + (sum2(t2) + sum2(t3))) - numsq;
+            const float b = __fdividef(num, norm);
+            const float val = p.atype == BOGP_ATYPE_CBF ? b : u.trK - b;
+            float* a = acc + (size_t)(j0 + s_first) * kTileR + tl;
+            *a = (f == 0) ? val : (p.mf == BOGP_MF_MEAN ? *a + val : *a * val);
           } else
           for (int s = s_first; s < njs && !(BOGP_UMMA_DBG && p.skip == 2); s += kEpiSub) {
             const int j = j0 + s;
@@ -1321,7 +1364,7 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   const int ZC = choose_zc(Nr, Nz, sms);
   if (!plan_tonals(h, p, ZC)) { set_error("UMMA engine: mode set does not fit (operator rows, Mp > 64 or complex source table)"); return BOGP_ERR_UNSUPPORTED; }
   p.Nr = Nr; p.Nz = Nz; p.ZC = ZC; p.atype = atype; p.mf = mf;
-  { const char* e = std::getenv("BOGP_UMMA_TWO_SLOT"); p.two_slot = e ? std::atoi(e) : 1; }
+  { const char* e = std::getenv("BOGP_UMMA_TWO_SLOT"); p.two_slot = e ? std::atoi(e) : 3; }      // bit 0: 16-row tonals (two slots at once), bit 1: 32-row tonals (both chunks at once)
   p.nrt = (Nr + kTileR - 1) / kTileR;
   const int nzc = (Nz + ZC - 1) / ZC;
   p.units = p.nrt * nzc;
