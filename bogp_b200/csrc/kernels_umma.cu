@@ -85,6 +85,7 @@ struct UTonal {
   unsigned b_zbytes;           // rowsP * Mp * 4: one depth of one split of Bop
   unsigned long long b_off;    // offset of the tonal inside the Bop tables
   float trK;
+  int src;                     // index of the tonal in the mode set (the plan may process the tonals in another order)
   int fold;                    // folded operator: numerator = |c1 y0 + c2 y1|^2 from the first two columns, norm = all columns
   float c1r, c1i, c2r, c2i;
   // tilted-array mode only
@@ -405,8 +406,8 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
     const int per_f = p.nrt * (kTileR / kTabRows);
     const int f = blockIdx.x / per_f, rem = blockIdx.x % per_f;
     const int rt = rem / (kTileR / kTabRows), row0 = (rem % (kTileR / kTabRows)) * kTabRows;
-    const TonalMeta& t = ms.t[f];
     const UTonal& u = p.t[f];
+    const TonalMeta& t = ms.t[u.src];
     for (int m = tid; m < u.Mp; m += kTabThreads) {
       double cr = 0.0, ci = 0.0;
       if (m < t.M) {
@@ -447,8 +448,8 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
   const int nzb = (p.Nz + kTabDepths - 1) / kTabDepths;
   const int bb = blockIdx.x - nE;
   const int f = bb / nzb, j0 = (bb % nzb) * kTabDepths;
-  const TonalMeta& t = ms.t[f];
   const UTonal& u = p.t[f];
+  const TonalMeta& t = ms.t[u.src];
   const int KC = u.Mp >> 2, n_q = u.rowsP * KC;
   // items q = tid, tid + 128, ...: q = (row group * KC + K chunk) * 8 + row8 is the float4 index inside a depth block
   float4 wq[kTabMaxQ];
@@ -666,6 +667,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + p.smem_bar;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.smem_bar + BAR_COUNT * 8);
+  // acc_seq[set][depth parity][quadrant]: tonals (global count) whose multi-frequency updates that epilogue warp has finished
+  volatile int* acc_seq = reinterpret_cast<volatile int*>(smem + p.smem_bar + 192);
+  static_assert(BAR_COUNT * 8 + 4 <= 192, "barriers | TMEM slot | acc_seq[16] share the 256-byte control block");
+  if (threadIdx.x < 16) acc_seq[threadIdx.x] = 0;
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   if (warp == 0 && lane == 0) {
@@ -1039,12 +1044,24 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
     float* acc = reinterpret_cast<float*>(smem + p.smem_acc);     // [ZC][128]
     uint32_t sc = 0;
     long long w_tfull = 0;
+    // The running mean / product of depth j lives in acc[j] and is updated tonal after tonal, by this warp or by its
+    // partner (other accumulator set, same depth parity and quadrant) depending on the stage parity.  Before it starts
+    // a tonal a warp makes sure the partner has finished the previous tonal (release / acquire on a counter
+    // in shared memory, once per tonal): with one-stage tonals on tiny grids two consecutive stages touch the same
+    // depth and the order of the two updates would otherwise be a race.
+    int gt = 0;                              // tonals finished by this warp (over all units)
+    const uint32_t seq_mine = smem_u32(const_cast<int*>(acc_seq) + (set * 2 + sub) * 4 + quad);
+    const uint32_t seq_partner = smem_u32(const_cast<int*>(acc_seq) + ((set ^ 1) * 2 + sub) * 4 + quad);
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int rt = unit % p.nrt, zc = unit / p.nrt;
       const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
       for (int f = 0; f < p.F; ++f) {
         const UTonal& u = p.t[f];
         const int rowsP = u.rowsP, nq = u.nq;
+        if (gt > 0) {
+          int v;
+          do { asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(seq_partner) : "memory"); } while (v < gt);
+        }
         const bool fast = (u.n1 == 2 * nq) && nq <= 8;
         for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
           if ((int)(sc & 1u) != set) continue;
@@ -1229,6 +1246,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           }
           if (tw && lane == 0 && unit == (int)blockIdx.x) { p.dbg[16 * 201 + f] += clock64() - tw; p.dbg[16 * 203 + f] += 1; }
         }
+        ++gt;
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(seq_mine), "r"(gt) : "memory");
       }
       // acc[j][tl] is updated by the two sets' warps of this (quadrant, parity) in stage order; the buffer hand-shake
       // orders those updates (release/acquire on the mbarriers), but the write-out below reads both sets' updates, so
@@ -1301,9 +1321,23 @@ static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
   if (d.src_complex) return false;     // complex source tables would need a complex Bop (not built yet)
   unsigned e_off = 0;
   int maxMp = 0, maxRows = 0;
+  // Tonal order: small and large tonals alternate (smallest, largest, second smallest, ...) so that the E images of
+  // consecutive tonals fit side by side in the TMEM A region and the loaders never wait for the previous tonal's MMAs
+  // (ascending order puts the 40- and 48-mode tonals next to each other: 4 (40 + 48) > 256 columns).  The mean /
+  // product over tonals is accumulated in this order.
+  int order[BOGP_MAX_TONALS];
+  {
+    int idx[BOGP_MAX_TONALS];
+    for (int f = 0; f < d.F; ++f) idx[f] = f;
+    std::stable_sort(idx, idx + d.F, [&](int a, int b) { return d.t[a].Mp < d.t[b].Mp; });
+    const char* e = std::getenv("BOGP_UMMA_TONAL_ORDER");
+    const bool interleave = !(e && e[0] == '0');
+    for (int i = 0, lo = 0, hi = d.F - 1; i < d.F; ++i) order[i] = !interleave ? i : ((i & 1) ? idx[hi--] : idx[lo++]);
+  }
   for (int f = 0; f < d.F; ++f) {
-    const TonalMeta& t = d.t[f];
+    const TonalMeta& t = d.t[order[f]];
     UTonal& u = p.t[f];
+    u.src = order[f];
     u.Mp = t.Mp; u.rowsP = t.u_rowsP; u.n1 = t.u_p0; u.nq = t.u_fold ? 0 : t.n_qpair; u.trK = t.trK;
     u.fold = t.u_fold; u.c1r = t.u_c[0]; u.c1i = t.u_c[1]; u.c2r = t.u_c[2]; u.c2i = t.u_c[3];
     u.e_bytes = 2048u * (unsigned)u.Mp;
@@ -1478,6 +1512,7 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   for (int f = 0; f < d.F; ++f) {
     const TonalMeta& t = d.t[f];
     UTonal& u = p.t[f];
+    u.src = f;
     u.Mp = t.Mp; u.rowsP = 64; u.nj = 1; u.nq = 0; u.n1 = 0; u.trK = t.trK;
     u.e_bytes = 2048u * (unsigned)u.Mp; u.e_off = e_off; e_off += u.e_bytes;
     u.b_zbytes = 64u * (unsigned)u.Mp * 4u;
