@@ -500,8 +500,8 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
 // K-major layout, hi and lo arrays.  The phase k_m l_n sin(tau) is formed in float64.
 __global__ void __launch_bounds__(128) umma_tilt_theta_kernel(ModesetDev ms, UParams p, const double* __restrict__ tilt_deg) {
   const int f = blockIdx.y, k = blockIdx.x;
-  const TonalMeta& t = ms.t[f];
   const UTonal& u = p.t[f];
+  const TonalMeta& t = ms.t[u.src];
   const int tau = min(2 * (k >> 2) + (k & 1), p.Nt - 1), half = (k >> 1) & 1;
   const double st = sin(tilt_deg[tau] * 0.017453292519943295);
   float* Bhi = reinterpret_cast<float*>(const_cast<unsigned char*>(p.Bhi) + u.b_off + (size_t)k * u.b_zbytes);
@@ -539,7 +539,7 @@ __global__ void umma_tilt_aux_kernel(ModesetDev ms, UParams p, const double* __r
     int f = 0;
     while (f + 1 < p.F && col >= p.t[f + 1].offM) ++f;
     const int m = col - p.t[f].offM;
-    const TonalMeta& t = ms.t[f];
+    const TonalMeta& t = ms.t[p.t[f].src];
     float v = 0.f;
     if (m < t.M) {
       int i0; float w;
@@ -1315,6 +1315,16 @@ static int device_sms() {
   return n;
 }
 
+// smallest, largest, second smallest, second largest, ... (by padded mode count); BOGP_UMMA_TONAL_ORDER=0: as given
+static void tonal_order(const ModesetDev& d, int* order) {
+  int idx[BOGP_MAX_TONALS];
+  for (int f = 0; f < d.F; ++f) idx[f] = f;
+  std::stable_sort(idx, idx + d.F, [&](int a, int b) { return d.t[a].Mp < d.t[b].Mp; });
+  const char* e = std::getenv("BOGP_UMMA_TONAL_ORDER");
+  const bool interleave = !(e && e[0] == '0');
+  for (int i = 0, lo = 0, hi = d.F - 1; i < d.F; ++i) order[i] = !interleave ? i : ((i & 1) ? idx[hi--] : idx[lo++]);
+}
+
 // Fills the size-independent part of the plan; returns false when the mode set does not fit the kernel.
 static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
   const ModesetDev& d = h->dev;
@@ -1326,14 +1336,7 @@ static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
   // (ascending order puts the 40- and 48-mode tonals next to each other: 4 (40 + 48) > 256 columns).  The mean /
   // product over tonals is accumulated in this order.
   int order[BOGP_MAX_TONALS];
-  {
-    int idx[BOGP_MAX_TONALS];
-    for (int f = 0; f < d.F; ++f) idx[f] = f;
-    std::stable_sort(idx, idx + d.F, [&](int a, int b) { return d.t[a].Mp < d.t[b].Mp; });
-    const char* e = std::getenv("BOGP_UMMA_TONAL_ORDER");
-    const bool interleave = !(e && e[0] == '0');
-    for (int i = 0, lo = 0, hi = d.F - 1; i < d.F; ++i) order[i] = !interleave ? i : ((i & 1) ? idx[hi--] : idx[lo++]);
-  }
+  tonal_order(d, order);
   for (int f = 0; f < d.F; ++f) {
     const TonalMeta& t = d.t[order[f]];
     UTonal& u = p.t[f];
@@ -1509,10 +1512,12 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   unsigned e_off = 0;
   unsigned long long b_off = 0;
   int sumMp = 0, maxMp = 0;
+  int order[BOGP_MAX_TONALS];
+  tonal_order(d, order);
   for (int f = 0; f < d.F; ++f) {
-    const TonalMeta& t = d.t[f];
+    const TonalMeta& t = d.t[order[f]];
     UTonal& u = p.t[f];
-    u.src = f;
+    u.src = order[f];
     u.Mp = t.Mp; u.rowsP = 64; u.nj = 1; u.nq = 0; u.n1 = 0; u.trK = t.trK;
     u.e_bytes = 2048u * (unsigned)u.Mp; u.e_off = e_off; e_off += u.e_bytes;
     u.b_zbytes = 64u * (unsigned)u.Mp * 4u;
