@@ -398,7 +398,7 @@ constexpr int kTabMaxQ = 8;           // float4 items of W_f per thread: rowsP *
 __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms, UParams p, const double* __restrict__ r,
                                                                   const double* __restrict__ z, int nE) {
   __shared__ double2 kinv[128];       // k_m^-1/2
-  __shared__ float phi_s[2][128];
+  __shared__ float phi_s[kTabDepths][64];     // phi_m(z_j) of the block's depths
   const int tid = threadIdx.x;
   if (blockIdx.x == 0 && tid == 0) { *p.err = 0; if (p.ext_mode) { *p.ext_key = 0ull; *p.ext_done = 0u; } }
   if ((int)blockIdx.x < nE) {
@@ -464,20 +464,22 @@ __global__ void __launch_bounds__(kTabThreads) umma_tables_kernel(ModesetDev ms,
   float4* Bhi = reinterpret_cast<float4*>(const_cast<unsigned char*>(p.Bhi) + u.b_off);
   float4* Blo = reinterpret_cast<float4*>(const_cast<unsigned char*>(p.Blo) + u.b_off);
   const int nd = min(kTabDepths, p.Nz - j0);
+  // all depths' mode shapes first (one barrier), then the stores stream without synchronisation
+  for (int e = tid; e < nd * u.Mp; e += kTabThreads) {
+    const int dj = e / u.Mp, m = e - dj * u.Mp;
+    float v = 0.f;
+    if (m < t.M) {
+      int i0; float w;
+      depth_index(z[j0 + dj], ms.z0, ms.dz, ms.nz_tab, i0, w);
+      const float* tr = ms.tab_re + t.offTab + (size_t)i0 * t.Mp + m;
+      v = fmaf(w, __ldg(tr + t.Mp) - __ldg(tr), __ldg(tr));
+    }
+    phi_s[dj][m] = v;
+  }
+  __syncthreads();
   for (int dj = 0; dj < nd; ++dj) {
     const int j = j0 + dj;
-    float* ph = phi_s[dj & 1];
-    if (tid < u.Mp) {
-      float v = 0.f;
-      if (tid < t.M) {
-        int i0; float w;
-        depth_index(z[j], ms.z0, ms.dz, ms.nz_tab, i0, w);
-        const float* tr = ms.tab_re + t.offTab + (size_t)i0 * t.Mp + tid;
-        v = fmaf(w, __ldg(tr + t.Mp) - __ldg(tr), __ldg(tr));
-      }
-      ph[tid] = v;
-    }
-    __syncthreads();
+    const float* ph = phi_s[dj];
     float4* hi = Bhi + (size_t)j * n_q;
     float4* lo = Blo + (size_t)j * n_q;
 #pragma unroll
