@@ -350,10 +350,36 @@ def run_ours(args) -> None:
     host_surf = torch.empty((NZ_PER_GPU, NR), dtype=torch.float32, pin_memory=True)
     host_surf_np = host_surf.numpy()
 
+    # final reduction across ranks: 16-byte records over peer memory (one kernel, NVLink P2P stores), NCCL all-gather as
+    # the fallback (BOGP_EXCHANGE=nccl forces it)
+    peer = None
+    exchange_kind = "none"
+    if world > 1:
+        exchange_kind = "nccl all_gather_into_tensor"
+        if os.environ.get("BOGP_EXCHANGE", "peer") == "peer":
+            from bogp_b200.sharding import PeerExchange
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+            try:
+                peer = PeerExchange()
+            except Exception as exc:      # noqa: BLE001  (no P2P mapping on this box: every rank must agree on the fallback)
+                print(f"bench.py: peer exchange unavailable on rank {rank}: {exc}", file=sys.stderr)
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                peer = None
+            else:
+                exchange_kind = "peer memory (bogp_peer_exchange: P2P stores over NVLink, one single-block kernel)"
+
+    def exchange_records():
+        if peer is not None:
+            peer.exchange(pair, pairs)
+        else:
+            dist.all_gather_into_tensor(pairs.view(-1), pair)
+
     def step_device():
         dms.bartlett_grid(r, z_slab, engine=args.engine, out=surf, argext=(pair, scratch, True))
         if world > 1:
-            dist.all_gather_into_tensor(pairs.view(-1), pair)
+            exchange_records()
 
     def step_e2e():
         out, (val, pos) = dms.bartlett_grid_host(r, z_slab, engine=args.engine, out=host_surf_np, argext="max")
@@ -362,7 +388,7 @@ def run_ours(args) -> None:
             rec = torch.tensor([lo * NR + flat, 0], dtype=torch.int64)
             rec[1] = int(np.float32(val).view(np.int32))
             pair.copy_(rec)
-            dist.all_gather_into_tensor(pairs.view(-1), pair)
+            exchange_records()
             pairs.cpu()
         return flat
 
@@ -377,6 +403,12 @@ def run_ours(args) -> None:
     val, pos = mfp.argmax(surf)
     if world == 1 and not (pos == TRUTH_NODE and abs(val - 1.0) < 2e-5):
         raise SystemExit(f"bench.py: parity gate failed: argmax {pos} value {val}")
+    if world > 1:
+        # the exchanged records must be what an NCCL all-gather of the same records gives
+        check = torch.zeros_like(pairs)
+        dist.all_gather_into_tensor(check.view(-1), pair)
+        if not torch.equal(check, pairs):
+            raise SystemExit(f"bench.py: record exchange mismatch on rank {rank}: {pairs.tolist()} vs {check.tolist()}")
 
     # ---- device-resident timing
     for _ in range(args.warmup):
@@ -453,7 +485,7 @@ def run_ours(args) -> None:
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), engine=args.engine),
+            "config": dict(workload_config(world), engine=args.engine, final_reduction=exchange_kind),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3 / args.steps,

@@ -7,7 +7,11 @@ The only exchange is the final reduction the reference does with ``np.unravel_in
 rank -- 16 bytes -- followed by a local reduce with np.argmax's first-occurrence tie rule.  Optionally the slabs
 themselves are all-gathered when every rank wants the full surface.
 
-Works over any ``torch.distributed`` backend (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+Works over any ``torch.distributed`` backend (NCCL over NVLink on the GPU box, gloo in the CPU tests).  On one box the
+16-byte records can also travel without a collective library at all: :class:`PeerExchange` maps every rank's record
+buffer into its peers (CUDA IPC) and one single-block kernel per step stores the record into all peers over NVLink and
+waits for theirs (``bogp_peer_exchange``, csrc/kernels_peer.cu) -- a few microseconds instead of the ~25 us of an NCCL
+all-gather, which is 12 % of the 0.19 ms step.
 """
 from __future__ import annotations
 
@@ -94,3 +98,64 @@ def sharded_surface(evaluate_rows: Callable[[int, int], torch.Tensor], n_rows: i
             full = torch.cat([p[: slab(n_rows, r, world)[1] - slab(n_rows, r, world)[0]] for r, p in enumerate(parts)])
     pos = tuple(int(x) for x in np.unravel_index(idx, (n_rows, n_cols))) if idx >= 0 else (-1, -1)
     return local, (val, pos), full
+
+
+class PeerExchange:
+    """All-gather of one ``int64[2]`` record per rank over peer memory (one box, one process per GPU).
+
+    ``torch.distributed`` is used once, to pass the CUDA IPC handles around; ``exchange(rec, out)`` is then a single
+    kernel launch on the current stream: ``out[r] = rec of rank r`` for every rank ``r``.  All ranks must call it the
+    same number of times.  Raises (``BogpError`` / ``RuntimeError``) when the GPUs cannot map each other's memory;
+    callers fall back to ``dist.all_gather_into_tensor``.
+    """
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        import ctypes as C
+
+        from . import _lib
+        if not dist.is_initialized():
+            raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
+        self._lib, self._C = _lib, C
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._h = C.c_void_p()
+        mine = (C.c_ubyte * 64)()
+        _lib.call("bogp_peer_create", C.byref(self._h), self.rank, self.world, C.cast(mine, C.c_void_p))
+        local = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        every = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(every, local, group=group)
+        blob = bytes(every.cpu().tolist())
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        failure = None
+        try:
+            _lib.call("bogp_peer_open", self._h, C.cast(buf, C.c_void_p))
+        except Exception as exc:      # noqa: BLE001  (reported below, on every rank, after the collective)
+            failure = exc
+        # one collective that is both the agreement on success and the barrier "every rank has mapped every buffer
+        # before the first record is stored"; a rank that failed must still take part in it
+        ok = torch.tensor([0 if failure is not None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.close()
+            raise RuntimeError(f"peer memory mapping failed on at least one rank (rank {self.rank}: {failure})")
+
+    def exchange(self, rec: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        C = self._C
+        if not (rec.is_cuda and rec.dtype == torch.int64 and rec.numel() == 2 and rec.is_contiguous()):
+            raise ValueError("rec must be a contiguous CUDA int64[2] tensor")
+        if not (out.is_cuda and out.dtype == torch.int64 and out.numel() == 2 * self.world and out.is_contiguous()):
+            raise ValueError("out must be a contiguous CUDA int64[world, 2] tensor")
+        self._lib.call("bogp_peer_exchange", self._h, C.c_void_p(rec.data_ptr()), C.c_void_p(out.data_ptr()),
+                       C.c_void_p(self._lib.current_stream_ptr()))
+        return out
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._lib.lib().bogp_peer_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -227,6 +227,20 @@ int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, const double* 
                               const double* lengthscale_bounds, const double* outputscale_bounds, int B,
                               double* raw_inout_host, double* loss_host, void* stream);
 
+/* ---- Final reduction across the GPUs of one box over peer memory (NVLink P2P stores), no collective library.
+ * Replaces the host-side np.argmax over collated surfaces (projects/swellex96_localization/data/collate.py:50) and the
+ * NCCL all-gather of one 16-byte (flat index, value bits) record per rank.  Set-up: every rank calls bogp_peer_create
+ * (allocates its buffer, returns a BOGP_IPC_HANDLE_BYTES CUDA IPC handle), the ranks exchange the handles by any means
+ * (torch.distributed all_gather), every rank calls bogp_peer_open with all handles in rank order.  Per step:
+ * bogp_peer_exchange stores rec_dev[2] into every peer and fills recs_out_dev[world][2] once every peer's record of
+ * the same step has arrived (one single-block kernel on `stream`; all ranks must call it the same number of times). */
+#define BOGP_IPC_HANDLE_BYTES 64
+typedef struct bogp_peer_s* bogp_peer_t;
+int bogp_peer_create(bogp_peer_t* out, int rank, int world, unsigned char* ipc_handle_out);
+int bogp_peer_open(bogp_peer_t p, const unsigned char* all_handles);
+int bogp_peer_exchange(bogp_peer_t p, const long long* rec_dev, long long* recs_out_dev, void* stream);
+int bogp_peer_destroy(bogp_peer_t p);
+
 #ifdef __cplusplus
 }
 #endif
