@@ -317,6 +317,23 @@ def other_paths(hbm_gbs: float, tf32x3_peak: float) -> dict:
     fit_gp_adamw(SingleTaskGP(Xf, yf), FitConfig(steps=100), engine="fused")
     out["gp_fit"] = {"workload": "100 AdamW steps of -mll, n=144 d=3 (ei.py:69-78), one kernel launch", "kernel": "gp_fit_kernel",
                      "call_ms": (time.perf_counter() - t0) * 1e3}
+    try:
+        # Thompson sampling over the BAxUS candidate set (baxus.py:45, :121-141): joint posterior draw + arg-max
+        from bogp_b200.generation import MaxPosteriorSampling
+        b, n, d = 5000, 500, 12
+        Xt = rng.uniform(-1, 1, (n, d))
+        yt = np.sin(3 * Xt[:, 0]) + 0.3 * np.cos(2 * Xt.sum(1))
+        yt = (yt - yt.mean()) / yt.std()
+        ts = MaxPosteriorSampling(SingleTaskGP(Xt, yt, lengthscale=rng.uniform(0.3, 1.5, d), outputscale=1.3, noise=1e-4))
+        Xc, zs = rng.uniform(-1, 1, (b, d)), rng.standard_normal((1, b))
+        ms = kernel_ms(lambda: ts(Xc, base_samples=zs), reps=3, warm=1)
+        flop = 2.0 * (b ** 3 / 3.0 + b * b * n / 2.0)
+        out["thompson"] = {"workload": f"BAxUS create_candidate: joint posterior draw over {b} candidates, n={n} d={d}, float64",
+                           "kernel": "ts_gemm_nt chain (FP64 tensor cores)", "covariance_factorisation_ms": ms,
+                           "fp64_tflops": flop / (ms * 1e-3) / 1e12, "fp64_mma_peak_tflops": 37.1,
+                           "frac": flop / (ms * 1e-3) / 1e12 / 37.1, "jitter": ts.last_jitter}
+    except Exception as exc:      # noqa: BLE001
+        out["thompson"] = {"error": repr(exc)}
     return out
 
 
