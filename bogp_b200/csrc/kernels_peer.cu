@@ -51,7 +51,11 @@ __global__ void peer_exchange_kernel(unsigned char* const* bufs, int rank, int w
   for (unsigned spin = 0;; ++spin) {
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
     if (seen >= epoch) break;
-    if ((spin & 1023u) == 1023u && clock64() - t0 > 20000000000LL) { atomicExch(err, 1 + t); return; }     // ~10 s
+    if ((spin & 1023u) == 1023u && clock64() - t0 > 20000000000LL) {      // ~10 s: a peer never reached this step
+      atomicExch(err, 1 + t);
+      __threadfence_system();
+      __trap();                                                               // surfaces as a CUDA error at the next sync
+    }
   }
   const long long* src = reinterpret_cast<const long long*>(mine + ((size_t)(epoch & 1ull) * world + t) * 16);
   recs_out[2 * t] = src[0];
