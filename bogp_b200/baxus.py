@@ -184,6 +184,22 @@ def _trust_region(state: BaxusState, model: SingleTaskGP, X: torch.Tensor, Y: to
     return center, lb, ub
 
 
+def thompson_candidates(center: torch.Tensor, lb: torch.Tensor, ub: torch.Tensor, n_candidates: int) -> torch.Tensor:
+    """The discrete candidate set of the Thompson step (ref :121-134): scrambled-Sobol points of the trust region, of
+    which every candidate keeps only a random subset of coordinates (each with probability ``min(20 / dim, 1)``, at
+    least one) and stays at the incumbent ``center`` in the others."""
+    dim = center.shape[-1]
+    pert = SobolEngine(dim, scramble=True).draw(n_candidates).to(DT)
+    pert = lb + (ub - lb) * pert
+    prob = min(20.0 / dim, 1.0)
+    mask = torch.rand(n_candidates, dim, dtype=DT) <= prob
+    stuck = torch.where(mask.sum(dim=1) == 0)[0]
+    mask[stuck, torch.randint(0, dim, size=(len(stuck),))] = True
+    X_cand = center.expand(n_candidates, dim).clone()
+    X_cand[mask] = pert[mask]
+    return X_cand
+
+
 def create_candidate(state: BaxusState, model: SingleTaskGP, X: torch.Tensor, Y: torch.Tensor,
                      dtype: torch.dtype = DT, device=None, n_candidates: Optional[int] = None, num_restarts: int = 10,
                      raw_samples: int = 512, acqf: str = "ts") -> torch.Tensor:
@@ -199,15 +215,7 @@ def create_candidate(state: BaxusState, model: SingleTaskGP, X: torch.Tensor, Y:
         n_candidates = min(5000, max(2000, 200 * dim))
     center, lb, ub = _trust_region(state, model, X, Y)
     if acqf == "ts":
-        pert = SobolEngine(dim, scramble=True).draw(n_candidates).to(DT)
-        pert = lb + (ub - lb) * pert
-        # each candidate moves a random subset of the coordinates (20 on average), at least one
-        prob = min(20.0 / dim, 1.0)
-        mask = torch.rand(n_candidates, dim, dtype=DT) <= prob
-        stuck = torch.where(mask.sum(dim=1) == 0)[0]
-        mask[stuck, torch.randint(0, dim, size=(len(stuck),))] = True
-        X_cand = center.expand(n_candidates, dim).clone()
-        X_cand[mask] = pert[mask]
+        X_cand = thompson_candidates(center, lb, ub, n_candidates)
         return MaxPosteriorSampling(model=model, replacement=False)(X_cand, num_samples=1)
     logei = LogExpectedImprovement(model, float(Y.max()))
     X_next, _ = optimize_acqf(logei, bounds=torch.stack([lb, ub]), q=1, num_restarts=num_restarts,

@@ -95,6 +95,35 @@ def test_increase_embedding_keeps_embedded_points():
         increase_embedding_and_observations(S, X[:, :2], 3)
 
 
+def test_trust_region_and_thompson_candidates():
+    """Trust region scaled by the length scales (volume-preserving weights, clipped to [-1, 1]) and the candidate set
+    of the Thompson step: inside the region, equal to the incumbent except in a random non-empty coordinate subset."""
+    from types import SimpleNamespace
+
+    from bogp_b200.baxus import BaxusState, _trust_region, thompson_candidates
+    torch.manual_seed(0)
+    d = 40
+    X = 2 * torch.rand(30, d, dtype=torch.float64) - 1
+    Y = torch.randn(30, dtype=torch.float64)
+    ls = torch.exp(torch.randn(d, dtype=torch.float64))
+    state = BaxusState(dim=206, eval_budget=400)
+    center, lb, ub = _trust_region(state, SimpleNamespace(lengthscale=ls), X, Y)
+    assert torch.equal(center, X[int(torch.argmax(Y))])
+    w = ls / ls.mean()
+    w = w / torch.prod(w.pow(1.0 / d))
+    assert abs(float(torch.prod(w.pow(1.0 / d))) - 1.0) < 1e-12
+    assert torch.allclose(lb, torch.clamp(center - w * state.length, -1, 1)) and torch.allclose(ub, torch.clamp(center + w * state.length, -1, 1))
+    assert torch.all(lb >= -1) and torch.all(ub <= 1) and torch.all(lb <= center) and torch.all(center <= ub)
+    Xc = thompson_candidates(center, lb, ub, 3000)
+    assert Xc.shape == (3000, d) and torch.all(Xc >= lb) and torch.all(Xc <= ub)
+    moved = (Xc != center).sum(1)
+    assert int(moved.min()) >= 1                                   # every candidate differs from the incumbent somewhere
+    assert 15.0 < float(moved.double().mean()) < 25.0              # 20 coordinates on average when dim > 20
+    assert int(moved.max()) < d                                    # and never all of them at dim = 40
+    Xc5 = thompson_candidates(center[:5], lb[:5], ub[:5], 500)
+    assert torch.all((Xc5 != center[:5]).sum(1) == 5)              # dim <= 20: every coordinate is perturbed
+
+
 def test_oracle_thompson_sample_properties():
     rng = np.random.default_rng(0)
     X = rng.uniform(-1, 1, (15, 2))
