@@ -34,6 +34,22 @@ def test_format_search_space_clipping_matches_reference_logic():
     np.testing.assert_allclose(sp.to_unit(sp.from_unit(u)), u, atol=1e-14)
 
 
+def test_format_search_space_matches_reference_code():
+    """Against the outputs of the reference's OWN ``format_search_space`` (optimization/utils.py:72-98), executed from its
+    source by tools/make_golden_frontend.py on the localisation / tilt search spaces and scenarios at and inside the
+    absolute limits -- this row of the front-end is pinned, not restated."""
+    import json
+    from pathlib import Path
+    g = json.loads((Path(__file__).parent / "golden" / "format_search_space.json").read_text())
+    assert len(g["cases"]) >= 12
+    for c in g["cases"]:
+        bounds = oao.SearchSpaceBounds(bounds=[oao.SearchParameterBounds(**b) for b in c["bounds"]])
+        sp = oao.format_search_space(bounds, c["scenario"])
+        got = [(p.name, p.type, [float(v) for v in p.bounds]) for p in sp.parameters]
+        want = [(p["name"], p["type"], [float(v) for v in p["bounds"]]) for p in c["parameters"]]
+        assert got == want, (c["space"], c["scenario"])
+
+
 def test_strategies_mirror_reference_signatures():
     s = GPEIStrategy(warmup_trials=8, warmup_parallelism=4, num_trials=3, max_parallelism=1, seed=7)()
     assert [st.model for st in s._steps] == [oao.Models.SOBOL, oao.Models.GPEI]
