@@ -9,6 +9,7 @@ cd "$(dirname "$0")/.."
 case "$1" in
   prepare)
     mkdir -p ab
+    if git diff --quiet; then echo "working tree has no changes against HEAD: nothing to compare"; exit 1; fi
     git stash -q
     python -c "from bogp_b200 import build; build.build()" > /dev/null
     cp bogp_b200/libbogp_sm100.so ab/old.so
