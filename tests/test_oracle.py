@@ -77,6 +77,21 @@ def test_gp_posterior_and_acq_match_sklearn_scipy(name, kind):
     np.testing.assert_allclose(logei[ok], np.log(g[f"{name}_ei"][ok]), rtol=1e-6, atol=1e-8)
 
 
+def test_workload_constants_match_reference_files(cfg1):
+    """Tonal sets, array geometry and the truth point of the synthetic configurations against the values read from the
+    reference's own files (tools/make_golden_constants.py -> tests/golden/reference_constants.json)."""
+    import json
+
+    from bogp_b200 import modes as M
+    g = json.loads((GOLD / "reference_constants.json").read_text())
+    assert M.INV_TONALS_3 == g["inv_tonals"] and M.SWELLEX_TONALS_13 == g["swellex_tonals_13"]
+    assert M.REC_Z_21 == g["rec_z_21"] and len(g["rec_z_21"]) == 21
+    assert np.array_equal(M.rec_z_64(), np.asarray(g["rec_z_64"])) and g["rec_z_64_linspace"] == [94.125, 212.25, 64]
+    assert (g["truth_r_km"], g["truth_src_z_m"]) == (1.07, 71.11)          # config 1's source (conftest cfg1)
+    assert [p["name"] for p in g["inv_search_space"]] == ["rec_r", "src_z", "tilt", "h_w", "h_sed", "c_p_sed_top", "dc_p_sed"]
+    assert cfg1["truth"] == (g["truth_r_km"], g["truth_src_z_m"])
+
+
 def test_acquisition_formulas_match_reference_code():
     """EI / UCB against the outputs of the reference's OWN numpy functions (bo_examples.py:61-84, :107-124), executed
     from its source by tools/make_golden_acq.py -- these two rows of the oracle are pinned, not recalled."""
