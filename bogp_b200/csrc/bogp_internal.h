@@ -46,6 +46,8 @@ inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
 // Pivoted Cholesky of a Hermitian PSD matrix A[n,n] (row-major): A ~= L L^H, L[n, rank] (row-major,
 // leading dimension n).  Stops when the largest remaining diagonal <= tol * max initial diagonal.
 int pivoted_cholesky(const std::vector<cplx>& A, int n, double tol, std::vector<cplx>& L, int& rank);
+// Same contract from the eigen-decomposition (optimal rank for the tolerance: eigenvalues above tol * lambda_max).
+int hermitian_eig_factor(const std::vector<cplx>& A, int n, double tol, std::vector<cplx>& L, int& rank);
 // Dense Cholesky A = L L^T (real SPD, row-major, lower); returns false if not PD.
 bool cholesky_lower(std::vector<double>& A, int n);
 // In-place inverse of a lower-triangular matrix (row-major).
@@ -119,6 +121,7 @@ struct bogp_modeset_s {
   std::vector<void*> cov_allocs;  // the five covariance-dependent device arrays (W, Wt, Wu, Ck re/im), reused while they fit
   std::vector<size_t> cov_capacity;
   // covariance-independent half of bogp_covariance_set, cached: pivoted Cholesky factor of G_f = Phi_f^H Phi_f
+  double rank_tol = 0.0;                 // relative eigenvalue below which directions of G = Phi^H Phi are dropped (0: pivoted Cholesky)
   std::vector<std::vector<bogp::cplx>> LG_cache;
   std::vector<int> rG_cache;
   // folded tcgen05 operator: R_f = LG_f^H (rG x M) and U_f = Phi_f R_f^+ (N x rG), both covariance-independent

@@ -77,6 +77,65 @@ int pivoted_cholesky(const std::vector<cplx>& A, int n, double tol, std::vector<
   return 0;
 }
 
+int hermitian_eig_factor(const std::vector<cplx>& A, int n, double tol, std::vector<cplx>& L, int& rank) {
+  // A = V diag(lambda) V^H by cyclic complex Jacobi rotations (n <= a few hundred, once per mode set); returns the
+  // optimal low-rank factor L = V_r diag(lambda_r)^1/2 over the eigenvalues above tol * lambda_max, columns in
+  // descending order, laid out like pivoted_cholesky's L ([n, n], column j = j-th factor column): A ~= L L^H with
+  // the FEWEST columns for a given accuracy (a pivoted Cholesky factor needs more for the same tolerance).
+  std::vector<cplx> B(A), V((size_t)n * n, cplx(0.0, 0.0));
+  for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
+  auto off2 = [&]() { double s = 0.0; for (int p = 0; p < n; ++p) for (int q = p + 1; q < n; ++q) s += std::norm(B[(size_t)p * n + q]); return s; };
+  double diag2 = 0.0;
+  for (int i = 0; i < n; ++i) diag2 += B[(size_t)i * n + i].real() * B[(size_t)i * n + i].real();
+  const double stop = 1e-30 * (diag2 + 2.0 * off2());
+  for (int sweep = 0; sweep < 60 && off2() > stop; ++sweep) {
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const cplx bpq = B[(size_t)p * n + q];
+        const double ab = std::abs(bpq);
+        if (ab == 0.0) continue;
+        const double app = B[(size_t)p * n + p].real(), aqq = B[(size_t)q * n + q].real();
+        if (ab <= 1e-18 * std::sqrt(std::fabs(app * aqq)) && sweep > 2) continue;
+        const cplx ph = bpq / ab;                       // e^{i phi}
+        const double theta = (aqq - app) / (2.0 * ab);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        const cplx sp = s * std::conj(ph), cp = c * std::conj(ph);     // J = [[c, s], [-s e^{-i phi}, c e^{-i phi}]]
+        for (int i = 0; i < n; ++i) {                   // B <- B J,  V <- V J  (columns p, q)
+          const cplx bp = B[(size_t)i * n + p], bq = B[(size_t)i * n + q];
+          B[(size_t)i * n + p] = c * bp - sp * bq;
+          B[(size_t)i * n + q] = s * bp + cp * bq;
+          const cplx vp = V[(size_t)i * n + p], vq = V[(size_t)i * n + q];
+          V[(size_t)i * n + p] = c * vp - sp * vq;
+          V[(size_t)i * n + q] = s * vp + cp * vq;
+        }
+        for (int j = 0; j < n; ++j) {                   // B <- J^H B  (rows p, q)
+          const cplx bp = B[(size_t)p * n + j], bq = B[(size_t)q * n + j];
+          B[(size_t)p * n + j] = c * bp - std::conj(sp) * bq;
+          B[(size_t)q * n + j] = s * bp + std::conj(cp) * bq;
+        }
+        B[(size_t)p * n + q] = B[(size_t)q * n + p] = 0.0;
+        B[(size_t)p * n + p] = B[(size_t)p * n + p].real();
+        B[(size_t)q * n + q] = B[(size_t)q * n + q].real();
+      }
+  }
+  std::vector<int> idx(n);
+  for (int i = 0; i < n; ++i) idx[i] = i;
+  std::sort(idx.begin(), idx.end(), [&](int a, int b) { return B[(size_t)a * n + a].real() > B[(size_t)b * n + b].real(); });
+  L.assign((size_t)n * n, cplx(0.0, 0.0));
+  rank = 0;
+  const double lmax = n ? B[(size_t)idx[0] * n + idx[0]].real() : 0.0;
+  if (!(lmax > 0.0)) return 0;
+  for (int j = 0; j < n; ++j) {
+    const double lam = B[(size_t)idx[j] * n + idx[j]].real();
+    if (!(lam > tol * lmax)) break;
+    const double sl = std::sqrt(lam);
+    for (int i = 0; i < n; ++i) L[(size_t)i * n + j] = V[(size_t)i * n + idx[j]] * sl;
+    rank = j + 1;
+  }
+  return 0;
+}
+
 bool cholesky_lower(std::vector<double>& A, int n) {
   // Row-oriented (Cholesky-Banachiewicz): inner dot products run along contiguous rows.
   for (int i = 0; i < n; ++i) {
