@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libbogp_sm100.so"
 STAMP = PKG / ".libbogp_sm100.stamp"
-SOURCES = ["hostmath.cu", "api_mfp.cu", "kernels_simt.cu", "kernels_umma.cu", "kernels_env.cu", "kernels_gp.cu", "kernels_gpfit.cu", "kernels_ts.cu", "kernels_peer.cu"]
+SOURCES = ["hostmath.cu", "api_mfp.cu", "kernels_simt.cu", "kernels_umma.cu", "kernels_umma16.cu", "kernels_env.cu", "kernels_gp.cu", "kernels_gpfit.cu", "kernels_ts.cu", "kernels_peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

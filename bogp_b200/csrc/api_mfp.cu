@@ -128,6 +128,8 @@ extern "C" int bogp_modeset_create(bogp_modeset_t* out, int F, int N, const int*
   h->F = F; h->N = N;
   h->M.assign(M_host, M_host + F);
   h->phi_rec.resize(F);
+  h->u16.k_host.resize(F);
+  h->u16.phi_max.assign(F, 0.f);
 
   int sumMp = 0, sumTab = 0, sumRec = 0;
   for (int f = 0; f < F; ++f) {
@@ -155,6 +157,7 @@ extern "C" int bogp_modeset_create(bogp_modeset_t* out, int F, int N, const int*
       cplx c = 1.0 / std::sqrt(cplx(k_re_host[ik + m], k_im_host[ik + m]));
       cre[t.offM + m] = (float)c.real();
       cim[t.offM + m] = (float)c.imag();
+      h->u16.k_host[f].push_back(cplx(k_re_host[ik + m], k_im_host[ik + m]));
     }
     h->phi_rec[f].resize((size_t)N * t.M);
     for (int n = 0; n < N; ++n)
@@ -170,6 +173,7 @@ extern "C" int bogp_modeset_create(bogp_modeset_t* out, int F, int N, const int*
     for (int i = 0; i < nz_tab; ++i)
       for (int m = 0; m < t.M; ++m) {
         tab_re[t.offTab + (size_t)i * t.Mp + m] = (float)phi_src_re_host[isrc + (size_t)i * t.M + m];
+        h->u16.phi_max[f] = std::max(h->u16.phi_max[f], std::fabs((float)phi_src_re_host[isrc + (size_t)i * t.M + m]));
         if (d.src_complex) tab_im[t.offTab + (size_t)i * t.Mp + m] = (float)phi_src_im_host[isrc + (size_t)i * t.M + m];
       }
     ik += t.M; irec += (size_t)N * t.M; isrc += (size_t)nz_tab * t.M;
@@ -198,6 +202,9 @@ extern "C" int bogp_modeset_destroy(bogp_modeset_t h) {
   if (h->grid_scratch) cudaFree(h->grid_scratch);
   if (h->io_scratch) cudaFree(h->io_scratch);
   if (h->pin_host) cudaFreeHost(h->pin_host);
+  if (h->u16.E) cudaFree(h->u16.E);
+  if (h->u16.B) cudaFree(h->u16.B);
+  if (h->u16.misc) cudaFree(h->u16.misc);
   delete h;
   return 0;
 }
@@ -481,6 +488,11 @@ extern "C" int bogp_covariance_set(bogp_modeset_t h, const double* K_re_host, co
       }
     h->max_rows = std::max(h->max_rows, t.rows);
     h->max_J = std::max(h->max_J, t.J);
+  }
+  h->u16.wu_max.assign(F, 0.f);
+  for (int f = 0; f < F; ++f) {
+    const bogp::TonalMeta& t = d.t[f];
+    for (size_t i = 0; i < (size_t)t.u_rowsP * t.Mp; ++i) h->u16.wu_max[f] = std::max(h->u16.wu_max[f], std::fabs(Wu[t.offWu + i]));
   }
   // kernels of a previous call may still be reading the arrays that are overwritten in place below
   BOGP_CUDA(cudaDeviceSynchronize());

@@ -143,6 +143,16 @@ struct bogp_modeset_s {
   unsigned char* pin_host = nullptr;
   unsigned char* pin_dev = nullptr;
   size_t pin_bytes = 0;
+  // FP16-split tcgen05 engine (kernels_umma16.cu): operand magnitudes for the per-tonal scales, its own device buffers,
+  // and the range vector the cached E table was built for
+  struct U16 {
+    std::vector<float> wu_max, phi_max;             // per tonal: max |Wu|, max |phi_src table|
+    std::vector<std::vector<bogp::cplx>> k_host;    // per tonal wavenumbers
+    void* E = nullptr; size_t E_bytes = 0;
+    void* B = nullptr; size_t B_bytes = 0;
+    void* misc = nullptr; size_t misc_bytes = 0;
+    std::vector<double> r_cached;
+  } u16;
 };
 
 namespace bogp {
@@ -166,6 +176,10 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
                           const double* tilt_host, int Nt, int atype, int mf, float* out_dev, cudaStream_t s,
                           int ext_mode = 0, float* ext_val_dev = nullptr, long long* ext_idx_dev = nullptr);
 int ensure_scratch(bogp_modeset_s* h, size_t bytes);
+// kernels_umma16.cu: the same surface with FP16-split operands (the default tcgen05 engine for a vertical array)
+bool umma16_supported(const bogp_modeset_s* h);
+int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype, int mf,
+                       float* out_dev, cudaStream_t s, int ext_mode, float* ext_val_dev, long long* ext_idx_dev);
 }  // namespace bogp
 
 // GP posterior handle (kernels_gp.cu creates it; kernels_ts.cu samples from it)

@@ -1,0 +1,770 @@
+// K1-UMMA-H: the separable (range x depth) Bartlett surface on the tcgen05 tensor cores with FP16-split operands.
+//
+// Same mathematics as kernels_umma.cu (mode-space operator, D[i, row] = sum_m E_f^T[i, m] * Bop[row, m], fused Bartlett
+// epilogue), different arithmetic and pipeline:
+//   * Operands are split x * 2^s = hi + lo into two FP16 numbers (s: a per-tonal power of two that puts the largest
+//     magnitude at 2^14, so hi and lo carry 11 significant bits each down to an absolute floor of 2^-38 of the largest
+//     value) and D = A_lo B_hi + A_hi B_lo + A_hi B_hi accumulates in fp32 in TMEM: the same three products and the same
+//     22-bit operand precision as the 3xTF32 split (both drop the lo * lo term, 2^-22), at the kind::f16 rate (K = 16
+//     per instruction: half the MMA instructions and half the operand bytes of kind::tf32).  The Bartlett value is a
+//     ratio of two quadratic forms of the same scaled D, so the scales cancel.
+//   * A = E_f^T comes from SHARED memory (one bulk copy per (range tile, tonal) of a table kept across calls for the
+//     same range vector), stages are N = 128 wide (8 depths of a 16-row tonal, 4 of a 32-row tonal): at N = 128 an MMA
+//     with A in shared memory runs at the full N/2 cycles (tools/micro/tc_peak.cu), the whole of TMEM is accumulators
+//     (2 buffers x (re | im) x 128 columns), and a stage carries twice the work of the TF32 kernel's N = 64 stage per
+//     barrier hand-shake -- the small tonals of that kernel were bound by the hand-shakes, not by the tensor pipe.
+//   * All 16 epilogue warps drain EVERY stage (4 per TMEM lane quadrant, depth j -> warp j % 4): a buffer is held for one
+//     TMEM round trip, and since a depth always belongs to the same warp the multi-frequency accumulation needs no
+//     ordering between warps and the write-out no block barrier.
+// Replaces the loop `for z in src_z: amb[zz,:] = MFP({"src_z": z, "rec_r": rvec})`
+// (ref/projects/swellex96_localization/data/mfp.py:213-214) for a vertical array.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include <cuda_fp16.h>
+
+#include "bogp_internal.h"
+#include "device_math.cuh"
+#include "umma_ptx.cuh"
+
+namespace bogp {
+namespace {
+
+constexpr int kTile = 128;              // ranges per tile = MMA M = TMEM lanes
+constexpr int kNA = 128;                // accumulator columns per part; buffer b = columns [256 b, 256 b + 256): re | im
+constexpr int kMaxStages = 6;           // Bop ring depth (as many as fit)
+constexpr int kEpiW = 16;               // epilogue warps: 4 TMEM lane quadrants x 4 depth residues
+constexpr int kProdW = 16;              // Bop producer
+constexpr int kIssW0 = 17, kIssW1 = 18; // MMA issuers (stage parity)
+constexpr int kAProdW = 19;             // E-image producer
+constexpr int kThr = 20 * 32;
+constexpr unsigned kSmemMax = 227u * 1024u;
+constexpr float kTargetMax = 16384.f;   // 2^14: largest scaled operand magnitude (fp16 max 65504)
+
+struct HTonal {
+  int Kp, rowsP;               // modes padded to 16, operator rows padded to 16
+  int nq, n1, nj, fold, src;
+  unsigned a_bytes, a_off;     // E image of one range tile: 1024 Kp bytes = [re_hi | re_lo | im_hi | im_lo] x [128 x Kp] halves
+  unsigned b_zbytes;           // rowsP * Kp * 2: one depth of one split of Bop
+  unsigned long long b_off;
+  float trK, c1r, c1i, c2r, c2i;
+  float sE, sB;                // operand scales (powers of two)
+};
+
+struct HParams {
+  int F, Nr, Nz, nrt, ZC, units, atype, mf, S, two_slot;
+  unsigned e_rt_stride, stage_bytes, AR, smem_B, smem_acc, smem_bar;
+  const unsigned char* E;
+  const unsigned char* Bhi;
+  const unsigned char* Blo;
+  float* out;
+  int* err;
+  int ext_mode;
+  unsigned long long* ext_key;
+  unsigned int* ext_done;
+  float* ext_val;
+  long long* ext_idx;
+  HTonal t[BOGP_MAX_TONALS];
+};
+
+// barrier slots (8 bytes each) at smem_bar
+enum { BAR_BFULL = 0, BAR_BEMPTY = kMaxStages, BAR_AFULL = 2 * kMaxStages, BAR_ADONE = 2 * kMaxStages + 2,
+       BAR_TFULL = 2 * kMaxStages + 4, BAR_TEMPTY = 2 * kMaxStages + 6, BAR_TURN = 2 * kMaxStages + 8, BAR_COUNT = 2 * kMaxStages + 10 };
+
+// kind::f16 MMA, both operands from shared memory; the 64-bit descriptors are passed as halves (A and B share the high
+// half: same LBO / SBO for K-major no-swizzle blocks of the same Kp).
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                           bool accumulate) {
+  if (accumulate)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+}
+
+// All MMAs of one stage: per K step of 16 modes, D += A_lo B_hi + A_hi B_lo + A_hi B_hi for the re and im accumulators.
+// a0 = descriptor low word of the image's first block (re_hi); blocks follow at `blk` (16-byte units): re_lo, im_hi, im_lo.
+template <int KS>
+__device__ __forceinline__ void issue_stage16(uint32_t d_re, uint32_t d_im, uint32_t a0, uint32_t blk, uint32_t bh, uint32_t bl,
+                                              uint32_t desc_hi, uint32_t idesc) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(a0));
+  asm volatile("mov.u32 %0, %0;" : "+r"(bh));
+  asm volatile("mov.u32 %0, %0;" : "+r"(bl));
+#pragma unroll
+  for (int part = 0; part < 2; ++part) {
+    const uint32_t d = part ? d_im : d_re;
+    const uint32_t a_hi = a0 + (uint32_t)(2 * part) * blk, a_lo = a_hi + blk;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      mma_f16_ss(d, a_lo + 16u * ks, bh + 16u * ks, desc_hi, idesc, ks > 0);
+      mma_f16_ss(d, a_hi + 16u * ks, bl + 16u * ks, desc_hi, idesc, true);
+      mma_f16_ss(d, a_hi + 16u * ks, bh + 16u * ks, desc_hi, idesc, true);
+    }
+  }
+}
+
+// shared-memory offset of tonal g's E image: even tonals at the low end of the A region, odd ones at the high end
+__device__ __forceinline__ uint32_t a_offset(const HParams& p, int g, unsigned a_bytes) {
+  return (g & 1) ? p.AR - a_bytes : 0u;
+}
+
+struct IssState {
+  const HParams* p;
+  uint32_t tmem_base, s_base, bar0;
+  uint32_t sc;
+  int g, nzu, id;
+};
+
+template <int KS>
+__device__ __forceinline__ void issue_tonal(IssState& st, const HTonal& u) {
+  const HParams& p = *st.p;
+  const uint32_t Kp = 16u * KS;
+  // K-major, no swizzle: LBO (next 16-byte K chunk) = 128 B, SBO (next 8-row group) = 16 Kp B
+  const uint32_t desc_hi = (uint32_t)(make_desc(0, 128u, 16u * Kp) >> 32);
+  const uint32_t desc_lo0 = (uint32_t)make_desc(0, 128u, 16u * Kp);
+  const uint32_t idesc0 = (1u << 4) | ((kTile >> 4) << 24);       // D fp32, A / B fp16 (format 0), K-major both
+  auto bar = [&](int i) { return st.bar0 + 8u * (uint32_t)i; };
+  mbar_wait(bar(BAR_AFULL + (st.g & 1)), (uint32_t)((st.g >> 1) & 1), p.err, 4);
+  const uint32_t a_addr = st.s_base + a_offset(p, st.g, u.a_bytes);
+  const uint32_t a0 = desc_lo0 | ((a_addr >> 4) & 0x3fffu);
+  const uint32_t blk = 16u * Kp;                                    // 256 Kp bytes per block, in 16-byte units
+  const int nj = u.nj, nzu = st.nzu;
+  uint32_t sc = st.sc;
+#pragma unroll 1
+  for (int j0 = 0; j0 < nzu; j0 += nj, ++sc) {
+    if ((int)(sc & 1u) != st.id) continue;
+    const int njs = min(nj, nzu - j0);
+    const uint32_t slot = sc % (uint32_t)p.S, ph = (sc / (uint32_t)p.S) & 1u;
+    const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
+    mbar_wait(bar(BAR_BFULL + slot), ph, p.err, 5);
+    mbar_wait(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6);
+    tc_fence_after();
+    const uint32_t N = (uint32_t)(njs * u.rowsP);
+    const uint32_t idesc = idesc0 | ((N >> 3) << 17);
+    const uint32_t b_hi = st.s_base + p.smem_B + slot * p.stage_bytes;
+    const uint32_t b_lo = b_hi + (uint32_t)njs * u.b_zbytes;
+    const uint32_t d_re = st.tmem_base + buf * (uint32_t)(2 * kNA), d_im = d_re + (uint32_t)kNA;
+    // stages enter the tensor pipe in order (see kernels_umma.cu: without the turn both buffers reach the epilogue together)
+    if (sc > 0) mbar_wait(bar(BAR_TURN + (st.id ^ 1)), ((sc - 1u) >> 1) & 1u, p.err, 8);
+    if (elect_one()) {
+      issue_stage16<KS>(d_re, d_im, a0, blk, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc);
+      mbar_arrive(bar(BAR_TURN + st.id));
+      tc_commit(bar(BAR_BEMPTY + slot));
+      tc_commit(bar(BAR_TFULL + buf));
+    }
+    __syncwarp();
+  }
+  st.sc = sc;
+  if (elect_one()) tc_commit(bar(BAR_ADONE + (st.g & 1)));
+  __syncwarp();
+}
+
+// Bartlett value of one depth slot from its accumulator columns (real receiver modes: every |T|^2 term is a plain
+// square; the numerator sits in the first two columns -- folded operator -- or in the nq leading (re, im) row pairs).
+struct EpiTonal {
+  float c1r, c1i, c2r, c2i, trK;
+  int fold, nq, atype;
+};
+__device__ __forceinline__ void numer_first(const EpiTonal& e, const float* re, const float* im, float& num, float& numsq) {
+  if (e.fold) {
+    const float tr = fmaf(e.c1r, re[0], fmaf(-e.c1i, im[0], fmaf(e.c2r, re[1], -e.c2i * im[1])));
+    const float ti = fmaf(e.c1r, im[0], fmaf(e.c1i, re[0], fmaf(e.c2r, im[1], e.c2i * re[1])));
+    num = fmaf(tr, tr, ti * ti);
+    numsq = 0.f;
+  } else if (e.nq == 1) {
+    const float tr = re[0] - im[1], ti = im[0] + re[1];
+    num = fmaf(tr, tr, ti * ti);
+    numsq = fmaf(re[0], re[0], fmaf(im[0], im[0], fmaf(re[1], re[1], im[1] * im[1])));
+  } else {
+    num = 0.f; numsq = 0.f;
+    numerator16(re, im, e.nq, num, numsq);
+  }
+}
+__device__ __forceinline__ void sq16(const float* re, const float* im, unsigned long long& t0, unsigned long long& t1,
+                                     unsigned long long& t2, unsigned long long& t3) {
+#pragma unroll
+  for (int q = 0; q < 16; q += 4) {
+    sq_acc2(t0, re[q], re[q + 1]);
+    sq_acc2(t1, im[q], im[q + 1]);
+    sq_acc2(t2, re[q + 2], re[q + 3]);
+    sq_acc2(t3, im[q + 2], im[q + 3]);
+  }
+}
+
+__global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_constant__ HParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t bar0 = s_base + p.smem_bar;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.smem_bar + BAR_COUNT * 8);
+  auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar(BAR_BFULL + s), 1); mbar_init(bar(BAR_BEMPTY + s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(BAR_AFULL + b), 1);
+      mbar_init(bar(BAR_ADONE + b), 2);          // both issuers commit
+      mbar_init(bar(BAR_TFULL + b), 1);
+      mbar_init(bar(BAR_TURN + b), 1);
+      mbar_init(bar(BAR_TEMPTY + b), kEpiW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kIssW0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == kProdW) {
+    // ============================================================== Bop producer
+    uint32_t sc = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int zc = unit / p.nrt, z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
+      for (int f = 0; f < p.F; ++f) {
+        const HTonal& u = p.t[f];
+        for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
+          const int njs = min(u.nj, nzu - j0);
+          const uint32_t slot = sc % (uint32_t)p.S, ph = (sc / (uint32_t)p.S) & 1u;
+          mbar_wait_relaxed<128>(bar(BAR_BEMPTY + slot), ph ^ 1u, p.err, 3);
+          const uint32_t bytes = (uint32_t)njs * u.b_zbytes;
+          const uint32_t dst = s_base + p.smem_B + slot * p.stage_bytes;
+          const size_t src = (size_t)u.b_off + (size_t)(z0 + j0) * u.b_zbytes;
+          if (elect_one()) {
+            mbar_expect_tx(bar(BAR_BFULL + slot), 2 * bytes);
+            bulk_g2s(dst, p.Bhi + src, bytes, bar(BAR_BFULL + slot));
+            bulk_g2s(dst + bytes, p.Blo + src, bytes, bar(BAR_BFULL + slot));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == kAProdW) {
+    // ============================================================== E-image producer (one bulk copy per tonal, one tonal ahead)
+    int g = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int rt = unit % p.nrt;
+      for (int f = 0; f < p.F; ++f, ++g) {
+        const HTonal& u = p.t[f];
+        if (g >= 2) mbar_wait_relaxed<256>(bar(BAR_ADONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1);
+        if (g >= 1) {
+          const HTonal& up = p.t[f == 0 ? p.F - 1 : f - 1];
+          if (up.a_bytes + u.a_bytes > p.AR)
+            mbar_wait_relaxed<256>(bar(BAR_ADONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2);
+        }
+        if (elect_one()) {
+          mbar_expect_tx(bar(BAR_AFULL + (g & 1)), u.a_bytes);
+          bulk_g2s(s_base + a_offset(p, g, u.a_bytes), p.E + (size_t)rt * p.e_rt_stride + u.a_off, u.a_bytes, bar(BAR_AFULL + (g & 1)));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kIssW0 || warp == kIssW1) {
+    // ============================================================== MMA issuers
+    IssState st{};
+    st.id = warp == kIssW0 ? 0 : 1;
+    st.p = &p; st.tmem_base = tmem_base; st.s_base = s_base; st.bar0 = bar0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int zc = unit / p.nrt, z0 = zc * p.ZC;
+      st.nzu = min(p.ZC, p.Nz - z0);
+      for (int f = 0; f < p.F; ++f, ++st.g) {
+        switch (p.t[f].Kp >> 4) {
+          case 1: issue_tonal<1>(st, p.t[f]); break;
+          case 2: issue_tonal<2>(st, p.t[f]); break;
+          case 3: issue_tonal<3>(st, p.t[f]); break;
+          default: issue_tonal<4>(st, p.t[f]); break;
+        }
+      }
+    }
+  } else {
+    // ============================================================== epilogue
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may read
+    const int sub = warp >> 2;               // depth residue: this warp owns the depths j with j % 4 == sub
+    const int tl = quad * 32 + lane;
+    const uint32_t t_lane0 = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float* acc = reinterpret_cast<float*>(smem + p.smem_acc);     // [ZC][128]
+    uint32_t sc = 0;
+    for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+      const int rt = unit % p.nrt, zc = unit / p.nrt;
+      const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
+      for (int f = 0; f < p.F; ++f) {
+        const HTonal& u = p.t[f];
+        const int rowsP = u.rowsP;
+        EpiTonal et;
+        et.c1r = u.c1r; et.c1i = u.c1i; et.c2r = u.c2r; et.c2i = u.c2i; et.trK = u.trK; et.fold = u.fold; et.nq = u.nq; et.atype = p.atype;
+        const bool fast = (u.n1 == 2 * u.nq) && u.nq <= 8;
+        const bool simple = fast && (u.nq == 1 || u.fold);
+        auto store = [&](int j, float num, float norm) {
+          const float b = __fdividef(num, norm);
+          const float val = et.atype == BOGP_ATYPE_CBF ? b : et.trK - b;
+          float* a = acc + (size_t)j * kTile + tl;
+          *a = (f == 0) ? val : (p.mf == BOGP_MF_MEAN ? *a + val : *a * val);
+        };
+        for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
+          const int njs = min(u.nj, nzu - j0);
+          const uint32_t buf = sc & 1u;
+          const uint32_t t_lane = t_lane0 + buf * (uint32_t)(2 * kNA);
+          mbar_wait(bar(BAR_TFULL + buf), (sc >> 1) & 1u, p.err, 7);
+          tc_fence_after();
+          const int s_first = (sub - (j0 & 3) + 4) & 3;      // first slot of this stage with (j0 + s) % 4 == sub
+          bool released = false;
+          if ((p.two_slot & 1) && simple && rowsP == 16 && s_first + 4 < njs && s_first + 8 >= njs) {
+            // two 16-column slots: all four loads in flight, one wait, release, then the arithmetic
+            const int sA = s_first, sB = s_first + 4;
+            float reA[16], imA[16], reB[16], imB[16];
+            const uint32_t tA = t_lane + (uint32_t)(sA * 16), tB = t_lane + (uint32_t)(sB * 16);
+            tc_ld16(tA, reA); tc_ld16(tA + kNA, imA);
+            tc_ld16(tB, reB); tc_ld16(tB + kNA, imB);
+            tc_wait_ld();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+            released = true;
+            {
+              float num, numsq;
+              numer_first(et, reA, imA, num, numsq);
+              unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
+              sq16(reA, imA, t0, t1, t2, t3);
+              store(j0 + sA, num, ((sum2(t0) + sum2(t1)) + (sum2(t2) + sum2(t3))) - numsq);
+            }
+            {
+              float num, numsq;
+              numer_first(et, reB, imB, num, numsq);
+              unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
+              sq16(reB, imB, t0, t1, t2, t3);
+              store(j0 + sB, num, ((sum2(t0) + sum2(t1)) + (sum2(t2) + sum2(t3))) - numsq);
+            }
+          } else if ((p.two_slot & 2) && simple && rowsP == 32 && s_first < njs && s_first + 4 >= njs) {
+            // one slot of two 16-column chunks: all four loads in flight, one wait
+            float reA[16], imA[16], reB[16], imB[16];
+            const uint32_t tA = t_lane + (uint32_t)(s_first * 32);
+            tc_ld16(tA, reA); tc_ld16(tA + kNA, imA);
+            tc_ld16(tA + 16u, reB); tc_ld16(tA + kNA + 16u, imB);
+            tc_wait_ld();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+            released = true;
+            float num, numsq;
+            numer_first(et, reA, imA, num, numsq);
+            unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
+            sq16(reA, imA, t0, t1, t2, t3);
+            sq16(reB, imB, t0, t1, t2, t3);
+            store(j0 + s_first, num, ((sum2(t0) + sum2(t1)) + (sum2(t2) + sum2(t3))) - numsq);
+          } else {
+            for (int s = s_first; s < njs; s += 4) {
+              const bool last_slot = s + 4 >= njs;
+              const uint32_t t_re = t_lane + (uint32_t)(s * rowsP);
+              float norm = 0.f, num = 0.f;
+              if (fast) {
+                unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
+                float numsq = 0.f;
+                const int c_last = rowsP - 16;
+                for (int c0 = 0; c0 <= c_last; c0 += 16) {
+                  float re[16], im[16];
+                  tc_ld16(t_re + (uint32_t)c0, re);
+                  tc_ld16(t_re + kNA + (uint32_t)c0, im);
+                  tc_wait_ld();
+                  if (last_slot && c0 == c_last) {
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+                    released = true;
+                  }
+                  if (c0 == 0) numer_first(et, re, im, num, numsq);
+                  sq16(re, im, t0, t1, t2, t3);
+                }
+                norm = ((sum2(t0) + sum2(t1)) + (sum2(t2) + sum2(t3))) - numsq;
+              } else {
+                // complex receiver modes / general layout: (re, im) row pairs below n1, plain rows from n1 on
+                const int nq2 = 2 * u.nq, n1 = u.n1;
+                for (int c0 = 0; c0 < rowsP; c0 += 16) {
+                  float re[16], im[16];
+                  tc_ld16(t_re + (uint32_t)c0, re);
+                  tc_ld16(t_re + kNA + (uint32_t)c0, im);
+                  tc_wait_ld();
+                  if (last_slot && c0 + 16 >= rowsP) {
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+                    released = true;
+                  }
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const int c = c0 + 2 * q;
+                    const float r0 = re[2 * q], r1 = re[2 * q + 1], i0 = im[2 * q], i1 = im[2 * q + 1];
+                    if (c >= n1) {
+                      norm += r0 * r0 + i0 * i0 + r1 * r1 + i1 * i1;
+                    } else {
+                      const float tr = r0 - i1, ti = i0 + r1;
+                      const float v = tr * tr + ti * ti;
+                      if (c < nq2) num += v; else norm += v;
+                    }
+                  }
+                }
+              }
+              store(j0 + s, num, norm);
+            }
+          }
+          if (!released) {      // no slot of this stage belongs to this warp
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+          }
+        }
+      }
+      // write-out: this warp's own depths (j % 4 == sub), nobody else touched them -- no barrier
+      __syncwarp();
+      const int i = rt * kTile + tl;
+      const float scale = p.mf == BOGP_MF_MEAN ? 1.f / (float)p.F : 1.f;
+      unsigned long long best = 0ull;
+      if (i < p.Nr)
+        for (int j = sub; j < nzu; j += 4) {
+          const float v = acc[(size_t)j * kTile + tl] * scale;
+          p.out[(size_t)(z0 + j) * p.Nr + i] = v;
+          if (p.ext_mode && v == v) {
+            uint32_t uu = __float_as_uint(v);
+            uu = (uu & 0x80000000u) ? ~uu : (uu | 0x80000000u);         // order-preserving map float -> uint32
+            if (p.ext_mode == 2) uu = ~uu;                               // arg-min: largest key = smallest value
+            const unsigned long long key = ((unsigned long long)uu << 32) | (0xffffffffu - ((uint32_t)(z0 + j) * (uint32_t)p.Nr + (uint32_t)i));
+            best = key > best ? key : best;                              // ties: lowest flat index (np.argmax rule)
+          }
+        }
+      if (p.ext_mode) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+          best = other > best ? other : best;
+        }
+        if (lane == 0 && best) atomicMax(p.ext_key, best);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.ext_mode && threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(p.ext_done, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const unsigned long long key = atomicMax(p.ext_key, 0ull);
+      if (key == 0ull) { *p.ext_val = 0.f; *p.ext_idx = -1; }
+      else {
+        uint32_t uu = (uint32_t)(key >> 32);
+        if (p.ext_mode == 2) uu = ~uu;
+        uu = (uu & 0x80000000u) ? (uu & 0x7fffffffu) : ~uu;
+        *p.ext_val = __uint_as_float(uu);
+        *p.ext_idx = (long long)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
+      }
+    }
+  }
+  if (warp == kIssW0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ operand tables
+// byte offset of the 16-byte chunk (row, K chunk kc) inside a K-major no-swizzle block with nch chunks per row
+__device__ __forceinline__ size_t chunk_off(int row, int kc, int nch) {
+  return ((size_t)((row >> 3) * nch + kc) * 8 + (row & 7)) * 16;
+}
+// x (already scaled) -> fp16 hi + fp16 lo, packed two modes per 32-bit word
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half h0 = __float2half_rn(x[2 * e]), h1 = __float2half_rn(x[2 * e + 1]);
+    const __half l0 = __float2half_rn(x[2 * e] - __half2float(h0)), l1 = __float2half_rn(x[2 * e + 1] - __half2float(h1));
+    h[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    l[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// E images: per (range tile, tonal) four blocks [re_hi | re_lo | im_hi | im_lo], each the [128 ranges x Kp] matrix
+// E_f^T * sE in K-major no-swizzle order.  E[m, i] = exp(-i k_m r_i) / sqrt(k_m r_i) in float64 (k r reaches 1.6e4 rad).
+// One thread = one (range, 8-mode chunk).  Kept across calls while the range vector is the same (the reference sweeps
+// one grid over all time steps of an event, ref/projects/swellex96_localization/data/mfp.py:166-216).
+constexpr int kETabRows = 32;
+__global__ void __launch_bounds__(128) umma16_E_kernel(ModesetDev ms, HParams p, const double* __restrict__ r) {
+  __shared__ double2 kinv[64];
+  const int per_f = p.nrt * (kTile / kETabRows);
+  const int f = blockIdx.x / per_f, rem = blockIdx.x % per_f;
+  const int rt = rem / (kTile / kETabRows), row0 = (rem % (kTile / kETabRows)) * kETabRows;
+  const HTonal& u = p.t[f];
+  const TonalMeta& t = ms.t[u.src];
+  for (int m = threadIdx.x; m < u.Kp; m += blockDim.x) {
+    double cr = 0.0, ci = 0.0;
+    if (m < t.M) {
+      const double kre = ms.k_re[t.offM + m], kim = ms.k_im[t.offM + m];
+      const double mag = rsqrt(sqrt(kre * kre + kim * kim)), ang = -0.5 * atan2(kim, kre);
+      sincos(ang, &ci, &cr);
+      cr *= mag; ci *= mag;
+    }
+    kinv[m] = make_double2(cr, ci);
+  }
+  __syncthreads();
+  const int nch = u.Kp >> 3;
+  unsigned char* base = const_cast<unsigned char*>(p.E) + (size_t)rt * p.e_rt_stride + u.a_off;
+  const size_t blk = (size_t)256 * u.Kp;
+  const double sE = (double)u.sE;
+  for (int idx = threadIdx.x; idx < kETabRows * nch; idx += blockDim.x) {
+    const int row = row0 + (idx % kETabRows), kc = idx / kETabRows, i = rt * kTile + row;
+    float xr[8], xi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int m = kc * 8 + e;
+      double vr = 0.0, vi = 0.0;
+      if (i < p.Nr && m < t.M) {
+        const double kre = ms.k_re[t.offM + m], kim = ms.k_im[t.offM + m], rr = r[i];
+        double s, c;
+        sincos(kre * rr, &s, &c);
+        const double amp = exp(kim * rr) * rsqrt(rr) * sE;
+        const double2 q = kinv[m];
+        vr = amp * (q.x * c + q.y * s);          // (q.x + i q.y) (c - i s)
+        vi = amp * (q.y * c - q.x * s);
+      }
+      xr[e] = (float)vr; xi[e] = (float)vi;
+    }
+    uint4 rh, rl, ih, il;
+    split8(xr, rh, rl);
+    split8(xi, ih, il);
+    const size_t o = chunk_off(row, kc, nch);
+    *reinterpret_cast<uint4*>(base + o) = rh;
+    *reinterpret_cast<uint4*>(base + blk + o) = rl;
+    *reinterpret_cast<uint4*>(base + 2 * blk + o) = ih;
+    *reinterpret_cast<uint4*>(base + 3 * blk + o) = il;
+  }
+}
+
+// Bop tables: per (tonal, depth) the block W_f diag(phi(z_j)) * sB, [rowsP x Kp] halves in K-major no-swizzle order, hi
+// and lo arrays.  One block = kBDepths depths of one tonal; a thread keeps its 8-mode chunks of W_f in registers.
+constexpr int kBDepths = 8;
+constexpr int kBThreads = 128;
+__global__ void __launch_bounds__(kBThreads) umma16_B_kernel(ModesetDev ms, HParams p, const double* __restrict__ z) {
+  __shared__ __align__(16) float phi_s[kBDepths][64];
+  const int nzb = (p.Nz + kBDepths - 1) / kBDepths;
+  const int f = blockIdx.x / nzb, j0 = (blockIdx.x % nzb) * kBDepths;
+  const HTonal& u = p.t[f];
+  const TonalMeta& t = ms.t[u.src];
+  const int nd = min(kBDepths, p.Nz - j0), tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid == 0) { *p.err = 0; if (p.ext_mode) { *p.ext_key = 0ull; *p.ext_done = 0u; } }
+  for (int e = tid; e < nd * u.Kp; e += kBThreads) {
+    const int dj = e / u.Kp, m = e - dj * u.Kp;
+    float v = 0.f;
+    if (m < t.M) {
+      int i0; float w;
+      depth_index(z[j0 + dj], ms.z0, ms.dz, ms.nz_tab, i0, w);
+      const float* tr = ms.tab_re + t.offTab + (size_t)i0 * t.Mp + m;
+      v = fmaf(w, __ldg(tr + t.Mp) - __ldg(tr), __ldg(tr)) * u.sB;
+    }
+    phi_s[dj][m] = v;
+  }
+  __syncthreads();
+  const int nch = u.Kp >> 3, n_q = u.rowsP * nch;
+  const size_t zstride = (size_t)u.b_zbytes;
+  unsigned char* Bhi = const_cast<unsigned char*>(p.Bhi) + u.b_off + (size_t)j0 * zstride;
+  unsigned char* Blo = const_cast<unsigned char*>(p.Blo) + u.b_off + (size_t)j0 * zstride;
+  for (int q = tid; q < n_q; q += kBThreads) {
+    const int pc = q >> 3, kc = pc % nch, rg = pc / nch, row = rg * 8 + (q & 7);
+    float w[8];
+    if (kc * 8 < t.Mp) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ms.Wu + t.offWu + (size_t)row * t.Mp + kc * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ms.Wu + t.offWu + (size_t)row * t.Mp + kc * 8) + 1);
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] = 0.f;
+    }
+    for (int dj = 0; dj < nd; ++dj) {
+      const float4 pa = *reinterpret_cast<const float4*>(&phi_s[dj][kc * 8]), pb = *reinterpret_cast<const float4*>(&phi_s[dj][kc * 8 + 4]);
+      const float x[8] = {w[0] * pa.x, w[1] * pa.y, w[2] * pa.z, w[3] * pa.w, w[4] * pb.x, w[5] * pb.y, w[6] * pb.z, w[7] * pb.w};
+      uint4 hi, lo;
+      split8(x, hi, lo);
+      *reinterpret_cast<uint4*>(Bhi + (size_t)dj * zstride + (size_t)q * 16) = hi;
+      *reinterpret_cast<uint4*>(Blo + (size_t)dj * zstride + (size_t)q * 16) = lo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int device_sms16() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+float pow2_scale(double bound) {
+  if (!(bound > 0.0) || !std::isfinite(bound)) return 1.f;
+  return (float)std::ldexp(1.0, (int)std::floor(std::log2((double)kTargetMax / bound)));
+}
+
+// smallest, largest, second smallest, ... by padded mode count: consecutive E images fit side by side in the A region
+void tonal_order16(const ModesetDev& d, int* order) {
+  int idx[BOGP_MAX_TONALS];
+  for (int f = 0; f < d.F; ++f) idx[f] = f;
+  std::stable_sort(idx, idx + d.F, [&](int a, int b) { return d.t[a].M < d.t[b].M; });
+  const char* e = std::getenv("BOGP_UMMA_TONAL_ORDER");
+  const bool interleave = !(e && e[0] == '0');
+  for (int i = 0, lo = 0, hi = d.F - 1; i < d.F; ++i) order[i] = !interleave ? i : ((i & 1) ? idx[hi--] : idx[lo++]);
+}
+
+bool plan16(const bogp_modeset_s* h, HParams& p, int ZC) {
+  const ModesetDev& d = h->dev;
+  if (d.src_complex || !h->has_cov) return false;
+  if ((int)h->u16.wu_max.size() != d.F || (int)h->u16.phi_max.size() != d.F) return false;
+  int order[BOGP_MAX_TONALS];
+  tonal_order16(d, order);
+  unsigned a_off = 0, max_stage = 0, max_a = 0;
+  for (int f = 0; f < d.F; ++f) {
+    const TonalMeta& t = d.t[order[f]];
+    HTonal& u = p.t[f];
+    u.src = order[f];
+    u.Kp = pad_to(t.M, 16);
+    u.rowsP = t.u_rowsP;
+    if (u.Kp > 64 || u.rowsP > kNA) return false;
+    u.n1 = t.u_p0; u.nq = t.u_fold ? 0 : t.n_qpair; u.trK = t.trK;
+    u.fold = t.u_fold; u.c1r = t.u_c[0]; u.c1i = t.u_c[1]; u.c2r = t.u_c[2]; u.c2i = t.u_c[3];
+    u.a_bytes = 1024u * (unsigned)u.Kp;
+    u.a_off = a_off;
+    a_off += u.a_bytes;
+    u.b_zbytes = (unsigned)(u.rowsP * u.Kp * 2);
+    u.nj = kNA / u.rowsP;
+    u.sB = pow2_scale((double)h->u16.wu_max[order[f]] * (double)h->u16.phi_max[order[f]]);
+    max_stage = std::max(max_stage, 2u * (unsigned)u.nj * u.b_zbytes);
+    max_a = std::max(max_a, u.a_bytes);
+  }
+  p.F = d.F;
+  p.e_rt_stride = a_off;
+  // A region: the largest pair of consecutive images (cyclic) when the shared memory allows it, else one image
+  unsigned pair = 0;
+  for (int f = 0; f < d.F; ++f) pair = std::max(pair, p.t[f].a_bytes + p.t[(f + 1) % d.F].a_bytes);
+  const unsigned acc_bytes = (unsigned)ZC * kTile * 4u, bar_bytes = 256u;
+  const unsigned avail = kSmemMax - acc_bytes - bar_bytes;
+  if (max_a + 2u * max_stage > avail) return false;
+  p.AR = (pair + 3u * max_stage <= avail) ? pair : max_a;
+  p.S = (int)std::min<unsigned>(kMaxStages, (avail - p.AR) / max_stage);
+  if (p.S < 2) return false;
+  p.stage_bytes = max_stage;
+  p.smem_B = p.AR;
+  p.smem_acc = p.smem_B + (unsigned)p.S * max_stage;
+  p.smem_bar = p.smem_acc + acc_bytes;
+  return true;
+}
+
+int choose_zc16(int Nr, int Nz, int sms) {
+  const int nrt = (Nr + kTile - 1) / kTile;
+  const int chunks = std::max(1, sms / nrt);
+  int zc = (Nz + chunks - 1) / chunks;
+  zc = std::max(8, std::min(64, (zc + 7) & ~7));
+  return zc;
+}
+
+int grow(void** ptr, size_t* have, size_t need) {
+  if (*have >= need) return 0;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr; *have = 0;
+  BOGP_CUDA(cudaMalloc(ptr, need + need / 8 + 256));
+  *have = need + need / 8 + 256;
+  return 0;
+}
+
+}  // namespace
+
+bool umma16_supported(const bogp_modeset_s* h) {
+  if (const char* e = std::getenv("BOGP_UMMA_KIND")) { if (e[0] == 't') return false; }      // "tf32": the 3xTF32 kernel
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10 || !h->has_cov) return false;
+  HParams p{};
+  return plan16(h, p, 64);
+}
+
+int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype, int mf,
+                       float* out_dev, cudaStream_t s, int ext_mode, float* ext_val_dev, long long* ext_idx_dev) {
+  const ModesetDev& d = h->dev;
+  const int sms = device_sms16();
+  HParams p{};
+  const int ZC = choose_zc16(Nr, Nz, sms);
+  if (!plan16(h, p, ZC)) { set_error("UMMA-H engine: mode set does not fit (operator rows > 128, more than 64 modes or complex source table)"); return BOGP_ERR_UNSUPPORTED; }
+  p.Nr = Nr; p.Nz = Nz; p.ZC = ZC; p.atype = atype; p.mf = mf;
+  { const char* e = std::getenv("BOGP_UMMA_TWO_SLOT"); p.two_slot = e ? std::atoi(e) : 3; }
+  p.nrt = (Nr + kTile - 1) / kTile;
+  p.units = p.nrt * ((Nz + ZC - 1) / ZC);
+  unsigned long long b_off = 0;
+  for (int f = 0; f < d.F; ++f) { p.t[f].b_off = b_off; b_off += (unsigned long long)Nz * p.t[f].b_zbytes; }
+  // E scale per tonal: |E| <= |k|^-1/2 r^-1/2 e^{Im k r} over the range vector
+  double rmin = r_host[0], rmax = r_host[0];
+  for (int i = 1; i < Nr; ++i) { rmin = std::min(rmin, r_host[i]); rmax = std::max(rmax, r_host[i]); }
+  for (int f = 0; f < d.F; ++f) {
+    double bound = 0.0;
+    for (const cplx& k : h->u16.k_host[p.t[f].src]) {
+      const double a = std::exp(std::max(k.imag() * rmin, k.imag() * rmax)) / std::sqrt(std::abs(k) * rmin);
+      bound = std::max(bound, a);
+    }
+    p.t[f].sE = pow2_scale(bound);
+  }
+  bogp_modeset_s::U16& c = h->u16;
+  const size_t bytes_E = (size_t)p.nrt * p.e_rt_stride;
+  const size_t off_z = ((size_t)Nr * sizeof(double) + 255) & ~(size_t)255;
+  const size_t off_err = (off_z + (size_t)Nz * sizeof(double) + 255) & ~(size_t)255;
+  if (int rc = grow(&c.misc, &c.misc_bytes, off_err + 256)) return rc;
+  if (int rc = grow(&c.B, &c.B_bytes, 2 * (size_t)b_off + 512)) return rc;
+  const bool e_cached = c.E && c.r_cached.size() == (size_t)Nr && std::memcmp(c.r_cached.data(), r_host, (size_t)Nr * sizeof(double)) == 0 &&
+                        !(std::getenv("BOGP_NO_TABLE_CACHE") && std::getenv("BOGP_NO_TABLE_CACHE")[0] == '1');
+  if (!e_cached) {
+    c.r_cached.clear();
+    if (int rc = grow(&c.E, &c.E_bytes, bytes_E + 256)) return rc;
+  }
+  unsigned char* misc = static_cast<unsigned char*>(c.misc);
+  double* r_dev = reinterpret_cast<double*>(misc);
+  double* z_dev = reinterpret_cast<double*>(misc + off_z);
+  p.err = reinterpret_cast<int*>(misc + off_err);
+  if (ext_mode && (long long)Nr * Nz < (1ll << 32)) {
+    p.ext_mode = ext_mode;
+    p.ext_key = reinterpret_cast<unsigned long long*>(misc + off_err + 16);
+    p.ext_done = reinterpret_cast<unsigned int*>(misc + off_err + 32);
+    p.ext_val = ext_val_dev; p.ext_idx = ext_idx_dev;
+  }
+  p.E = static_cast<unsigned char*>(c.E);
+  p.Bhi = static_cast<unsigned char*>(c.B);
+  p.Blo = p.Bhi + (((size_t)b_off + 255) & ~(size_t)255);
+  p.out = out_dev;
+  if (!e_cached) {
+    BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
+    umma16_E_kernel<<<d.F * p.nrt * (kTile / kETabRows), 128, 0, s>>>(d, p, r_dev);
+    count_launch();
+    BOGP_CUDA(cudaGetLastError());
+    c.r_cached.assign(r_host, r_host + Nr);
+  }
+  BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  umma16_B_kernel<<<d.F * ((Nz + kBDepths - 1) / kBDepths), kBThreads, 0, s>>>(d, p, z_dev);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  const size_t smem = (size_t)p.smem_bar + 256;
+  BOGP_CUDA(cudaFuncSetAttribute(umma16_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t ev = timing_begin(s);
+  umma16_grid_kernel<<<std::min(p.units, sms), kThr, smem, s>>>(p);
+  timing_end(ev, s);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bogp
