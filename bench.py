@@ -427,13 +427,14 @@ def run_ours(args) -> None:
         if not torch.equal(check, pairs):
             raise SystemExit(f"bench.py: record exchange mismatch on rank {rank}: {pairs.tolist()} vs {check.tolist()}")
 
-    # ---- device-resident timing
+    # ---- device-resident timing.  Two passes over the same K steps: (1) `value`: CUDA events around each step, nothing
+    # recorded inside it (the library then launches the surface kernel as a programmatic dependent of its table kernel);
+    # (2) roofline: the library brackets the dominant kernel with its own event pair on the launching stream -- an
+    # event between the two launches serialises them, so this pass only yields the kernel's own duration.
     for _ in range(args.warmup):
         step_device()
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    _lib.timing_read()
-    _lib.timing_enable(True)
     launches0 = _lib.kernel_launches()
     with ClockSampler(local) as clocks:
         t_wall0 = time.perf_counter()
@@ -445,8 +446,6 @@ def run_ours(args) -> None:
         barrier()
         t_wall = time.perf_counter() - t_wall0
     launches = _lib.kernel_launches() - launches0
-    _lib.timing_enable(False)
-    kern_ms, kern_n = _lib.timing_read()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -455,6 +454,19 @@ def run_ours(args) -> None:
     total_ms = float(t.item())
     evals_per_step = world * NZ_PER_GPU * NR * modes.n_freq
     value = evals_per_step * args.steps / (total_ms * 1e-3)
+
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    _lib.timing_read()
+    _lib.timing_enable(True)
+    for a, b in ev2:
+        flush.zero_()
+        a.record()
+        step_device()
+        b.record()
+    barrier()
+    _lib.timing_enable(False)
+    kern_ms, kern_n = _lib.timing_read()
+    serial_step_ms = float(sum(a.elapsed_time(b) for a, b in ev2)) / args.steps
 
     # ---- end-to-end through the host-buffer entry point
     for _ in range(max(3, args.warmup)):
@@ -483,25 +495,46 @@ def run_ours(args) -> None:
         peak_src = "MEASURED_PEAKS.json bf16_tflops (burst)"
     else:
         bf16, peak_src = 1590.0, "fallback 1.59 PFLOP/s bf16 (B200_PROFILING.md)"
-    peak = bf16 / 2.0 / 3.0     # TF32 runs at half the bf16 rate; 3xTF32 spends three MMAs per product
+    # Three split products per real MAC either way; the FP16-split engine runs them at the 16-bit rate (the rate
+    # MEASURED_PEAKS.json measures), the TF32-split engine at half of it.
+    kind = dms.umma_kind() if args.engine in ("auto", "umma") else 0
+    peak_tf32x3 = bf16 / 2.0 / 3.0
+    peak = bf16 / 3.0 if kind == 16 else peak_tf32x3
     flop_per_launch = dms.flops_per_candidate("umma" if args.engine in ("auto", "umma") else "simt") * NZ_PER_GPU * NR
     kern_avg_ms = kern_ms / max(kern_n, 1)
     achieved = flop_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_n else None
+    # measured denominators of this round (profiles/peaks_r2.json: cuBLAS TF32 burst, tcgen05 back-to-back MMAs at bench
+    # clocks) and the nominal 4096 flop / clk / SM (TF32) at the clock sampled during the timed region
+    other = {}
+    p2 = ROOT / "profiles" / "peaks_r2.json"
+    if achieved and p2.exists():
+        pj = json.loads(p2.read_text())
+        f16_micro = max(r_["tflops"] for r_ in pj["tcgen05_micro"]["rows"] if r_["kind"] == "f16")
+        other = {"frac_vs_3xtf32_measured_bf16_div6": achieved / peak_tf32x3,
+                 "frac_vs_3xtf32_cublas_tf32_burst_div3": achieved / (pj["cublas_tf32_8192"]["burst_tflops"] / 3.0),
+                 "frac_vs_3xtf32_tcgen05_micro_div3": achieved / (pj["tf32_micro_burst_tflops"] / 3.0),
+                 "frac_vs_3xf16_tcgen05_micro_div3": achieved / (f16_micro / 3.0)}
     traffic = None
     tpath = ROOT / "profiles" / "umma_traffic.json"
     if tpath.exists() and args.engine in ("auto", "umma"):
         tj = json.loads(tpath.read_text())
-        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]      # bytes per launch, from one ncu --set full capture
+        # a capture belongs to one build of the library: refuse it when the digest recorded with it is not the one loaded
+        from bogp_b200 import build as _build
+        if tj.get("library_digest") == _build._digest() and tj.get("kind") == kind:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]      # bytes per launch, from one ncu --set full capture
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
-                "flop_per_launch": flop_per_launch,
-                "peak_def": f"{peak_src} / 2 (TF32 rate) / 3 (3xTF32 split) of measured",
+                "flop_per_launch": flop_per_launch, "arithmetic": {16: "3xFP16 split, fp32 accumulate (kind::f16)", 32: "3xTF32 split (kind::tf32)"}.get(kind, "fp32 CUDA cores"),
+                "peak_def": f"{peak_src} / 3 (three split products per MAC)" + ("" if kind == 16 else " / 2 (TF32 rate)") + " of measured",
+                "kernel_ms_from": "second pass of the same steps with the library's per-kernel event pair (serialised launches)",
+                "ms_per_step_serialised_pass": serial_step_ms,
                 "algorithmic": "sum_f 4*rows_f*M_f flop per candidate (mode-space operator of the engine that ran: rows_f = rank(G_f) with the rank-1 numerator folded into the norm rows on the tcgen05 engine, rank(G_f) + 2 otherwise; DESIGN.md)"}
+    roofline.update(other)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xFP16-split tensor-core products, fp32 accumulate)" if kind == 16 else "f32", "data": "synthetic",
             "config": dict(workload_config(world), engine=args.engine, final_reduction=exchange_kind),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -517,7 +550,7 @@ def run_ours(args) -> None:
             line["bo_iter"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_paths:
         try:
-            line["paths"] = other_paths(peaks_hbm, peak)
+            line["paths"] = other_paths(peaks_hbm, peak_tf32x3)   # the tilt engine is 3xTF32
         except Exception as exc:
             line["paths"] = {"error": repr(exc)}
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -38,6 +38,7 @@ SIGNATURES = {
     "bogp_modeset_destroy": (C.c_int, [_vp]),
     "bogp_modeset_info": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip]),
     "bogp_modeset_info_umma": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "bogp_umma_kind": (C.c_int, [_vp]),
     "bogp_covariance_set": (C.c_int, [_vp, _dp, _dp]),
     "bogp_bartlett_grid": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "bogp_bartlett_grid_argext": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _vp,

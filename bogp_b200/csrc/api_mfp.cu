@@ -525,6 +525,12 @@ extern "C" int bogp_modeset_info_umma(bogp_modeset_t h, int f, int* rows, int* r
   return 0;
 }
 
+extern "C" int bogp_umma_kind(bogp_modeset_t h) {
+  if (!h || !h->has_cov) return 0;
+  if (bogp::umma16_supported(h)) return 16;
+  return bogp::umma_supported(h) ? 32 : 0;
+}
+
 static int check_modes(int atype, int mf) {
   BOGP_REQUIRE(atype == BOGP_ATYPE_CBF || atype == BOGP_ATYPE_CBF_ML, "unknown atype %d", atype);
   BOGP_REQUIRE(mf == BOGP_MF_MEAN || mf == BOGP_MF_PRODUCT, "unknown multifreq method %d", mf);

@@ -151,7 +151,7 @@ struct bogp_modeset_s {
     void* E = nullptr; size_t E_bytes = 0;
     void* B = nullptr; size_t B_bytes = 0;
     void* misc = nullptr; size_t misc_bytes = 0;
-    std::vector<double> r_cached;
+    std::vector<double> r_cached, z_cached;   // host copies of the vectors the device copies / the E table were built from
   } u16;
 };
 

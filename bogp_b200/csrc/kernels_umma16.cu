@@ -29,6 +29,12 @@
 #include "device_math.cuh"
 #include "umma_ptx.cuh"
 
+// Per-tonal time stamps of CTA 0 (issuer 0 and epilogue warp 0) are compiled in only with -DBOGP_UMMA_DBG=1
+// (BOGP_UMMA_DBG_BUILD=1 python -m bogp_b200.build) and printed when BOGP_UMMA_DBG=1 is set at run time.
+#ifndef BOGP_UMMA_DBG
+#define BOGP_UMMA_DBG 0
+#endif
+
 namespace bogp {
 namespace {
 
@@ -66,12 +72,35 @@ struct HParams {
   unsigned int* ext_done;
   float* ext_val;
   long long* ext_idx;
+  long long* dbg;              // debug build: [0, 64) issuer 0 tonal starts, [64, 128) epilogue warp 0 tonal starts (CTA 0)
+  int skip;                    // debug build: 1 = no MMAs issued, 2 = epilogue releases without reading
   HTonal t[BOGP_MAX_TONALS];
 };
 
 // barrier slots (8 bytes each) at smem_bar
 enum { BAR_BFULL = 0, BAR_BEMPTY = kMaxStages, BAR_AFULL = 2 * kMaxStages, BAR_ADONE = 2 * kMaxStages + 2,
        BAR_TFULL = 2 * kMaxStages + 4, BAR_TEMPTY = 2 * kMaxStages + 6, BAR_TURN = 2 * kMaxStages + 8, BAR_COUNT = 2 * kMaxStages + 10 };
+
+// Hot-path wait of the lean epilogue / issuers: try_wait, branch, counter -- no clock reads inside the loop (the spinning
+// roles share their scheduler with four epilogue warps that are bound by instruction issue).  Still bounded: a
+// protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity, int* err, int code) {
+  uint32_t ok = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  atomicExch(err, code + 1000 * (int)blockIdx.x);
+  __threadfence_system();
+  __trap();
+}
 
 // kind::f16 MMA, both operands from shared memory; the 64-bit descriptors are passed as halves (A and B share the high
 // half: same LBO / SBO for K-major no-swizzle blocks of the same Kp).
@@ -99,9 +128,16 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint32_t a_lo, uint3
 
 // All MMAs of one stage: per K step of 16 modes, D += A_lo B_hi + A_hi B_lo + A_hi B_hi for the re and im accumulators.
 // a0 = descriptor low word of the image's first block (re_hi); blocks follow at `blk` (16-byte units): re_lo, im_hi, im_lo.
+// The turn is passed to the other issuer kTurnLeft MMAs before the end of the stage: the hop (mbarrier arrive -> the other
+// warp's try_wait returns) takes ~300 cycles, about the time the pipe needs for the MMAs still to be issued here, so the
+// next stage's first MMA reaches the queue as this stage's last one leaves it.
+#ifndef BOGP_U16_TURN_LEFT
+#define BOGP_U16_TURN_LEFT 4
+#endif
 template <int KS>
 __device__ __forceinline__ void issue_stage16(uint32_t d_re, uint32_t d_im, uint32_t a0, uint32_t blk, uint32_t bh, uint32_t bl,
-                                              uint32_t desc_hi, uint32_t idesc) {
+                                              uint32_t desc_hi, uint32_t idesc, uint32_t turn_bar) {
+  constexpr int kTurnAt = (6 * KS - BOGP_U16_TURN_LEFT) > 1 ? (6 * KS - BOGP_U16_TURN_LEFT) : 1;      // after this many MMAs
   asm volatile("mov.u32 %0, %0;" : "+r"(a0));
   asm volatile("mov.u32 %0, %0;" : "+r"(bh));
   asm volatile("mov.u32 %0, %0;" : "+r"(bl));
@@ -111,11 +147,23 @@ __device__ __forceinline__ void issue_stage16(uint32_t d_re, uint32_t d_im, uint
     const uint32_t a_hi = a0 + (uint32_t)(2 * part) * blk, a_lo = a_hi + blk;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
+      const int n0 = (part * KS + ks) * 3;
       mma_f16_ss(d, a_lo + 16u * ks, bh + 16u * ks, desc_hi, idesc, ks > 0);
+      if (n0 + 1 == kTurnAt) mbar_arrive(turn_bar);
       mma_f16_ss(d, a_hi + 16u * ks, bl + 16u * ks, desc_hi, idesc, true);
+      if (n0 + 2 == kTurnAt) mbar_arrive(turn_bar);
       mma_f16_ss(d, a_hi + 16u * ks, bh + 16u * ks, desc_hi, idesc, true);
+      if (n0 + 3 == kTurnAt) mbar_arrive(turn_bar);
     }
   }
+}
+
+// debug build: time stamp `ev` of stage sc (CTA 0, first 128 stages): 0 issuer ready (all waits passed), 1 issued + committed,
+// 2 epilogue warp 0 woken, 3 epilogue warp 0 released, 4 epilogue warp 0 done with the stage, 5 epilogue warp 15 released
+__device__ __forceinline__ void stamp16(const HParams& p, int ev, uint32_t sc) {
+#if BOGP_UMMA_DBG
+  if (p.dbg && blockIdx.x == 0 && sc < 128u && (threadIdx.x & 31) == 0) p.dbg[128 + ev * 128 + (int)sc] = clock64();
+#endif
 }
 
 // shared-memory offset of tonal g's E image: even tonals at the low end of the A region, odd ones at the high end
@@ -140,6 +188,7 @@ __device__ __forceinline__ void issue_tonal(IssState& st, const HTonal& u) {
   const uint32_t idesc0 = (1u << 4) | ((kTile >> 4) << 24);       // D fp32, A / B fp16 (format 0), K-major both
   auto bar = [&](int i) { return st.bar0 + 8u * (uint32_t)i; };
   mbar_wait(bar(BAR_AFULL + (st.g & 1)), (uint32_t)((st.g >> 1) & 1), p.err, 4);
+  if (BOGP_UMMA_DBG && p.dbg && st.id == 0 && blockIdx.x == 0 && st.g < 63 && (threadIdx.x & 31) == 0) p.dbg[st.g] = clock64();
   const uint32_t a_addr = st.s_base + a_offset(p, st.g, u.a_bytes);
   const uint32_t a0 = desc_lo0 | ((a_addr >> 4) & 0x3fffu);
   const uint32_t blk = 16u * Kp;                                    // 256 Kp bytes per block, in 16-byte units
@@ -151,8 +200,8 @@ __device__ __forceinline__ void issue_tonal(IssState& st, const HTonal& u) {
     const int njs = min(nj, nzu - j0);
     const uint32_t slot = sc % (uint32_t)p.S, ph = (sc / (uint32_t)p.S) & 1u;
     const uint32_t buf = sc & 1u, tph = (sc >> 1) & 1u;
-    mbar_wait(bar(BAR_BFULL + slot), ph, p.err, 5);
-    mbar_wait(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6);
+    mbar_wait_lean(bar(BAR_BFULL + slot), ph, p.err, 5);
+    mbar_wait_lean(bar(BAR_TEMPTY + buf), tph ^ 1u, p.err, 6);
     tc_fence_after();
     const uint32_t N = (uint32_t)(njs * u.rowsP);
     const uint32_t idesc = idesc0 | ((N >> 3) << 17);
@@ -160,14 +209,17 @@ __device__ __forceinline__ void issue_tonal(IssState& st, const HTonal& u) {
     const uint32_t b_lo = b_hi + (uint32_t)njs * u.b_zbytes;
     const uint32_t d_re = st.tmem_base + buf * (uint32_t)(2 * kNA), d_im = d_re + (uint32_t)kNA;
     // stages enter the tensor pipe in order (see kernels_umma.cu: without the turn both buffers reach the epilogue together)
-    if (sc > 0) mbar_wait(bar(BAR_TURN + (st.id ^ 1)), ((sc - 1u) >> 1) & 1u, p.err, 8);
+    if (sc > 0) mbar_wait_lean(bar(BAR_TURN + (st.id ^ 1)), ((sc - 1u) >> 1) & 1u, p.err, 8);
+    stamp16(p, 0, sc);
     if (elect_one()) {
-      issue_stage16<KS>(d_re, d_im, a0, blk, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc);
-      mbar_arrive(bar(BAR_TURN + st.id));
+      if (!(BOGP_UMMA_DBG && (p.skip & 1)))
+      if (BOGP_UMMA_DBG && (p.skip & 1)) mbar_arrive(bar(BAR_TURN + st.id));
+      issue_stage16<KS>(d_re, d_im, a0, blk, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc, bar(BAR_TURN + st.id));
       tc_commit(bar(BAR_BEMPTY + slot));
       tc_commit(bar(BAR_TFULL + buf));
     }
     __syncwarp();
+    stamp16(p, 1, sc);
   }
   st.sc = sc;
   if (elect_one()) tc_commit(bar(BAR_ADONE + (st.g & 1)));
@@ -206,6 +258,34 @@ __device__ __forceinline__ void sq16(const float* re, const float* im, unsigned 
   }
 }
 
+
+// Lean epilogue (all tonals folded, real modes, cbf + mean): Bartlett value of one depth slot.
+struct FoldC { float c1r, c1i, c2r, c2i; };
+__device__ __forceinline__ float fold_num(const FoldC& c, const float* re, const float* im) {
+  const float tr = fmaf(c.c1r, re[0], fmaf(-c.c1i, im[0], fmaf(c.c2r, re[1], -c.c2i * im[1])));
+  const float ti = fmaf(c.c1r, im[0], fmaf(c.c1i, re[0], fmaf(c.c2r, im[1], c.c2i * re[1])));
+  return fmaf(tr, tr, ti * ti);
+}
+__device__ __forceinline__ float sum4(f32x2 t0, f32x2 t1, f32x2 t2, f32x2 t3) {
+  float x, y;
+  upk(add2(add2(t0, t1), add2(t2, t3)), x, y);
+  return x + y;
+}
+__device__ __forceinline__ float lean_slot16(const FoldC& c, const float* re, const float* im) {
+  const float num = fold_num(c, re, im);
+  f32x2 t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
+  sq16(re, im, t0, t1, t2, t3);
+  return __fdividef(num, sum4(t0, t1, t2, t3));
+}
+__device__ __forceinline__ float lean_slot32(const FoldC& c, const float* reA, const float* imA, const float* reB, const float* imB) {
+  const float num = fold_num(c, reA, imA);
+  f32x2 t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
+  sq16(reA, imA, t0, t1, t2, t3);
+  sq16(reB, imB, t0, t1, t2, t3);
+  return __fdividef(num, sum4(t0, t1, t2, t3));
+}
+
+template <bool LEAN>
 __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_constant__ HParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -236,6 +316,7 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
 
   if (warp == kProdW) {
     // ============================================================== Bop producer
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // the Bop tables of this call (no-op without a programmatic launch)
     uint32_t sc = 0;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int zc = unit / p.nrt, z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
@@ -249,9 +330,12 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
           const uint32_t dst = s_base + p.smem_B + slot * p.stage_bytes;
           const size_t src = (size_t)u.b_off + (size_t)(z0 + j0) * u.b_zbytes;
           if (elect_one()) {
+            if (BOGP_UMMA_DBG && (p.skip & 4)) mbar_arrive(bar(BAR_BFULL + slot));
+            else {
             mbar_expect_tx(bar(BAR_BFULL + slot), 2 * bytes);
             bulk_g2s(dst, p.Bhi + src, bytes, bar(BAR_BFULL + slot));
             bulk_g2s(dst + bytes, p.Blo + src, bytes, bar(BAR_BFULL + slot));
+            }
           }
           __syncwarp();
         }
@@ -302,6 +386,120 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
     const uint32_t t_lane0 = tmem_base + ((uint32_t)(quad * 32) << 16);
     float* acc = reinterpret_cast<float*>(smem + p.smem_acc);     // [ZC][128]
     uint32_t sc = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // err / arg-ext words are reset by the table kernel
+    if (LEAN) {
+      // ---- lean path: every tonal folded with 16 or 32 padded rows, cbf + mean.  Straight-line stages: wait, four
+      // loads, one wait, release, arithmetic; acc starts at zero so that every tonal is a plain +=.
+      const uint32_t tb0 = t_lane0 + (uint32_t)(sub * 16), tb1 = t_lane0 + (uint32_t)(sub * 32);
+      for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
+        const int rt = unit % p.nrt, zc = unit / p.nrt;
+        const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
+        for (int j = sub; j < nzu; j += 4) acc[(size_t)j * kTile + tl] = 0.f;
+        for (int f = 0; f < p.F; ++f) {
+          const HTonal& u = p.t[f];
+          FoldC fc;
+          fc.c1r = u.c1r; fc.c1i = u.c1i; fc.c2r = u.c2r; fc.c2i = u.c2i;
+          if (BOGP_UMMA_DBG && p.dbg && warp == 0 && lane == 0 && blockIdx.x == 0 && unit == 0 && f < 63) p.dbg[64 + f] = clock64();
+          float* a = acc + (size_t)sub * kTile + tl;
+          if (u.rowsP == 16) {
+            const int full = nzu >> 3;
+#pragma unroll 1
+            for (int st = 0; st < full; ++st, ++sc, a += 8 * kTile) {
+              const uint32_t buf = sc & 1u;
+              mbar_wait_lean(bar(BAR_TFULL + buf), (sc >> 1) & 1u, p.err, 7);
+              tc_fence_after();
+              if (warp == 0) stamp16(p, 2, sc);
+              const uint32_t tA = tb0 + buf * (uint32_t)(2 * kNA);
+              float reA[16], imA[16], reB[16], imB[16];
+              tc_ld16(tA, reA); tc_ld16(tA + kNA, imA);
+              tc_ld16(tA + 64u, reB); tc_ld16(tA + kNA + 64u, imB);
+              tc_wait_ld();
+              tc_fence_before();
+              if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+              if (warp == 0) stamp16(p, 3, sc); else if (warp == 15) stamp16(p, 5, sc);
+              a[0] += lean_slot16(fc, reA, imA);
+              a[4 * kTile] += lean_slot16(fc, reB, imB);
+              if (warp == 0) stamp16(p, 4, sc);
+            }
+            if (nzu & 7) {          // ragged last stage: slots sub and sub + 4 if they exist
+              const int njs = nzu & 7;
+              const uint32_t buf = sc & 1u;
+              mbar_wait_lean(bar(BAR_TFULL + buf), (sc >> 1) & 1u, p.err, 7);
+              tc_fence_after();
+              const uint32_t tA = tb0 + buf * (uint32_t)(2 * kNA);
+              float reA[16], imA[16], reB[16], imB[16];
+              tc_ld16(tA, reA); tc_ld16(tA + kNA, imA);
+              tc_ld16(tA + 64u, reB); tc_ld16(tA + kNA + 64u, imB);
+              tc_wait_ld();
+              tc_fence_before();
+              if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+              if (sub < njs) a[0] += lean_slot16(fc, reA, imA);
+              if (sub + 4 < njs) a[4 * kTile] += lean_slot16(fc, reB, imB);
+              ++sc;
+            }
+          } else {
+            const int full = nzu >> 2;
+#pragma unroll 1
+            for (int st = 0; st < full; ++st, ++sc, a += 4 * kTile) {
+              const uint32_t buf = sc & 1u;
+              mbar_wait_lean(bar(BAR_TFULL + buf), (sc >> 1) & 1u, p.err, 7);
+              tc_fence_after();
+              if (warp == 0) stamp16(p, 2, sc);
+              const uint32_t tA = tb1 + buf * (uint32_t)(2 * kNA);
+              float reA[16], imA[16], reB[16], imB[16];
+              tc_ld16(tA, reA); tc_ld16(tA + kNA, imA);
+              tc_ld16(tA + 16u, reB); tc_ld16(tA + kNA + 16u, imB);
+              tc_wait_ld();
+              tc_fence_before();
+              if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+              if (warp == 0) stamp16(p, 3, sc); else if (warp == 15) stamp16(p, 5, sc);
+              a[0] += lean_slot32(fc, reA, imA, reB, imB);
+              if (warp == 0) stamp16(p, 4, sc);
+            }
+            if (nzu & 3) {
+              const int njs = nzu & 3;
+              const uint32_t buf = sc & 1u;
+              mbar_wait_lean(bar(BAR_TFULL + buf), (sc >> 1) & 1u, p.err, 7);
+              tc_fence_after();
+              const uint32_t tA = tb1 + buf * (uint32_t)(2 * kNA);
+              float reA[16], imA[16], reB[16], imB[16];
+              tc_ld16(tA, reA); tc_ld16(tA + kNA, imA);
+              tc_ld16(tA + 16u, reB); tc_ld16(tA + kNA + 16u, imB);
+              tc_wait_ld();
+              tc_fence_before();
+              if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+              if (sub < njs) a[0] += lean_slot32(fc, reA, imA, reB, imB);
+              ++sc;
+            }
+          }
+        }
+        // write-out: this warp's own depths (j % 4 == sub), nobody else touched them -- no barrier
+        __syncwarp();
+        const int i = rt * kTile + tl;
+        const float scale = 1.f / (float)p.F;
+        unsigned long long best = 0ull;
+        if (i < p.Nr)
+          for (int j = sub; j < nzu; j += 4) {
+            const float v = acc[(size_t)j * kTile + tl] * scale;
+            p.out[(size_t)(z0 + j) * p.Nr + i] = v;
+            if (p.ext_mode && v == v) {
+              uint32_t uu = __float_as_uint(v);
+              uu = (uu & 0x80000000u) ? ~uu : (uu | 0x80000000u);
+              if (p.ext_mode == 2) uu = ~uu;
+              const unsigned long long key = ((unsigned long long)uu << 32) | (0xffffffffu - ((uint32_t)(z0 + j) * (uint32_t)p.Nr + (uint32_t)i));
+              best = key > best ? key : best;
+            }
+          }
+        if (p.ext_mode) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+          }
+          if (lane == 0 && best) atomicMax(p.ext_key, best);
+        }
+      }
+    } else
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int rt = unit % p.nrt, zc = unit / p.nrt;
       const int z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
@@ -311,7 +509,8 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
         EpiTonal et;
         et.c1r = u.c1r; et.c1i = u.c1i; et.c2r = u.c2r; et.c2i = u.c2i; et.trK = u.trK; et.fold = u.fold; et.nq = u.nq; et.atype = p.atype;
         const bool fast = (u.n1 == 2 * u.nq) && u.nq <= 8;
-        const bool simple = fast && (u.nq == 1 || u.fold);
+        const bool simple = fast && (u.nq == 1 || u.fold) && !(BOGP_UMMA_DBG && (p.skip & 2));
+        if (BOGP_UMMA_DBG && p.dbg && warp == 0 && lane == 0 && blockIdx.x == 0 && unit == 0 && f < 63) p.dbg[64 + f] = clock64();
         auto store = [&](int j, float num, float norm) {
           const float b = __fdividef(num, norm);
           const float val = et.atype == BOGP_ATYPE_CBF ? b : et.trK - b;
@@ -322,8 +521,9 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
           const int njs = min(u.nj, nzu - j0);
           const uint32_t buf = sc & 1u;
           const uint32_t t_lane = t_lane0 + buf * (uint32_t)(2 * kNA);
-          mbar_wait(bar(BAR_TFULL + buf), (sc >> 1) & 1u, p.err, 7);
+          mbar_wait_lean(bar(BAR_TFULL + buf), (sc >> 1) & 1u, p.err, 7);
           tc_fence_after();
+          if (warp == 0) stamp16(p, 2, sc);
           const int s_first = (sub - (j0 & 3) + 4) & 3;      // first slot of this stage with (j0 + s) % 4 == sub
           bool released = false;
           if ((p.two_slot & 1) && simple && rowsP == 16 && s_first + 4 < njs && s_first + 8 >= njs) {
@@ -337,6 +537,7 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
             released = true;
+            if (warp == 0) stamp16(p, 3, sc); else if (warp == 15) stamp16(p, 5, sc);
             {
               float num, numsq;
               numer_first(et, reA, imA, num, numsq);
@@ -361,6 +562,7 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
             released = true;
+            if (warp == 0) stamp16(p, 3, sc); else if (warp == 15) stamp16(p, 5, sc);
             float num, numsq;
             numer_first(et, reA, imA, num, numsq);
             unsigned long long t0 = 0ull, t1 = 0ull, t2 = 0ull, t3 = 0ull;
@@ -368,7 +570,7 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
             sq16(reB, imB, t0, t1, t2, t3);
             store(j0 + s_first, num, ((sum2(t0) + sum2(t1)) + (sum2(t2) + sum2(t3))) - numsq);
           } else {
-            for (int s = s_first; s < njs; s += 4) {
+            for (int s = s_first; s < njs && !(BOGP_UMMA_DBG && (p.skip & 2)); s += 4) {
               const bool last_slot = s + 4 >= njs;
               const uint32_t t_re = t_lane + (uint32_t)(s * rowsP);
               float norm = 0.f, num = 0.f;
@@ -423,7 +625,9 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
           if (!released) {      // no slot of this stage belongs to this warp
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar(BAR_TEMPTY + buf));
+            if (warp == 0) stamp16(p, 3, sc); else if (warp == 15) stamp16(p, 5, sc);
           }
+          if (warp == 0) stamp16(p, 4, sc);
         }
       }
       // write-out: this warp's own depths (j % 4 == sub), nobody else touched them -- no barrier
@@ -452,6 +656,10 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
         if (lane == 0 && best) atomicMax(p.ext_key, best);
       }
     }
+  }
+  if (BOGP_UMMA_DBG && p.dbg && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    if (warp == kIssW0) p.dbg[63] = clock64();
+    if (warp == 0) p.dbg[127] = clock64();
   }
   tc_fence_before();
   __syncthreads();
@@ -562,6 +770,9 @@ __global__ void __launch_bounds__(kBThreads) umma16_B_kernel(ModesetDev ms, HPar
   const HTonal& u = p.t[f];
   const TonalMeta& t = ms.t[u.src];
   const int nd = min(kBDepths, p.Nz - j0), tid = threadIdx.x;
+  // programmatic dependent launch: the surface kernel may start its prologue (barriers, TMEM, E images) while these
+  // blocks run; its Bop producer and epilogue warps wait for this grid's completion with griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;");
   if (blockIdx.x == 0 && tid == 0) { *p.err = 0; if (p.ext_mode) { *p.ext_key = 0ull; *p.ext_done = 0u; } }
   for (int e = tid; e < nd * u.Kp; e += kBThreads) {
     const int dj = e / u.Kp, m = e - dj * u.Kp;
@@ -730,6 +941,7 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
                         !(std::getenv("BOGP_NO_TABLE_CACHE") && std::getenv("BOGP_NO_TABLE_CACHE")[0] == '1');
   if (!e_cached) {
     c.r_cached.clear();
+    c.z_cached.clear();
     if (int rc = grow(&c.E, &c.E_bytes, bytes_E + 256)) return rc;
   }
   unsigned char* misc = static_cast<unsigned char*>(c.misc);
@@ -753,17 +965,74 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
     BOGP_CUDA(cudaGetLastError());
     c.r_cached.assign(r_host, r_host + Nr);
   }
-  BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  // the depth vector stays on the device while it is the same (one grid for all time steps of a sweep)
+  if (!(e_cached && c.z_cached.size() == (size_t)Nz && std::memcmp(c.z_cached.data(), z_host, (size_t)Nz * sizeof(double)) == 0)) {
+    BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
+    c.z_cached.assign(z_host, z_host + Nz);
+  }
   umma16_B_kernel<<<d.F * ((Nz + kBDepths - 1) / kBDepths), kBThreads, 0, s>>>(d, p, z_dev);
   count_launch();
   BOGP_CUDA(cudaGetLastError());
+  static long long* dbg_dev = nullptr;
+  const char* dbg_env = BOGP_UMMA_DBG ? std::getenv("BOGP_UMMA_DBG") : nullptr;
+  if (BOGP_UMMA_DBG) { const char* sk = std::getenv("BOGP_UMMA_SKIP"); p.skip = sk ? std::atoi(sk) : 0; }
+  if (dbg_env && dbg_env[0] == '1') {
+    if (!dbg_dev) BOGP_CUDA(cudaMalloc(&dbg_dev, 1024 * sizeof(long long)));
+    BOGP_CUDA(cudaMemsetAsync(dbg_dev, 0, 1024 * sizeof(long long), s));
+    p.dbg = dbg_dev;
+  }
   const size_t smem = (size_t)p.smem_bar + 256;
-  BOGP_CUDA(cudaFuncSetAttribute(umma16_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // lean instance: every tonal folded (rank-1 covariance, real modes) with 16 or 32 padded rows, cbf + mean
+  bool lean = atype == BOGP_ATYPE_CBF && mf == BOGP_MF_MEAN && !(BOGP_UMMA_DBG && (p.skip & 2));
+  for (int f = 0; f < d.F; ++f) lean = lean && p.t[f].fold && (p.t[f].rowsP == 16 || p.t[f].rowsP == 32);
+  if (const char* e = std::getenv("BOGP_UMMA_LEAN")) lean = lean && e[0] != '0';
+  auto kern = lean ? umma16_grid_kernel<true> : umma16_grid_kernel<false>;
+  BOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t ev = timing_begin(s);
-  umma16_grid_kernel<<<std::min(p.units, sms), kThr, smem, s>>>(p);
+  const char* pdl_env = std::getenv("BOGP_UMMA_PDL");
+  if (!ev && !p.dbg && !(pdl_env && pdl_env[0] == '0')) {
+    // no event between the two launches: let the surface kernel's prologue overlap the table kernel
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)std::min(p.units, sms)); cfg.blockDim = dim3(kThr); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    BOGP_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    kern<<<std::min(p.units, sms), kThr, smem, s>>>(p);
+  }
   timing_end(ev, s);
   count_launch();
   BOGP_CUDA(cudaGetLastError());
+  if (p.dbg) {
+    static long long hd[1024];
+    BOGP_CUDA(cudaMemcpyAsync(hd, dbg_dev, sizeof(hd), cudaMemcpyDeviceToHost, s));
+    BOGP_CUDA(cudaStreamSynchronize(s));
+    const int nzu = std::min(ZC, Nz);
+    fprintf(stderr, "[umma16 dbg] S=%d AR=%u stage=%u ZC=%d units=%d; per tonal of unit 0 (CTA 0): Kp rowsP stages | MMA cycles | issuer | epilogue\n", p.S, p.AR, p.stage_bytes, ZC, p.units);
+    long long tot_mma = 0;
+    for (int f = 0; f < d.F; ++f) {
+      const HTonal& u = p.t[f];
+      const int stages = (nzu + u.nj - 1) / u.nj;
+      const long long mma = (long long)6 * (u.Kp / 16) * (long long)(nzu * u.rowsP) / 2;
+      tot_mma += mma;
+      const long long iss = (f + 1 < d.F ? hd[f + 1] : hd[d.F]) - hd[f], epi = (f + 1 < d.F ? hd[64 + f + 1] : hd[127]) - hd[64 + f];
+      fprintf(stderr, "[umma16 dbg]   %2d %3d %3d | %6lld | %7lld | %7lld\n", u.Kp, u.rowsP, stages, mma, iss, epi);
+    }
+    fprintf(stderr, "[umma16 dbg] stage | ready->issued | issued->wake | wake->release(w0) | release->done(w0) | w15 release - w0 release | release(w0)->ready(sc+2) | ready delta\n");
+    {
+      const long long* e = hd + 128;
+      int sc = 0;
+      for (int f = 0; f < d.F && sc < 126; ++f) {
+        const int stages = (nzu + p.t[f].nj - 1) / p.t[f].nj;
+        for (int k = 0; k < stages && sc < 126; ++k, ++sc)
+          if (k < 6) fprintf(stderr, "   %3d (Kp %2d rows %2d)  %6lld %6lld %6lld %6lld %6lld %6lld   %6lld\n", sc, p.t[f].Kp, p.t[f].rowsP, e[128 + sc] - e[sc], e[256 + sc] - e[128 + sc],
+                  e[384 + sc] - e[256 + sc], e[512 + sc] - e[384 + sc], e[640 + sc] - e[384 + sc], e[sc + 2] - e[384 + sc], e[sc + 1] - e[sc]);
+      }
+    }
+    fprintf(stderr, "[umma16 dbg] unit 0: MMA %lld cycles, issuer first tonal -> end of kernel %lld\n", tot_mma, hd[63] - hd[0]);
+  }
   return 0;
 }
 

@@ -98,6 +98,11 @@ class DeviceModeSet:
             out.append((M, rows.value, rp.value, bool(fold.value)))
         return out
 
+    def umma_kind(self) -> int:
+        """Arithmetic of the tcgen05 engine a vertical-array grid call runs: 16 (three FP16-split products), 32 (three
+        TF32-split products) or 0 (mode set / device not covered by the tensor-core engines)."""
+        return int(_lib.lib().bogp_umma_kind(self._h))
+
     def flops_per_candidate(self, engine: str = "simt") -> float:
         """Algorithmic flop of one candidate over all tonals on the vertical-array path: sum_f 4 rows_f M_f, with the
         row count of the operator the engine actually needs (the tcgen05 engine folds a rank-1 numerator into the norm

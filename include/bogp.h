@@ -100,6 +100,11 @@ int bogp_modeset_info(bogp_modeset_t h, int f, int* M, int* rows, int* J);
  * rotation of R puts the numerator row into the span of its first two rows, so the operator has rank(G) rows instead
  * of rank(G) + 2).  Valid after bogp_covariance_set. */
 int bogp_modeset_info_umma(bogp_modeset_t h, int f, int* rows, int* rows_padded, int* folded);
+/* Arithmetic of the tcgen05 engine a vertical-array grid call on this handle runs: 16 = three FP16-split products
+ * (kind::f16, csrc/kernels_umma16.cu), 32 = three TF32-split products (kind::tf32, csrc/kernels_umma.cu; also
+ * BOGP_UMMA_KIND=tf32), 0 = the tensor-core engines do not take this mode set / device.  Same 22-bit operand precision
+ * either way (bench.py picks the roofline denominator from it).  Valid after bogp_covariance_set. */
+int bogp_umma_kind(bogp_modeset_t h);
 
 /* Ambiguity surface: replaces the loop `for z in src_z: amb[zz,:] = MFP({"src_z": z, "rec_r": rvec})`
  * (mfp.py:213-214) including runner + beamformer + multifreq combine.
