@@ -560,6 +560,14 @@ def run_ours(args) -> None:
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{rows} of 1000 depth rows x {NR} ranges x 13 tonals, {dt:.1f} s, "
                                           f"{cores} processes x 1 BLAS thread"}
+        # parity of the WHOLE benchmark surface (every one of the 10^6 nodes) against the float64 oracle, the oracle as
+        # the checker only: arg-max, and the relative-error distribution with and without the 0.05 floor of the tests
+        from oracle import bartlett as ob
+        ref = ob.ambiguity_surface_pool(modes, K, r, z_slab, workers=cores)
+        st = ob.parity_stats(surf.cpu().numpy(), ref)
+        line["parity"] = dict(st, nodes=int(ref.size), bar="1e-5 relative (north_star), identical arg-max")
+        if not (st["same_argmax"] and st["max_floored"] <= 1e-5):
+            raise SystemExit(f"bench.py: full-surface parity gate failed: {st}")
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

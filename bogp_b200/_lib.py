@@ -50,6 +50,7 @@ SIGNATURES = {
     "bogp_bartlett_points_host": (C.c_int, [_vp, _dp, _ll, C.c_int, C.c_int, _fp, _vp]),
     "bogp_envbatch_create": (C.c_int, [C.POINTER(_vp), _ll, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _fp, _dp]),
     "bogp_envbatch_set_covariance": (C.c_int, [_vp, _dp, _dp]),
+    "bogp_envbatch_set_tilt": (C.c_int, [_vp, _dp, _dp]),
     "bogp_envbatch_bartlett": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "bogp_envbatch_destroy": (C.c_int, [_vp]),
     "bogp_argmax_f32": (C.c_int, [_vp, _ll, _fp, C.POINTER(_ll), _vp]),

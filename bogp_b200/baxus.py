@@ -137,11 +137,13 @@ def embedding_matrix(input_dim: int, target_dim: int, dtype: torch.dtype = DT, d
     ``target_dim >= input_dim`` (ref :156-185).  ``x_input = x_target @ S``."""
     if target_dim >= input_dim:
         return torch.eye(input_dim, dtype=dtype)
+    # same draws from the global generator as the reference (one permutation, one [target_dim, input_dim] sign table of
+    # which row i uses its first len(bin i) entries): identical embeddings on a fixed torch seed
     perm = torch.randperm(input_dim)
+    signs = 2 * torch.randint(2, (target_dim, input_dim), dtype=dtype) - 1
     S = torch.zeros(target_dim, input_dim, dtype=dtype)
     for row, members in enumerate(torch.tensor_split(perm, target_dim)):
-        signs = 2.0 * torch.randint(2, (len(members),)).to(dtype) - 1.0
-        S[row, members] = signs
+        S[row, members] = signs[row, :len(members)]
     return S
 
 
@@ -162,9 +164,15 @@ def increase_embedding_and_observations(S: torch.Tensor, X: torch.Tensor, n_new_
             raise EmbeddingExhausted(f"target dimension {row} has a single input dimension left")
         members = members[torch.randperm(len(members))]
         bins = torch.tensor_split(members, min(n_new_bins, len(members)))[1:]
+        longest = max((len(b) for b in bins), default=0)
         for moved in bins:
             new_row = torch.zeros(S.shape[1], dtype=S.dtype)
             new_row[moved] = S[row, moved]
+            # Reference behaviour kept for identical trajectories (ref :215-224): the moved bins of a row are zero-padded
+            # to the longest one before the scatter, and the padding entries (index 0, value 0) are written after the
+            # real ones -- a bin that is shorter than the longest AND contains input dimension 0 loses that dimension.
+            if len(moved) < longest and bool((moved == 0).any()):
+                new_row[0] = 0
             S_new[row, moved] = 0
             extra_rows.append(new_row)
             extra_cols.append(X[:, row])

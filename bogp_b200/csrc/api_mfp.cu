@@ -575,7 +575,8 @@ static int grid_impl(bogp_modeset_t h, const double* r_m_host, int Nr, const dou
     rc = bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
     if (rc || !ext_mode || fuse_ext) return rc;
   } else {
-    rc = bogp::launch_grid_simt(h, r_m_host, Nr, z_host, Nz, tilted ? tilt_deg_host : nullptr, Nt, atype, mf_method, out_dev, s);
+    // (a tilt axis of zeros still has Nt planes to fill)
+    rc = bogp::launch_grid_simt(h, r_m_host, Nr, z_host, Nz, (tilted || Nt > 1) ? tilt_arg : nullptr, Nt, atype, mf_method, out_dev, s);
     if (rc || !ext_mode) return rc;
   }
   return bogp_argext_f32_dev(out_dev, (long long)std::max(Nt, 1) * Nz * Nr, ext_mode == 1, ext_val_dev, ext_idx_dev, ext_scratch, 8192, stream);

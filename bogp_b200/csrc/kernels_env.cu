@@ -26,6 +26,9 @@ struct bogp_envbatch_s {
   // double-buffered in shared memory
   unsigned char* rec = nullptr;
   unsigned rec_bytes = 0, off_kre = 0, off_kim = 0, off_g = 0, off_r = 0;
+  // tilted array (bogp_envbatch_set_tilt): per candidate sin(tilt) and per (candidate, receiver) lever z_pivot - z_n
+  double *sin_tilt = nullptr, *lever = nullptr;
+  bool tilted = false;
 };
 
 namespace bogp {
@@ -93,6 +96,87 @@ envbatch_kernel(long long C, int F, int N, int Mmax, const double* __restrict__ 
           const float a = __ldg(cr + (size_t)n * Jmax + j), b = __ldg(ci + (size_t)n * Jmax + j);
           sr += a * p.x - b * p.y;
           si += a * p.y + b * p.x;
+        }
+        num += sr * sr + si * si;
+      }
+      norm = warp_sum(norm);
+      num = warp_sum(num);
+      __syncwarp();
+      const float b = num / norm;
+      acc = combine_tonal(acc, atype == BOGP_ATYPE_CBF ? b : trK[f] - b, mf, f == 0);
+    }
+    if (lane == 0) out[c] = (mf == BOGP_MF_MEAN) ? acc / (float)F : acc;
+  }
+}
+
+// ---- tilted array, one environment per candidate (the inversion's search space has `tilt` in [-3, 3] degrees,
+// ref/projects/swellex96_inv/data/bo/common.py:63, and the simulated truth is tilted): receiver n sits at range
+// r_n = r - (z_pivot - z_n) sin(tau), so the phase depends on (receiver, mode) and the replica is evaluated term by term
+//     p_n = r_n^-1/2 sum_m Phi[n, m] g_m exp(-i k_m r_n),   g_m = phi_m(z_s) k_m^-1/2
+// with the phase product and its reduction in float64 (as everywhere else).  One warp per candidate, lanes over
+// receivers; same Bartlett epilogue as envbatch_kernel.
+__global__ void __launch_bounds__(kEnvWarps * 32)
+envbatch_tilt_kernel(long long C, int F, int N, int Mmax, const double* __restrict__ k_re, const double* __restrict__ k_im,
+                     const float* __restrict__ amp_re, const float* __restrict__ amp_im, const float* __restrict__ phiT,
+                     const double* __restrict__ range, const double* __restrict__ sin_tilt, const double* __restrict__ lever,
+                     const float* __restrict__ CkT_re, const float* __restrict__ CkT_im, const int* __restrict__ Jf,
+                     const float* __restrict__ trK, int Jmax, int atype, int mf, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t per_warp = (size_t)Mmax * (sizeof(double) + sizeof(float) + sizeof(float2)) + (size_t)N * sizeof(float2);
+  unsigned char* base = tsm + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+  double* kre_s = reinterpret_cast<double*>(base);
+  float2* g_s = reinterpret_cast<float2*>(kre_s + Mmax);
+  float2* p_s = g_s + Mmax;
+  float* kim_s = reinterpret_cast<float*>(p_s + N);
+  for (long long c = (long long)blockIdx.x * kEnvWarps + warp; c < C; c += (long long)gridDim.x * kEnvWarps) {
+    const double r = range[c], st = sin_tilt[c];
+    float acc = 0.f;
+    for (int f = 0; f < F; ++f) {
+      const size_t cf = (size_t)c * F + f;
+      for (int m = lane; m < Mmax; m += 32) {
+        const double kre = k_re[cf * Mmax + m], kim = k_im[cf * Mmax + m];
+        const float ar = amp_re[cf * Mmax + m], ai = amp_im ? amp_im[cf * Mmax + m] : 0.f;
+        float2 g = make_float2(0.f, 0.f);
+        if (ar != 0.f || ai != 0.f) {
+          const double mag = rsqrt(sqrt(kre * kre + kim * kim)), ang = -0.5 * atan2(kim, kre);
+          double s2, c2;
+          sincos(ang, &s2, &c2);
+          g = cmul(make_float2(ar, ai), make_float2((float)(mag * c2), (float)(mag * s2)));
+        }
+        kre_s[m] = kre; kim_s[m] = (float)kim; g_s[m] = g;
+      }
+      __syncwarp();
+      const float* P = phiT + cf * (size_t)Mmax * N;
+      float norm = 0.f;
+      for (int n = lane; n < N; n += 32) {
+        const double rn = r - lever[(size_t)c * N + n] * st;
+        const float rnf = (float)rn, rs = (float)rsqrt(rn);
+        float pr = 0.f, pi = 0.f;
+        for (int m = 0; m < Mmax; ++m) {
+          const float2 g = g_s[m];
+          if (g.x == 0.f && g.y == 0.f) continue;
+          float s, co;
+          sincos_big(kre_s[m] * rn, s, co);
+          const float a = expf(kim_s[m] * rnf) * rs * __ldg(P + (size_t)m * N + n);
+          const float2 t = cmul(g, make_float2(a * co, -a * s));
+          pr += t.x; pi += t.y;
+        }
+        p_s[n] = make_float2(pr, pi);
+        norm += pr * pr + pi * pi;
+      }
+      __syncwarp();
+      float num = 0.f;
+      const int J = Jf[f];
+      const float* cr = CkT_re + (size_t)f * N * Jmax;
+      const float* ci = CkT_im + (size_t)f * N * Jmax;
+      for (int j = lane; j < J; j += 32) {
+        float sr = 0.f, si = 0.f;
+        for (int n = 0; n < N; ++n) {
+          const float2 pp = p_s[n];
+          const float a = __ldg(cr + (size_t)n * Jmax + j), b = __ldg(ci + (size_t)n * Jmax + j);
+          sr += a * pp.x - b * pp.y;
+          si += a * pp.y + b * pp.x;
         }
         num += sr * sr + si * si;
       }
@@ -462,6 +546,25 @@ extern "C" int bogp_envbatch_set_covariance(bogp_envbatch_t h, const double* K_r
   return 0;
 }
 
+extern "C" int bogp_envbatch_set_tilt(bogp_envbatch_t h, const double* tilt_deg_host, const double* lever_host) {
+  BOGP_REQUIRE(h != nullptr, "bogp_envbatch_set_tilt: NULL handle");
+  cudaFree(h->sin_tilt); cudaFree(h->lever);
+  h->sin_tilt = h->lever = nullptr;
+  h->tilted = false;
+  if (!tilt_deg_host) return 0;                      // back to a vertical array
+  BOGP_REQUIRE(lever_host != nullptr, "bogp_envbatch_set_tilt: lever is NULL");
+  std::vector<double> st((size_t)h->C);
+  bool any = false;
+  for (long long c = 0; c < h->C; ++c) {
+    st[(size_t)c] = std::sin(tilt_deg_host[c] * 0.017453292519943295);
+    any |= tilt_deg_host[c] != 0.0;
+  }
+  if (!any) return 0;
+  if (dev_copy(&h->sin_tilt, st.data(), st.size()) || dev_copy(&h->lever, lever_host, (size_t)h->C * h->N)) return BOGP_ERR_CUDA;
+  h->tilted = true;
+  return 0;
+}
+
 extern "C" int bogp_envbatch_bartlett(bogp_envbatch_t h, int atype, int mf_method, float* out_dev, void* stream) {
   BOGP_REQUIRE(h && out_dev, "bogp_envbatch_bartlett: NULL argument");
   BOGP_REQUIRE(h->has_cov, "bogp_envbatch_bartlett: call bogp_envbatch_set_covariance first");
@@ -469,6 +572,19 @@ extern "C" int bogp_envbatch_bartlett(bogp_envbatch_t h, int atype, int mf_metho
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (h->tilted) {
+    const size_t per_warp = (((size_t)h->Mmax * (sizeof(double) + sizeof(float) + sizeof(float2)) + (size_t)h->N * sizeof(float2)) + 15) & ~(size_t)15;
+    const size_t smem_t = (size_t)bogp::kEnvWarps * per_warp;
+    BOGP_REQUIRE(smem_t <= 227 * 1024, "bogp_envbatch_bartlett: Mmax+N too large");
+    if (smem_t > 48 * 1024) BOGP_CUDA(cudaFuncSetAttribute(bogp::envbatch_tilt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    const int grid_t = (int)std::max<long long>(1, std::min<long long>((h->C + bogp::kEnvWarps - 1) / bogp::kEnvWarps, (long long)sms * 8));
+    bogp::envbatch_tilt_kernel<<<grid_t, bogp::kEnvWarps * 32, smem_t, static_cast<cudaStream_t>(stream)>>>(
+        h->C, h->F, h->N, h->Mmax, h->k_re, h->k_im, h->amp_re, h->amp_im, h->phiT, h->range, h->sin_tilt, h->lever,
+        h->CkT_re, h->CkT_im, h->J, h->trK, h->Jmax, atype, mf_method, out_dev);
+    bogp::count_launch();
+    BOGP_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int force_simt = std::getenv("BOGP_ENV_SIMT") ? std::atoi(std::getenv("BOGP_ENV_SIMT")) : 0;
   if (h->rec && h->Jmax <= bogp::kEnvJ && !force_simt) {
     // streaming kernel: as many warps as fit with `stages` record buffers each.  Measured (profiles/paths_r1b.jsonl):
@@ -509,7 +625,7 @@ extern "C" int bogp_envbatch_bartlett(bogp_envbatch_t h, int atype, int mf_metho
 extern "C" int bogp_envbatch_destroy(bogp_envbatch_t h) {
   if (!h) return 0;
   cudaFree(h->k_re); cudaFree(h->k_im); cudaFree(h->range); cudaFree(h->amp_re); cudaFree(h->amp_im);
-  cudaFree(h->phiT); cudaFree(h->rec); cudaFree(h->CkT_re); cudaFree(h->CkT_im); cudaFree(h->J); cudaFree(h->trK);
+  cudaFree(h->phiT); cudaFree(h->rec); cudaFree(h->sin_tilt); cudaFree(h->lever); cudaFree(h->CkT_re); cudaFree(h->CkT_im); cudaFree(h->J); cudaFree(h->trK);
   delete h;
   return 0;
 }

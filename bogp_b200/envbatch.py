@@ -49,7 +49,7 @@ class EnvBatch:
     """``bogp_envbatch_t`` handle over C candidate environments."""
 
     def __init__(self, mode_sets: Sequence[ModeSet], rec_r_km: np.ndarray, src_z: np.ndarray,
-                 covariance_matrix: Optional[np.ndarray] = None):
+                 covariance_matrix: Optional[np.ndarray] = None, tilt_deg: Optional[np.ndarray] = None):
         rec_r_km = np.atleast_1d(np.asarray(rec_r_km, dtype=np.float64))
         src_z = np.atleast_1d(np.asarray(src_z, dtype=np.float64))
         if not (len(mode_sets) == len(rec_r_km) == len(src_z)):
@@ -65,6 +65,11 @@ class EnvBatch:
         _lib.call("bogp_envbatch_create", C.byref(self._h), self.C, self.F, self.N, Mmax, _lib.dptr(k_re),
                   _lib.dptr(k_im), _lib.dptr(a_re), _lib.dptr(a_im), _lib.fptr(phiT), _lib.dptr(rng))
         self.device = torch.device("cuda", torch.cuda.current_device())
+        if tilt_deg is not None and np.any(np.asarray(tilt_deg, dtype=np.float64) != 0.0):
+            # per-candidate array tilt (search key `tilt`, swellex96_inv/data/bo/common.py:63): levers of every candidate's own array
+            tilt = np.ascontiguousarray(np.broadcast_to(np.asarray(tilt_deg, dtype=np.float64), (self.C,)))
+            lever = np.ascontiguousarray(np.stack([ms.z_pivot - ms.rec_z for ms in mode_sets]), dtype=np.float64)
+            _lib.call("bogp_envbatch_set_tilt", self._h, _lib.dptr(tilt), _lib.dptr(lever))
         if covariance_matrix is not None:
             self.set_covariance(covariance_matrix)
 

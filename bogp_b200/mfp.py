@@ -17,6 +17,7 @@ HBM).  There is no CPU fallback: an objective built from callables the library c
 from __future__ import annotations
 
 import ctypes as C
+import copy
 from functools import partial
 from typing import Callable, Dict, List, Optional, Sequence, Union
 
@@ -235,12 +236,13 @@ def covariance(d: np.ndarray) -> np.ndarray:
     return d @ d.conj().T
 
 
-def simulate_covariance(runner: "ModeRunner", parameters: dict, freq: Sequence[float]) -> np.ndarray:
+def simulate_covariance(runner, parameters: dict, freq: Sequence[float]) -> np.ndarray:
     """``optimization.utils.simulate_covariance(runner, parameters, freq)`` (ref/optimization/utils.py:23-32):
     ``K[F, N, N]`` with ``K_f = d d^H``, ``d = p/||p||`` the replica at the truth in ``parameters`` (``src_z``,
-    ``rec_r`` [km], optional ``tilt``).  Host float64, set-up only (one modal sum per tonal)."""
+    ``rec_r`` [km], optional ``tilt``).  ``runner`` is :func:`run_kraken` (or a partial of it, as the configs build it)
+    or a :class:`ModeRunner`.  Host float64, set-up only (one modal sum per tonal)."""
     from .modes import synthetic_covariance
-    modes = runner.modes_for(parameters)
+    modes = _as_mode_runner(runner).modes_for(parameters)
     idx = []
     for f in freq:
         hits = [i for i, g in enumerate(modes.freq) if abs(g - float(f)) < 1e-9]
@@ -287,6 +289,59 @@ class ModeRunner:
             "ModeRunner does not materialise replica fields; use it as MatchedFieldProcessor(runner=...)")
 
 
+# ---- run_kraken: the function the unchanged configs name (conf/optimization/run.py:99 `pbuilds(run_kraken)`)
+_MODE_PROVIDER: Union[None, ModeSet, Callable[[dict], ModeSet]] = None
+
+
+def set_mode_provider(provider: Union[None, ModeSet, Callable[[dict], ModeSet]]) -> None:
+    """Registers what :func:`run_kraken` gets its modes from: a :class:`ModeSet` (one fixed environment) or a callable
+    ``parameters -> ModeSet`` that runs the host normal-mode program (KRAKEN stays external, north_star) for the
+    environment in ``parameters`` -- e.g. ``lambda env: modeset_from_tables(...)`` around TritonOA's KRAKEN wrapper."""
+    global _MODE_PROVIDER
+    _MODE_PROVIDER = provider
+
+
+def get_mode_provider():
+    return _MODE_PROVIDER
+
+
+def run_kraken(parameters: dict) -> np.ndarray:
+    """``tritonoa.at.models.kraken.runner.run_kraken`` as the reference calls it.
+
+    Two uses.  (1) As the ``runner`` of :class:`MatchedFieldProcessor` -- directly or as the ``functools.partial`` that
+    ``pbuilds(run_kraken)`` / ``instantiate`` produce (ref/projects/swellex96_localization/conf/optimization/run.py:89-99)
+    -- it is recognised by identity and never called: the modal sum is fused into the CUDA kernels and the modes come
+    from the registered provider (:func:`set_mode_provider`).  (2) Called with an environment dict carrying ``freq``
+    (``runner(parameters | {"freq": f})``, ref/optimization/utils.py:29) it returns the replica field ``p[N]``
+    (``p[N, Nr]`` for a vector ``rec_r``) of that single source position in float64 on the host: the set-up step that
+    builds the simulated covariance, one modal sum per tonal."""
+    from .modes import replica_field
+    modes = _as_mode_runner(run_kraken).modes_for(parameters)
+    if "freq" not in parameters:
+        raise KeyError("run_kraken(parameters): parameters['freq'] is required")
+    hits = [i for i, g in enumerate(modes.freq) if abs(g - float(parameters["freq"])) < 1e-9]
+    if not hits:
+        raise ValueError(f"mode set has no tonal at {parameters['freq']} Hz")
+    return replica_field(modes, hits[0], float(parameters["src_z"]), parameters["rec_r"],
+                         float(parameters.get("tilt", 0.0) or 0.0))
+
+
+def _as_mode_runner(runner) -> "ModeRunner":
+    """ModeRunner behind what the caller passed as ``runner``: a ModeRunner, :func:`run_kraken`, or partials of either
+    without bound arguments (hydra-zen ``zen_partial`` builds)."""
+    while isinstance(runner, partial) and not runner.args and not runner.keywords:
+        runner = runner.func
+    if isinstance(runner, ModeRunner):
+        return runner
+    if runner is run_kraken:
+        if _MODE_PROVIDER is None:
+            raise RuntimeError("run_kraken needs a mode provider: call bogp_b200.mfp.set_mode_provider(ModeSet | "
+                               "callable(parameters) -> ModeSet) first (KRAKEN itself stays on the host, outside this package)")
+        return ModeRunner(_MODE_PROVIDER)
+    raise TypeError("runner must be bogp_b200.mfp.run_kraken (or functools.partial of it) or a bogp_b200.mfp.ModeRunner; "
+                    "the modal sum is fused into the CUDA kernel and there is no CPU fallback for arbitrary runner callables")
+
+
 def _atype_of(bf: Callable) -> str:
     """Recover ``atype`` from ``beamformer`` or ``partial(beamformer, atype=...)``."""
     if bf is beamformer:
@@ -308,12 +363,10 @@ class MatchedFieldProcessor:
     a *list* of such dicts (the batch that obj.py:28-30 spreads over a process pool) and returns ``ndarray[C]``.
     """
 
-    def __init__(self, runner: ModeRunner, covariance_matrix, freq: Sequence[float], parameters: dict,
+    def __init__(self, runner, covariance_matrix, freq: Sequence[float], parameters: dict,
                  parameter_formatter: Optional[Callable] = None, beamformer: Callable = beamformer,
                  multifreq_method: str = "mean"):
-        if not isinstance(runner, ModeRunner):
-            raise TypeError("runner must be a bogp_b200.mfp.ModeRunner (mode provider); the modal sum is fused "
-                            "into the CUDA kernel and there is no CPU fallback for arbitrary runner callables")
+        runner = _as_mode_runner(runner)
         if multifreq_method not in _lib.MF_METHOD:
             raise ValueError(f"unknown multifreq_method {multifreq_method!r}")
         self.runner = runner
@@ -343,8 +396,11 @@ class MatchedFieldProcessor:
         for f in self.freq:
             title = f"{f:.1f}Hz"
             if self.parameter_formatter is not None:
-                m = self.parameter_formatter(freq=f, title=title, fixed_parameters=self.parameters,
-                                             search_parameters=parameters)
+                # the reference's formatter (swellex96_inv/data/bo/param_map.py) pops keys from the search dict and
+                # edits fixed_parameters['layerdata'] in place, and what it returns shares those nested lists: every
+                # tonal and every candidate gets its own copies, the caller's dicts are never handed over
+                m = self.parameter_formatter(freq=f, title=title, fixed_parameters=copy.deepcopy(self.parameters),
+                                             search_parameters=copy.deepcopy(parameters))
             else:
                 m = self.parameters | {"freq": f, "title": title} | parameters
             if merged is None:
@@ -420,8 +476,6 @@ class MatchedFieldProcessor:
         mode_sets = [self._select(self.runner.modes_for(m)) for m in merged]
         cand = np.array([[float(np.asarray(m["rec_r"])), float(np.asarray(m["src_z"])),
                           float(m.get("tilt", 0.0) or 0.0)] for m in merged], dtype=np.float64).reshape(-1, 3)
-        if np.any(cand[:, 2] != 0.0):
-            raise NotImplementedError("tilt with per-candidate environments is not supported")
-        with EnvBatch(mode_sets, cand[:, 0], cand[:, 1], self.covariance_matrix) as eb:
+        with EnvBatch(mode_sets, cand[:, 0], cand[:, 1], self.covariance_matrix, tilt_deg=cand[:, 2]) as eb:
             out = eb.bartlett(atype=self.atype, multifreq_method=self.multifreq_method)
         return out.cpu().numpy().astype(np.float64)

@@ -167,6 +167,47 @@ def perturbed_pekeris_batch(freq: Sequence[float], rec_z: Sequence[float], depth
             for d, c in zip(depths, c_bs)]
 
 
+def replica_field(modes: ModeSet, f: int, src_z: float, rec_r_km, tilt_deg: float = 0.0) -> np.ndarray:
+    """Replica pressure ``p[N]`` (scalar range) or ``p[N, Nr]`` of tonal index ``f`` for ONE source position: what a
+    single ``run_kraken(parameters | {"freq": f})`` call returns to ``simulate_covariance``
+    (ref/optimization/utils.py:29-31).  Host float64, set-up only -- the scored path never materialises a field."""
+    r = np.asarray(rec_r_km, dtype=np.float64)
+    lever = modes.z_pivot - modes.rec_z
+    dr = -lever * np.sin(np.deg2rad(float(tilt_deg)))
+    phi_s = modes.phi_src(f, src_z)[0]
+    rn = 1000.0 * np.atleast_1d(r)[None, :] + dr[:, None]                       # [N, Nr]
+    kr = modes.k[f][None, :, None] * rn[:, None, :]                             # [N, M, Nr]
+    p_ = np.einsum("nm,m,nmr->nr", modes.phi_rec[f], phi_s, np.exp(-1j * kr) / np.sqrt(kr))
+    return p_[:, 0] if r.ndim == 0 else p_
+
+
+def modeset_from_tables(freq: Sequence[float], k: Sequence[np.ndarray], z: Sequence[np.ndarray],
+                        phi: Sequence[np.ndarray], rec_z: Sequence[float], *, z_pivot: Optional[float] = None,
+                        dz_tab: float = 0.25, meta: Optional[dict] = None) -> ModeSet:
+    """ModeSet from the tables a host normal-mode program hands back: per tonal the eigenvalues ``k[f] [M_f]`` and the
+    mode shapes ``phi[f] [nz_f, M_f]`` sampled at the depths ``z[f] [nz_f]`` (the content of a KRAKEN ``.mod`` file as
+    TritonOA's reader exposes it: ``modes.k``, ``modes.z``, ``modes.phi``).  Receiver rows are the linear interpolation
+    at ``rec_z``; the source table is the same interpolation onto the uniform mesh ``0, dz_tab, ...`` of the data
+    contract (module docstring), shared by all tonals."""
+    rec_z = np.asarray(rec_z, dtype=np.float64)
+    zmax = max(float(np.max(zf)) for zf in z)
+    nz_tab = int(np.floor(zmax / dz_tab)) + 1
+    z_tab = dz_tab * np.arange(nz_tab)
+    ks, prs, pss = [], [], []
+    for kf, zf, pf in zip(k, z, phi):
+        zf = np.asarray(zf, dtype=np.float64)
+        pf = np.asarray(pf)
+        if pf.shape != (zf.shape[0], np.asarray(kf).shape[0]):
+            raise ValueError("modeset_from_tables: phi[f] must be [len(z[f]), len(k[f])]")
+        interp = lambda zq: np.stack([np.interp(zq, zf, pf[:, m].real) + (1j * np.interp(zq, zf, pf[:, m].imag) if np.iscomplexobj(pf) else 0.0)
+                                      for m in range(pf.shape[1])], axis=1)
+        ks.append(np.asarray(kf, dtype=np.complex128))
+        prs.append(interp(rec_z))
+        pss.append(interp(z_tab))
+    return ModeSet([float(f) for f in freq], ks, prs, pss, 0.0, float(dz_tab), rec_z,
+                   float(np.max(rec_z) if z_pivot is None else z_pivot), dict(meta or {}))
+
+
 def _outer(d: np.ndarray) -> np.ndarray:
     d = np.asarray(d, dtype=np.complex128).reshape(-1, 1)
     return d @ d.conj().T

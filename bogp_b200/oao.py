@@ -285,7 +285,7 @@ class BayesianOptimization(_Optimizer):
         from .acquisition import ExpectedImprovement, qExpectedImprovement
         from .gp import FitConfig, SingleTaskGP
         from .optim import optimize_acqf
-        torch.manual_seed(seed)
+        gen = torch.Generator().manual_seed(int(seed))      # local stream: the caller's global torch RNG is left alone
         d = U.shape[1]
         model = SingleTaskGP(torch.as_tensor(U), torch.as_tensor(y), covar_module=self.covar_module)
         cfg = FitConfig(steps=self.fit_steps)
@@ -296,7 +296,7 @@ class BayesianOptimization(_Optimizer):
         acq = (ExpectedImprovement(model, best_f) if q == 1 else
                qExpectedImprovement(model, best_f, q=q, mc_samples=self.mc_samples, seed=seed))
         bounds = torch.stack([torch.zeros(d, dtype=torch.float64), torch.ones(d, dtype=torch.float64)])
-        cand, _ = optimize_acqf(acq, bounds=bounds, q=q, num_restarts=self.num_restarts, raw_samples=self.raw_samples)
+        cand, _ = optimize_acqf(acq, bounds=bounds, q=q, num_restarts=self.num_restarts, raw_samples=self.raw_samples, generator=gen)
         return cand.reshape(q, d).numpy()
 
     def run(self, name: str = "bo") -> Client:

@@ -25,54 +25,56 @@ def draw_sobol_samples(bounds: torch.Tensor, n: int, q: int, seed: Optional[int]
     return bounds[0] + (bounds[1] - bounds[0]) * u
 
 
-def _boltzmann(X: torch.Tensor, Y: torch.Tensor, n: int, eta: float = 2.0) -> torch.Tensor:
+def _boltzmann(X: torch.Tensor, Y: torch.Tensor, n: int, eta: float = 2.0, generator=None) -> torch.Tensor:
     if n >= X.shape[0]:
         return X
     std = Y.std()
     if float(std) == 0.0:
-        return X[torch.randperm(X.shape[0])[:n]]
+        return X[torch.randperm(X.shape[0], generator=generator)[:n]]
     max_idx = int(torch.argmax(Y))
     etaZ = eta * (Y - Y.mean()) / std
     w = torch.exp(etaZ)
     while bool(torch.isinf(w).any()):
         etaZ = etaZ * 0.5
         w = torch.exp(etaZ)
-    idcs = torch.multinomial(w, n)
+    idcs = torch.multinomial(w, n, generator=generator)
     if max_idx not in idcs:
         idcs[-1] = max_idx
     return X[idcs]
 
 
-def _boltzmann_nonneg(X: torch.Tensor, Y: torch.Tensor, n: int, eta: float = 1.0, alpha: float = 1e-4) -> torch.Tensor:
+def _boltzmann_nonneg(X: torch.Tensor, Y: torch.Tensor, n: int, eta: float = 1.0, alpha: float = 1e-4, generator=None) -> torch.Tensor:
     if n >= X.shape[0]:
         return X
     max_val, max_idx = float(Y.max()), int(torch.argmax(Y))
     if max_val <= 0.0:
-        return X[torch.randperm(X.shape[0])[:n]]
+        return X[torch.randperm(X.shape[0], generator=generator)[:n]]
     pos = Y >= alpha * max_val
     while int(pos.sum()) < n:
         alpha *= 0.1
         pos = Y >= alpha * max_val
     pos_idcs = torch.nonzero(pos).squeeze(-1)
     w = torch.exp(eta * (Y[pos] / max_val - 1.0))
-    idcs = pos_idcs[torch.multinomial(w, n)]
+    idcs = pos_idcs[torch.multinomial(w, n, generator=generator)]
     if max_idx not in idcs:
         idcs[-1] = max_idx
     return X[idcs]
 
 
 def optimize_acqf(acq_function, bounds, q: int, num_restarts: int, raw_samples: int, options: Optional[dict] = None,
-                  return_best_only: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Returns ``(candidates[q, d], acq_value)`` as float64 CPU tensors."""
+                  return_best_only: bool = True, generator: Optional[torch.Generator] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns ``(candidates[q, d], acq_value)`` as float64 CPU tensors.  Random draws (Sobol seed, restart selection)
+    come from the torch global generator as in BoTorch, or from ``generator`` when one is given (callers that must
+    not disturb the user's random stream)."""
     options = options or {}
     bounds = torch.as_tensor(bounds, dtype=DT).cpu()
     d = bounds.shape[-1]
-    seed = int(torch.randint(0, 10000, (1,)).item())
+    seed = int(torch.randint(0, 10000, (1,), generator=generator).item())
     X_raw = draw_sobol_samples(bounds, raw_samples, q, seed)
     with torch.no_grad():
         Y_raw = acq_function(X_raw).detach().cpu()
     init = _boltzmann_nonneg if getattr(acq_function, "nonneg", False) else _boltzmann
-    X0 = init(X_raw, Y_raw, num_restarts)
+    X0 = init(X_raw, Y_raw, num_restarts, generator=generator)
     shape = X0.shape
     lo = bounds[0].repeat(shape[0] * q).numpy()
     hi = bounds[1].repeat(shape[0] * q).numpy()

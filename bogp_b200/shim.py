@@ -73,7 +73,7 @@ def install(force: bool = False) -> Dict[str, bool]:
         _module("tritonoa.sp.mfp", MatchedFieldProcessor=mfp.MatchedFieldProcessor)
         _module("tritonoa.sp.beamforming", beamformer=mfp.beamformer, covariance=mfp.covariance)
         _module("tritonoa.sp.processing", simulate_covariance=mfp.simulate_covariance)
-        _module("tritonoa.at.models.kraken.runner", run_kraken=mfp.ModeRunner)
+        _module("tritonoa.at.models.kraken.runner", run_kraken=mfp.run_kraken)
         _module("tritonoa.at.models.kraken.kraken", clean_up_kraken_files=clean_up_kraken_files)
         done["tritonoa"] = True
     else:

@@ -139,6 +139,7 @@ int bogp_bartlett_points(bogp_modeset_t h, const double* cand_dev, long long C, 
 int bogp_bartlett_points_host(bogp_modeset_t h, const double* cand_host, long long C, int atype,
                               int mf_method, float* out_host, void* stream);
 
+
 /* Geoacoustic inversion (obj.py:73-83): candidate c has its OWN mode set (host KRAKEN run per candidate).
  * Mode-major packing, padded to Mmax:  k_re/k_im_host[C, F, Mmax], amp_re/amp_im_host[C, F, Mmax] =
  * phi_m(z_s) already evaluated at the candidate's source depth (0 for padded modes),
@@ -148,6 +149,11 @@ int bogp_envbatch_create(bogp_envbatch_t* out, long long C, int F, int N, int Mm
                          const double* amp_re_host, const double* amp_im_host,
                          const float* phi_rec_T_host, const double* range_m_host);
 int bogp_envbatch_set_covariance(bogp_envbatch_t h, const double* K_re_host, const double* K_im_host);
+/* Tilted array for the environment batch: tilt_deg_host[C] and lever_host[C][N] = z_pivot - z_n of each candidate's
+ * array (receiver n then sits at range r - lever_n sin(tilt): the `tilt` key of the inversion's search space,
+ * projects/swellex96_inv/data/bo/common.py:63, evaluated through obj.py:62-70).  tilt_deg_host = NULL or all zeros
+ * returns the batch to the vertical-array kernels. */
+int bogp_envbatch_set_tilt(bogp_envbatch_t h, const double* tilt_deg_host, const double* lever_host);
 int bogp_envbatch_bartlett(bogp_envbatch_t h, int atype, int mf_method, float* out_dev, void* stream);
 int bogp_envbatch_destroy(bogp_envbatch_t h);
 

@@ -133,3 +133,49 @@ def bartlett_envbatch(mode_sets, K: np.ndarray, cand: np.ndarray, *, atype: str 
         out[c] = bartlett_points(ms, K, np.asarray(cand)[c:c + 1], atype=atype,
                                  multifreq_method=multifreq_method)[0]
     return out
+
+
+def _surface_rows(args):
+    modes, K, r_km, z, kw = args
+    return ambiguity_surface(modes, K, r_km, z, **kw)
+
+
+def ambiguity_surface_pool(modes, K: np.ndarray, r_km: np.ndarray, z: np.ndarray, workers: Optional[int] = None,
+                           **kw) -> np.ndarray:
+    """:func:`ambiguity_surface` with the depth rows spread over a process pool, the way the reference spreads its time
+    steps (ref/projects/swellex96_localization/data/mfp.py:166-177): the full 1000 x 1000 x 13 surface of BASELINE
+    configs[1] takes a few seconds on 16 cores.  One BLAS thread per worker."""
+    import os
+    from concurrent.futures import ProcessPoolExecutor
+    workers = workers or os.cpu_count() or 1
+    z = np.asarray(z, dtype=np.float64)
+    chunks = [c for c in np.array_split(np.arange(len(z)), min(len(z), 4 * workers)) if len(c)]
+    old = {k: os.environ.get(k) for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS")}
+    for k in old:
+        os.environ[k] = "1"
+    try:
+        import multiprocessing as mp
+        with ProcessPoolExecutor(workers, mp_context=mp.get_context("spawn")) as ex:
+            parts = list(ex.map(_surface_rows, [(modes, K, np.asarray(r_km), z[c], kw) for c in chunks]))
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return np.concatenate(parts, axis=0)
+
+
+def parity_stats(got: np.ndarray, ref: np.ndarray, floor: float = 0.05) -> dict:
+    """Relative-error distribution of a surface against the float64 reference: un-floored (|got - ref| / |ref|, the
+    literal reading of "within 1e-5 relative") and floored at `floor` * max|ref| (sidelobes far below the peak carry
+    the peak's absolute FP32 noise)."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    d = np.abs(got - ref)
+    un = d / np.maximum(np.abs(ref), 1e-300)
+    fl = d / np.maximum(np.abs(ref), floor * np.abs(ref).max())
+    return {"max_unfloored": float(un.max()), "p99_unfloored": float(np.quantile(un, 0.99)),
+            "p999_unfloored": float(np.quantile(un, 0.999)), "frac_unfloored_gt_1e-5": float((un > 1e-5).mean()),
+            "max_floored": float(fl.max()), "p99_floored": float(np.quantile(fl, 0.99)), "max_abs": float(d.max()),
+            "min_ref": float(np.abs(ref).min()), "same_argmax": bool(int(got.argmax()) == int(ref.argmax()))}

@@ -28,6 +28,11 @@ def assert_parity(got, ref, rtol=RTOL, floor=FLOOR):
     err = np.abs(got - ref) / scale
     assert np.isfinite(got).all()
     assert err.max() <= rtol, f"max rel err {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+    if floor < 1.0 and got.size >= 100:
+        # the literal reading of the bar (no floor) holds for 99 % of the nodes of every surface tested; the floor only
+        # covers isolated near-zero sidelobes (tools/parity_full.py: no floor needed at all on BASELINE configs[1])
+        un = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)
+        assert np.quantile(un, 0.99) <= rtol, f"p99 un-floored rel err {np.quantile(un, 0.99):.3e}"
 
 
 @pytest.fixture(scope="module")
@@ -69,6 +74,29 @@ def test_cfg2_shape_surface_vs_oracle(cfg2_small, dms2, engine):
     surf = dms2.bartlett_grid(c["r"], c["z"], engine=engine).cpu().numpy()
     assert_parity(surf, ref)
     assert np.unravel_index(surf.argmax(), surf.shape) == np.unravel_index(ref.argmax(), ref.shape)
+
+
+@pytest.mark.parametrize("shape", [(160, 24), (300, 70), (129, 9)])
+def test_tf32_engine_still_matches_oracle(cfg2_small, shape, monkeypatch):
+    """BOGP_UMMA_KIND=tf32 keeps the 3xTF32 kernel (kernels_umma.cu) selectable: same parity as the FP16-split default,
+    rank-1 folded and rank-8 covariances, and the two engines agree with each other far inside the bar."""
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import synthetic_covariance
+    c = cfg2_small
+    nr, nz = shape
+    r, z = np.linspace(0.3, 10.0, nr), np.linspace(2.0, 199.0, nz)
+    for K in (c["K"], synthetic_covariance(c["modes"], 60.0, 5.0, snapshots=8, seed=3)):
+        dms = DeviceModeSet(c["modes"], K)
+        assert dms.umma_kind() == 16
+        f16 = dms.bartlett_grid(r, z, engine="umma").cpu().numpy()
+        monkeypatch.setenv("BOGP_UMMA_KIND", "tf32")
+        assert dms.umma_kind() == 32
+        tf32 = dms.bartlett_grid(r, z, engine="umma").cpu().numpy()
+        monkeypatch.delenv("BOGP_UMMA_KIND")
+        ref = ob.ambiguity_surface(c["modes"], K, r, z)
+        assert_parity(f16, ref)
+        assert_parity(tf32, ref)
+        assert_parity(f16, tf32, rtol=4e-6)
 
 
 def test_folded_operator_matches_unfolded(cfg2_small, monkeypatch):
@@ -319,6 +347,30 @@ def test_edge_cases(cfg1, dms1):
     assert mfp.argmin(x) == (pytest.approx(-1.0), (4,))
 
 
+@pytest.mark.parametrize("kind", ["f16", "tf32"])
+def test_full_size_surface_vs_oracle(kind, monkeypatch):
+    """BASELINE configs[1] at full size, EVERY node: 1000 x 1000 x 13 tonals on both tcgen05 engines against the float64
+    oracle (depth rows over a process pool, ~2 s on 16 cores).  Identical arg-max, and the literal bar -- relative error
+    <= 1e-5 with NO floor -- on all 10^6 nodes (measured: 1.5e-6 / 1.1e-6 max, profiles/parity_full_r2.jsonl)."""
+    from bogp_b200.mfp import DeviceModeSet
+    from bogp_b200.modes import SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    r, z = np.linspace(0.1, 10.0, 1000), np.linspace(1.0, 200.0, 1000)
+    K = synthetic_covariance(modes, z[296], r[495])
+    ref = ob.ambiguity_surface_pool(modes, K, r, z)
+    if kind == "tf32":
+        monkeypatch.setenv("BOGP_UMMA_KIND", "tf32")
+    dms = DeviceModeSet(modes, K)
+    assert dms.umma_kind() == (32 if kind == "tf32" else 16)
+    got = dms.bartlett_grid(r, z, engine="umma").cpu().numpy()
+    st = ob.parity_stats(got, ref)
+    assert st["same_argmax"] and np.unravel_index(got.argmax(), got.shape) == (296, 495)
+    assert st["max_unfloored"] <= RTOL, st
+    ml = dms.bartlett_grid(r, z, engine="umma", atype="cbf_ml", multifreq_method="product").cpu().numpy()
+    ml_ref = ob.ambiguity_surface_pool(modes, K, r, z, atype="cbf_ml", multifreq_method="product")
+    assert np.abs(ml - ml_ref).max() <= RTOL and int(ml.argmin()) == int(ml_ref.argmin())
+
+
 def test_full_size_surface_properties():
     """BASELINE config 2 at full size (1000 x 1000 x 13 tonals): size-independent properties.
 
@@ -477,3 +529,51 @@ def test_full_size_envbatch_properties():
     pick = rng.choice(C, 40, replace=False)
     ref = ob.bartlett_envbatch([base[env[c]] for c in pick], K, np.stack([r[pick], zs[pick], np.zeros(40)], 1))
     assert_parity(got[pick], ref)
+
+
+def test_envbatch_tilted_array_vs_oracle():
+    """Per-candidate environments WITH array tilt (the inversion's search space has tilt in [-3, 3] deg and a tilted
+    truth, ref/projects/swellex96_inv/data/bo/common.py:63): EnvBatch and the objective protocol against the oracle."""
+    from bogp_b200 import mfp
+    from bogp_b200.envbatch import EnvBatch
+    from bogp_b200.modes import INV_TONALS_3, REC_Z_21, pekeris_modes, perturbed_pekeris_batch, synthetic_covariance
+    truth = pekeris_modes(INV_TONALS_3, REC_Z_21)
+    K = synthetic_covariance(truth, 71.11, 1.07, tilt_deg=2.067787)
+    rng = np.random.default_rng(11)
+    C = 40
+    depths = np.r_[217.0, rng.uniform(212.0, 222.0, C - 1)]
+    cbs = np.r_[1650.0, rng.uniform(1600.0, 1700.0, C - 1)]
+    sets = perturbed_pekeris_batch(INV_TONALS_3, REC_Z_21, depths, cbs)
+    r = np.r_[1.07, rng.uniform(0.9, 1.3, C - 1)]
+    zs = np.r_[71.11, rng.uniform(60.0, 80.0, C - 1)]
+    tilt = np.r_[2.067787, rng.uniform(-3.0, 3.0, C - 1)]
+    tilt[3] = 0.0
+    cand = np.stack([r, zs, tilt], 1)
+    for atype, mf in (("cbf", "mean"), ("cbf_ml", "product")):
+        ref = ob.bartlett_envbatch(sets, K, cand, atype=atype, multifreq_method=mf)
+        with EnvBatch(sets, r, zs, K, tilt_deg=tilt) as eb:
+            got = eb.bartlett(atype=atype, multifreq_method=mf).cpu().numpy()
+        assert_parity(got, ref, floor=1.0 if atype == "cbf_ml" else FLOOR)
+    assert abs(got[0]) < 2e-5                        # the true (tilted) environment scores 0 under cbf_ml
+
+    def provider(p):
+        return pekeris_modes(INV_TONALS_3, REC_Z_21, depth=p["h_w"], c_b=p["c_b"])
+
+    proc = mfp.MatchedFieldProcessor(mfp.ModeRunner(provider), K, INV_TONALS_3, {"src_z": 71.11, "rec_r": 1.07},
+                                     beamformer=partial(mfp.beamformer, atype="cbf_ml"), multifreq_method="product")
+    vals = proc([{"h_w": float(d), "c_b": float(c), "tilt": float(t)} for d, c, t in zip(depths[:6], cbs[:6], tilt[:6])])
+    ref6 = ob.bartlett_envbatch(sets[:6], K, np.stack([np.full(6, 1.07), np.full(6, 71.11), tilt[:6]], 1), atype="cbf_ml", multifreq_method="product")
+    assert_parity(vals, ref6, floor=1.0)
+    one = proc({"h_w": 217.0, "c_b": 1650.0, "tilt": 2.067787})
+    assert isinstance(one, float) and abs(one) < 2e-5
+
+
+def test_simt_zero_tilt_axis_fills_every_plane(cfg1, dms1):
+    """A tilt axis of zeros through the CUDA-core engine: every plane written, equal to the vertical array."""
+    base = dms1.bartlett_grid(cfg1["r"], cfg1["z"], engine="simt").cpu().numpy()
+    vol = dms1.bartlett_grid(cfg1["r"], cfg1["z"], [0.0, 0.0, 0.0], engine="simt")
+    assert vol.shape == (3,) + base.shape
+    for k in range(3):
+        np.testing.assert_allclose(vol[k].cpu().numpy(), base, rtol=0, atol=2e-6)
+    _, pos = __import__("bogp_b200").mfp.argmax(vol)
+    assert pos[1:] == tuple(int(i) for i in np.unravel_index(base.argmax(), base.shape))

@@ -145,7 +145,7 @@ def test_shims_resolve_reference_import_paths():
         from gpytorch.constraints import Interval
         from gpytorch.likelihoods import GaussianLikelihood
         import bogp_b200.mfp as m, bogp_b200.gp as g
-        assert MatchedFieldProcessor is m.MatchedFieldProcessor and run_kraken is m.ModeRunner
+        assert MatchedFieldProcessor is m.MatchedFieldProcessor and run_kraken is m.run_kraken
         assert SingleTaskGP is g.SingleTaskGP and BayesianOptimization is oao.BayesianOptimization
         lik = GaussianLikelihood(noise_constraint=Interval(1e-8, 1e-3))
         gp = SingleTaskGP(np.random.default_rng(0).random((5, 2)), np.arange(5.0), likelihood=lik)
