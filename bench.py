@@ -42,7 +42,15 @@ METRIC = "bartlett_cand_freq_evals_per_s"
 UNIT = "cand*freq/s"
 
 
-def workload_config(n_gpus: int) -> dict:
+def workload_config(n_gpus: int, strong: bool = False) -> dict:
+    if strong:
+        cfg = workload_config(1)
+        cfg["sharding"] = f"strong scaling: the ONE {NZ_PER_GPU} x {NR} surface split into depth-row slabs over {n_gpus} rank(s), replicated mode tables"
+        return cfg
+    return _workload_config(n_gpus)
+
+
+def _workload_config(n_gpus: int) -> dict:
     return {"workload": "configs[1]: 13-tonal incoherent Bartlett surface, 1000 ranges x 1000 depths per GPU, "
                         "64-element VLA, synthetic Pekeris mode set (276 modes), rank-1 K",
             "grid": [NZ_PER_GPU * n_gpus, NR], "tonals": 13, "receivers": 64,
@@ -355,16 +363,22 @@ def run_ours(args) -> None:
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
 
-    modes, K, r, z = build_inputs(world)
-    lo, hi = rank * NZ_PER_GPU, (rank + 1) * NZ_PER_GPU
+    strong = args.scaling == "strong"
+    modes, K, r, z = build_inputs(1 if strong else world)
+    if strong:
+        from bogp_b200.sharding import slab
+        lo, hi = slab(NZ_PER_GPU, rank, world)
+    else:
+        lo, hi = rank * NZ_PER_GPU, (rank + 1) * NZ_PER_GPU
+    rows = hi - lo
     z_slab = np.ascontiguousarray(z[lo:hi])
     dms = mfp.DeviceModeSet(modes, K)
-    surf = torch.empty((NZ_PER_GPU, NR), dtype=torch.float32, device=dev)
+    surf = torch.empty((rows, NR), dtype=torch.float32, device=dev)
     pair = torch.zeros(2, dtype=torch.int64, device=dev)
     pairs = torch.zeros((world, 2), dtype=torch.int64, device=dev)
     scratch = torch.empty(8192, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    host_surf = torch.empty((NZ_PER_GPU, NR), dtype=torch.float32, pin_memory=True)
+    host_surf = torch.empty((rows, NR), dtype=torch.float32, pin_memory=True)
     host_surf_np = host_surf.numpy()
 
     # final reduction across ranks: 16-byte records over peer memory (one kernel, NVLink P2P stores), NCCL all-gather as
@@ -385,7 +399,8 @@ def run_ours(args) -> None:
             if int(ok.item()) == 0:
                 peer = None
             else:
-                exchange_kind = "peer memory (bogp_peer_exchange: P2P stores over NVLink, one single-block kernel)"
+                exchange_kind = ("peer memory, fused: the surface kernel's last CTA stores the record into the peers' buffers over "
+                                 "NVLink and collects theirs (bogp_bartlett_grid_argext_peer, no launch of its own)")
 
     def exchange_records():
         if peer is not None:
@@ -393,12 +408,21 @@ def run_ours(args) -> None:
         else:
             dist.all_gather_into_tensor(pairs.view(-1), pair)
 
+    from bogp_b200.sharding import reduce_records
+
     def step_device():
+        if peer is not None:
+            dms.bartlett_grid(r, z_slab, engine=args.engine, out=surf, argext=(pair, scratch, True), peer=(peer, lo * NR, pairs))
+            return
         dms.bartlett_grid(r, z_slab, engine=args.engine, out=surf, argext=(pair, scratch, True))
         if world > 1:
+            pair[0] += lo * NR
             exchange_records()
 
     def step_e2e():
+        if peer is not None:      # one call: surface to the host buffer, records of every rank back with it
+            out, recs = dms.bartlett_grid_host(r, z_slab, engine=args.engine, out=host_surf_np, argext="max", peer=(peer, lo * NR))
+            return reduce_records(recs)[1]
         out, (val, pos) = dms.bartlett_grid_host(r, z_slab, engine=args.engine, out=host_surf_np, argext="max")
         flat = pos[0] * NR + pos[1]          # final reduction (collate.py:50), computed on the device with the surface
         if world > 1:
@@ -421,11 +445,17 @@ def run_ours(args) -> None:
     if world == 1 and not (pos == TRUTH_NODE and abs(val - 1.0) < 2e-5):
         raise SystemExit(f"bench.py: parity gate failed: argmax {pos} value {val}")
     if world > 1:
-        # the exchanged records must be what an NCCL all-gather of the same records gives
+        # the exchanged records must be what an NCCL all-gather of the same records gives, and their reduction the node
+        # nearest the truth
+        mine = pair.clone()
+        if peer is not None:
+            mine[0] += lo * NR
         check = torch.zeros_like(pairs)
-        dist.all_gather_into_tensor(check.view(-1), pair)
+        dist.all_gather_into_tensor(check.view(-1), mine)
         if not torch.equal(check, pairs):
             raise SystemExit(f"bench.py: record exchange mismatch on rank {rank}: {pairs.tolist()} vs {check.tolist()}")
+        if strong and reduce_records(pairs)[1] != TRUTH_NODE[0] * NR + TRUTH_NODE[1]:
+            raise SystemExit(f"bench.py: global arg-max {reduce_records(pairs)} is not the truth node")
 
     # ---- device-resident timing.  Two passes over the same K steps: (1) `value`: CUDA events around each step, nothing
     # recorded inside it (the library then launches the surface kernel as a programmatic dependent of its table kernel);
@@ -452,7 +482,7 @@ def run_ours(args) -> None:
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    evals_per_step = world * NZ_PER_GPU * NR * modes.n_freq
+    evals_per_step = (NZ_PER_GPU if strong else world * NZ_PER_GPU) * NR * modes.n_freq
     value = evals_per_step * args.steps / (total_ms * 1e-3)
 
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -483,7 +513,7 @@ def run_ours(args) -> None:
     e2e_s = float(t.item())
     e2e_value = evals_per_step * args.steps / e2e_s
     h2d = (len(r) + len(z_slab)) * 8 + (16 if world > 1 else 0)
-    d2h = NZ_PER_GPU * NR * 4 + (16 * world if world > 1 else 0)
+    d2h = rows * NR * 4 + (16 * world if world > 1 else 0)
 
     # ---- roofline of the dominant kernel
     peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -500,7 +530,7 @@ def run_ours(args) -> None:
     kind = dms.umma_kind() if args.engine in ("auto", "umma") else 0
     peak_tf32x3 = bf16 / 2.0 / 3.0
     peak = bf16 / 3.0 if kind == 16 else peak_tf32x3
-    flop_per_launch = dms.flops_per_candidate("umma" if args.engine in ("auto", "umma") else "simt") * NZ_PER_GPU * NR
+    flop_per_launch = dms.flops_per_candidate("umma" if args.engine in ("auto", "umma") else "simt") * rows * NR
     kern_avg_ms = kern_ms / max(kern_n, 1)
     achieved = flop_per_launch / (kern_avg_ms * 1e-3) / 1e12 if kern_n else None
     # measured denominators of this round (profiles/peaks_r2.json: cuBLAS TF32 burst, tcgen05 back-to-back MMAs at bench
@@ -534,8 +564,8 @@ def run_ours(args) -> None:
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xFP16-split tensor-core products, fp32 accumulate)" if kind == 16 else "f32", "data": "synthetic",
-            "config": dict(workload_config(world), engine=args.engine, final_reduction=exchange_kind),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32 (3xFP16-split tensor-core products, fp32 accumulate)" if kind == 16 else "f32", "data": "synthetic",
+            "config": dict(workload_config(world, strong), engine=args.engine, final_reduction=exchange_kind),
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3 / args.steps,
@@ -581,6 +611,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--engine", choices=["auto", "simt", "umma"], default="auto")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak (default, what the driver runs): 1000 depth rows per GPU; strong: the one 1000 x 1000 surface of configs[1] split over the GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-bo", action="store_true", help="skip the BO-iteration (GP acquisition optimisation) timing")
     ap.add_argument("--no-paths", action="store_true", help="skip the other kernels of the path (tilt, env batch, GP)")

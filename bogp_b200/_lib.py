@@ -69,6 +69,10 @@ SIGNATURES = {
     "bogp_peer_open": (C.c_int, [_vp, _vp]),
     "bogp_peer_exchange": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bogp_peer_destroy": (C.c_int, [_vp]),
+    "bogp_bartlett_grid_argext_peer": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
+                                                C.c_int, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "bogp_bartlett_grid_host_argmax_peer": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                     _fp, C.c_int, _vp, _ll, C.POINTER(_ll), _vp]),
     "bogp_gp_thompson": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _dp, _vp]),
     "bogp_gp_posterior": (C.c_int, [_vp, _vp, _ll, C.c_int, _vp, _vp, _vp]),
     "bogp_gp_acq": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp, _ll, _vp, _vp, _vp]),

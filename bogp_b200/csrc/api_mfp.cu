@@ -539,9 +539,17 @@ static int check_modes(int atype, int mf) {
 
 // ext_mode 0: surface only.  1 / 2: arg-max / arg-min of the surface into (ext_val_dev, ext_idx_dev) as well -- inside the
 // tcgen05 kernel when that engine runs (no extra launch), by the two arg-ext kernels otherwise.
+__global__ void pack_record_kernel(const float* val, const long long* idx, long long offset, long long* rec) {
+  const long long i = *idx;
+  rec[0] = i < 0 ? i : i + offset;
+  rec[1] = (long long)__float_as_uint(*val);
+}
+
 static int grid_impl(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
                      const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine, float* out_dev,
-                     void* stream, int ext_mode, float* ext_val_dev, long long* ext_idx_dev, void* ext_scratch) {
+                     void* stream, int ext_mode, float* ext_val_dev, long long* ext_idx_dev, void* ext_scratch,
+                     const bogp::PeerArgs* peer = nullptr, bool* peer_done = nullptr) {
+  if (peer_done) *peer_done = false;
   BOGP_REQUIRE(h != nullptr, "bogp_bartlett_grid: NULL handle");
   BOGP_REQUIRE(h->has_cov, "bogp_bartlett_grid: call bogp_covariance_set first");
   BOGP_REQUIRE(Nr >= 0 && Nz >= 0 && Nt >= 1, "bogp_bartlett_grid: bad sizes Nr=%d Nz=%d Nt=%d", Nr, Nz, Nt);
@@ -572,7 +580,7 @@ static int grid_impl(bogp_modeset_t h, const double* r_m_host, int Nr, const dou
     rc = bogp::launch_grid_umma_tilt(h, r_m_host, Nr, z_host, Nz, tilt_arg, Nt, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
     if (rc || !ext_mode || fuse_ext) return rc;
   } else if (!tilt_axis && (engine == BOGP_ENGINE_UMMA || (engine == BOGP_ENGINE_AUTO && bogp::umma_supported(h) && total >= 16384))) {
-    rc = bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
+    rc = bogp::launch_grid_umma(h, r_m_host, Nr, z_host, Nz, atype, mf_method, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev, peer, peer_done);
     if (rc || !ext_mode || fuse_ext) return rc;
   } else {
     // (a tilt axis of zeros still has Nt planes to fill)
@@ -678,6 +686,69 @@ extern "C" int bogp_bartlett_grid_host_argmax(bogp_modeset_t h, const double* r_
       *idx_host = *reinterpret_cast<volatile long long*>(h->pin_host);
       *val_host = *reinterpret_cast<volatile float*>(h->pin_host + 8);
     }
+  }
+  return rc;
+}
+
+// Surface + arg-ext + exchange of the (index_offset + index, value) records with the other GPUs of the box.  On the
+// FP16-split tcgen05 engine the exchange runs in the surface kernel's last CTA (no launch of its own); otherwise the
+// record is packed by a one-thread kernel and exchanged by peer_exchange_kernel.
+static int grid_peer_impl(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                          const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine, float* out_dev,
+                          int maximize, bogp_peer_t peer, long long index_offset, long long* recs_out_dev, float* val_dev,
+                          long long* idx_dev, void* scratch_dev, void* stream) {
+  BOGP_REQUIRE(peer && recs_out_dev && val_dev && idx_dev && scratch_dev, "bogp_bartlett_grid_argext_peer: NULL argument");
+  BOGP_REQUIRE((long long)std::max(Nt, 1) * Nz * Nr > 0, "bogp_bartlett_grid_argext_peer: empty surface");
+  bogp::PeerArgs a;
+  if (int rc = bogp::peer_next(peer, index_offset, recs_out_dev, a)) return rc;
+  bool done = false;
+  int rc = grid_impl(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, out_dev, stream,
+                     maximize ? 1 : 2, val_dev, idx_dev, scratch_dev, &a, &done);
+  if (rc || done) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  long long* rec = reinterpret_cast<long long*>(static_cast<char*>(scratch_dev) + 8192 - 16);      // the arg-ext kernels use the first 7104 bytes
+  pack_record_kernel<<<1, 1, 0, s>>>(val_dev, idx_dev, index_offset, rec);
+  bogp::count_launch();
+  return bogp::peer_exchange_launch(a, rec, s);
+}
+
+extern "C" int bogp_bartlett_grid_argext_peer(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                                              const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                                              float* out_dev, int maximize, bogp_peer_t peer, long long index_offset,
+                                              long long* recs_out_dev, float* val_dev, long long* idx_dev,
+                                              void* scratch_dev, long long scratch_bytes, void* stream) {
+  BOGP_REQUIRE(scratch_bytes >= 8192, "bogp_bartlett_grid_argext_peer: scratch must be >= 8192 bytes");
+  return grid_peer_impl(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, out_dev, maximize, peer,
+                        index_offset, recs_out_dev, val_dev, idx_dev, scratch_dev, stream);
+}
+
+extern "C" int bogp_bartlett_grid_host_argmax_peer(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host,
+                                                   int Nz, const double* tilt_deg_host, int Nt, int atype, int mf_method,
+                                                   int engine, float* out_host, int maximize, bogp_peer_t peer,
+                                                   long long index_offset, long long* recs_host, void* stream) {
+  BOGP_REQUIRE(out_host && recs_host && peer, "bogp_bartlett_grid_host_argmax_peer: NULL argument");
+  BOGP_REQUIRE(h != nullptr, "bogp_bartlett_grid_host_argmax_peer: NULL handle");
+  const size_t n = (size_t)std::max(Nt, 1) * Nz * Nr;
+  BOGP_REQUIRE(n > 0, "bogp_bartlett_grid_host_argmax_peer: empty surface");
+  const int world = peer->world;
+  const size_t off_pair = (n * sizeof(float) + 15) & ~(size_t)15;
+  if (int rc0 = io_scratch(h, off_pair + 16 + 8192)) return rc0;
+  char* base = static_cast<char*>(h->io_scratch);
+  float* alias = picks_tensor_engine(h, engine, tilt_deg_host, Nt, (long long)n) ? mapped_alias(out_host) : nullptr;
+  float* tmp = alias ? alias : reinterpret_cast<float*>(base);
+  // mapped page-locked block: [idx, val | records of every rank], written by the kernels, read after the one synchronisation
+  if (int rc1 = bogp::ensure_pinned(h, 64 + (size_t)world * 16)) return rc1;
+  long long* idx_dev = reinterpret_cast<long long*>(h->pin_dev);
+  float* val_dev = reinterpret_cast<float*>(h->pin_dev + 8);
+  long long* recs_dev = reinterpret_cast<long long*>(h->pin_dev + 64);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = grid_peer_impl(h, r_m_host, Nr, z_host, Nz, tilt_deg_host, Nt, atype, mf_method, engine, tmp, maximize, peer,
+                          index_offset, recs_dev, val_dev, idx_dev, base + off_pair + 16, stream);
+  if (rc == 0) {
+    cudaError_t e = alias ? cudaSuccess : cudaMemcpyAsync(out_host, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { bogp::set_error("bogp_bartlett_grid_host_argmax_peer: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
+    else std::memcpy(recs_host, h->pin_host + 64, (size_t)world * 16);
   }
   return rc;
 }

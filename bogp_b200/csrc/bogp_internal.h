@@ -166,9 +166,12 @@ int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const doub
 // kernels_umma.cu
 // ext_mode 1 / 2: also write arg-max / arg-min (value, flat index) to ext_val_dev / ext_idx_dev from inside the kernel;
 // returns with ext_mode ignored (caller falls back to the arg-ext kernels) only when Nr * Nz >= 2^32.
+struct PeerArgs;
+// peer != nullptr: the last CTA also publishes (index_offset + index, value) to the peers and collects theirs; *peer_done
+// tells the caller whether the engine that ran did so (the 3xTF32 kernel does not)
 int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype,
                      int mf, float* out_dev, cudaStream_t s, int ext_mode = 0, float* ext_val_dev = nullptr,
-                     long long* ext_idx_dev = nullptr);
+                     long long* ext_idx_dev = nullptr, const PeerArgs* peer = nullptr, bool* peer_done = nullptr);
 bool umma_supported(const bogp_modeset_s* h);
 // tilted-array grid (tilt axis) on the tensor cores: N <= 64 receivers, covariance rank <= 4, real source tables
 bool umma_tilt_supported(const bogp_modeset_s* h);
@@ -178,8 +181,35 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
 int ensure_scratch(bogp_modeset_s* h, size_t bytes);
 // kernels_umma16.cu: the same surface with FP16-split operands (the default tcgen05 engine for a vertical array)
 bool umma16_supported(const bogp_modeset_s* h);
+struct PeerArgs;
 int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype, int mf,
-                       float* out_dev, cudaStream_t s, int ext_mode, float* ext_val_dev, long long* ext_idx_dev);
+                       float* out_dev, cudaStream_t s, int ext_mode, float* ext_val_dev, long long* ext_idx_dev,
+                       const PeerArgs* peer = nullptr);
+}  // namespace bogp
+
+// Peer-memory record exchange (kernels_peer.cu); the tcgen05 surface kernel can run the exchange from its last CTA
+struct bogp_peer_s {
+  int rank = 0, world = 1;
+  unsigned char* local = nullptr;               // this rank's buffer (device)
+  std::vector<unsigned char*> mapped;           // peers' buffers as mapped here (mapped[rank] == local)
+  unsigned char** mapped_dev = nullptr;         // the same array on the device
+  unsigned long long epoch = 0;
+  size_t bytes = 0;
+};
+namespace bogp {
+// What a surface kernel needs to run the exchange of the (index, value) record itself: see peer_exchange_kernel.
+struct PeerArgs {
+  unsigned char* const* bufs = nullptr;      // every rank's buffer as mapped here (device array), null = no exchange
+  int rank = 0, world = 1;
+  unsigned long long epoch = 0;
+  long long index_offset = 0;                // added to the local flat index before the record is published
+  long long* recs_out = nullptr;             // [world][2] records of every rank (device or mapped host memory)
+  int* err = nullptr;
+};
+// fills `a` for the next exchange of `p` (advances its epoch)
+int peer_next(bogp_peer_s* p, long long index_offset, long long* recs_out, PeerArgs& a);
+// the stand-alone exchange kernel on a record already on the device (engines without the fused exchange)
+int peer_exchange_launch(const PeerArgs& a, const long long* rec_dev, cudaStream_t s);
 }  // namespace bogp
 
 // GP posterior handle (kernels_gp.cu creates it; kernels_ts.cu samples from it)

@@ -17,14 +17,6 @@
 
 #include "bogp_internal.h"
 
-struct bogp_peer_s {
-  int rank = 0, world = 1;
-  unsigned char* local = nullptr;               // this rank's buffer (device)
-  std::vector<unsigned char*> mapped;           // peers' buffers as mapped here (mapped[rank] == local)
-  unsigned char** mapped_dev = nullptr;         // the same array on the device
-  unsigned long long epoch = 0;
-  size_t bytes = 0;
-};
 
 namespace bogp {
 
@@ -60,6 +52,21 @@ __global__ void peer_exchange_kernel(unsigned char* const* bufs, int rank, int w
   const long long* src = reinterpret_cast<const long long*>(mine + ((size_t)(epoch & 1ull) * world + t) * 16);
   recs_out[2 * t] = src[0];
   recs_out[2 * t + 1] = src[1];
+}
+
+int peer_next(bogp_peer_s* p, long long index_offset, long long* recs_out, PeerArgs& a) {
+  BOGP_REQUIRE(p && p->mapped_dev, "peer exchange: call bogp_peer_open first");
+  ++p->epoch;
+  a.bufs = p->mapped_dev; a.rank = p->rank; a.world = p->world; a.epoch = p->epoch; a.index_offset = index_offset;
+  a.recs_out = recs_out; a.err = reinterpret_cast<int*>(p->local + p->bytes - 64);
+  return 0;
+}
+
+int peer_exchange_launch(const PeerArgs& a, const long long* rec_dev, cudaStream_t s) {
+  peer_exchange_kernel<<<1, 64, 0, s>>>(a.bufs, a.rank, a.world, a.epoch, rec_dev, a.recs_out, a.err);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace bogp
@@ -115,13 +122,9 @@ extern "C" int bogp_peer_open(bogp_peer_t p, const unsigned char* all_handles) {
 extern "C" int bogp_peer_exchange(bogp_peer_t p, const long long* rec_dev, long long* recs_out_dev, void* stream) {
   BOGP_REQUIRE(p && rec_dev && recs_out_dev, "bogp_peer_exchange: NULL argument");
   BOGP_REQUIRE(p->mapped_dev, "bogp_peer_exchange: call bogp_peer_open first");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  ++p->epoch;
-  int* err = reinterpret_cast<int*>(p->local + p->bytes - 64);
-  bogp::peer_exchange_kernel<<<1, 64, 0, s>>>(p->mapped_dev, p->rank, p->world, p->epoch, rec_dev, recs_out_dev, err);
-  bogp::count_launch();
-  BOGP_CUDA(cudaGetLastError());
-  return 0;
+  bogp::PeerArgs a;
+  if (int rc = bogp::peer_next(p, 0, recs_out_dev, a)) return rc;
+  return bogp::peer_exchange_launch(a, rec_dev, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int bogp_peer_destroy(bogp_peer_t p) {

@@ -1155,9 +1155,15 @@ bool umma_supported(const bogp_modeset_s* h) {
 }
 
 int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype, int mf,
-                     float* out_dev, cudaStream_t s, int ext_mode, float* ext_val_dev, long long* ext_idx_dev) {
+                     float* out_dev, cudaStream_t s, int ext_mode, float* ext_val_dev, long long* ext_idx_dev,
+                     const PeerArgs* peer, bool* peer_done) {
   // FP16-split engine (kernels_umma16.cu) unless BOGP_UMMA_KIND=tf32 or the mode set does not fit it
-  if (umma16_supported(h)) return launch_grid_umma16(h, r_host, Nr, z_host, Nz, atype, mf, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev);
+  if (peer_done) *peer_done = false;
+  if (umma16_supported(h)) {
+    const bool fuse = peer && ext_mode && (long long)Nr * Nz < (1ll << 32);
+    if (peer_done) *peer_done = fuse;
+    return launch_grid_umma16(h, r_host, Nr, z_host, Nz, atype, mf, out_dev, s, ext_mode, ext_val_dev, ext_idx_dev, fuse ? peer : nullptr);
+  }
   const ModesetDev& d = h->dev;
   const int sms = device_sms();
   UParams p{};

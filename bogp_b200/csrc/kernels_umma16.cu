@@ -72,6 +72,14 @@ struct HParams {
   unsigned int* ext_done;
   float* ext_val;
   long long* ext_idx;
+  // fused final reduction across the GPUs of a box: the last CTA publishes (index_offset + index, value) to every peer's
+  // buffer and collects theirs (what csrc/kernels_peer.cu does in a launch of its own); peer_bufs == null: off
+  unsigned char* const* peer_bufs;
+  int peer_rank, peer_world;
+  unsigned long long peer_epoch;
+  long long peer_offset;
+  long long* peer_out;
+  int* peer_err;
   long long* dbg;              // debug build: [0, 64) issuer 0 tonal starts, [64, 128) epilogue warp 0 tonal starts (CTA 0)
   int skip;                    // debug build: 1 = no MMAs issued, 2 = epilogue releases without reading
   HTonal t[BOGP_MAX_TONALS];
@@ -663,19 +671,58 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  long long* xrec = reinterpret_cast<long long*>(smem + p.smem_acc);      // (index, value bits, last-CTA flag): acc is free now
   if (p.ext_mode && threadIdx.x == 0) {
+    xrec[2] = 0;
     __threadfence();
     if (atomicAdd(p.ext_done, 1u) == gridDim.x - 1) {
       __threadfence();
       const unsigned long long key = atomicMax(p.ext_key, 0ull);
-      if (key == 0ull) { *p.ext_val = 0.f; *p.ext_idx = -1; }
-      else {
+      float val = 0.f;
+      long long idx = -1;
+      if (key != 0ull) {
         uint32_t uu = (uint32_t)(key >> 32);
         if (p.ext_mode == 2) uu = ~uu;
         uu = (uu & 0x80000000u) ? (uu & 0x7fffffffu) : ~uu;
-        *p.ext_val = __uint_as_float(uu);
-        *p.ext_idx = (long long)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
+        val = __uint_as_float(uu);
+        idx = (long long)(0xffffffffu - (uint32_t)(key & 0xffffffffu));
       }
+      *p.ext_val = val;
+      *p.ext_idx = idx;
+      xrec[0] = idx < 0 ? idx : idx + p.peer_offset;
+      xrec[1] = (long long)__float_as_uint(val);
+      xrec[2] = 1;
+    }
+  }
+  if (p.ext_mode && p.peer_bufs) {
+    __syncthreads();
+    if (xrec[2] == 1 && (int)threadIdx.x < p.peer_world) {
+      // thread t: store this rank's record and the epoch flag into peer t's buffer, then wait for peer t's flag here
+      // (same protocol and buffers as peer_exchange_kernel)
+      const int t = threadIdx.x, world = p.peer_world, rank = p.peer_rank;
+      const unsigned long long epoch = p.peer_epoch;
+      const size_t rec_off = ((size_t)(epoch & 1ull) * world + rank) * 16, flag_off = (size_t)2 * world * 16 + (size_t)rank * 8;
+      long long* dst = reinterpret_cast<long long*>(p.peer_bufs[t] + rec_off);
+      dst[0] = xrec[0];
+      dst[1] = xrec[1];
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_bufs[t] + flag_off), "l"(epoch) : "memory");
+      const unsigned char* mine = p.peer_bufs[rank];
+      const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(mine + (size_t)2 * world * 16 + (size_t)t * 8);
+      unsigned long long seen = 0;
+      const long long t0 = clock64();
+      for (unsigned spin = 0;; ++spin) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+        if (seen >= epoch) break;
+        if ((spin & 1023u) == 1023u && clock64() - t0 > 20000000000LL) {      // ~10 s: a peer never reached this step
+          atomicExch(p.peer_err, 1 + t);
+          __threadfence_system();
+          __trap();
+        }
+      }
+      const long long* src = reinterpret_cast<const long long*>(mine + ((size_t)(epoch & 1ull) * world + t) * 16);
+      p.peer_out[2 * t] = src[0];
+      p.peer_out[2 * t + 1] = src[1];
     }
   }
   if (warp == kIssW0) {
@@ -908,7 +955,8 @@ bool umma16_supported(const bogp_modeset_s* h) {
 }
 
 int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const double* z_host, int Nz, int atype, int mf,
-                       float* out_dev, cudaStream_t s, int ext_mode, float* ext_val_dev, long long* ext_idx_dev) {
+                       float* out_dev, cudaStream_t s, int ext_mode, float* ext_val_dev, long long* ext_idx_dev,
+                       const PeerArgs* peer) {
   const ModesetDev& d = h->dev;
   const int sms = device_sms16();
   HParams p{};
@@ -953,6 +1001,10 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
     p.ext_key = reinterpret_cast<unsigned long long*>(misc + off_err + 16);
     p.ext_done = reinterpret_cast<unsigned int*>(misc + off_err + 32);
     p.ext_val = ext_val_dev; p.ext_idx = ext_idx_dev;
+    if (peer && peer->bufs) {
+      p.peer_bufs = peer->bufs; p.peer_rank = peer->rank; p.peer_world = peer->world; p.peer_epoch = peer->epoch;
+      p.peer_offset = peer->index_offset; p.peer_out = peer->recs_out; p.peer_err = peer->err;
+    }
   }
   p.E = static_cast<unsigned char*>(c.E);
   p.Bhi = static_cast<unsigned char*>(c.B);

@@ -115,13 +115,16 @@ class DeviceModeSet:
     # ------------------------------------------------------------------ evaluation
     def bartlett_grid(self, r_km: ArrayLike, z: ArrayLike, tilt_deg: Optional[ArrayLike] = None, *,
                       atype: str = "cbf", multifreq_method: str = "mean", engine: str = "auto",
-                      out: Optional[torch.Tensor] = None, argext: Optional[tuple] = None) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, argext: Optional[tuple] = None,
+                      peer: Optional[tuple] = None) -> torch.Tensor:
         """Ambiguity surface ``[Nz, Nr]`` (or ``[Nt, Nz, Nr]`` with a tilt axis), float32 on the device.
 
         Replaces the row loop of ref/projects/swellex96_localization/data/mfp.py:213-214.  ``argext=(pair, scratch,
         maximize)`` also writes the extremum record of :func:`argext_device` (``pair`` int64[2], ``scratch`` >= 8192
         bytes) -- inside the surface kernel when the tcgen05 engine runs, so the final reduction of collate.py:50 costs
-        no extra launch.
+        no extra launch.  With ``peer=(PeerExchange, index_offset, pairs)`` the record ``(index_offset + index, value)``
+        is also exchanged with the other GPUs of the box (``pairs`` int64[world, 2] gets every rank's record) -- from
+        inside the same kernel on the FP16-split engine.
         """
         r_m = np.ascontiguousarray(1000.0 * np.atleast_1d(np.asarray(r_km, dtype=np.float64)))
         zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
@@ -136,6 +139,16 @@ class DeviceModeSet:
             pair, scratch, maximize = argext
             if pair.dtype != torch.int64 or pair.numel() < 2 or not pair.is_cuda:
                 raise ValueError("argext pair must be an int64[2] CUDA tensor")
+            if peer is not None:
+                px, offset, pairs = peer
+                if not (pairs.is_cuda and pairs.dtype == torch.int64 and pairs.numel() == 2 * px.world and pairs.is_contiguous()):
+                    raise ValueError("peer pairs must be a contiguous CUDA int64[world, 2] tensor")
+                _lib.call("bogp_bartlett_grid_argext_peer", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
+                          _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
+                          C.c_void_p(out.data_ptr()), 1 if maximize else 0, px._h, int(offset), C.c_void_p(pairs.data_ptr()),
+                          C.c_void_p(pair.data_ptr() + 8), C.c_void_p(pair.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                          scratch.numel() * scratch.element_size(), C.c_void_p(_lib.current_stream_ptr()))
+                return out
             _lib.call("bogp_bartlett_grid_argext", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
                       _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
                       C.c_void_p(out.data_ptr()), 1 if maximize else 0, C.c_void_p(pair.data_ptr() + 8),
@@ -149,11 +162,13 @@ class DeviceModeSet:
 
     def bartlett_grid_host(self, r_km: ArrayLike, z: ArrayLike, tilt_deg: Optional[ArrayLike] = None, *,
                            atype: str = "cbf", multifreq_method: str = "mean", engine: str = "auto",
-                           out: Optional[np.ndarray] = None, argext: Optional[str] = None):
+                           out: Optional[np.ndarray] = None, argext: Optional[str] = None, peer: Optional[tuple] = None):
         """Same through the host-buffer entry point (device->host copy inside the call).  ``out``: optional
         C-contiguous float32 host array of the result shape (pass page-locked memory for a DMA copy).
         ``argext="max"|"min"`` also returns ``(value, unravelled index)`` of the extremum (collate.py:50), computed
-        on the device while the surface is still there: ``(surface, (value, index))``."""
+        on the device while the surface is still there: ``(surface, (value, index))``.  With ``peer=(PeerExchange,
+        index_offset)`` the call returns ``(surface, records)``: the int64[world, 2] ``(index_offset + index, value
+        bits)`` records of every rank of the box, exchanged over peer memory inside the same call."""
         r_m = np.ascontiguousarray(1000.0 * np.atleast_1d(np.asarray(r_km, dtype=np.float64)))
         zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
         tt = None if tilt_deg is None else np.ascontiguousarray(np.atleast_1d(np.asarray(tilt_deg, dtype=np.float64)))
@@ -166,6 +181,14 @@ class DeviceModeSet:
         if argext is not None:
             if argext not in ("max", "min"):
                 raise ValueError("argext must be 'max', 'min' or None")
+            if peer is not None:
+                px, offset = peer
+                recs = np.zeros((px.world, 2), dtype=np.int64)
+                _lib.call("bogp_bartlett_grid_host_argmax_peer", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
+                          _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
+                          _lib.fptr(out), 1 if argext == "max" else 0, px._h, int(offset),
+                          recs.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_void_p(_lib.current_stream_ptr()))
+                return out, recs
             val, idx = C.c_float(), C.c_longlong()
             _lib.call("bogp_bartlett_grid_host_argmax", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
                       _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],

@@ -100,6 +100,21 @@ def sharded_surface(evaluate_rows: Callable[[int, int], torch.Tensor], n_rows: i
     return local, (val, pos), full
 
 
+def reduce_records(recs, maximize: bool = True) -> Tuple[float, int]:
+    """``(value, global flat index)`` of the extremum over the exchanged int64[world, 2] ``(index, value bits)`` records,
+    with np.argmax's first-occurrence rule across ranks (ties -> lowest global index); records with index < 0 (a rank
+    whose slab was all NaN) are skipped."""
+    r = np.asarray(recs.cpu() if torch.is_tensor(recs) else recs, dtype=np.int64).reshape(-1, 2)
+    vals = (r[:, 1] & 0xffffffff).astype(np.uint32).view(np.float32)
+    best = None
+    for v, i in zip(vals, r[:, 0]):
+        if i < 0 or v != v:
+            continue
+        if best is None or (v > best[0] if maximize else v < best[0]) or (v == best[0] and i < best[1]):
+            best = (float(v), int(i))
+    return best if best is not None else (0.0, -1)
+
+
 class PeerExchange:
     """All-gather of one ``int64[2]`` record per rank over peer memory (one box, one process per GPU).
 
@@ -113,9 +128,15 @@ class PeerExchange:
         import ctypes as C
 
         from . import _lib
-        if not dist.is_initialized():
-            raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
         self._lib, self._C = _lib, C
+        if not dist.is_initialized():
+            # one process, one GPU: the exchange degenerates to a copy of the own record (same kernels, same entry points)
+            self.rank, self.world = 0, 1
+            self._h = C.c_void_p()
+            mine = (C.c_ubyte * 64)()
+            _lib.call("bogp_peer_create", C.byref(self._h), 0, 1, C.cast(mine, C.c_void_p))
+            _lib.call("bogp_peer_open", self._h, C.cast(mine, C.c_void_p))
+            return
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         dev = torch.device("cuda", torch.cuda.current_device())
         self._h = C.c_void_p()

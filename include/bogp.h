@@ -251,6 +251,21 @@ int bogp_peer_create(bogp_peer_t* out, int rank, int world, unsigned char* ipc_h
 int bogp_peer_open(bogp_peer_t p, const unsigned char* all_handles);
 int bogp_peer_exchange(bogp_peer_t p, const long long* rec_dev, long long* recs_out_dev, void* stream);
 int bogp_peer_destroy(bogp_peer_t p);
+/* Surface + arg-ext + the exchange above in ONE call: record = (index_offset + flat index of this rank's extremum,
+ * value bits); recs_out[world][2] gets every rank's record of the same step.  On the FP16-split tcgen05 engine the
+ * exchange runs inside the surface kernel (its last CTA stores the record into the peers' buffers and waits for
+ * theirs: no launch of its own); other engines pack the record and run the exchange kernel.  The _host form takes host
+ * buffers like bogp_bartlett_grid_host_argmax and returns the records of all ranks after its one synchronisation (what
+ * the reference's collate step reduces with np.argmax, projects/swellex96_localization/data/collate.py:50). */
+int bogp_bartlett_grid_argext_peer(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                                   const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                                   float* out_dev, int maximize, bogp_peer_t peer, long long index_offset,
+                                   long long* recs_out_dev, float* val_dev, long long* idx_dev, void* scratch_dev,
+                                   long long scratch_bytes, void* stream);
+int bogp_bartlett_grid_host_argmax_peer(bogp_modeset_t h, const double* r_m_host, int Nr, const double* z_host, int Nz,
+                                        const double* tilt_deg_host, int Nt, int atype, int mf_method, int engine,
+                                        float* out_host, int maximize, bogp_peer_t peer, long long index_offset,
+                                        long long* recs_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,40 @@ def test_peer_exchange_world1_self_exchange():
         _lib.call("bogp_peer_create", C.byref(C.c_void_p()), 3, 2, C.cast((C.c_ubyte * 64)(), C.c_void_p))
 
 
+@pytest.mark.parametrize("engine", ["umma", "simt"])
+def test_surface_with_fused_exchange_world1(engine):
+    """bogp_bartlett_grid_argext_peer / _host_argmax_peer on one GPU: the record that comes back through the exchange is
+    (index_offset + arg-max index, value bits) of the surface -- published from inside the surface kernel on the
+    FP16-split engine (no extra launch), by the pack + exchange kernels on the others."""
+    from bogp_b200 import _lib, mfp
+    from bogp_b200.modes import SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    from bogp_b200.sharding import PeerExchange, reduce_records
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    r, z = np.linspace(0.1, 10.0, 300), np.linspace(1.0, 200.0, 120)
+    dms = mfp.DeviceModeSet(modes, synthetic_covariance(modes, z[37], r[140]))
+    px = PeerExchange()
+    pair = torch.zeros(2, dtype=torch.int64, device="cuda")
+    pairs = torch.zeros(1, 2, dtype=torch.int64, device="cuda")
+    scratch = torch.empty(8192, dtype=torch.uint8, device="cuda")
+    for step, off in enumerate((0, 7_000_000, 123)):
+        n0 = _lib.kernel_launches()
+        surf = dms.bartlett_grid(r, z, engine=engine, argext=(pair, scratch, True), peer=(px, off, pairs))
+        launches = _lib.kernel_launches() - n0
+        torch.cuda.synchronize()
+        host = surf.cpu().numpy()
+        val, idx = reduce_records(pairs)
+        assert idx == off + int(host.argmax()) == off + 37 * 300 + 140 and val == host.max()
+        assert int(pair[0]) == int(host.argmax())
+        if engine == "umma" and step > 0:
+            assert launches == 2          # table kernel + surface kernel: arg-max and exchange are inside the latter
+    out, recs = dms.bartlett_grid_host(r, z, engine=engine, argext="max", peer=(px, 55))
+    np.testing.assert_array_equal(out, host)
+    assert reduce_records(recs) == (float(host.max()), 55 + int(host.argmax()))
+    _, recs = dms.bartlett_grid_host(r, z, engine=engine, argext="min", peer=(px, 0))
+    assert reduce_records(recs, maximize=False) == (float(host.min()), int(host.argmin()))
+    px.close()
+
+
 def _free_port() -> int:
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -61,6 +95,23 @@ def _peer_worker(rank: int, world: int, port: int, q):
             dist.all_gather_into_tensor(check.view(-1), rec)
             torch.cuda.synchronize()
             ok = ok and torch.equal(out, check)
+        # the same through the surface kernel: every rank evaluates its slab of depth rows, the exchange runs in the
+        # surface kernel's last CTA
+        from bogp_b200 import mfp
+        from bogp_b200.modes import SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+        from bogp_b200.sharding import reduce_records, slab
+        modes = pekeris_modes(SWELLEX_TONALS_13)
+        r, z = np.linspace(0.1, 10.0, 300), np.linspace(1.0, 200.0, 128)
+        dms = mfp.DeviceModeSet(modes, synthetic_covariance(modes, z[90], r[140]))
+        lo, hi = slab(len(z), rank, world)
+        pair = torch.zeros(2, dtype=torch.int64, device="cuda")
+        scratch = torch.empty(8192, dtype=torch.uint8, device="cuda")
+        for _ in range(3):
+            dms.bartlett_grid(r, z[lo:hi], engine="umma", argext=(pair, scratch, True), peer=(px, lo * len(r), out))
+            torch.cuda.synchronize()
+            ok = ok and reduce_records(out)[1] == 90 * 300 + 140
+        _, recs = dms.bartlett_grid_host(r, z[lo:hi], engine="umma", argext="max", peer=(px, lo * len(r)))
+        ok = ok and reduce_records(recs)[1] == 90 * 300 + 140
         px.close()
         q.put((rank, ok))
     finally:
