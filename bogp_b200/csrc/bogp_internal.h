@@ -224,7 +224,16 @@ struct bogp_gp_s {
   // workspace of bogp_gp_thompson (grown on demand)
   void* ts_ws = nullptr;
   size_t ts_bytes = 0;
+  // large-batch posterior / acquisition path (FP64 tensor cores): padded L^-1, L^-T, alpha (built once per model) and
+  // the per-call [b x n] panels
+  void* mm_ws = nullptr;
+  size_t mm_bytes = 0;
+  int mm_np = 0;               // padding the cached L^-1 / L^-T / alpha were built for (0: not built)
 };
 namespace bogp {
+// kernels_ts.cu: FP64 tensor-core building blocks shared with the large-batch acquisition path
+int ts_pad(const bogp_gp_s* g, int np, double* Linv_p, double* alpha_p, cudaStream_t s);
+int ts_cross_kernel(const bogp_gp_s* g, const double* Xc_dev, int b, int bp, int np, double* Kt, cudaStream_t s);
+int ts_gemm_tri(const double* A, const double* B, double* C, int bp, int np, int tri, cudaStream_t s);
 constexpr int kGpMaxDim = 256;      // input dimensions a model may have (the acquisition kernels take <= 16 of them)
 }

@@ -18,6 +18,7 @@
 //   5  grad_c = sum_i (dA/dmu alpha_i - 2 dA/dvar W_ic) gk_ic (x_c - X_i)/l^2    warp <-> candidate c
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "bogp_internal.h"
@@ -474,7 +475,128 @@ static int pick_bc(const bogp_gp_s* g, long long b, bool grad) {
   return bc;
 }
 
+// ---------------------------------------------------------------------------------------------- large batches
+// Thousands of candidates against one model (the raw-sample pass of optimize_acqf: 4096 points, ei.py:81-92): the two
+// triangular solves are GEMMs with the candidates as one dimension, V^T = K*^T L^-T and W^T = V^T L^-1, run as 64 x 64
+// tiles on the FP64 tensor cores (ts_gemm_nt) instead of per-thread dot products that re-stream L^-1 from L2 for every
+// 8 candidates.  Panels are [b padded to 64][n padded to 64] in global memory (L2-resident: 16 MB at b = 4096, n = 512).
+//   1 cross-covariances  2 V^T (DMMA)  3 moments + acquisition (warp per candidate)  [4 W^T (DMMA)  5 gradient]
+__global__ void __launch_bounds__(256)
+gp_moments_kernel(GpDev gp, GpArgs a, const double* __restrict__ Kt, const double* __restrict__ Vt,
+                  const double* __restrict__ alpha_p, int np, double* __restrict__ coef) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long c = (long long)blockIdx.x * 8 + warp;
+  if (c >= a.b) return;
+  const double* kr = Kt + (size_t)c * np;
+  const double* vr = Vt + (size_t)c * np;
+  double m = 0.0, ss = 0.0;
+  for (int i = lane; i < np; i += 32) {
+    m = fma(alpha_p[i], kr[i], m);
+    const double v = vr[i];
+    ss = fma(v, v, ss);
+  }
+  m = warp_sum_d(m) + gp.mean;
+  ss = warp_sum_d(ss);
+  double var = gp.outputscale - ss;
+  if (lane != 0) return;
+  if (a.mode == kModePosterior) {
+    if (a.observation_noise) var += gp.noise;
+    a.out0[c] = m;
+    a.out1[c] = fmax(var, kMinVariance);
+  } else {
+    double val, dmu, dvar;
+    acquisition(a.acq_kind, m, var, a.best_f, a.beta, val, dmu, dvar);
+    a.out0[c] = val;
+    if (coef) { coef[2 * c] = dmu; coef[2 * c + 1] = dvar; }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gp_grad_kernel(GpDev gp, GpArgs a, const double* __restrict__ Wt, const double* __restrict__ alpha_p, int np,
+               const double* __restrict__ coef) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long c = (long long)blockIdx.x * 8 + warp;
+  if (c >= a.b) return;
+  const int d = gp.d, n = gp.n;
+  double xc[kGpMaxD], g_acc[kGpMaxD];
+#pragma unroll
+  for (int dim = 0; dim < kGpMaxD; ++dim) { xc[dim] = dim < d ? a.Xs[c * d + dim] : 0.0; g_acc[dim] = 0.0; }
+  const double dmu = coef[2 * c], dvar = coef[2 * c + 1];
+  const double* wr = Wt + (size_t)c * np;
+  for (int i = lane; i < n; i += 32) {
+    double d2 = 0.0;
+#pragma unroll
+    for (int dim = 0; dim < kGpMaxD; ++dim)
+      if (dim < d) {
+        const double df = (xc[dim] - __ldg(gp.X + (size_t)i * d + dim)) * __ldg(gp.inv_ls + dim);
+        d2 = fma(df, df, d2);
+      }
+    double k, g;
+    kernel_eval(gp.kind, gp.outputscale, d2, k, g);
+    const double cf = (dmu * alpha_p[i] - 2.0 * dvar * wr[i]) * g;
+#pragma unroll
+    for (int dim = 0; dim < kGpMaxD; ++dim)
+      if (dim < d) g_acc[dim] = fma(cf, xc[dim] - __ldg(gp.X + (size_t)i * d + dim), g_acc[dim]);
+  }
+#pragma unroll
+  for (int dim = 0; dim < kGpMaxD; ++dim)
+    if (dim < d) {
+      const double v = warp_sum_d(g_acc[dim]);
+      if (lane == 0) a.grad[c * d + dim] = v * gp.inv_ls[dim] * gp.inv_ls[dim];
+    }
+}
+
+__global__ void gp_transpose_pad_kernel(const double* __restrict__ Linv_p, int np, double* __restrict__ LinvT_p) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)np * np; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / np), j = (int)(e % np);
+    LinvT_p[(size_t)j * np + i] = Linv_p[e];
+  }
+}
+
+static bool use_dmma_path(const bogp_gp_s* g, const GpArgs& a) {
+  if (const char* e = std::getenv("BOGP_GP_DMMA")) { if (e[0] == '0') return false; if (e[0] == '2') return a.q == 1; }
+  return a.q == 1 && (a.mode == kModePosterior || a.mode == kModeAcq) && a.b >= 1024 && g->n >= 96 && g->d <= kGpMaxD;
+}
+
+static int launch_gp_dmma(bogp_gp_s* g, const GpArgs& a, bool grad, cudaStream_t s) {
+  const int n = g->n, np = (n + 63) / 64 * 64;
+  const int b = (int)a.b, bp = (b + 63) / 64 * 64;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_li = 0, o_lt = al((size_t)np * np * 8), o_al = o_lt + al((size_t)np * np * 8), o_kt = o_al + al((size_t)np * 8);
+  const size_t o_vt = o_kt + al((size_t)bp * np * 8), o_cf = o_vt + al((size_t)bp * np * 8), total = o_cf + al((size_t)bp * 16);
+  if (g->mm_bytes < total) {
+    if (g->mm_ws) cudaFree(g->mm_ws);
+    g->mm_ws = nullptr; g->mm_bytes = 0; g->mm_np = 0;
+    BOGP_CUDA(cudaMalloc(&g->mm_ws, total + total / 4));
+    g->mm_bytes = total + total / 4;
+  }
+  unsigned char* ws = static_cast<unsigned char*>(g->mm_ws);
+  double *Li = (double*)(ws + o_li), *Lt = (double*)(ws + o_lt), *alp = (double*)(ws + o_al);
+  double *Kt = (double*)(ws + o_kt), *Vt = (double*)(ws + o_vt), *coef = (double*)(ws + o_cf);
+  if (g->mm_np != np) {          // once per model: padded L^-1 (identity on the padded diagonal), its transpose, alpha
+    if (int rc = ts_pad(g, np, Li, alp, s)) return rc;
+    gp_transpose_pad_kernel<<<296, 256, 0, s>>>(Li, np, Lt);
+    count_launch();
+    g->mm_np = np;
+  }
+  GpDev dev{g->n, g->d, g->kind, g->outputscale, g->mean, g->noise, g->X, g->inv_ls, g->alpha, g->Linv, g->LinvT};
+  cudaEvent_t ev = bogp::timing_begin(s);
+  if (int rc = ts_cross_kernel(g, a.Xs, b, bp, np, Kt, s)) return rc;
+  if (int rc = ts_gemm_tri(Kt, Li, Vt, bp, np, 1, s)) return rc;              // V^T = K*^T L^-T: B = L^-1 rows, lower triangular
+  gp_moments_kernel<<<(b + 7) / 8, 256, 0, s>>>(dev, a, Kt, Vt, alp, np, grad ? coef : nullptr);
+  count_launch();
+  if (grad) {
+    if (int rc = ts_gemm_tri(Vt, Lt, Kt, bp, np, 2, s)) return rc;            // W^T = V^T L^-1: B = L^-T rows, upper triangular (into Kt)
+    gp_grad_kernel<<<(b + 7) / 8, 256, 0, s>>>(dev, a, Kt, alp, np, coef);
+    count_launch();
+  }
+  bogp::timing_end(ev, s);
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int dispatch_gp(const bogp_gp_s* g, const GpArgs& a, int bc, bool grad, cudaStream_t s) {
+  if (use_dmma_path(g, a)) return launch_gp_dmma(const_cast<bogp_gp_s*>(g), a, grad, s);
   BOGP_REQUIRE(g->d <= kGpMaxD, "posterior / acquisition kernels take d <= %d input dimensions (model has %d); only "
                "bogp_gp_thompson accepts more", kGpMaxD, g->d);
   switch (bc) {
@@ -577,6 +699,7 @@ extern "C" int bogp_gp_destroy(bogp_gp_t g) {
   if (g->io_dev) cudaFree(g->io_dev);
   if (g->io_pin) cudaFreeHost(g->io_pin);
   if (g->ts_ws) cudaFree(g->ts_ws);
+  if (g->mm_ws) cudaFree(g->mm_ws);
   delete g;
   return 0;
 }

@@ -262,7 +262,7 @@ __device__ __forceinline__ void diag_factor_invert(double (*D)[kDiagLd], double 
 struct GemmArgs {
   const double *A, *B;
   double* C;
-  int lda, ldb, ldc, K, tiles_n, lower, accumulate, ktri;
+  int lda, ldb, ldc, K, tiles_n, lower, accumulate, ktri;      // ktri 1: B lower triangular (K stops after tile column tj); 2: B upper triangular (K starts at tile column tj)
   // fuse_diag: the CTA of tile (0, 0) -- the next diagonal block of the blocked Cholesky -- factors and inverts it
   // right after updating it, while the other CTAs are still on the rest of the trailing matrix
   int fuse_diag;
@@ -297,16 +297,17 @@ __global__ void __launch_bounds__(kTsThreads) ts_gemm_nt(GemmArgs g) {
   const int lr = tid & 63, lk = (tid >> 6) * 4;
   const double* Ap = g.A + (size_t)(ti * kTsT + lr) * g.lda + lk;
   const double* Bp = g.B + (size_t)(tj * kTsT + lr) * g.ldb + lk;
-  const int K = g.ktri ? min(g.K, (tj + 1) * kTsT) : g.K;
+  const int K = g.ktri == 1 ? min(g.K, (tj + 1) * kTsT) : g.K;
+  const int Kfirst = g.ktri == 2 ? tj * kTsT : 0;
   double acc[4][2][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  double2 a0 = *reinterpret_cast<const double2*>(Ap), a1 = *reinterpret_cast<const double2*>(Ap + 2);
-  double2 b0 = *reinterpret_cast<const double2*>(Bp), b1 = *reinterpret_cast<const double2*>(Bp + 2);
+  double2 a0 = *reinterpret_cast<const double2*>(Ap + Kfirst), a1 = *reinterpret_cast<const double2*>(Ap + Kfirst + 2);
+  double2 b0 = *reinterpret_cast<const double2*>(Bp + Kfirst), b1 = *reinterpret_cast<const double2*>(Bp + Kfirst + 2);
   int buf = 0;
-  for (int k0 = 0; k0 < K; k0 += kTsKC) {
+  for (int k0 = Kfirst; k0 < K; k0 += kTsKC) {
     As[buf][lk][lr] = a0.x; As[buf][lk + 1][lr] = a0.y; As[buf][lk + 2][lr] = a1.x; As[buf][lk + 3][lr] = a1.y;
     Bs[buf][lk][lr] = b0.x; Bs[buf][lk + 1][lr] = b0.y; Bs[buf][lk + 2][lr] = b1.x; Bs[buf][lk + 3][lr] = b1.y;
     __syncthreads();
@@ -429,6 +430,34 @@ __global__ void __launch_bounds__(1024) ts_argmax_kernel(const double* f, int b,
 }
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// ---- building blocks for the large-batch posterior / acquisition path (kernels_gp.cu): everything padded to 64
+int ts_pad(const bogp_gp_s* g, int np, double* Linv_p, double* alpha_p, cudaStream_t s) {
+  ts_pad_kernel<<<std::min(1184, (np * np + 255) / 256), 256, 0, s>>>(g->Linv, g->alpha, g->n, np, Linv_p, alpha_p);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
+}
+// Kt[bp][np] = k(Xc_i, X_j) (zero outside the b x n block)
+int ts_cross_kernel(const bogp_gp_s* g, const double* Xc_dev, int b, int bp, int np, double* Kt, cudaStream_t s) {
+  KmArgs km{};
+  km.P = Xc_dev; km.Q = g->X; km.inv_ls = g->inv_ls; km.out = Kt; km.ldo = np; km.d = g->d; km.Pvalid = b; km.Qvalid = g->n;
+  km.kind = g->kind; km.lower = 0; km.tiles_n = np / kTsT; km.os = g->outputscale; km.diag_add = 0.0;
+  ts_kernel_matrix<<<(bp / kTsT) * (np / kTsT), kTsThreads, 0, s>>>(km);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
+}
+// C[bp][np] = A[bp][np] B^T with B[np][np] lower (tri = 1) or upper (tri = 2) triangular, on the FP64 tensor cores
+int ts_gemm_tri(const double* A, const double* B, double* C, int bp, int np, int tri, cudaStream_t s) {
+  GemmArgs wh{};
+  wh.A = A; wh.lda = np; wh.B = B; wh.ldb = np; wh.C = C; wh.ldc = np; wh.K = np; wh.tiles_n = np / kTsT; wh.ktri = tri;
+  BOGP_CUDA(cudaFuncSetAttribute(ts_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmDiagSmem));
+  ts_gemm_nt<<<(bp / kTsT) * (np / kTsT), kTsThreads, kGemmSmem, s>>>(wh);
+  count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
+}
 
 }  // namespace bogp
 

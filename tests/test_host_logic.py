@@ -135,3 +135,52 @@ def test_time_step_sweep_partition_and_gather_gloo():
     want = {t: (t / 10.0, (t, 2 * t)) for t in range(n_steps)}
     for _, _, merged in res:
         assert merged == want and list(merged) == sorted(merged)
+
+
+class _ToyAcq:
+    """CPU stand-in for an acquisition function: a smooth multi-modal surface on [0, 1]^d with a known global maximum."""
+    nonneg = True
+
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, X):
+        self.calls.append(int(X.shape[0]))
+        x = X.reshape(X.shape[0], -1)
+        peak = torch.tensor([0.7, 0.2, 0.55], dtype=x.dtype)[: x.shape[1]]
+        return torch.exp(-8.0 * ((x - peak) ** 2).sum(-1)) + 0.3 * torch.exp(-30.0 * ((x - 0.1) ** 2).sum(-1))
+
+
+def _optim_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bogp_b200.optim import optimize_acqf
+        torch.manual_seed(100 + rank)                      # different local streams: the seed / restarts come from rank 0
+        acq = _ToyAcq()
+        bounds = torch.stack([torch.zeros(3, dtype=torch.float64), torch.ones(3, dtype=torch.float64)])
+        cand, val = optimize_acqf(acq, bounds, q=1, num_restarts=8, raw_samples=256, shard=True)
+        allX, allv = optimize_acqf(acq, bounds, q=1, num_restarts=8, raw_samples=256, shard=True, return_best_only=False)
+        q.put((rank, cand.numpy(), float(val), acq.calls[0], tuple(allX.shape), tuple(allv.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_optimize_acqf_sharded_raw_samples_and_restarts_gloo():
+    """SURVEY 8e for K2 on CPU (world 2, gloo): each rank evaluates half of the raw samples and optimises half of the
+    restarts, values and candidates are all-gathered, every rank returns the same best candidate -- the global maximum."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_optim_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=180) for _ in range(world))
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    (r0, c0, v0, n0, sx0, sv0), (r1, c1, v1, n1, sx1, sv1) = res
+    assert n0 == n1 == 128                                  # raw_samples / P evaluations per rank
+    np.testing.assert_array_equal(c0, c1)
+    assert v0 == v1 and sx0 == sx1 == (8, 1, 3) and sv0 == sv1 == (8,)
+    np.testing.assert_allclose(c0.reshape(-1), [0.7, 0.2, 0.55], atol=1e-4)
+    assert abs(v0 - 1.0) < 1e-3
