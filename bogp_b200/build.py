@@ -15,7 +15,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libbogp_sm100.so"
 STAMP = PKG / ".libbogp_sm100.stamp"
-SOURCES = ["hostmath.cu", "api_mfp.cu", "kernels_simt.cu", "kernels_umma.cu", "kernels_umma16.cu", "kernels_env.cu", "kernels_gp.cu", "kernels_gpfit.cu", "kernels_ts.cu", "kernels_peer.cu"]
+SOURCES = ["hostmath.cu", "api_mfp.cu", "kernels_simt.cu", "kernels_umma.cu", "kernels_umma16.cu", "kernels_env.cu", "kernels_gp.cu", "kernels_gpfit.cu", "kernels_gpfit_coop.cu", "kernels_ts.cu", "kernels_peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -38,12 +38,14 @@ def _digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every CUDA source for sm_100a and link the shared library.  Returns its path."""
-    digest = _digest() + ("+dbg" if os.environ.get("BOGP_UMMA_DBG_BUILD") == "1" else "")
+    digest = _digest() + ("+dbg" if os.environ.get("BOGP_UMMA_DBG_BUILD") == "1" else "") + ("+coopdbg" if os.environ.get("BOGP_COOP_DBG_BUILD") == "1" else "")
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
         return LIB
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     if os.environ.get("BOGP_UMMA_DBG_BUILD") == "1":      # per-role wait counters in the tcgen05 kernel (tools/umma_dbg_counters.py)
         flags.append("-DBOGP_UMMA_DBG=1")
+    if os.environ.get("BOGP_COOP_DBG_BUILD") == "1":      # per-phase cycle counts of the cooperative GP fit (one step, CTA 0)
+        flags.append("-DBOGP_COOP_DBG=1")
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
     procs = []

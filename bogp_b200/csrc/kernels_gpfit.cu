@@ -16,102 +16,13 @@
 //     K^-1 = X^T X into the (free) upper triangle: warp-per-row loops over shared memory, odd leading dimension.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "bogp_internal.h"
+#include "gpfit_device.cuh"
 
 namespace bogp {
-
-constexpr int kFitThreads = 512;
-constexpr int kFitWarps = kFitThreads / 32;
-constexpr int kFitMaxD = 16;
-constexpr int kFitMaxN = 1024;
-constexpr int kFitNP = kFitMaxD + 3;        // raw parameters: lengthscale[d], outputscale, noise, mean
-
-struct FitArgs {
-  int n, d, kind, steps, ld, a_in_smem, x_in_smem;
-  double lr, wd, noise_lo, noise_hi;
-  double ls_lo, ls_hi, os_lo, os_hi;      // Interval constraints (hi > lo) instead of softplus (baxus.py:310-319)
-  int has_ls_prior, has_os_prior;
-  double ls_conc, ls_rate, os_conc, os_rate;
-  const double* X;       // [n, d]
-  const double* y;       // [n]
-  double* raw;           // [B][d + 3] in/out
-  double* loss;          // [B][steps] or null
-  double* work;          // [B][n * ld] when the matrix does not fit in shared memory
-  int* status;           // [B]: 0 ok, 1 not positive definite after jitter 1e-6
-};
-
-constexpr unsigned kFull = 0xffffffffu;
-
-// Cholesky AND inverse of the bs x bs diagonal block at (r0, r0) by the whole CTA, fused level by level (two block
-// barriers per level): on exit the block of A holds D^-1 (lower) -- the factor D itself is never needed again: the
-// panel solve, the blocked inverse and log det all use D^-1 -- and Xb holds D^-1 with a zero upper triangle.
-// Thread (warp w, lane c) owns elements (w, c) and (w + 16, c) of the 32 x 32 tiles Db (factor) and Xb (inverse);
-// rows >= bs are identity.  Level j:  A(j) column j of the factor (into Lc[j & 1]) | C(j-1) inverse rows > j-1 -= ..
-// -- barrier --  B(j) trailing update, store column j, finalise inverse row j  -- barrier --.
-// Returns false (uniform) on a non-positive pivot.
-__device__ __forceinline__ bool block_chol_inv(double* A, int ld, int r0, int bs, double* Db, double* Xb, double* Lc, int* flag) {
-  const int w = threadIdx.x >> 5, c = threadIdx.x & 31;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int i = w + 16 * h;
-    Db[i * 33 + c] = (i < bs && c <= i) ? A[(r0 + i) * ld + r0 + c] : (i == c ? 1.0 : 0.0);
-    Xb[i * 33 + c] = i == c ? 1.0 : 0.0;
-  }
-  __syncthreads();
-  for (int j = 0; j < 32; ++j) {
-    double* Lj = Lc + 32 * (j & 1);
-    if (w == 0) {                                            // A(j): one warp, lane = row (the sqrt / reciprocal
-      double ajj = Db[j * 33 + j];                           // sequences are ~60 instructions: not on all 16 warps)
-      if (!(ajj > 0.0)) { if (c == 0) *flag = 1; ajj = 1.0; }
-      const double dj = sqrt(ajj);
-      if (c >= j) Lj[c] = c == j ? dj : Db[c * 33 + j] / dj;
-    }
-    if (j > 0 && c <= j - 1) {                               // C(j-1)
-      const double* Lp = Lc + 32 * ((j - 1) & 1);
-      const double xk = Xb[(j - 1) * 33 + c];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = w + 16 * h;
-        if (i > j - 1) Xb[i * 33 + c] = fma(-Lp[i], xk, Xb[i * 33 + c]);
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {                            // B(j)
-      const int i = w + 16 * h;
-      if (c > j && i >= c) Db[i * 33 + c] = fma(-Lj[i], Lj[c], Db[i * 33 + c]);
-      if (c == j && i >= j) Db[i * 33 + j] = Lj[i];
-      if (i == j && c <= j) Xb[j * 33 + c] = Xb[j * 33 + c] / Lj[j];
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int i = w + 16 * h;
-    if (i < bs && c <= i) A[(r0 + i) * ld + r0 + c] = Xb[i * 33 + c];
-  }
-  __syncthreads();
-  return *flag == 0;
-}
-
-__device__ __forceinline__ double softplus_d(double x) { return x > 20.0 ? x : log1p(exp(x)); }
-__device__ __forceinline__ double sigmoid_d(double x) { return 1.0 / (1.0 + exp(-x)); }
-
-// correlation k(r) (no outputscale) and g = -2 dk/d(r^2) so that dk/dl_k = g * s_k^2 / l_k with s_k = delta_k / l_k
-__device__ __forceinline__ void corr_and_grad(int kind, double d2, double& kc, double& g) {
-  if (kind == BOGP_KERNEL_RBF) {
-    kc = exp(-0.5 * d2);
-    g = kc;
-  } else {
-    const double s5 = 2.23606797749978969641;
-    const double r = sqrt(fmax(d2, 1e-30));
-    const double e = exp(-s5 * r);
-    kc = (1.0 + s5 * r + (5.0 / 3.0) * d2) * e;
-    g = (5.0 / 3.0) * (1.0 + s5 * r) * e;
-  }
-}
 
 // SMEM = true: the matrix and X live in shared memory (the compiler sees shared-space pointers: LDS/STS with
 // 32-bit addressing instead of generic loads); SMEM = false: matrix in the global scratch.
@@ -463,13 +374,29 @@ extern "C" int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, con
   FIT_CUDA(cudaMalloc(&draw, (size_t)B * np * sizeof(double)));
   FIT_CUDA(cudaMalloc(&dstatus, B * sizeof(int)));
   if (loss_host) FIT_CUDA(cudaMalloc(&dloss, (size_t)B * steps * sizeof(double)));
-  if (!p.a_in_smem) FIT_CUDA(cudaMalloc(&dwork, (size_t)B * a_bytes));
+  if (!p.a_in_smem) FIT_CUDA(cudaMalloc(&dwork, (size_t)B * a_bytes));      // (one-CTA kernel only; the cooperative path brings its own)
   FIT_CUDA(cudaMemcpyAsync(dX, X_host, x_bytes, cudaMemcpyHostToDevice, s));
   FIT_CUDA(cudaMemcpyAsync(dy, y_host, n * sizeof(double), cudaMemcpyHostToDevice, s));
   FIT_CUDA(cudaMemcpyAsync(draw, raw_inout_host, (size_t)B * np * sizeof(double), cudaMemcpyHostToDevice, s));
   p.X = dX; p.y = dy; p.raw = draw; p.loss = dloss; p.work = dwork; p.status = dstatus;
   const bool in_smem = p.a_in_smem && p.x_in_smem;
   const int dl = d <= 4 ? 4 : (d <= 8 ? 8 : 16);
+  // models whose matrix does not fit one SM's shared memory: one fit over a cooperative grid (kernels_gpfit_coop.cu),
+  // starting points one after the other.  BOGP_FIT_COOP=0 keeps them on the one-CTA kernel, =1 forces the grid.
+  bool coop = !p.a_in_smem;
+  if (const char* ce = std::getenv("BOGP_FIT_COOP")) coop = ce[0] == '1' ? true : (ce[0] == '0' ? false : coop);
+  if (coop) {
+    int dev_id = 0, sms = 148;
+    cudaGetDevice(&dev_id);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id);
+    for (int b = 0; b < B; ++b) {
+      FitArgs pb = p;
+      pb.raw = draw + (size_t)b * np;
+      pb.loss = dloss ? dloss + (size_t)b * steps : nullptr;
+      pb.status = dstatus + b;
+      FIT_CUDA(launch_gp_fit_coop(pb, sms, s));
+    }
+  } else {
   auto launch = [&](auto kern) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -481,6 +408,7 @@ extern "C" int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, con
   if (in_smem) FIT_CUDA(dl == 4 ? launch(gp_fit_kernel<true, 4>) : dl == 8 ? launch(gp_fit_kernel<true, 8>) : launch(gp_fit_kernel<true, 16>));
   else FIT_CUDA(dl == 4 ? launch(gp_fit_kernel<false, 4>) : dl == 8 ? launch(gp_fit_kernel<false, 8>) : launch(gp_fit_kernel<false, 16>));
   count_launch();
+  }
   FIT_CUDA(cudaGetLastError());
   std::vector<int> status(B);
   FIT_CUDA(cudaMemcpyAsync(raw_inout_host, draw, (size_t)B * np * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -252,8 +252,9 @@ def _gamma_logpdf(x, conc, rate):
     return conc * math.log(rate) - math.lgamma(conc) + (conc - 1.0) * torch.log(x) - rate * x
 
 
-FUSED_FIT_MAX_D = 16       # input dimensions the fused kernel takes (kFitMaxD)
-FUSED_FIT_MAX_N = 320      # above this the single-CTA kernel loses to the cuSOLVER loop (profiles/paths_r1b.jsonl)
+FUSED_FIT_MAX_D = 16       # input dimensions the fused kernels take (kFitMaxD)
+FUSED_FIT_MAX_N = 640      # measured (profiles/paths_r2.jsonl): the cooperative kernel beats the cuSOLVER loop up to n ~ 700 (n = 512: 1.3x,
+                           # n = 1000: 0.7x); the reference's budgets end at 500 trials (ei.py:22-23)
 
 
 def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), raw_init: Optional[np.ndarray] = None,
@@ -266,9 +267,11 @@ def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), raw_init: Op
     ``raw_init[B, d+3]`` (raw lengthscale[d], outputscale, noise, mean) runs B independent fits concurrently and keeps
     the one with the lowest final loss.  ``return_loss`` also returns the loss history ``[B, steps]``.
 
-    ``engine``: ``"fused"`` (the kernel), ``"torch"`` (:func:`fit_gp_adamw_torch`, cuSOLVER per step) or ``"auto"``:
-    the fused kernel keeps one fit on one SM, which wins by 7-24x up to n ~ 150 (the reference's sizes: 64-144 trials)
-    and breaks even near n ~ 320 (measured: profiles/paths_r1b.jsonl); larger n go to the cuSOLVER loop on the GPU.
+    ``engine``: ``"fused"`` / ``"auto"`` (the kernels: one CTA with the matrix in shared memory up to n ~ 150, a
+    cooperative grid with the matrix in L2 above -- csrc/kernels_gpfit_coop.cu) or ``"torch"``
+    (:func:`fit_gp_adamw_torch`, cuSOLVER per step: the timing comparison).  ``auto`` only leaves the kernels for more
+    than 16 input dimensions or more than 640 observations (beyond the reference's 500-trial budgets, where the serial
+    column chain of the blocked factorisation makes the cooperative kernel slower than cuSOLVER).
     """
     if engine not in ("auto", "fused", "torch"):
         raise ValueError("engine must be 'auto', 'fused' or 'torch'")
@@ -306,7 +309,7 @@ def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), raw_init: Op
 
 def fit_gp_adamw_torch(model: SingleTaskGP, cfg: FitConfig = FitConfig(), device=None) -> SingleTaskGP:
     """The same loop as torch float64 ops with autograd (cuSOLVER Cholesky per step): kept as the timing comparison
-    for the fused kernel (tools/bench_paths.py fit); not used by :meth:`SingleTaskGP.fit`."""
+    for the fused kernels (tools/bench_paths.py fit); :func:`fit_gp_adamw` only routes here for d > 16 or n > 640."""
     dev = _cuda_device() if device is None else torch.device(device)
     X = model.train_X.to(dev)
     y = model.train_Y.to(dev)

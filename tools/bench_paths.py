@@ -83,7 +83,7 @@ def bench_fit():
     """K2-FIT: 100 AdamW steps of the GP hyper-parameter fit, fused kernel (one launch) vs the torch/cuSOLVER loop."""
     from bogp_b200.gp import FitConfig, fit_gp_adamw, fit_gp_adamw_torch
     rng = np.random.default_rng(0)
-    for n, d in ((64, 2), (144, 2), (144, 7), (256, 3), (512, 7)):
+    for n, d in ((64, 2), (144, 2), (144, 7), (256, 3), (512, 7), (1000, 7)):
         X = rng.uniform(-1, 1, (n, d))
         y = np.sin(3 * X[:, 0]) + 0.3 * np.cos(2 * X.sum(1))
         y = (y - y.mean()) / y.std()
@@ -99,7 +99,7 @@ def bench_fit():
         t = fit_gp_adamw_torch(SingleTaskGP(X, y), FitConfig(steps=100)); torch.cuda.synchronize()
         torch_ms = (time.perf_counter() - t0) * 1e3
         flop = 100 * (n ** 3 / 3 + n ** 3 / 3 + n ** 3 / 3 + 2 * n * n * (3 * d + 25) / 2)      # chol + inverse + X^T X + 2 elementwise passes
-        print(json.dumps({"kernel": "gp_fit_kernel (K2-FIT)", "case": f"n={n} d={d} Matern-5/2, 100 AdamW steps, one CTA",
+        print(json.dumps({"kernel": "gp_fit_kernel (K2-FIT)", "case": f"n={n} d={d} Matern-5/2, 100 AdamW steps, " + ("one CTA" if n <= 144 else "cooperative grid"),
                           "dtype": "f64", "kernel_ms": k_ms, "call_ms": call_ms, "torch_cusolver_loop_ms": torch_ms,
                           "speedup_vs_torch_loop": torch_ms / call_ms, "ms_per_step": k_ms / 100, "alg_gflop": flop / 1e9,
                           "gflops": flop / (k_ms * 1e-3) / 1e9,
