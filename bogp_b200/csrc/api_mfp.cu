@@ -146,7 +146,7 @@ extern "C" int bogp_modeset_create(bogp_modeset_t* out, int F, int N, const int*
   std::vector<float> rec_re(sumRec, 0.f), rec_im(d.rec_complex ? sumRec : 0, 0.f);
   std::vector<float> recT_re(sumRec, 0.f), recT_im(d.rec_complex ? sumRec : 0, 0.f);
   std::vector<float> lever(N);
-  for (int n = 0; n < N; ++n) lever[n] = (float)(z_pivot - rec_z_host[n]);
+  for (int n = 0; n < N; ++n) { lever[n] = (float)(z_pivot - rec_z_host[n]); h->u16.lever_max = std::max(h->u16.lever_max, std::fabs(z_pivot - rec_z_host[n])); }
 
   size_t ik = 0, irec = 0, isrc = 0;
   for (int f = 0; f < F; ++f) {

@@ -147,6 +147,7 @@ struct bogp_modeset_s {
   // and the range vector the cached E table was built for
   struct U16 {
     std::vector<float> wu_max, phi_max;             // per tonal: max |Wu|, max |phi_src table|
+    double lever_max = 0.0;                         // max |z_pivot - z_n|
     std::vector<std::vector<bogp::cplx>> k_host;    // per tonal wavenumbers
     void* E = nullptr; size_t E_bytes = 0;
     void* B = nullptr; size_t B_bytes = 0;

@@ -42,6 +42,8 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <cuda_fp16.h>
+
 #include "bogp_internal.h"
 #include "device_math.cuh"
 #include "umma_ptx.cuh"
@@ -77,6 +79,8 @@ constexpr unsigned kSmemLimit = 227u * 1024u;
 
 struct UTonal {
   int Mp, rowsP;
+  int kc;                      // TMEM columns of one split of the A image: Mp (TF32, one mode per column) or Kp / 2 (FP16 pairs, Kp = Mp padded to 16)
+  float sA, sB;                // FP16 mode: power-of-two scales of the A and B operands (largest magnitude -> 2^14)
   int nq;                      // numerator (re, im) row pairs = rank of Phi^H K Phi: columns [0, 2 nq)
   int n1;                      // 2 nq + 2 n_npair: pair columns in [2 nq, n1) feed the norm; plain columns from n1 on
   int nj;                      // depths stacked per stage
@@ -128,6 +132,7 @@ struct UParams {
   const float* lever;          // [64]          z_pivot - z_n (0 beyond N)
   const float* CkT_re;         // receiver-space covariance factor (ModesetDev::CkT_re / CkT_im)
   const float* CkT_im;
+  int f16;                     // tilt engine: FP16-split operands (kind::f16) instead of 3xTF32
   int skip;                    // debug build only: 1 = issue no MMAs, 2 = epilogue releases without reading (bottleneck bracketing)
   UTonal t[BOGP_MAX_TONALS];
 };
@@ -266,8 +271,9 @@ __global__ void __launch_bounds__(128) umma_tilt_theta_kernel(ModesetDev ms, UPa
   const double st = sin(tilt_deg[tau] * 0.017453292519943295);
   float* Bhi = reinterpret_cast<float*>(const_cast<unsigned char*>(p.Bhi) + u.b_off + (size_t)k * u.b_zbytes);
   float* Blo = reinterpret_cast<float*>(const_cast<unsigned char*>(p.Blo) + u.b_off + (size_t)k * u.b_zbytes);
-  for (int idx = threadIdx.x; idx < 32 * u.Mp; idx += blockDim.x) {
-    const int q = idx / u.Mp, m = idx - q * u.Mp, n = 32 * half + q;
+  const int Mcols = p.f16 ? 2 * u.kc : u.Mp;          // modes per row of the tile (padded)
+  for (int idx = threadIdx.x; idx < 32 * Mcols; idx += blockDim.x) {
+    const int q = idx / Mcols, m = idx - q * Mcols, n = 32 * half + q;
     double vr = 0.0, vi = 0.0;
     if (n < ms.N && m < t.M) {
       const double ls = (double)ms.rec_lever[n] * st;
@@ -279,10 +285,22 @@ __global__ void __launch_bounds__(128) umma_tilt_theta_kernel(ModesetDev ms, UPa
       vr = amp * (pr * cs - pi * sn);
       vi = amp * (pr * sn + pi * cs);
     }
-    const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
     // rows of a receiver pair (q even, q + 1): Re q, Re q+1, Im q, Im q+1 -- the epilogue then forms T of both
     // receivers with packed fp32x2 instructions on adjacent accumulator columns
     const int row_re = 4 * (q >> 1) + (q & 1);
+    if (p.f16) {
+      // FP16-split operands: [64 rows x Kp] halves, 8 halves per 16-byte K chunk, scaled by sB
+      const int Kp = 2 * u.kc;
+      __half* Hhi = reinterpret_cast<__half*>(Bhi);
+      __half* Hlo = reinterpret_cast<__half*>(Blo);
+      auto hoff = [&](int row) { return ((size_t)((row >> 3) * (Kp >> 3) + (m >> 3)) * 8 + (row & 7)) * 8 + (m & 7); };
+      const float xr = (float)(vr * (double)u.sB), xi = (float)(vi * (double)u.sB);
+      const __half hr = __float2half_rn(xr), hi_ = __float2half_rn(xi);
+      Hhi[hoff(row_re)] = hr; Hlo[hoff(row_re)] = __float2half_rn(xr - __half2float(hr));
+      Hhi[hoff(row_re + 2)] = hi_; Hlo[hoff(row_re + 2)] = __float2half_rn(xi - __half2float(hi_));
+      continue;
+    }
+    const float rh = tf32_rna((float)vr), ih = tf32_rna((float)vi);
     const size_t o0 = canon_off(row_re, m, u.Mp), o1 = canon_off(row_re + 2, m, u.Mp);
     Bhi[o0] = rh; Blo[o0] = tf32_rna((float)(vr - (double)rh));
     Bhi[o1] = ih; Blo[o1] = tf32_rna((float)(vi - (double)ih));
@@ -369,14 +387,16 @@ struct MmaState {
 // single issuer blocks on the MMA queue and then leaves the pipe idle while it prepares the next stage).  Templated on the K steps so that a stage is straight-line code: two barrier
 // waits, 6 * KS tcgen05.mma, two commits.  (The per-stage scalar code runs on a single warp at ~5 cycles per dependent
 // instruction, while a 128 x 64 x 8 MMA lasts 32 cycles: anything not hoisted out of the stage loop idles the pipe.)
-template <int KS>
+template <int KS, bool F16 = false>
 __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
   const UParams& p = *st.p;
+  // Mp = TMEM columns per split = 8 per K step in both modes (TF32: 8 modes, FP16: 16 modes as 8 packed pairs), and the
+  // B tile's 8-row-group stride is 256 bytes per K step in both (32 Mp bytes of floats = 16 Kp bytes of halves)
   const uint32_t Mp = 8u * KS;
   const uint32_t a_col = st.tmem_base + a_column(p, st.g, (int)Mp);
   const uint32_t desc_hi = (uint32_t)(make_desc(0, 128u, 32u * Mp) >> 32);
   const uint32_t desc_lo0 = (uint32_t)make_desc(0, 128u, 32u * Mp);       // LBO field; start address added per stage
-  const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((kTileR >> 4) << 24);
+  const uint32_t idesc0 = F16 ? ((1u << 4) | ((kTileR >> 4) << 24)) : ((1u << 4) | (2u << 7) | (2u << 10) | ((kTileR >> 4) << 24));
   auto bar = [&](int i) { return st.bar0 + 8u * (uint32_t)i; };
   mbar_wait_t(bar(BAR_EFULL + (st.g & 1)), (uint32_t)((st.g >> 1) & 1), p.err, 4, (BOGP_UMMA_DBG && st.dbg) ? &st.w_efull : nullptr);
   if (BOGP_UMMA_DBG && st.dbg && st.id == 0 && blockIdx.x == 0 && st.g < 32 && (threadIdx.x & 31) == 0) p.dbg[16 * 200 + st.g] = clock64();
@@ -407,7 +427,7 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
     if (sc > 0) mbar_wait(bar(BAR_TURN + (st.id ^ 1)), ((sc - 1u) >> 1) & 1u, p.err, 8);
     if (elect_one()) {
       if (!(BOGP_UMMA_DBG && p.skip == 1))
-        issue_stage<KS>(d_re, d_im, a_col, Mp, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc);
+        issue_stage<KS, F16>(d_re, d_im, a_col, Mp, desc_lo0 | ((b_hi >> 4) & 0x3fffu), desc_lo0 | ((b_lo >> 4) & 0x3fffu), desc_hi, idesc);
       mbar_arrive(bar(BAR_TURN + st.id));
       tc_commit(bar(BAR_BEMPTY + slot));
       tc_commit(bar(BAR_TFULL + buf));
@@ -420,7 +440,7 @@ __device__ __forceinline__ void mma_tonal(MmaState& st, const UTonal& u) {
   __syncwarp();
 }
 
-template <bool TILT>
+template <bool TILT, bool F16 = false>
 __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid_constant__ UParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -514,7 +534,15 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
       int rt_, z0_, jr_;
       unit_decode<TILT>(p, unit, rt_, z0_, st.nzu, jr_);
       for (int f = 0; f < p.F; ++f, ++st.g) {
-        switch (p.t[f].Mp >> 3) {
+        if (F16) {
+          switch (p.t[f].kc >> 3) {
+            case 1: mma_tonal<1, F16>(st, p.t[f]); break;
+            case 2: mma_tonal<2, F16>(st, p.t[f]); break;
+            case 3: mma_tonal<3, F16>(st, p.t[f]); break;
+            default: mma_tonal<4, F16>(st, p.t[f]); break;
+          }
+        } else
+        switch (p.t[f].kc >> 3) {
           case 1: mma_tonal<1>(st, p.t[f]); break;
           case 2: mma_tonal<2>(st, p.t[f]); break;
           case 3: mma_tonal<3>(st, p.t[f]); break;
@@ -544,12 +572,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
         if (g >= 2) mbar_wait_relaxed<TILT ? 4096 : 256>(bar(BAR_EDONE + (g & 1)), (uint32_t)(((g - 2) >> 1) & 1), p.err, 1);
         if (g >= 1) {
           const UTonal& up = p.t[f == 0 ? p.F - 1 : f - 1];
-          if (4 * (up.Mp + u.Mp) > p.AR)
+          if (4 * (up.kc + u.kc) > p.AR)
             mbar_wait_relaxed<TILT ? 2048 : 256>(bar(BAR_EDONE + ((g - 1) & 1)), (uint32_t)(((g - 1) >> 1) & 1), p.err, 2);
         }
         tc_fence_after();
         const float4* src = reinterpret_cast<const float4*>(p.E + (size_t)rt * p.e_rt_stride + u.e_off) + tl;
-        const uint32_t dst = tmem_base + ((uint32_t)(quad * 32) << 16) + a_column(p, g, u.Mp);
+        const uint32_t dst = tmem_base + ((uint32_t)(quad * 32) << 16) + a_column(p, g, u.kc);
         const int n16 = u.Mp >> 2;            // 4 Mp columns in groups of 16
         if (TILT) {
           // tilted array: the depth goes into the A operand, A[i, m] = E[i, m] phi_m(z_j), because the B operand
@@ -557,6 +585,58 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) umma_grid_kernel(const __grid
           // split again.  Eight modes per step: (re | im) x (hi, lo) chunks in, two 8-column stores out per part.
           const float* phi = p.phiz + (size_t)jreal * p.sumMp + u.offM;
           const int mc = u.Mp >> 2;           // 16-byte chunks per block of Mp columns
+          if (F16) {
+            // FP16-split operands: 16 modes per step -> the scaled value x sA, hi = fp16(x), lo = fp16(x - hi), two
+            // modes per 32-bit TMEM column; image = [re_hi | re_lo | im_hi | im_lo] x kc columns
+            const float* phj = p.phiz_im ? p.phiz_im + (size_t)jreal * p.sumMp + u.offM : nullptr;
+            const uint32_t kc = (uint32_t)u.kc;
+            for (int q16 = 0; q16 < (u.kc >> 3); ++q16) {
+              float xr[16], xi[16];
+#pragma unroll
+              for (int h4 = 0; h4 < 4; ++h4) {
+                const int c = 4 * q16 + h4;           // 16-byte chunk (4 modes) of the table's blocks
+                if (4 * c < u.Mp) {
+                  const float4 rh = __ldg(src + (size_t)(0 * mc + c) * kTileR), rl = __ldg(src + (size_t)(1 * mc + c) * kTileR);
+                  const float4 ih = __ldg(src + (size_t)(2 * mc + c) * kTileR), il = __ldg(src + (size_t)(3 * mc + c) * kTileR);
+                  const float4 a = __ldg(reinterpret_cast<const float4*>(phi + 4 * c));
+                  const float er[4] = {rh.x + rl.x, rh.y + rl.y, rh.z + rl.z, rh.w + rl.w};
+                  const float ei[4] = {ih.x + il.x, ih.y + il.y, ih.z + il.z, ih.w + il.w};
+                  const float pr[4] = {a.x * u.sA, a.y * u.sA, a.z * u.sA, a.w * u.sA};
+                  if (phj) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(phj + 4 * c));
+                    const float pi[4] = {b.x * u.sA, b.y * u.sA, b.z * u.sA, b.w * u.sA};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { xr[4 * h4 + e] = fmaf(er[e], pr[e], -ei[e] * pi[e]); xi[4 * h4 + e] = fmaf(er[e], pi[e], ei[e] * pr[e]); }
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { xr[4 * h4 + e] = er[e] * pr[e]; xi[4 * h4 + e] = ei[e] * pr[e]; }
+                  }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) { xr[4 * h4 + e] = 0.f; xi[4 * h4 + e] = 0.f; }
+                }
+              }
+              float hi[8], lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const __half h0 = __float2half_rn(xr[2 * e]), h1 = __float2half_rn(xr[2 * e + 1]);
+                const __half l0 = __float2half_rn(xr[2 * e] - __half2float(h0)), l1 = __float2half_rn(xr[2 * e + 1] - __half2float(h1));
+                hi[e] = __uint_as_float((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16));
+                lo[e] = __uint_as_float((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16));
+              }
+              tc_st8(dst + (uint32_t)(8 * q16), hi);
+              tc_st8(dst + kc + (uint32_t)(8 * q16), lo);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const __half h0 = __float2half_rn(xi[2 * e]), h1 = __float2half_rn(xi[2 * e + 1]);
+                const __half l0 = __float2half_rn(xi[2 * e] - __half2float(h0)), l1 = __float2half_rn(xi[2 * e + 1] - __half2float(h1));
+                hi[e] = __uint_as_float((uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16));
+                lo[e] = __uint_as_float((uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16));
+              }
+              tc_st8(dst + 2u * kc + (uint32_t)(8 * q16), hi);
+              tc_st8(dst + 3u * kc + (uint32_t)(8 * q16), lo);
+            }
+          } else
           if (p.phiz_im) {
             // complex source mode shapes (KRAKENC): a = (E_re + i E_im)(phi_re + i phi_im), both parts per 8 modes
             const float* phj = p.phiz_im + (size_t)jreal * p.sumMp + u.offM;
@@ -1101,7 +1181,7 @@ static bool plan_tonals(const bogp_modeset_s* h, UParams& p, int ZC) {
     const TonalMeta& t = d.t[order[f]];
     UTonal& u = p.t[f];
     u.src = order[f];
-    u.Mp = t.Mp; u.rowsP = t.u_rowsP; u.n1 = t.u_p0; u.nq = t.u_fold ? 0 : t.n_qpair; u.trK = t.trK;
+    u.Mp = t.Mp; u.kc = t.Mp; u.rowsP = t.u_rowsP; u.n1 = t.u_p0; u.nq = t.u_fold ? 0 : t.n_qpair; u.trK = t.trK;
     u.fold = t.u_fold; u.c1r = t.u_c[0]; u.c1i = t.u_c[1]; u.c2r = t.u_c[2]; u.c2i = t.u_c[3];
     u.e_bytes = 2048u * (unsigned)u.Mp;
     u.e_off = e_off;
@@ -1283,17 +1363,39 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   int sumMp = 0, maxMp = 0;
   int order[BOGP_MAX_TONALS];
   tonal_order(d, order);
+  // FP16-split operands (default; BOGP_UMMA_KIND=tf32 keeps 3xTF32): same three products per MAC at the kind::f16 rate,
+  // operands scaled by per-tonal powers of two (the Bartlett value is a ratio: the scales cancel)
+  bool f16 = true;
+  if (const char* e = std::getenv("BOGP_UMMA_KIND")) f16 = e[0] != 't';
+  if ((int)h->u16.k_host.size() != d.F || (int)h->u16.phi_max.size() != d.F) f16 = false;
+  p.f16 = f16 ? 1 : 0;
+  double rmin = r_host[0], rmax = r_host[0];
+  const double lmax = h->u16.lever_max;
+  for (int i = 1; i < Nr; ++i) { rmin = std::min(rmin, r_host[i]); rmax = std::max(rmax, r_host[i]); }
+  auto pow2 = [](double bound) { return (bound > 0.0 && std::isfinite(bound)) ? (float)std::ldexp(1.0, (int)std::floor(std::log2(16384.0 / bound))) : 1.f; };
   for (int f = 0; f < d.F; ++f) {
     const TonalMeta& t = d.t[order[f]];
     UTonal& u = p.t[f];
     u.src = order[f];
     u.Mp = t.Mp; u.rowsP = 64; u.nj = 1; u.nq = 0; u.n1 = 0; u.trK = t.trK;
+    u.kc = f16 ? pad_to(t.M, 16) / 2 : t.Mp;
     u.e_bytes = 2048u * (unsigned)u.Mp; u.e_off = e_off; e_off += u.e_bytes;
-    u.b_zbytes = 64u * (unsigned)u.Mp * 4u;
+    u.b_zbytes = f16 ? 64u * (unsigned)(2 * u.kc) * 2u : 64u * (unsigned)u.Mp * 4u;
     u.b_off = b_off; b_off += (unsigned long long)p.Nz * u.b_zbytes;
     u.offM = sumMp; sumMp += t.Mp;
     u.offC = t.offC; u.J = t.J;
     maxMp = std::max(maxMp, t.Mp);
+    u.sA = u.sB = 1.f;
+    if (f16) {
+      double be = 0.0, kim = 0.0, pr = 0.0;
+      for (const cplx& k : h->u16.k_host[order[f]]) {
+        be = std::max(be, std::exp(std::max(k.imag() * rmin, k.imag() * rmax)) / std::sqrt(std::abs(k) * std::max(rmin * 0.5, 1e-3)));
+        kim = std::max(kim, std::fabs(k.imag()));
+      }
+      for (const cplx& v : h->phi_rec[order[f]]) pr = std::max(pr, std::abs(v));
+      u.sA = pow2(be * (double)h->u16.phi_max[order[f]]);      // |E phi|: E bounded at half the smallest range (receivers of a tilted array sit closer)
+      u.sB = pow2(pr * std::exp(kim * lmax));                   // |Phi e^{i k l sin(tau)}|
+    }
   }
   p.sumMp = sumMp;
   p.e_rt_stride = e_off;
@@ -1301,7 +1403,8 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   const unsigned aux_bytes = (64u * 4u + (unsigned)d.F * 256u * 8u + 2u * 2u * 4u * 9u * 32u * 4u + (unsigned)d.F * 32u * 16u + 127u) & ~127u;
   unsigned stage = (kSmemLimit - acc_bytes - aux_bytes - 256u) / kStages;
   stage = std::min(stage & ~127u, 32u * 1024u);
-  if (2u * 64u * (unsigned)maxMp * 4u > stage) { set_error("UMMA tilt engine: mode set does not fit"); return BOGP_ERR_UNSUPPORTED; }
+  for (int f = 0; f < d.F; ++f)
+    if (2u * p.t[f].b_zbytes > stage || 4 * p.t[f].kc > 256) { set_error("UMMA tilt engine: mode set does not fit"); return BOGP_ERR_UNSUPPORTED; }
   p.stage_bytes = stage; p.smem_B = 0; p.smem_acc = kStages * stage; p.smem_aux = p.smem_acc + acc_bytes;
   p.smem_bar = p.smem_aux + aux_bytes;
   // scratch: [r | z | tilt doubles][err][phiz][sin][rinv][lever][E table][Bhi][Blo]
@@ -1349,9 +1452,10 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   count_launch(3);
   BOGP_CUDA(cudaGetLastError());
   const size_t smem = (size_t)p.smem_bar + 256;
-  BOGP_CUDA(cudaFuncSetAttribute(umma_grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = p.f16 ? umma_grid_kernel<true, true> : umma_grid_kernel<true, false>;
+  BOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t ev = timing_begin(s);
-  umma_grid_kernel<true><<<std::min(p.units, sms), kUmmaThreads, smem, s>>>(p);
+  kern<<<std::min(p.units, sms), kUmmaThreads, smem, s>>>(p);
   timing_end(ev, s);
   count_launch();
   BOGP_CUDA(cudaGetLastError());

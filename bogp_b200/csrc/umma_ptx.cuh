@@ -133,11 +133,32 @@ __device__ __forceinline__ void tc_mma_tf32_ts2(uint32_t d_tmem, uint32_t a_tmem
         "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc)
         : "memory");
 }
+// kind::f16 with A in TMEM (two FP16 values per 32-bit column, K = 16 per instruction = 8 columns): same operand
+// addressing as the TF32 form above.
+__device__ __forceinline__ void tc_mma_f16_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_desc_lo, uint32_t b_desc_hi,
+                                               uint32_t idesc, bool accumulate) {
+  if (accumulate)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 d;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 d;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], d, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_desc_lo), "r"(b_desc_hi), "r"(idesc)
+        : "memory");
+}
 // All MMAs of one stage, fully unrolled over the KS K-steps: per K-step D += A_lo B_hi + A_hi B_lo + A_hi B_hi for
 // the re and the im accumulator.  Called by ONE elected lane; a single warp must keep the tensor pipe fed with
 // 128 x N x 8 MMAs of only N/2 cycles each, so the instruction count per MMA matters (v1 spent ~90 cycles per MMA
 // in address arithmetic and R2UR moves).
-template <int KS>
+template <int KS, bool F16 = false>
 __device__ __forceinline__ void issue_stage(uint32_t d_re, uint32_t d_im, uint32_t a_col, uint32_t Mp, uint32_t bh_lo,
                                             uint32_t bl_lo, uint32_t desc_hi, uint32_t idesc) {
   // Opaque copies: keeps ptxas from hoisting the 4 KS derived addresses out of the stage loop into vector registers
@@ -151,9 +172,15 @@ __device__ __forceinline__ void issue_stage(uint32_t d_re, uint32_t d_im, uint32
     const uint32_t a_hi = a_col + (uint32_t)(2 * part) * Mp, a_lo = a_hi + Mp;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      tc_mma_tf32_ts2(d, a_lo + 8u * ks, bh_lo + 16u * ks, desc_hi, idesc, ks > 0);
-      tc_mma_tf32_ts2(d, a_hi + 8u * ks, bl_lo + 16u * ks, desc_hi, idesc, true);
-      tc_mma_tf32_ts2(d, a_hi + 8u * ks, bh_lo + 16u * ks, desc_hi, idesc, true);
+      if (F16) {
+        tc_mma_f16_ts2(d, a_lo + 8u * ks, bh_lo + 16u * ks, desc_hi, idesc, ks > 0);
+        tc_mma_f16_ts2(d, a_hi + 8u * ks, bl_lo + 16u * ks, desc_hi, idesc, true);
+        tc_mma_f16_ts2(d, a_hi + 8u * ks, bh_lo + 16u * ks, desc_hi, idesc, true);
+      } else {
+        tc_mma_tf32_ts2(d, a_lo + 8u * ks, bh_lo + 16u * ks, desc_hi, idesc, ks > 0);
+        tc_mma_tf32_ts2(d, a_hi + 8u * ks, bl_lo + 16u * ks, desc_hi, idesc, true);
+        tc_mma_tf32_ts2(d, a_hi + 8u * ks, bh_lo + 16u * ks, desc_hi, idesc, true);
+      }
     }
   }
 }

@@ -128,16 +128,21 @@ def bench_tilt():
     dms = mfp.DeviceModeSet(modes, K)
     N, sumM = 64, sum(modes.n_modes)
     r, z = np.linspace(0.1, 10.0, 1000), np.linspace(1.0, 200.0, 100)
-    for nt, engines in ((10, ("simt", "umma")), (100, ("simt", "umma"))):
+    import os
+    for nt, engines in ((10, ("simt", "umma", "umma_tf32")), (100, ("simt", "umma", "umma_tf32"))):
         tilt = np.linspace(-4.0, 4.0, nt)
         C = len(r) * len(z) * len(tilt)
         out = torch.empty((len(tilt), len(z), len(r)), dtype=torch.float32, device="cuda")
-        for engine in engines:
+        for engine_tag in engines:
+            engine = "umma" if engine_tag.startswith("umma") else engine_tag
+            if engine_tag == "umma_tf32":
+                os.environ["BOGP_UMMA_KIND"] = "tf32"
             call_ms, k_ms = timed(lambda: dms.bartlett_grid(r, z, tilt, out=out, engine=engine), reps=3, warm=1)
+            os.environ.pop("BOGP_UMMA_KIND", None)
             name = ("grid_tilt_kernel (K1-SIMT, receiver space, Theta_tau in shared memory)" if engine == "simt" else
-                    "umma_grid_kernel<tilt> (K1-UMMA-TILT: tcgen05 3xTF32, Theta_tau as B operand, receiver-space epilogue)")
+                    "umma_grid_kernel<tilt> (K1-UMMA-TILT: tcgen05 " + ("3xTF32" if engine_tag == "umma_tf32" else "3xFP16-split") + ", Theta_tau as B operand, receiver-space epilogue)")
             flop = 8.0 * N * sumM          # complex Theta x complex a: 4 real MACs per (receiver, mode)
-            print(json.dumps({"kernel": name, "engine": engine,
+            print(json.dumps({"kernel": name, "engine": engine_tag,
                               "case": f"configs[3]: 1000 r x 100 z x {nt} tilt = {C:.0e} candidates, 13 tonals, 64 receivers",
                               "kernel_ms": k_ms, "call_ms": call_ms, "cand_freq_per_s": C * 13 / (k_ms * 1e-3),
                               "alg_tflops": C * flop / (k_ms * 1e-3) / 1e12, "alg_flop_per_cand": flop,
