@@ -925,9 +925,13 @@ bool plan16(const bogp_modeset_s* h, HParams& p, int ZC) {
   return true;
 }
 
-int choose_zc16(int Nr, int Nz, int sms) {
+// Depths per unit.  waves = 1: one unit per SM.  waves = 2 (output in mapped host memory): half-size units, two per SM, so
+// that the first half of the surface crosses PCIe while the second half is being computed (all units of a single wave
+// finish -- and write -- at the same time).
+int choose_zc16(int Nr, int Nz, int sms, int waves) {
+  if (const char* e = std::getenv("BOGP_UMMA_ZC")) { const int v = std::atoi(e); if (v >= 8) return std::min(64, v & ~7); }
   const int nrt = (Nr + kTile - 1) / kTile;
-  const int chunks = std::max(1, sms / nrt);
+  const int chunks = std::max(1, waves * sms / nrt);
   int zc = (Nz + chunks - 1) / chunks;
   zc = std::max(8, std::min(64, (zc + 7) & ~7));
   return zc;
@@ -960,7 +964,12 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
   const ModesetDev& d = h->dev;
   const int sms = device_sms16();
   HParams p{};
-  const int ZC = choose_zc16(Nr, Nz, sms);
+  cudaPointerAttributes pat{};
+  const bool host_out = cudaPointerGetAttributes(&pat, out_dev) == cudaSuccess && pat.type == cudaMemoryTypeHost;
+  if (!host_out) cudaGetLastError();
+  int waves = host_out ? 2 : 1;
+  if (const char* e = std::getenv("BOGP_UMMA_WAVES")) waves = std::max(1, std::min(4, std::atoi(e)));
+  const int ZC = choose_zc16(Nr, Nz, sms, waves);
   if (!plan16(h, p, ZC)) { set_error("UMMA-H engine: mode set does not fit (operator rows > 128, more than 64 modes or complex source table)"); return BOGP_ERR_UNSUPPORTED; }
   p.Nr = Nr; p.Nz = Nz; p.ZC = ZC; p.atype = atype; p.mf = mf;
   { const char* e = std::getenv("BOGP_UMMA_TWO_SLOT"); p.two_slot = e ? std::atoi(e) : 3; }
