@@ -55,7 +55,7 @@ def _workload_config(n_gpus: int) -> dict:
                         "64-element VLA, synthetic Pekeris mode set (276 modes), rank-1 K",
             "grid": [NZ_PER_GPU * n_gpus, NR], "tonals": 13, "receivers": 64,
             "sharding": f"depth-row slabs over {n_gpus} rank(s), replicated mode tables",
-            "l2": "flushed between timed steps (256 MiB device memset, untimed); tables are L2-resident by design"}
+            "l2": "flushed between timed steps (256 MiB device memset, untimed); tables are L2-resident by design", "start": "timed steps follow the barrier after 2 un-timed steps (no cold first step); ranks leave the barrier on a common host clock deadline"}
 
 
 def build_inputs(n_gpus: int):
@@ -85,6 +85,11 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # nvidia-smi's start-up (fork, NVML initialisation inside the driver) delays this process's launches by tens of
+            # microseconds: wait until it is over before any timed work is queued
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 3.0:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
@@ -401,6 +406,15 @@ def run_ours(args) -> None:
             else:
                 exchange_kind = ("peer memory, fused: the surface kernel's last CTA stores the record into the peers' buffers over "
                                  "NVLink and collects theirs (bogp_bartlett_grid_argext_peer, no launch of its own)")
+    # BOGP_EXCHANGE_MODE=pipelined: step k publishes its record without waiting for the peers and picks up the records of
+    # step k - 1; one collect kernel after the last step, inside the timed region, returns the last records.  Measured on
+    # 8 GPUs (profiles/scaling_r2.md): the collective form -- every step waits for every peer's record of the same step --
+    # is as fast in steady state (median step 0.0975 vs 0.0954 ms) and steadier over 20 steps (the pipelined form pays the
+    # accumulated skew in its final collect), so it stays the default.
+    pipelined = peer is not None and os.environ.get("BOGP_EXCHANGE_MODE", "collective") == "pipelined"
+    if pipelined:
+        exchange_kind += ("; pipelined by one step (bogp_peer_set_pipelined): a step hands back the records of the step "
+                          "before, bogp_peer_collect closes the sequence inside the timed region")
 
     def exchange_records():
         if peer is not None:
@@ -433,10 +447,19 @@ def run_ours(args) -> None:
             pairs.cpu()
         return flat
 
-    def barrier():
+    def barrier(align: bool = False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        if align and world > 1:
+            # the ranks leave an NCCL barrier tens of microseconds apart, and with one exchange per step that skew is
+            # paid as a wait inside the first timed step: start the timed region on a common host wall-clock deadline
+            # (all ranks share the box's clock)
+            t = torch.tensor([time.time() + 0.002], dtype=torch.float64, device=dev)
+            dist.broadcast(t, src=0)
+            deadline = float(t.item())
+            while time.time() < deadline:
+                pass
 
     # ---- correctness gate before timing: peak on the truth node, value ~ 1
     step_device()
@@ -461,23 +484,42 @@ def run_ours(args) -> None:
     # recorded inside it (the library then launches the surface kernel as a programmatic dependent of its table kernel);
     # (2) roofline: the library brackets the dominant kernel with its own event pair on the launching stream -- an
     # event between the two launches serialises them, so this pass only yields the kernel's own duration.
+    if pipelined:
+        peer.set_pipelined(True)
+    clocks = ClockSampler(local)
+    clocks.__enter__()          # sampling runs from here to the end of the end-to-end loop (started outside the timed region)
     for _ in range(args.warmup):
         step_device()
-    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier(align=os.environ.get("BOGP_BENCH_ALIGN", "1") == "1")
+    # two un-timed steps after the barrier: the first timed step then starts on a GPU with work queued behind it like
+    # every later one, not on a device that has idled through the barrier (first step 0.101 -> 0.094 ms at N = 1, and
+    # with one exchange per step the slowest rank's cold start is otherwise paid by all of them)
+    presteps = int(os.environ.get("BOGP_BENCH_PRESTEPS", "2"))
+    for _ in range(presteps):
+        flush.zero_()
+        step_device()
     launches0 = _lib.kernel_launches()
-    with ClockSampler(local) as clocks:
-        t_wall0 = time.perf_counter()
-        for a, b in ev:
-            flush.zero_()
-            a.record()
-            step_device()
-            b.record()
-        barrier()
-        t_wall = time.perf_counter() - t_wall0
+    t_wall0 = time.perf_counter()
+    for i, (a, b) in enumerate(ev):
+        flush.zero_()
+        a.record()
+        step_device()
+        if pipelined and i == args.steps - 1:
+            peer.collect(pairs)          # the records of the last step: part of the timed work
+        b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
     launches = _lib.kernel_launches() - launches0
+    if pipelined and not torch.equal(check, pairs):
+        raise SystemExit(f"bench.py: pipelined record exchange mismatch on rank {rank}: {pairs.tolist()} vs {check.tolist()}")
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
+    if os.environ.get("BOGP_BENCH_DEBUG") == "1":      # per-rank distribution of the step times and of the gaps between steps
+        gaps = [ev[i][1].elapsed_time(ev[i + 1][0]) for i in range(len(ev) - 1)]
+        print(f"bench.py[rank {rank}]: step ms min/med/max {min(step_ms):.4f}/{sorted(step_ms)[len(step_ms) // 2]:.4f}/{max(step_ms):.4f}"
+              f"  gap ms min/med/max {min(gaps):.4f}/{sorted(gaps)[len(gaps) // 2]:.4f}/{max(gaps):.4f}  first five {[round(x, 4) for x in step_ms[:5]]}",
+              file=sys.stderr)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -505,6 +547,11 @@ def run_ours(args) -> None:
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
+    if pipelined:
+        peer.collect(pairs)
+        last = pairs.cpu()
+        if not torch.equal(check.cpu(), last):
+            raise SystemExit(f"bench.py: pipelined e2e record mismatch on rank {rank}: {last.tolist()} vs {check.tolist()}")
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -512,6 +559,7 @@ def run_ours(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = evals_per_step * args.steps / e2e_s
+    clocks.__exit__(None, None, None)
     h2d = (len(r) + len(z_slab)) * 8 + (16 if world > 1 else 0)
     d2h = rows * NR * 4 + (16 * world if world > 1 else 0)
 

@@ -69,6 +69,8 @@ SIGNATURES = {
     "bogp_peer_open": (C.c_int, [_vp, _vp]),
     "bogp_peer_exchange": (C.c_int, [_vp, _vp, _vp, _vp]),
     "bogp_peer_destroy": (C.c_int, [_vp]),
+    "bogp_peer_set_pipelined": (C.c_int, [_vp, C.c_int]),
+    "bogp_peer_collect": (C.c_int, [_vp, _vp, _vp]),
     "bogp_bartlett_grid_argext_peer": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _vp,
                                                 C.c_int, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp]),
     "bogp_bartlett_grid_host_argmax_peer": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int,

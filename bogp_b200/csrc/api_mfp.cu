@@ -205,6 +205,8 @@ extern "C" int bogp_modeset_destroy(bogp_modeset_t h) {
   if (h->u16.E) cudaFree(h->u16.E);
   if (h->u16.B) cudaFree(h->u16.B);
   if (h->u16.misc) cudaFree(h->u16.misc);
+  if (h->u16.tab_cnt) cudaFree(h->u16.tab_cnt);
+  if (h->u16.phi) cudaFree(h->u16.phi);
   delete h;
   return 0;
 }

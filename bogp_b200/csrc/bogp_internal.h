@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...);
 // Number of kernels this library has launched (bench.py reports it as gpu_launches).
 void count_launch(int n = 1);
 // Event bracket around a dominant kernel (no-ops returning nullptr unless bogp_timing_enable(1)).
+bool timing_enabled();
 cudaEvent_t timing_begin(cudaStream_t s);
 void timing_end(cudaEvent_t stop, cudaStream_t s);
 
@@ -152,6 +153,13 @@ struct bogp_modeset_s {
     void* E = nullptr; size_t E_bytes = 0;
     void* B = nullptr; size_t B_bytes = 0;
     void* misc = nullptr; size_t misc_bytes = 0;
+    // streamed Bop tables: per tonal position a device counter of finished table blocks (never reset) and the value it
+    // reaches when the tonal's tables of the current call are complete
+    unsigned int* tab_cnt = nullptr;
+    unsigned int tab_target[BOGP_MAX_TONALS] = {};
+    // source mode shapes at the depths of z_cached, [tonal position][depth][Kp] floats (covariance-independent)
+    void* phi = nullptr; size_t phi_bytes = 0;
+    bool phi_valid = false;
     std::vector<double> r_cached, z_cached;   // host copies of the vectors the device copies / the E table were built from
   } u16;
 };
@@ -196,6 +204,8 @@ struct bogp_peer_s {
   unsigned char** mapped_dev = nullptr;         // the same array on the device
   unsigned long long epoch = 0;
   size_t bytes = 0;
+  int pipelined = 0;                            // bogp_peer_set_pipelined: publish step k, hand back the records of step k - 1
+  int last_pipelined = 0;                       // mode of the previous step
 };
 namespace bogp {
 // What a surface kernel needs to run the exchange of the (index, value) record itself: see peer_exchange_kernel.
@@ -206,6 +216,7 @@ struct PeerArgs {
   long long index_offset = 0;                // added to the local flat index before the record is published
   long long* recs_out = nullptr;             // [world][2] records of every rank (device or mapped host memory)
   int* err = nullptr;
+  int pipelined = 0;                         // 1: collect epoch - 1, then publish epoch (no wait for the peers' current step); 2: collective step after a pipelined one
 };
 // fills `a` for the next exchange of `p` (advances its epoch)
 int peer_next(bogp_peer_s* p, long long index_offset, long long* recs_out, PeerArgs& a);

@@ -1,69 +1,62 @@
 // Final reduction across the GPUs of one box without a collective library: every rank owns a small device buffer that
 // its peers map through CUDA IPC; one tiny kernel per step stores this rank's 16-byte (index, value) record straight
-// into every peer's buffer over NVLink (P2P stores), publishes an epoch flag, and waits for the peers' flags.  This is
+// into every peer's buffer over NVLink (P2P stores, every word tagged with the step's epoch) and waits for the peers'
+// records of the same step -- or, pipelined, picks up those of the step before.  This is
 // the exchange the reference does on the host with np.argmax over the collated surfaces
 // (ref/projects/swellex96_localization/data/collate.py:50); an NCCL all-gather of 16 bytes per rank costs ~25 us per
 // step on 4-8 GPUs, a fixed cost that is 12 % of the 0.19 ms step.
 //
-// Buffer layout per rank: records[2][world] (16 B each, double-buffered by epoch parity) | flags[world] (8 B each).
-// Rank A writes records[e & 1][A] and then flags[A] = e in every peer.  A peer reads records[e & 1][*] once all its
-// flags have reached e.  A rank can only start epoch e + 2 (same parity) after its epoch e + 1 kernel has finished,
-// i.e. after every peer has published e + 1 -- which a peer does only after its epoch-e kernel (the reader of the
-// slot that is about to be overwritten) has completed.
+// Buffer layout per rank: records[2][world] slots of 32 bytes, double-buffered by epoch parity; every 8-byte word of a
+// slot carries the epoch it was written in (peer_device.cuh), so there are no flags and no fences.  Rank A writes
+// records[e & 1][A] in every peer; a peer reads records[e & 1][*] once all words carry e.  A rank can only start epoch
+// e + 2 (same parity) after its epoch e + 1 kernel has finished, i.e. after every peer has published e + 1 -- which a
+// peer does only after its epoch-e kernel (the reader of the slot that is about to be overwritten) has completed.
 #include <cuda_runtime.h>
 
 #include <cstring>
 #include <vector>
 
 #include "bogp_internal.h"
+#include "peer_device.cuh"
 
 
 namespace bogp {
 
 constexpr int kPeerMaxWorld = 64;
 
-__global__ void peer_exchange_kernel(unsigned char* const* bufs, int rank, int world, unsigned long long epoch,
+// One thread per peer.  Collective form (pipelined == 0): publish this rank's record of `epoch`, wait for every peer's
+// record of the same epoch.  Pipelined form: first pick up the peers' records of epoch - 1 (published one whole step
+// ago, so the wait is normally over before it starts), then publish this rank's record of `epoch` without waiting for
+// anybody -- the step no longer ends on the slowest rank of the box; the records of the last step are picked up by
+// peer_collect_kernel.  Collect-before-publish keeps the two record slots safe: a peer can only publish epoch e + 1
+// (the slot of e - 1) after it has seen this rank's epoch e, which is stored after this rank has read e - 1.
+__global__ void peer_exchange_kernel(unsigned char* const* bufs, int rank, int world, unsigned long long epoch, int pipelined,
                                      const long long* rec_in, long long* recs_out, int* err) {
   const int t = threadIdx.x;
   if (t >= world) return;
-  const size_t rec_off = ((size_t)(epoch & 1ull) * world + rank) * 16, flag_off = (size_t)2 * world * 16 + (size_t)rank * 8;
-  const long long r0 = rec_in[0], r1 = rec_in[1];
-  {
-    long long* dst = reinterpret_cast<long long*>(bufs[t] + rec_off);
-    dst[0] = r0;
-    dst[1] = r1;
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(bufs[t] + flag_off), "l"(epoch) : "memory");
-  }
-  // wait for peer t's record of this epoch in the local buffer
-  const unsigned char* mine = bufs[rank];
-  const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(mine + (size_t)2 * world * 16 + (size_t)t * 8);
-  unsigned long long seen = 0;
-  long long t0 = clock64();
-  for (unsigned spin = 0;; ++spin) {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
-    if (seen >= epoch) break;
-    if ((spin & 1023u) == 1023u && clock64() - t0 > 20000000000LL) {      // ~10 s: a peer never reached this step
-      atomicExch(err, 1 + t);
-      __threadfence_system();
-      __trap();                                                               // surfaces as a CUDA error at the next sync
-    }
-  }
-  const long long* src = reinterpret_cast<const long long*>(mine + ((size_t)(epoch & 1ull) * world + t) * 16);
-  recs_out[2 * t] = src[0];
-  recs_out[2 * t + 1] = src[1];
+  peer_step(bufs, t, rank, world, epoch, pipelined, rec_in[0], rec_in[1], recs_out, err);
+}
+
+// the records of the latest published epoch (closes a pipelined sequence)
+__global__ void peer_collect_kernel(unsigned char* const* bufs, int rank, int world, unsigned long long epoch,
+                                    long long* recs_out, int* err) {
+  const int t = threadIdx.x;
+  if (t >= world) return;
+  if (epoch == 0) { recs_out[2 * t] = -1; recs_out[2 * t + 1] = 0; return; }
+  peer_wait_read(bufs[rank], t, world, epoch, recs_out, err);
 }
 
 int peer_next(bogp_peer_s* p, long long index_offset, long long* recs_out, PeerArgs& a) {
   BOGP_REQUIRE(p && p->mapped_dev, "peer exchange: call bogp_peer_open first");
   ++p->epoch;
   a.bufs = p->mapped_dev; a.rank = p->rank; a.world = p->world; a.epoch = p->epoch; a.index_offset = index_offset;
-  a.recs_out = recs_out; a.err = reinterpret_cast<int*>(p->local + p->bytes - 64);
+  a.recs_out = recs_out; a.pipelined = p->pipelined ? 1 : (p->last_pipelined ? 2 : 0); a.err = reinterpret_cast<int*>(p->local + p->bytes - 64);
+  p->last_pipelined = p->pipelined;
   return 0;
 }
 
 int peer_exchange_launch(const PeerArgs& a, const long long* rec_dev, cudaStream_t s) {
-  peer_exchange_kernel<<<1, 64, 0, s>>>(a.bufs, a.rank, a.world, a.epoch, rec_dev, a.recs_out, a.err);
+  peer_exchange_kernel<<<1, 64, 0, s>>>(a.bufs, a.rank, a.world, a.epoch, a.pipelined, rec_dev, a.recs_out, a.err);
   count_launch();
   BOGP_CUDA(cudaGetLastError());
   return 0;
@@ -78,7 +71,7 @@ extern "C" int bogp_peer_create(bogp_peer_t* out, int rank, int world, unsigned 
   static_assert(sizeof(cudaIpcMemHandle_t) == BOGP_IPC_HANDLE_BYTES, "IPC handle size");
   bogp_peer_s* p = new bogp_peer_s();
   p->rank = rank; p->world = world;
-  p->bytes = (size_t)2 * world * 16 + (size_t)world * 8 + 64;
+  p->bytes = (size_t)2 * world * bogp::kPeerSlotBytes + 64;
   if (cudaMalloc(&p->local, p->bytes) != cudaSuccess || cudaMemset(p->local, 0, p->bytes) != cudaSuccess) {
     bogp::set_error("bogp_peer_create: %s", cudaGetErrorString(cudaGetLastError()));
     delete p;
@@ -125,6 +118,22 @@ extern "C" int bogp_peer_exchange(bogp_peer_t p, const long long* rec_dev, long 
   bogp::PeerArgs a;
   if (int rc = bogp::peer_next(p, 0, recs_out_dev, a)) return rc;
   return bogp::peer_exchange_launch(a, rec_dev, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bogp_peer_set_pipelined(bogp_peer_t p, int on) {
+  BOGP_REQUIRE(p, "bogp_peer_set_pipelined: NULL handle");
+  p->pipelined = on ? 1 : 0;
+  return 0;
+}
+
+extern "C" int bogp_peer_collect(bogp_peer_t p, long long* recs_out_dev, void* stream) {
+  BOGP_REQUIRE(p && recs_out_dev, "bogp_peer_collect: NULL argument");
+  BOGP_REQUIRE(p->mapped_dev, "bogp_peer_collect: call bogp_peer_open first");
+  bogp::peer_collect_kernel<<<1, 64, 0, static_cast<cudaStream_t>(stream)>>>(p->mapped_dev, p->rank, p->world, p->epoch, recs_out_dev,
+                                                                            reinterpret_cast<int*>(p->local + p->bytes - 64));
+  bogp::count_launch();
+  BOGP_CUDA(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int bogp_peer_destroy(bogp_peer_t p) {

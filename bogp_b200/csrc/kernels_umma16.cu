@@ -27,6 +27,7 @@
 
 #include "bogp_internal.h"
 #include "device_math.cuh"
+#include "peer_device.cuh"
 #include "umma_ptx.cuh"
 
 // Per-tonal time stamps of CTA 0 (issuer 0 and epilogue warp 0) are compiled in only with -DBOGP_UMMA_DBG=1
@@ -75,11 +76,17 @@ struct HParams {
   // fused final reduction across the GPUs of a box: the last CTA publishes (index_offset + index, value) to every peer's
   // buffer and collects theirs (what csrc/kernels_peer.cu does in a launch of its own); peer_bufs == null: off
   unsigned char* const* peer_bufs;
-  int peer_rank, peer_world;
+  int peer_rank, peer_world, peer_mode;
   unsigned long long peer_epoch;
   long long peer_offset;
   long long* peer_out;
   int* peer_err;
+  // streamed Bop tables: tab_cnt[f] counts the finished table blocks of tonal position f (monotonic over calls), the
+  // tonal's tables of this call are complete when it has reached tab_target[f]; null = wait for the whole table grid
+  const unsigned int* tab_cnt;
+  unsigned int tab_target[BOGP_MAX_TONALS];
+  const float* phi;            // cached source mode shapes [tonal position][depth][Kp] (streamed tables)
+  unsigned int phi_off[BOGP_MAX_TONALS];
   long long* dbg;              // debug build: [0, 64) issuer 0 tonal starts, [64, 128) epilogue warp 0 tonal starts (CTA 0)
   int skip;                    // debug build: 1 = no MMAs issued, 2 = epilogue releases without reading
   HTonal t[BOGP_MAX_TONALS];
@@ -324,12 +331,32 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
 
   if (warp == kProdW) {
     // ============================================================== Bop producer
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // the Bop tables of this call (no-op without a programmatic launch)
+    // The Bop tables of this call.  Streamed tables (tab_cnt): the table grid is still running -- it was launched as this
+    // grid's programmatic primary and produces the tonals in the order they are consumed here -- and a tonal's copies
+    // start as soon as its counter has reached the call's target.  Otherwise: wait for the whole table grid (no-op
+    // without a programmatic launch).
+    if (!p.tab_cnt) asm volatile("griddepcontrol.wait;" ::: "memory");
     uint32_t sc = 0;
+    int f_ready = 0;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int zc = unit / p.nrt, z0 = zc * p.ZC, nzu = min(p.ZC, p.Nz - z0);
       for (int f = 0; f < p.F; ++f) {
         const HTonal& u = p.t[f];
+        if (p.tab_cnt && f >= f_ready) {
+          const long long t0 = clock64();
+          for (unsigned spin = 0;; ++spin) {
+            unsigned int seen;
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.tab_cnt + f) : "memory");
+            if ((int)(seen - p.tab_target[f]) >= 0) break;
+            if ((spin & 255u) == 255u && clock64() - t0 > 4000000000LL) {      // ~2 s: the table grid never got there
+              atomicExch(p.err, 9 + 1000 * (int)blockIdx.x);
+              __threadfence_system();
+              __trap();
+            }
+          }
+          asm volatile("fence.proxy.async.global;" ::: "memory");      // generic-proxy table stores -> this warp's bulk copies
+          f_ready = f + 1;
+        }
         for (int j0 = 0; j0 < nzu; j0 += u.nj, ++sc) {
           const int njs = min(u.nj, nzu - j0);
           const uint32_t slot = sc % (uint32_t)p.S, ph = (sc / (uint32_t)p.S) & 1u;
@@ -394,7 +421,9 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
     const uint32_t t_lane0 = tmem_base + ((uint32_t)(quad * 32) << 16);
     float* acc = reinterpret_cast<float*>(smem + p.smem_acc);     // [ZC][128]
     uint32_t sc = 0;
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // err / arg-ext words are reset by the table kernel
+    // err / arg-ext words are reset by the table kernel: with streamed tables the wait for that grid's completion moves
+    // to the first write-out (long over by then)
+    if (!p.tab_cnt) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (LEAN) {
       // ---- lean path: every tonal folded with 16 or 32 padded rows, cbf + mean.  Straight-line stages: wait, four
       // loads, one wait, release, arithmetic; acc starts at zero so that every tonal is a plain +=.
@@ -483,6 +512,7 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
         }
         // write-out: this warp's own depths (j % 4 == sub), nobody else touched them -- no barrier
         __syncwarp();
+        if (p.tab_cnt) asm volatile("griddepcontrol.wait;" ::: "memory");
         const int i = rt * kTile + tl;
         const float scale = 1.f / (float)p.F;
         unsigned long long best = 0ull;
@@ -640,6 +670,7 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
       }
       // write-out: this warp's own depths (j % 4 == sub), nobody else touched them -- no barrier
       __syncwarp();
+      if (p.tab_cnt) asm volatile("griddepcontrol.wait;" ::: "memory");
       const int i = rt * kTile + tl;
       const float scale = p.mf == BOGP_MF_MEAN ? 1.f / (float)p.F : 1.f;
       unsigned long long best = 0ull;
@@ -697,32 +728,9 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
   if (p.ext_mode && p.peer_bufs) {
     __syncthreads();
     if (xrec[2] == 1 && (int)threadIdx.x < p.peer_world) {
-      // thread t: store this rank's record and the epoch flag into peer t's buffer, then wait for peer t's flag here
-      // (same protocol and buffers as peer_exchange_kernel)
-      const int t = threadIdx.x, world = p.peer_world, rank = p.peer_rank;
-      const unsigned long long epoch = p.peer_epoch;
-      const size_t rec_off = ((size_t)(epoch & 1ull) * world + rank) * 16, flag_off = (size_t)2 * world * 16 + (size_t)rank * 8;
-      long long* dst = reinterpret_cast<long long*>(p.peer_bufs[t] + rec_off);
-      dst[0] = xrec[0];
-      dst[1] = xrec[1];
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_bufs[t] + flag_off), "l"(epoch) : "memory");
-      const unsigned char* mine = p.peer_bufs[rank];
-      const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(mine + (size_t)2 * world * 16 + (size_t)t * 8);
-      unsigned long long seen = 0;
-      const long long t0 = clock64();
-      for (unsigned spin = 0;; ++spin) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
-        if (seen >= epoch) break;
-        if ((spin & 1023u) == 1023u && clock64() - t0 > 20000000000LL) {      // ~10 s: a peer never reached this step
-          atomicExch(p.peer_err, 1 + t);
-          __threadfence_system();
-          __trap();
-        }
-      }
-      const long long* src = reinterpret_cast<const long long*>(mine + ((size_t)(epoch & 1ull) * world + t) * 16);
-      p.peer_out[2 * t] = src[0];
-      p.peer_out[2 * t + 1] = src[1];
+      // thread t: this rank's record into peer t's buffer, peer t's record out of this rank's buffer (peer_device.cuh:
+      // collective or pipelined by one step)
+      peer_step(p.peer_bufs, threadIdx.x, p.peer_rank, p.peer_world, p.peer_epoch, p.peer_mode, xrec[0], xrec[1], p.peer_out, p.peer_err);
     }
   }
   if (warp == kIssW0) {
@@ -736,15 +744,16 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
 __device__ __forceinline__ size_t chunk_off(int row, int kc, int nch) {
   return ((size_t)((row >> 3) * nch + kc) * 8 + (row & 7)) * 16;
 }
-// x (already scaled) -> fp16 hi + fp16 lo, packed two modes per 32-bit word
+// x (already scaled) -> fp16 hi + fp16 lo, packed two modes per 32-bit word (packed conversions: one instruction per pair)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const __half h0 = __float2half_rn(x[2 * e]), h1 = __float2half_rn(x[2 * e + 1]);
-    const __half l0 = __float2half_rn(x[2 * e] - __half2float(h0)), l1 = __float2half_rn(x[2 * e + 1] - __half2float(h1));
-    h[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    l[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const __half2 hh = __floats2half2_rn(x[2 * e], x[2 * e + 1]);          // low half = even mode
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(x[2 * e] - hf.x, x[2 * e + 1] - hf.y);
+    h[e] = *reinterpret_cast<const uint32_t*>(&hh);
+    l[e] = *reinterpret_cast<const uint32_t*>(&ll);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -810,17 +819,11 @@ __global__ void __launch_bounds__(128) umma16_E_kernel(ModesetDev ms, HParams p,
 // and lo arrays.  One block = kBDepths depths of one tonal; a thread keeps its 8-mode chunks of W_f in registers.
 constexpr int kBDepths = 8;
 constexpr int kBThreads = 128;
-__global__ void __launch_bounds__(kBThreads) umma16_B_kernel(ModesetDev ms, HParams p, const double* __restrict__ z) {
-  __shared__ __align__(16) float phi_s[kBDepths][64];
-  const int nzb = (p.Nz + kBDepths - 1) / kBDepths;
-  const int f = blockIdx.x / nzb, j0 = (blockIdx.x % nzb) * kBDepths;
+__device__ __forceinline__ void b_block(const ModesetDev& ms, const HParams& p, const double* __restrict__ z, int f, int j0,
+                                        float (*phi_s)[64]) {
   const HTonal& u = p.t[f];
   const TonalMeta& t = ms.t[u.src];
   const int nd = min(kBDepths, p.Nz - j0), tid = threadIdx.x;
-  // programmatic dependent launch: the surface kernel may start its prologue (barriers, TMEM, E images) while these
-  // blocks run; its Bop producer and epilogue warps wait for this grid's completion with griddepcontrol.wait
-  asm volatile("griddepcontrol.launch_dependents;");
-  if (blockIdx.x == 0 && tid == 0) { *p.err = 0; if (p.ext_mode) { *p.ext_key = 0ull; *p.ext_done = 0u; } }
   for (int e = tid; e < nd * u.Kp; e += kBThreads) {
     const int dj = e / u.Kp, m = e - dj * u.Kp;
     float v = 0.f;
@@ -855,6 +858,116 @@ __global__ void __launch_bounds__(kBThreads) umma16_B_kernel(ModesetDev ms, HPar
       split8(x, hi, lo);
       *reinterpret_cast<uint4*>(Bhi + (size_t)dj * zstride + (size_t)q * 16) = hi;
       *reinterpret_cast<uint4*>(Blo + (size_t)dj * zstride + (size_t)q * 16) = lo;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBThreads) umma16_B_kernel(ModesetDev ms, HParams p, const double* __restrict__ z) {
+  __shared__ __align__(16) float phi_s[kBDepths][64];
+  const int nzb = (p.Nz + kBDepths - 1) / kBDepths;
+  // programmatic dependent launch: the surface kernel may start its prologue (barriers, TMEM, E images) while these
+  // blocks run; its Bop producer and epilogue warps wait for this grid's completion with griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *p.err = 0; if (p.ext_mode) { *p.ext_key = 0ull; *p.ext_done = 0u; } }
+  b_block(ms, p, z, blockIdx.x / nzb, (blockIdx.x % nzb) * kBDepths, phi_s);
+}
+
+// Source mode shapes at the call's depths, interpolated from the handle's depth table: phi[f][j][m] (unscaled, zero for
+// m >= M).  Covariance-independent: kept while the depth vector is the same (one grid for all time steps of a sweep).
+__global__ void __launch_bounds__(256) umma16_phi_kernel(ModesetDev ms, HParams p, const double* __restrict__ z, float* __restrict__ phi) {
+  const int f = blockIdx.y;
+  const HTonal& u = p.t[f];
+  const TonalMeta& t = ms.t[u.src];
+  const int n = p.Nz * u.Kp;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int j = e / u.Kp, m = e - j * u.Kp;
+    float v = 0.f;
+    if (m < t.M) {
+      int i0; float w;
+      depth_index(z[j], ms.z0, ms.dz, ms.nz_tab, i0, w);
+      const float* tr = ms.tab_re + t.offTab + (size_t)i0 * t.Mp + m;
+      v = fmaf(w, __ldg(tr + t.Mp) - __ldg(tr), __ldg(tr));
+    }
+    phi[p.phi_off[f] + e] = v;
+  }
+}
+
+// Streamed form: one small block per SM (128 threads, <= 64 registers: it has to fit NEXT to a surface-kernel block,
+// which leaves 9 216 registers and ~9 KB of shared memory on its SM) walks the (tonal, 8-depth block) items in the order
+// the surface kernel consumes the tonals and counts every finished item in tab_cnt[tonal position].  The surface kernel
+// is launched as this grid's programmatic dependent and runs AT THE SAME TIME: its Bop producer starts a tonal's bulk
+// copies when the counter has reached the call's target, so only the first (smallest) tonal's tables are waited for
+// and the rest of the table build hides under the MMAs of the tonals before.  With four warps per SM every latency is
+// exposed, so: no shared memory and no block barrier (mode shapes come from the cached phi table, the operator chunk
+// from L1), and the (depth, row, K chunk) triples of an item are independent iterations the compiler can overlap.
+// Same values as umma16_B_kernel: (W * sB) * phi == W * (phi * sB) for a power-of-two sB.
+__global__ void __launch_bounds__(kBThreads, 8) umma16_B_stream_kernel(ModesetDev ms, HParams p, unsigned int* tab_cnt) {
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *p.err = 0; if (p.ext_mode) { *p.ext_key = 0ull; *p.ext_done = 0u; } }
+  const int nzb = (p.Nz + kBDepths - 1) / kBDepths, items = p.F * nzb;
+  const int tid = threadIdx.x;
+  for (int it = blockIdx.x; it < items; it += gridDim.x) {
+    const int f = it / nzb, j0 = (it - f * nzb) * kBDepths;
+    const HTonal& u = p.t[f];
+    const TonalMeta& t = ms.t[u.src];
+    const int nd = min(kBDepths, p.Nz - j0);
+    const int Kp = u.Kp, nch = Kp >> 3, n_q = u.rowsP * nch, Mp = t.Mp;
+    const float sB = u.sB;
+    const size_t zstride = (size_t)u.b_zbytes;
+    unsigned char* Bhi = const_cast<unsigned char*>(p.Bhi) + u.b_off + (size_t)j0 * zstride;
+    unsigned char* Blo = const_cast<unsigned char*>(p.Blo) + u.b_off + (size_t)j0 * zstride;
+    const float* W = ms.Wu + t.offWu;
+    const float* ph = p.phi + p.phi_off[f] + (size_t)j0 * Kp;
+    // a thread keeps its (row, K chunk) of the scaled operator in registers and walks the item's depths (independent
+    // iterations: the loads of all eight are issued ahead of the arithmetic)
+    for (int q = tid; q < n_q; q += kBThreads) {
+      const int pc = q >> 3, kc = pc % nch, row = (pc / nch) * 8 + (q & 7);
+      float w[8];
+      if (kc * 8 < Mp) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(W + (size_t)row * Mp + kc * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(W + (size_t)row * Mp + kc * 8) + 1);
+        w[0] = a.x * sB; w[1] = a.y * sB; w[2] = a.z * sB; w[3] = a.w * sB; w[4] = b.x * sB; w[5] = b.y * sB; w[6] = b.z * sB; w[7] = b.w * sB;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = 0.f;
+      }
+      const float* pq = ph + kc * 8;
+      unsigned char* oh = Bhi + (size_t)q * 16;
+      unsigned char* ol = Blo + (size_t)q * 16;
+      if (nd == kBDepths) {
+        // full item: no predicates, so the eight pairs of loads are issued ahead of the arithmetic
+        float4 pa[kBDepths], pb[kBDepths];
+#pragma unroll
+        for (int dj = 0; dj < kBDepths; ++dj) {
+          pa[dj] = __ldg(reinterpret_cast<const float4*>(pq + dj * Kp));
+          pb[dj] = __ldg(reinterpret_cast<const float4*>(pq + dj * Kp) + 1);
+        }
+#pragma unroll
+        for (int dj = 0; dj < kBDepths; ++dj) {
+          const float x[8] = {w[0] * pa[dj].x, w[1] * pa[dj].y, w[2] * pa[dj].z, w[3] * pa[dj].w, w[4] * pb[dj].x, w[5] * pb[dj].y, w[6] * pb[dj].z, w[7] * pb[dj].w};
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          *reinterpret_cast<uint4*>(oh + (size_t)dj * zstride) = hi;
+          *reinterpret_cast<uint4*>(ol + (size_t)dj * zstride) = lo;
+        }
+      } else {
+        for (int dj = 0; dj < nd; ++dj) {
+          const float4 pa = __ldg(reinterpret_cast<const float4*>(pq + dj * Kp)), pb = __ldg(reinterpret_cast<const float4*>(pq + dj * Kp) + 1);
+          const float x[8] = {w[0] * pa.x, w[1] * pa.y, w[2] * pa.z, w[3] * pa.w, w[4] * pb.x, w[5] * pb.y, w[6] * pb.z, w[7] * pb.w};
+          uint4 hi, lo;
+          split8(x, hi, lo);
+          *reinterpret_cast<uint4*>(oh + (size_t)dj * zstride) = hi;
+          *reinterpret_cast<uint4*>(ol + (size_t)dj * zstride) = lo;
+        }
+      }
+    }
+    // one count per warp (target: 4 per item): no block barrier, the warps of a block run decoupled
+    // (release at gpu scope: the lanes' stores are ordered before lane 0 by the warp barrier; no L1 invalidation, the
+    // operator chunks and mode shapes stay cached for the next item)
+    __syncwarp();
+    if ((tid & 31) == 0) {
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(tab_cnt + f) : "memory");
     }
   }
 }
@@ -1012,7 +1125,7 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
     p.ext_val = ext_val_dev; p.ext_idx = ext_idx_dev;
     if (peer && peer->bufs) {
       p.peer_bufs = peer->bufs; p.peer_rank = peer->rank; p.peer_world = peer->world; p.peer_epoch = peer->epoch;
-      p.peer_offset = peer->index_offset; p.peer_out = peer->recs_out; p.peer_err = peer->err;
+      p.peer_offset = peer->index_offset; p.peer_out = peer->recs_out; p.peer_err = peer->err; p.peer_mode = peer->pipelined;
     }
   }
   p.E = static_cast<unsigned char*>(c.E);
@@ -1030,27 +1143,68 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
   if (!(e_cached && c.z_cached.size() == (size_t)Nz && std::memcmp(c.z_cached.data(), z_host, (size_t)Nz * sizeof(double)) == 0)) {
     BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
     c.z_cached.assign(z_host, z_host + Nz);
+    c.phi_valid = false;
   }
-  umma16_B_kernel<<<d.F * ((Nz + kBDepths - 1) / kBDepths), kBThreads, 0, s>>>(d, p, z_dev);
+  if (BOGP_UMMA_DBG) { const char* sk = std::getenv("BOGP_UMMA_SKIP"); p.skip = sk ? std::atoi(sk) : 0; }
+  // lean instance: every tonal folded (rank-1 covariance, real modes) with 16 or 32 padded rows, cbf + mean
+  bool lean = atype == BOGP_ATYPE_CBF && mf == BOGP_MF_MEAN && !(BOGP_UMMA_DBG && (p.skip & 2));
+  for (int f = 0; f < d.F; ++f) lean = lean && p.t[f].fold && (p.t[f].rowsP == 16 || p.t[f].rowsP == 32);
+  if (const char* e = std::getenv("BOGP_UMMA_LEAN")) lean = lean && e[0] != '0';
+  // Streamed tables: see umma16_B_stream_kernel.  Only when the two launches are chained programmatically (no timing
+  // event between them) and with the lean instance of the surface kernel: 88 registers x 640 threads leave room for
+  // the table block on the same SM, the general instance (96 allocated) does not.
+  const char* pdl_env = std::getenv("BOGP_UMMA_PDL");
+  const char* ts_env = std::getenv("BOGP_UMMA_TABSTREAM");
+  const bool chained = !timing_enabled() && !(pdl_env && pdl_env[0] == '0') && !(BOGP_UMMA_DBG && std::getenv("BOGP_UMMA_DBG"));
+  const bool stream_tabs = chained && lean && !(ts_env && ts_env[0] == '0');
+  const int nzb = (Nz + kBDepths - 1) / kBDepths;
+  if (stream_tabs) {
+    if (!c.tab_cnt) {
+      BOGP_CUDA(cudaMalloc(&c.tab_cnt, BOGP_MAX_TONALS * sizeof(unsigned int)));
+      BOGP_CUDA(cudaMemsetAsync(c.tab_cnt, 0, BOGP_MAX_TONALS * sizeof(unsigned int), s));
+      std::memset(c.tab_target, 0, sizeof(c.tab_target));
+    }
+    for (int f = 0; f < d.F; ++f) { c.tab_target[f] += (unsigned int)nzb * (kBThreads / 32); p.tab_target[f] = c.tab_target[f]; }
+    p.tab_cnt = c.tab_cnt;
+    size_t phi_n = 0;
+    for (int f = 0; f < d.F; ++f) { p.phi_off[f] = (unsigned int)phi_n; phi_n += (size_t)Nz * p.t[f].Kp; }
+    if (c.phi_bytes < phi_n * sizeof(float)) c.phi_valid = false;
+    if (int rc = grow(&c.phi, &c.phi_bytes, phi_n * sizeof(float))) return rc;
+    p.phi = static_cast<const float*>(c.phi);
+    if (!c.phi_valid) {
+      umma16_phi_kernel<<<dim3((unsigned)std::min(64, (Nz * 64 + 255) / 256), (unsigned)d.F), 256, 0, s>>>(d, p, z_dev, static_cast<float*>(c.phi));
+      count_launch();
+      BOGP_CUDA(cudaGetLastError());
+      c.phi_valid = true;
+    }
+    // the SM's shared-memory carve-out cannot change while a block is resident: ask for the largest one, or the
+    // surface kernel's 217 KB block would have to wait for the table block to leave
+    static bool carve_set = false;
+    if (!carve_set) {
+      BOGP_CUDA(cudaFuncSetAttribute(umma16_B_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      carve_set = true;
+    }
+    umma16_B_stream_kernel<<<std::min(sms, d.F * nzb), kBThreads, 0, s>>>(d, p, c.tab_cnt);
+  } else {
+    umma16_B_kernel<<<d.F * nzb, kBThreads, 0, s>>>(d, p, z_dev);
+  }
   count_launch();
-  BOGP_CUDA(cudaGetLastError());
+  if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+    if (stream_tabs) for (int f = 0; f < d.F; ++f) c.tab_target[f] -= (unsigned int)nzb * (kBThreads / 32);      // the counters did not move
+    set_error("UMMA-H engine: table kernel launch: %s", cudaGetErrorString(e));
+    return BOGP_ERR_CUDA;
+  }
   static long long* dbg_dev = nullptr;
   const char* dbg_env = BOGP_UMMA_DBG ? std::getenv("BOGP_UMMA_DBG") : nullptr;
-  if (BOGP_UMMA_DBG) { const char* sk = std::getenv("BOGP_UMMA_SKIP"); p.skip = sk ? std::atoi(sk) : 0; }
   if (dbg_env && dbg_env[0] == '1') {
     if (!dbg_dev) BOGP_CUDA(cudaMalloc(&dbg_dev, 1024 * sizeof(long long)));
     BOGP_CUDA(cudaMemsetAsync(dbg_dev, 0, 1024 * sizeof(long long), s));
     p.dbg = dbg_dev;
   }
   const size_t smem = (size_t)p.smem_bar + 256;
-  // lean instance: every tonal folded (rank-1 covariance, real modes) with 16 or 32 padded rows, cbf + mean
-  bool lean = atype == BOGP_ATYPE_CBF && mf == BOGP_MF_MEAN && !(BOGP_UMMA_DBG && (p.skip & 2));
-  for (int f = 0; f < d.F; ++f) lean = lean && p.t[f].fold && (p.t[f].rowsP == 16 || p.t[f].rowsP == 32);
-  if (const char* e = std::getenv("BOGP_UMMA_LEAN")) lean = lean && e[0] != '0';
   auto kern = lean ? umma16_grid_kernel<true> : umma16_grid_kernel<false>;
   BOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t ev = timing_begin(s);
-  const char* pdl_env = std::getenv("BOGP_UMMA_PDL");
   if (!ev && !p.dbg && !(pdl_env && pdl_env[0] == '0')) {
     // no event between the two launches: let the surface kernel's prologue overlap the table kernel
     cudaLaunchConfig_t cfg{};

@@ -170,6 +170,20 @@ class PeerExchange:
                        C.c_void_p(self._lib.current_stream_ptr()))
         return out
 
+    def set_pipelined(self, on: bool) -> None:
+        """Pipelined exchange: every following exchange (stand-alone or fused into a surface call) publishes this rank's
+        record of step k without waiting for the peers and returns the records of step k - 1 (index -1 on the first
+        step); :meth:`collect` returns the records of the last step.  All ranks must switch at the same step."""
+        self._lib.call("bogp_peer_set_pipelined", self._h, 1 if on else 0)
+
+    def collect(self, out: torch.Tensor) -> torch.Tensor:
+        """Records of the last published step (waits for the peers that have not published it yet): one kernel."""
+        C = self._C
+        if not (out.is_cuda and out.dtype == torch.int64 and out.numel() == 2 * self.world and out.is_contiguous()):
+            raise ValueError("out must be a contiguous CUDA int64[world, 2] tensor")
+        self._lib.call("bogp_peer_collect", self._h, C.c_void_p(out.data_ptr()), C.c_void_p(self._lib.current_stream_ptr()))
+        return out
+
     def close(self):
         if self._h is not None and self._h.value:
             self._lib.lib().bogp_peer_destroy(self._h)

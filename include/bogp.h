@@ -251,6 +251,15 @@ int bogp_peer_create(bogp_peer_t* out, int rank, int world, unsigned char* ipc_h
 int bogp_peer_open(bogp_peer_t p, const unsigned char* all_handles);
 int bogp_peer_exchange(bogp_peer_t p, const long long* rec_dev, long long* recs_out_dev, void* stream);
 int bogp_peer_destroy(bogp_peer_t p);
+/* Pipelined form of the exchange (for a sequence of steps such as the time-step sweep of
+ * projects/swellex96_localization/data/mfp.py:166-216, where the reduced record of a step is only consumed when its
+ * results are written): with bogp_peer_set_pipelined(p, 1) every exchange -- stand-alone or fused into a surface call
+ * below -- publishes this rank's record of step k without waiting for anybody and fills recs_out with the records of
+ * step k - 1 (index -1 on the first step), so a step never ends on the slowest rank of the box; bogp_peer_collect
+ * (one single-block kernel) waits for and returns the records of the last published step.  All ranks must switch
+ * modes at the same step. */
+int bogp_peer_set_pipelined(bogp_peer_t p, int on);
+int bogp_peer_collect(bogp_peer_t p, long long* recs_out_dev, void* stream);
 /* Surface + arg-ext + the exchange above in ONE call: record = (index_offset + flat index of this rank's extremum,
  * value bits); recs_out[world][2] gets every rank's record of the same step.  On the FP16-split tcgen05 engine the
  * exchange runs inside the surface kernel (its last CTA stores the record into the peers' buffers and waits for

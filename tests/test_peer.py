@@ -70,6 +70,53 @@ def test_surface_with_fused_exchange_world1(engine):
     px.close()
 
 
+def test_pipelined_exchange_world1():
+    """bogp_peer_set_pipelined: an exchange hands back the records of the PREVIOUS step (index -1 on the first), collect
+    returns those of the last one; a collective step after pipelined ones still returns its own records.  Stand-alone
+    kernel and the surface kernel's fused exchange."""
+    from bogp_b200 import mfp
+    from bogp_b200.modes import SWELLEX_TONALS_13, pekeris_modes, synthetic_covariance
+    from bogp_b200.sharding import PeerExchange, reduce_records
+    px = PeerExchange()
+    rec = torch.zeros(2, dtype=torch.int64, device="cuda")
+    out = torch.full((1, 2), -7, dtype=torch.int64, device="cuda")
+    px.set_pipelined(True)
+    sent = []
+    for step in range(5):
+        sent.append([500 + step, int(np.float32(0.25 * step).view(np.int32))])
+        rec.copy_(torch.tensor(sent[-1], dtype=torch.int64))
+        px.exchange(rec, out)
+        torch.cuda.synchronize()
+        assert out.cpu().tolist() == ([sent[-2]] if step else [[-1, 0]])
+    px.collect(out)
+    torch.cuda.synchronize()
+    assert out.cpu().tolist() == [sent[-1]]
+    px.set_pipelined(False)
+    rec.copy_(torch.tensor([77, 5], dtype=torch.int64))
+    px.exchange(rec, out)
+    torch.cuda.synchronize()
+    assert out.cpu().tolist() == [[77, 5]]
+    # fused: three surfaces with different truths, each step's records arrive with the next call
+    modes = pekeris_modes(SWELLEX_TONALS_13)
+    r, z = np.linspace(0.1, 10.0, 300), np.linspace(1.0, 200.0, 120)
+    pair = torch.zeros(2, dtype=torch.int64, device="cuda")
+    pairs = torch.zeros(1, 2, dtype=torch.int64, device="cuda")
+    scratch = torch.empty(8192, dtype=torch.uint8, device="cuda")
+    px.set_pipelined(True)
+    truths = [(37, 140), (80, 20), (5, 299)]
+    prev = 77
+    for jz, ir in truths:
+        dms = mfp.DeviceModeSet(modes, synthetic_covariance(modes, z[jz], r[ir]))
+        dms.bartlett_grid(r, z, engine="umma", argext=(pair, scratch, True), peer=(px, 1000, pairs))
+        torch.cuda.synchronize()
+        assert reduce_records(pairs)[1] == prev
+        prev = 1000 + jz * 300 + ir
+    px.collect(pairs)
+    torch.cuda.synchronize()
+    assert reduce_records(pairs)[1] == prev
+    px.close()
+
+
 def _free_port() -> int:
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -112,6 +159,24 @@ def _peer_worker(rank: int, world: int, port: int, q):
             ok = ok and reduce_records(out)[1] == 90 * 300 + 140
         _, recs = dms.bartlett_grid_host(r, z[lo:hi], engine="umma", argext="max", peer=(px, lo * len(r)))
         ok = ok and reduce_records(recs)[1] == 90 * 300 + 140
+        # pipelined: no rank waits for the others inside a step; step k hands back the global record of step k - 1
+        px.set_pipelined(True)
+        truth = [(90, 140), (10, 7), (120, 250), (64, 64), (3, 299)]
+        sets = [mfp.DeviceModeSet(modes, synthetic_covariance(modes, z[jz], r[ir])) for jz, ir in truth]
+        prev = None
+        for k, d in enumerate(sets):
+            d.bartlett_grid(r, z[lo:hi], engine="umma", argext=(pair, scratch, True), peer=(px, lo * len(r), out))
+            torch.cuda.synchronize()
+            if prev is not None:
+                ok = ok and reduce_records(out)[1] == prev
+            prev = truth[k][0] * 300 + truth[k][1]
+        px.collect(out)
+        torch.cuda.synchronize()
+        ok = ok and reduce_records(out)[1] == prev
+        px.set_pipelined(False)
+        sets[0].bartlett_grid(r, z[lo:hi], engine="umma", argext=(pair, scratch, True), peer=(px, lo * len(r), out))
+        torch.cuda.synchronize()
+        ok = ok and reduce_records(out)[1] == 90 * 300 + 140
         px.close()
         q.put((rank, ok))
     finally:
