@@ -65,6 +65,8 @@ SIGNATURES = {
                                     C.c_double, _dp, _dp, C.c_int, _dp, _dp, _vp]),
     "bogp_gp_fit_adamw_bounded": (C.c_int, [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                             C.c_double, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp, _vp]),
+    "bogp_gp_mll_grad": (C.c_int, [C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_double, _dp, _dp, _dp, _dp, C.c_int,
+                                   _dp, _dp, _dp, _vp]),
     "bogp_peer_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp]),
     "bogp_peer_open": (C.c_int, [_vp, _vp]),
     "bogp_peer_exchange": (C.c_int, [_vp, _vp, _vp, _vp]),

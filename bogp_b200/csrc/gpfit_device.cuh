@@ -21,6 +21,7 @@ struct FitArgs {
   const double* y;       // [n]
   double* raw;           // [B][d + 3] in/out
   double* loss;          // [B][steps] or null
+  double* grad_out;      // null, or [B][d + 3]: write d(loss)/d(raw) of every step here and leave raw alone (bogp_gp_mll_grad)
   double* work;          // [B][n * ld] when the matrix does not fit in shared memory
   int* status;           // [B]: 0 ok, 1 not positive definite after jitter 1e-6
 };

@@ -302,9 +302,11 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_kernel(const FitArgs p)
         grad[d + 2] = -sum_alpha / nn;
       }
       if (p.loss) p.loss[(size_t)blockIdx.x * p.steps + step - 1] = -ll / nn;
+      if (p.grad_out)
+        for (int k = 0; k < np; ++k) p.grad_out[(size_t)blockIdx.x * np + k] = grad[k];
       const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
       const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
-      for (int k = 0; k < np; ++k) {
+      for (int k = 0; k < np && !p.grad_out; ++k) {
         double x = raw[k] * (1.0 - p.lr * p.wd);
         am[k] = b1 * am[k] + (1.0 - b1) * grad[k];
         av[k] = b2 * av[k] + (1.0 - b2) * grad[k] * grad[k];
@@ -329,11 +331,12 @@ extern "C" int bogp_gp_fit_adamw(int n, int d, const double* X_host, const doubl
                                    stream);
 }
 
-extern "C" int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, const double* y_host, int kernel_kind,
-                                         int steps, double lr, double weight_decay, double noise_lo, double noise_hi,
-                                         const double* lengthscale_prior, const double* outputscale_prior,
-                                         const double* lengthscale_bounds, const double* outputscale_bounds, int B,
-                                         double* raw_inout_host, double* loss_host, void* stream) {
+// grad_host != null: one evaluation -- loss[B] and d(loss)/d(raw)[B][d + 3] at raw_inout_host, which is left unchanged
+static int fit_impl(int n, int d, const double* X_host, const double* y_host, int kernel_kind,
+                    int steps, double lr, double weight_decay, double noise_lo, double noise_hi,
+                    const double* lengthscale_prior, const double* outputscale_prior,
+                    const double* lengthscale_bounds, const double* outputscale_bounds, int B,
+                    double* raw_inout_host, double* loss_host, double* grad_host, void* stream) {
   using namespace bogp;
   BOGP_REQUIRE(!lengthscale_bounds || (lengthscale_bounds[0] > 0.0 && lengthscale_bounds[1] > lengthscale_bounds[0]),
                "bogp_gp_fit_adamw: bad lengthscale bounds");
@@ -365,20 +368,21 @@ extern "C" int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, con
   p.a_in_smem = fixed + (p.x_in_smem ? x_bytes : 0) + a_bytes <= limit ? 1 : 0;
   const size_t smem = fixed + (p.x_in_smem ? x_bytes : 0) + (p.a_in_smem ? a_bytes : 0);
   const int np = d + 3;
-  double *dX = nullptr, *dy = nullptr, *draw = nullptr, *dloss = nullptr, *dwork = nullptr;
+  double *dX = nullptr, *dy = nullptr, *draw = nullptr, *dloss = nullptr, *dwork = nullptr, *dgrad = nullptr;
   int* dstatus = nullptr;
-  auto cleanup = [&]() { cudaFree(dX); cudaFree(dy); cudaFree(draw); cudaFree(dloss); cudaFree(dwork); cudaFree(dstatus); };
+  auto cleanup = [&]() { cudaFree(dX); cudaFree(dy); cudaFree(draw); cudaFree(dloss); cudaFree(dwork); cudaFree(dstatus); cudaFree(dgrad); };
 #define FIT_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); cleanup(); return BOGP_ERR_CUDA; } } while (0)
   FIT_CUDA(cudaMalloc(&dX, x_bytes));
   FIT_CUDA(cudaMalloc(&dy, n * sizeof(double)));
   FIT_CUDA(cudaMalloc(&draw, (size_t)B * np * sizeof(double)));
   FIT_CUDA(cudaMalloc(&dstatus, B * sizeof(int)));
   if (loss_host) FIT_CUDA(cudaMalloc(&dloss, (size_t)B * steps * sizeof(double)));
+  if (grad_host) FIT_CUDA(cudaMalloc(&dgrad, (size_t)B * np * sizeof(double)));
   if (!p.a_in_smem) FIT_CUDA(cudaMalloc(&dwork, (size_t)B * a_bytes));      // (one-CTA kernel only; the cooperative path brings its own)
   FIT_CUDA(cudaMemcpyAsync(dX, X_host, x_bytes, cudaMemcpyHostToDevice, s));
   FIT_CUDA(cudaMemcpyAsync(dy, y_host, n * sizeof(double), cudaMemcpyHostToDevice, s));
   FIT_CUDA(cudaMemcpyAsync(draw, raw_inout_host, (size_t)B * np * sizeof(double), cudaMemcpyHostToDevice, s));
-  p.X = dX; p.y = dy; p.raw = draw; p.loss = dloss; p.work = dwork; p.status = dstatus;
+  p.X = dX; p.y = dy; p.raw = draw; p.loss = dloss; p.work = dwork; p.status = dstatus; p.grad_out = dgrad;
   const bool in_smem = p.a_in_smem && p.x_in_smem;
   const int dl = d <= 4 ? 4 : (d <= 8 ? 8 : 16);
   // models whose matrix does not fit one SM's shared memory: one fit over a cooperative grid (kernels_gpfit_coop.cu),
@@ -394,6 +398,7 @@ extern "C" int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, con
       pb.raw = draw + (size_t)b * np;
       pb.loss = dloss ? dloss + (size_t)b * steps : nullptr;
       pb.status = dstatus + b;
+      pb.grad_out = dgrad ? dgrad + (size_t)b * np : nullptr;
       FIT_CUDA(launch_gp_fit_coop(pb, sms, s));
     }
   } else {
@@ -411,7 +416,8 @@ extern "C" int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, con
   }
   FIT_CUDA(cudaGetLastError());
   std::vector<int> status(B);
-  FIT_CUDA(cudaMemcpyAsync(raw_inout_host, draw, (size_t)B * np * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (grad_host) FIT_CUDA(cudaMemcpyAsync(grad_host, dgrad, (size_t)B * np * sizeof(double), cudaMemcpyDeviceToHost, s));
+  else FIT_CUDA(cudaMemcpyAsync(raw_inout_host, draw, (size_t)B * np * sizeof(double), cudaMemcpyDeviceToHost, s));
   FIT_CUDA(cudaMemcpyAsync(status.data(), dstatus, B * sizeof(int), cudaMemcpyDeviceToHost, s));
   if (loss_host) FIT_CUDA(cudaMemcpyAsync(loss_host, dloss, (size_t)B * steps * sizeof(double), cudaMemcpyDeviceToHost, s));
   FIT_CUDA(cudaStreamSynchronize(s));
@@ -423,4 +429,22 @@ extern "C" int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, con
       return BOGP_ERR_NUMERIC;
     }
   return 0;
+}
+
+extern "C" int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, const double* y_host, int kernel_kind,
+                                         int steps, double lr, double weight_decay, double noise_lo, double noise_hi,
+                                         const double* lengthscale_prior, const double* outputscale_prior,
+                                         const double* lengthscale_bounds, const double* outputscale_bounds, int B,
+                                         double* raw_inout_host, double* loss_host, void* stream) {
+  return fit_impl(n, d, X_host, y_host, kernel_kind, steps, lr, weight_decay, noise_lo, noise_hi, lengthscale_prior,
+                  outputscale_prior, lengthscale_bounds, outputscale_bounds, B, raw_inout_host, loss_host, nullptr, stream);
+}
+
+extern "C" int bogp_gp_mll_grad(int n, int d, const double* X_host, const double* y_host, int kernel_kind, double noise_lo,
+                                double noise_hi, const double* lengthscale_prior, const double* outputscale_prior,
+                                const double* lengthscale_bounds, const double* outputscale_bounds, int B,
+                                const double* raw_host, double* loss_host, double* grad_host, void* stream) {
+  BOGP_REQUIRE(loss_host && grad_host, "bogp_gp_mll_grad: NULL output");
+  return fit_impl(n, d, X_host, y_host, kernel_kind, 1, 1.0, 0.0, noise_lo, noise_hi, lengthscale_prior, outputscale_prior,
+                  lengthscale_bounds, outputscale_bounds, B, const_cast<double*>(raw_host), loss_host, grad_host, stream);
 }

@@ -385,9 +385,11 @@ __global__ void __launch_bounds__(kFitThreads, 1) gp_fit_coop_kernel(const CoopA
         grad[d + 2] = -gsum[kFitMaxD + 4] / nn;
       }
       if (p.loss && blockIdx.x == 0) p.loss[step - 1] = -ll / nn;
+      if (p.grad_out && blockIdx.x == 0)
+        for (int k = 0; k < np; ++k) p.grad_out[k] = grad[k];
       const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
       const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
-      for (int k = 0; k < np; ++k) {
+      for (int k = 0; k < np && !p.grad_out; ++k) {
         double x = raw[k] * (1.0 - p.lr * p.wd);
         am[k] = b1 * am[k] + (1.0 - b1) * grad[k];
         av[k] = b2 * av[k] + (1.0 - b2) * grad[k] * grad[k];

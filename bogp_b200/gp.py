@@ -9,9 +9,13 @@ Mirrors what the reference uses from BoTorch/GPyTorch (all external to ref/, SUR
 * ``model.posterior(X)`` -> ``.mean [b,q,1]``, ``.variance [b,q,1]``, ``.covariance``, ``.rsample(...)``
   (ref/projects/swellex96_localization/data/demo_1d.py:141; gpmodels.py:27-30).
 
-All posterior arithmetic is float64 on the GPU (``bogp_gp_posterior*``); the n x n factorisation happens once per
-hyper-parameter setting inside ``bogp_gp_create``.  The hyper-parameter fit is one launch of the
-persistent fit kernel ``bogp_gp_fit_adamw`` (all AdamW steps on the device).
+All posterior arithmetic is float64 on the GPU (``bogp_gp_posterior*``); the n x n factorisation and ``L^-1`` are
+computed once per hyper-parameter setting inside ``bogp_gp_create`` ON THE HOST (one thread, float64, jitter retries
+1e-8 ... 1e-6: set-up cost, csrc/hostmath.cu).  The hyper-parameter fit is one launch of the
+persistent fit kernel ``bogp_gp_fit_adamw`` (all AdamW steps on the device); the GPyTorch-side protocol of the reference's
+hand-rolled loops (``model.parameters()``, ``ExactMarginalLogLikelihood``, ``fit_gpytorch_mll``, the explicit
+``ScaleKernel(MaternKernel)``) is mirrored below on the same kernels (``bogp_gp_mll_grad``: one evaluation of the fit
+objective and its gradient).
 """
 from __future__ import annotations
 
@@ -68,6 +72,11 @@ class GPPosterior:
     def stddev(self) -> torch.Tensor:
         return self.variance.sqrt()
 
+    def confidence_region(self):
+        """``(mean - 2 std, mean + 2 std)`` as GPyTorch's ``MultivariateNormal.confidence_region`` (demo_1d.py:143)."""
+        m, s2 = self.mean.squeeze(-1), 2.0 * self.stddev.squeeze(-1)
+        return m - s2, m + s2
+
     def rsample(self, sample_shape=torch.Size([1]), base_samples: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``mean + L z`` with ``L = chol(cov)``; ``base_samples[*sample_shape, b, q, 1]`` standard normal."""
         mean = self.mean.squeeze(-1)                                  # [..., q]
@@ -94,8 +103,21 @@ class SingleTaskGP:
         nc = getattr(likelihood, "noise_constraint", None)
         if nc is not None and hasattr(nc, "lower_bound"):
             noise_bounds = (float(nc.lower_bound), float(nc.upper_bound))
+        # ``covar_module=ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=d, lengthscale_constraint=Interval(..)),
+        # outputscale_constraint=Interval(..))`` (baxus.py:310-319): an explicit GPyTorch kernel carries no priors, and
+        # its Interval constraints replace the softplus transforms of the raw parameters
+        self.fit_defaults = FitConfig(noise_bounds=tuple(noise_bounds))
+        if isinstance(covar_module, ScaleKernel):
+            base = covar_module.base_kernel
+            self.fit_defaults = FitConfig(noise_bounds=tuple(noise_bounds), lengthscale_prior=None, outputscale_prior=None,
+                                          lengthscale_bounds=_interval(base.lengthscale_constraint),
+                                          outputscale_bounds=_interval(covar_module.outputscale_constraint))
+            covar_module = base.kind
         if covar_module not in _lib.KERNEL:
-            raise ValueError(f"covar_module must be one of {sorted(_lib.KERNEL)}")
+            raise ValueError(f"covar_module must be one of {sorted(_lib.KERNEL)} or a ScaleKernel(MaternKernel | RBFKernel)")
+        self.likelihood = likelihood if likelihood is not None else GaussianLikelihood()
+        self._raw: Optional[torch.nn.Parameter] = None       # raw parameters of a hand-rolled fit (see parameters())
+        self._raw_version = -1
         X = torch.as_tensor(train_X, dtype=DT)
         Y = torch.as_tensor(train_Y, dtype=DT).reshape(-1)
         if X.ndim != 2 or X.shape[0] != Y.shape[0]:
@@ -125,6 +147,7 @@ class SingleTaskGP:
             pass
 
     def handle(self) -> C.c_void_p:
+        self._sync_raw()
         if self._h is None:
             self.device = _cuda_device()
             X = np.ascontiguousarray(self.train_X.cpu().numpy(), dtype=np.float64)
@@ -158,13 +181,45 @@ class SingleTaskGP:
 
     def fit(self, cfg: Optional["FitConfig"] = None) -> "SingleTaskGP":
         """The reference's hyper-parameter fit (100 x AdamW on -mll, ei.py:69-78); see :func:`fit_gp_adamw`."""
-        return fit_gp_adamw(self, cfg if cfg is not None else FitConfig(noise_bounds=self.noise_bounds))
+        self._raw = None
+        if cfg is None:
+            cfg = self.fit_defaults
+            cfg = FitConfig(**{**cfg.__dict__, "noise_bounds": tuple(self.noise_bounds)})
+        return fit_gp_adamw(self, cfg)
 
     def eval(self):
+        self.training = False
         return self
 
     def train(self, mode: bool = True):
+        self.training = bool(mode)
         return self
+
+    # ------------------------------------------------------------------ hand-rolled fit loops (ei.py:65-78)
+    def parameters(self):
+        """The raw (unconstrained) hyper-parameters as ONE float64 ``torch.nn.Parameter`` ``[d + 3]`` -- raw
+        lengthscale[d], outputscale, noise, mean, initialised at 0 as GPyTorch's raw parameters are -- for
+        ``torch.optim.AdamW([{"params": model.parameters()}], lr=0.1)`` (ei.py:69).  Its gradient comes from
+        :class:`ExactMarginalLogLikelihood`; the constrained values are read back from it whenever the posterior is
+        needed (``_sync_raw``)."""
+        if self._raw is None:
+            init = getattr(self, "raw_parameters", None)
+            t = torch.zeros(self.train_X.shape[1] + 3, dtype=DT) if init is None else torch.as_tensor(init, dtype=DT).clone()
+            self._raw = torch.nn.Parameter(t)
+            self._raw_version = -1
+        return [self._raw]
+
+    def _sync_raw(self) -> None:
+        r = self._raw
+        if r is None or r._version == self._raw_version:
+            return
+        self._raw_version = r._version
+        cfg = self.fit_defaults
+        d = self.train_X.shape[1]
+        v = r.detach().cpu().numpy().astype(np.float64)
+        ls, os_, noise = _constrained(v, d, cfg.lengthscale_bounds, cfg.outputscale_bounds, self.noise_bounds)
+        self.raw_parameters = v.copy()
+        self.set_hyperparameters(lengthscale=torch.as_tensor(ls), outputscale=float(os_), mean=float(v[d + 2]), noise=float(noise))
 
     # ------------------------------------------------------------------ posterior
     def _prep(self, X) -> Tuple[torch.Tensor, Tuple[int, ...]]:
@@ -198,8 +253,12 @@ class SingleTaskGP:
         return GPPosterior(mean.reshape(*batch_shape, q), var.reshape(*batch_shape, q),
                            cov.reshape(*batch_shape, q, q))
 
-    # gpmodels.py:27-30 ``forward(x) -> MultivariateNormal``: the prior is not on the hot path; expose the posterior
+    # gpmodels.py:27-30 ``forward(x) -> MultivariateNormal``: the prior is not on the hot path; expose the posterior.
+    # In training mode (``model.train()``, ei.py:70) the output of ``model(X)`` only travels into ``mll(output, y)``,
+    # which evaluates the training data itself: nothing is computed here.
     def __call__(self, X):
+        if getattr(self, "training", False):
+            return None
         return self.posterior(X)
 
 
@@ -236,6 +295,154 @@ class _JointPosterior(torch.autograd.Function):
 def joint_posterior(model: SingleTaskGP, X: torch.Tensor, observation_noise: bool = False):
     """Differentiable joint posterior over ``X[b, q, d]`` (CUDA float64)."""
     return _JointPosterior.apply(X, model, observation_noise)
+
+
+# ---------------------------------------------------------------------------------------------- GPyTorch-side protocol
+class Interval:
+    """``gpytorch.constraints.Interval(lower, upper)`` (ei.py:66, baxus.py:306-317): the bounds of a constrained
+    parameter, value = lower + (upper - lower) sigmoid(raw)."""
+
+    def __init__(self, lower_bound, upper_bound):
+        self.lower_bound, self.upper_bound = float(lower_bound), float(upper_bound)
+
+
+def _interval(c) -> Optional[Tuple[float, float]]:
+    return None if c is None else (float(c.lower_bound), float(c.upper_bound))
+
+
+class GaussianLikelihood:
+    """``gpytorch.likelihoods.GaussianLikelihood(noise_constraint=Interval(lo, hi))`` (ei.py:66)."""
+
+    def __init__(self, noise_constraint=None):
+        self.noise_constraint = noise_constraint
+
+    def train(self, mode: bool = True):
+        return self
+
+    def eval(self):
+        return self
+
+
+class _Kernel:
+    def __init__(self, kind: str, ard_num_dims: Optional[int] = None, lengthscale_constraint=None, **_ignored):
+        self.kind, self.ard_num_dims, self.lengthscale_constraint = kind, ard_num_dims, lengthscale_constraint
+
+
+class MaternKernel(_Kernel):
+    """``gpytorch.kernels.MaternKernel(nu=2.5, ard_num_dims=d, lengthscale_constraint=Interval(..))`` (baxus.py:308-313);
+    only nu = 2.5 has a kernel on the device."""
+
+    def __init__(self, nu: float = 2.5, **kw):
+        if float(nu) != 2.5:
+            raise NotImplementedError("only the Matern-5/2 kernel (nu=2.5) is implemented")
+        super().__init__("matern52", **kw)
+
+
+class RBFKernel(_Kernel):
+    """``gpytorch.kernels.RBFKernel(ard_num_dims=d)`` (ref/optimization/gpmodels.py:22-25)."""
+
+    def __init__(self, **kw):
+        super().__init__("rbf", **kw)
+
+
+class ScaleKernel:
+    """``gpytorch.kernels.ScaleKernel(base_kernel, outputscale_constraint=Interval(..))`` (baxus.py:307-318)."""
+
+    def __init__(self, base_kernel: _Kernel, outputscale_constraint=None, **_ignored):
+        if not isinstance(base_kernel, _Kernel):
+            raise TypeError("ScaleKernel needs a MaternKernel or an RBFKernel")
+        self.base_kernel, self.outputscale_constraint = base_kernel, outputscale_constraint
+
+
+class ModelFittingError(RuntimeError):
+    """``botorch.exceptions.ModelFittingError`` (baxus.py:12,344)."""
+
+
+def _constrained(raw: np.ndarray, d: int, lsb, osb, noise_bounds):
+    """raw -> (lengthscale[d], outputscale, noise): softplus, or the Interval transform where bounds are given."""
+    sp = lambda v: np.where(v > 20.0, v, np.log1p(np.exp(np.minimum(v, 20.0))))     # noqa: E731
+    iv = lambda v, b: b[0] + (b[1] - b[0]) / (1.0 + np.exp(-v))                      # noqa: E731
+    ls = sp(raw[:d]) if lsb is None else iv(raw[:d], lsb)
+    os_ = sp(raw[d]) if osb is None else iv(raw[d], osb)
+    lo, hi = noise_bounds
+    return ls, float(os_), float(lo + (hi - lo) / (1.0 + math.exp(-raw[d + 1])))
+
+
+def mll_value_and_grad(model: "SingleTaskGP", raw: np.ndarray, cfg: Optional[FitConfig] = None):
+    """``(loss, grad[d + 3])`` of the fit objective ``-(log N(y | m, K + s2 I) + log priors) / n`` at the raw
+    parameters, by one step of the fit kernels with the update switched off (``bogp_gp_mll_grad``)."""
+    cfg = model.fit_defaults if cfg is None else cfg
+    X = np.ascontiguousarray(model.train_X.cpu().numpy(), dtype=np.float64)
+    y = np.ascontiguousarray(model.train_Y.cpu().numpy(), dtype=np.float64)
+    n, d = X.shape
+    raw = np.ascontiguousarray(np.asarray(raw, dtype=np.float64).reshape(1, d + 3))
+    loss, grad = np.zeros(1), np.zeros((1, d + 3))
+    lsp = None if cfg.lengthscale_prior is None else np.array(cfg.lengthscale_prior, dtype=np.float64)
+    osp = None if cfg.outputscale_prior is None else np.array(cfg.outputscale_prior, dtype=np.float64)
+    lsb = None if cfg.lengthscale_bounds is None else np.array(cfg.lengthscale_bounds, dtype=np.float64)
+    osb = None if cfg.outputscale_bounds is None else np.array(cfg.outputscale_bounds, dtype=np.float64)
+    lo, hi = model.noise_bounds
+    _cuda_device()
+    _lib.call("bogp_gp_mll_grad", n, d, _lib.dptr(X), _lib.dptr(y), _lib.KERNEL[model.kind], float(lo), float(hi),
+              _lib.dptr(lsp), _lib.dptr(osp), _lib.dptr(lsb), _lib.dptr(osb), 1, _lib.dptr(raw), _lib.dptr(loss),
+              _lib.dptr(grad), C.c_void_p(_lib.current_stream_ptr()))
+    return float(loss[0]), grad[0]
+
+
+class _MLL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, model):
+        loss, grad = mll_value_and_grad(model, raw.detach().cpu().numpy())
+        ctx.grad = torch.as_tensor(grad, dtype=raw.dtype, device=raw.device)
+        return torch.tensor(-loss, dtype=raw.dtype, device=raw.device)         # the mll itself: GPyTorch's sign
+
+    @staticmethod
+    def backward(ctx, gout):
+        return -gout * ctx.grad, None
+
+
+class ExactMarginalLogLikelihood:
+    """``gpytorch.mlls.ExactMarginalLogLikelihood(model.likelihood, model)`` (ei.py:68, baxus.py:326): calling it returns
+    the marginal log likelihood per observation plus the log priors, ``(log N(y | m, K + s2 I) + sum log p) / n``, as a
+    scalar tensor whose backward fills ``model.parameters()[0].grad`` -- value and gradient both from the fit kernels
+    (``bogp_gp_mll_grad``), so the reference's loop ``loss = -mll(model(X), y); loss.backward(); optimizer.step()``
+    runs unchanged, one kernel launch per step.  (``model.fit()`` runs the same 100 steps in one launch.)"""
+
+    def __init__(self, likelihood, model: "SingleTaskGP"):
+        self.likelihood, self.model = likelihood, model
+
+    def __call__(self, output=None, target=None):
+        return _MLL.apply(self.model.parameters()[0], self.model)
+
+    def train(self, mode: bool = True):
+        self.model.train(mode)
+        return self
+
+    def eval(self):
+        self.model.eval()
+        return self
+
+
+def fit_gpytorch_mll(mll: ExactMarginalLogLikelihood, maxiter: int = 200, **_ignored) -> ExactMarginalLogLikelihood:
+    """``botorch.fit.fit_gpytorch_mll(mll)`` (demo_1d.py:137, baxus.py:343): scipy L-BFGS-B over the raw parameters from
+    their current values, objective and gradient from the fit kernels.  BoTorch's own routine is external to the
+    reference and absent here, so its defaults are recalled, not pinned: L-BFGS-B on the unconstrained raw parameters,
+    ``maxiter`` 200 [recalled]; raises :class:`ModelFittingError` when the kernel matrix is not positive definite."""
+    from scipy.optimize import minimize
+    model = mll.model
+    raw = model.parameters()[0]
+
+    def fun(v):
+        try:
+            return mll_value_and_grad(model, v)
+        except _lib.BogpError as exc:
+            raise ModelFittingError(str(exc)) from exc
+
+    res = minimize(fun, raw.detach().cpu().numpy().astype(np.float64), jac=True, method="L-BFGS-B", options={"maxiter": int(maxiter)})
+    with torch.no_grad():
+        raw.copy_(torch.as_tensor(res.x, dtype=raw.dtype))
+    model._sync_raw()
+    return mll
 
 
 # ---------------------------------------------------------------------------------------------- hyper-parameter fit
@@ -296,13 +503,9 @@ def fit_gp_adamw(model: SingleTaskGP, cfg: FitConfig = FitConfig(), raw_init: Op
               _lib.dptr(lsb), _lib.dptr(osb), B, _lib.dptr(raw), _lib.dptr(loss), C.c_void_p(_lib.current_stream_ptr()))
     best = int(np.argmin(loss[:, -1])) if B > 1 else 0
     r = raw[best]
-    sp = lambda v: np.where(v > 20.0, v, np.log1p(np.exp(np.minimum(v, 20.0))))     # noqa: E731
-    iv = lambda v, b: b[0] + (b[1] - b[0]) / (1.0 + np.exp(-v))                      # noqa: E731
-    ls_v = sp(r[:d]) if lsb is None else iv(r[:d], lsb)
-    os_v = sp(r[d]) if osb is None else iv(r[d], osb)
+    ls_v, os_v, noise_v = _constrained(r, d, cfg.lengthscale_bounds, cfg.outputscale_bounds, (lo, hi))
     model.noise_bounds = (lo, hi)
-    model.set_hyperparameters(lengthscale=torch.as_tensor(ls_v), outputscale=float(os_v),
-                              mean=float(r[d + 2]), noise=float(lo + (hi - lo) / (1.0 + math.exp(-r[d + 1]))))
+    model.set_hyperparameters(lengthscale=torch.as_tensor(ls_v), outputscale=float(os_v), mean=float(r[d + 2]), noise=noise_v)
     model.raw_parameters = r.copy()
     return (model, loss) if return_loss else model
 

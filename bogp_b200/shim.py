@@ -3,7 +3,7 @@
 The Hydra / hydra-zen configs and the hand-rolled BO loops name their callables by dotted path
 (``tritonoa.sp.mfp.MatchedFieldProcessor``, ``tritonoa.sp.beamforming.beamformer``,
 ``tritonoa.at.models.kraken.runner.run_kraken``, ``oao.optimizer.BayesianOptimization``,
-``botorch.models.SingleTaskGP`` ... -- ref/projects/swellex96_localization/conf/optimization/run.py:15-21,89-99;
+``botorch.models.SingleTaskGP``, ``gpytorch.mlls.ExactMarginalLogLikelihood``, ``botorch.fit.fit_gpytorch_mll`` ... -- ref/projects/swellex96_localization/conf/optimization/run.py:15-21,89-99;
 ref/projects/swellex96_inv/data/bo/ei.py:8-18; ref/optimization/strategy.py:5-7).  ``install()`` registers module
 objects under those names that resolve to the CUDA-backed mirrors of this package.  A real installation of one of
 the packages is never shadowed unless ``force=True``.
@@ -50,18 +50,18 @@ def clean_up_kraken_files(path=None) -> None:
     ``.env/.mod/.prt`` files, so there is nothing to remove."""
 
 
-class _Interval:
-    """``gpytorch.constraints.Interval(lower, upper)`` (ei.py:66): carried into FitConfig.noise_bounds."""
+class _NoOpSetting:
+    """``botorch.settings.validate_input_scaling(False)`` (ei.py:61) / ``gpytorch.settings.max_cholesky_size(n)``
+    (baxus.py:329): context managers that switch library checks this implementation does not have."""
 
-    def __init__(self, lower_bound, upper_bound):
-        self.lower_bound, self.upper_bound = float(lower_bound), float(upper_bound)
+    def __init__(self, *args, **kwargs):
+        pass
 
+    def __enter__(self):
+        return self
 
-class _GaussianLikelihood:
-    """``gpytorch.likelihoods.GaussianLikelihood(noise_constraint=Interval(lo, hi))`` (ei.py:66)."""
-
-    def __init__(self, noise_constraint=None):
-        self.noise_constraint = noise_constraint
+    def __exit__(self, *exc):
+        return False
 
 
 def install(force: bool = False) -> Dict[str, bool]:
@@ -110,12 +110,18 @@ def install(force: bool = False) -> Dict[str, bool]:
                 UpperConfidenceBound=acquisition.UpperConfidenceBound)
         _module("botorch.optim", optimize_acqf=optim.optimize_acqf)
         _module("botorch.generation", MaxPosteriorSampling=generation.MaxPosteriorSampling)
+        _module("botorch.fit", fit_gpytorch_mll=gp.fit_gpytorch_mll)
+        _module("botorch.exceptions", ModelFittingError=gp.ModelFittingError)
+        _module("botorch.settings", validate_input_scaling=_NoOpSetting, debug=_NoOpSetting)
         done["botorch"] = True
     else:
         done["botorch"] = False
     if force or not _present("gpytorch"):
-        _module("gpytorch.constraints", Interval=_Interval)
-        _module("gpytorch.likelihoods", GaussianLikelihood=_GaussianLikelihood)
+        _module("gpytorch.constraints", Interval=gp.Interval)
+        _module("gpytorch.likelihoods", GaussianLikelihood=gp.GaussianLikelihood)
+        _module("gpytorch.mlls", ExactMarginalLogLikelihood=gp.ExactMarginalLogLikelihood)
+        _module("gpytorch.kernels", MaternKernel=gp.MaternKernel, RBFKernel=gp.RBFKernel, ScaleKernel=gp.ScaleKernel)
+        _module("gpytorch.settings", max_cholesky_size=_NoOpSetting, cholesky_jitter=_NoOpSetting)
         done["gpytorch"] = True
     else:
         done["gpytorch"] = False

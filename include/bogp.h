@@ -237,6 +237,15 @@ int bogp_gp_fit_adamw_bounded(int n, int d, const double* X_host, const double* 
                               const double* lengthscale_prior, const double* outputscale_prior,
                               const double* lengthscale_bounds, const double* outputscale_bounds, int B,
                               double* raw_inout_host, double* loss_host, void* stream);
+/* One evaluation of the same objective: loss_host[B] = -(log marginal likelihood + log priors) / n and
+ * grad_host[B][d + 3] = d(loss)/d(raw) at raw_host[B][d + 3] (raw lengthscale[d], outputscale, noise, mean), on the
+ * same kernels (one step, no update).  What a hand-rolled loop `loss = -mll(model(X), y); loss.backward()`
+ * (projects/swellex96_inv/data/bo/ei.py:72-77) and botorch.fit.fit_gpytorch_mll's scipy L-BFGS-B closure
+ * (projects/swellex96_localization/data/demo_1d.py:137, projects/swellex96_inv/data/bo/baxus.py:333) evaluate. */
+int bogp_gp_mll_grad(int n, int d, const double* X_host, const double* y_host, int kernel_kind, double noise_lo,
+                     double noise_hi, const double* lengthscale_prior, const double* outputscale_prior,
+                     const double* lengthscale_bounds, const double* outputscale_bounds, int B,
+                     const double* raw_host, double* loss_host, double* grad_host, void* stream);
 
 /* ---- Final reduction across the GPUs of one box over peer memory (NVLink P2P stores), no collective library.
  * Replaces the host-side np.argmax over collated surfaces (projects/swellex96_localization/data/collate.py:50) and the

@@ -365,6 +365,98 @@ def test_fused_fit_kernel_matches_oracle_adamw(n, d, kind):
                               Xt, yt, cfg_o)), rel=0.05)
 
 
+@pytest.mark.parametrize("n,d,kind,bounded", [(40, 3, "matern52", False), (200, 6, "matern52", True), (64, 2, "rbf", False)])
+def test_mll_value_and_gradient_vs_oracle_autograd(n, d, kind, bounded):
+    """bogp_gp_mll_grad (one step of the fit kernels, update off) at a non-trivial raw point: loss and gradient against
+    torch autograd through the oracle's neg_mll, softplus and Interval transforms, one-CTA and cooperative kernels."""
+    from bogp_b200.gp import FitConfig, SingleTaskGP, mll_value_and_grad
+    _, _, X, y = make_problem(n, d, kind)
+    rng = np.random.default_rng(5)
+    rawv = 0.4 * rng.standard_normal(d + 3)
+    kw = dict(lengthscale_prior=None, outputscale_prior=None, lengthscale_bounds=(0.005, 10.0), outputscale_bounds=(0.05, 10.0)) if bounded else {}
+    raw = {"lengthscale": torch.tensor(rawv[:d], requires_grad=True), "outputscale": torch.tensor(rawv[d], requires_grad=True),
+           "noise": torch.tensor(rawv[d + 1], requires_grad=True), "mean": torch.tensor(rawv[d + 2], requires_grad=True)}
+    ref = ogp.neg_mll(raw, torch.as_tensor(X), torch.as_tensor(y), ogp.FitConfig(kind=kind, **kw))
+    ref.backward()
+    gref = np.concatenate([raw["lengthscale"].grad.numpy(), [float(raw["outputscale"].grad), float(raw["noise"].grad), float(raw["mean"].grad)]])
+    loss, grad = mll_value_and_grad(SingleTaskGP(X, y, kind), rawv, FitConfig(**kw))
+    assert loss == pytest.approx(float(ref), rel=1e-9, abs=1e-11)
+    np.testing.assert_allclose(grad, gref, rtol=1e-6, atol=1e-10)
+
+
+def test_reference_fit_loops_run_unchanged_under_the_shim():
+    """The hand-rolled fit of ref/projects/swellex96_inv/data/bo/ei.py:65-78 and the explicit-kernel model with
+    ``fit_gpytorch_mll`` of ref/projects/swellex96_inv/data/bo/baxus.py:304-343, written with the reference's own imports
+    and call sequence, under shim.install(): the AdamW loop lands on the fused one-launch fit's parameters (same
+    arithmetic, one kernel launch per step instead of one in all), the acquisition sees the fitted model, and the
+    L-BFGS-B fit ends at a stationary point no worse than the 100 AdamW steps."""
+    from bogp_b200 import shim
+    shim.install(force=True)
+    try:
+        import botorch
+        import gpytorch
+        from botorch.acquisition.analytic import ExpectedImprovement
+        from botorch.exceptions import ModelFittingError                     # noqa: F401  (baxus.py:12)
+        from botorch.fit import fit_gpytorch_mll
+        from botorch.models import SingleTaskGP
+        from botorch.optim import optimize_acqf
+        from gpytorch.constraints import Interval
+        from gpytorch.kernels import MaternKernel, ScaleKernel
+        from gpytorch.likelihoods import GaussianLikelihood
+        from gpytorch.mlls import ExactMarginalLogLikelihood
+        _, _, Xn, yn = make_problem(48, 3, "matern52")
+        dtype, device, dim = torch.double, torch.device("cuda"), 3
+        X = torch.tensor(Xn, dtype=dtype, device=device)
+        Y = torch.tensor(yn, dtype=dtype, device=device)
+        with botorch.settings.validate_input_scaling(False):
+            train_Y = (Y - Y.mean()) / Y.std()
+            likelihood = GaussianLikelihood(noise_constraint=Interval(1e-8, 1e-3))
+            model = SingleTaskGP(X, train_Y, likelihood=likelihood)
+            mll = ExactMarginalLogLikelihood(model.likelihood, model)
+            optimizer = torch.optim.AdamW([{"params": model.parameters()}], lr=0.1)
+            model.train()
+            model.likelihood.train()
+            losses = []
+            for _ in range(100):
+                optimizer.zero_grad()
+                output = model(X)
+                loss = -mll(output, train_Y.squeeze())
+                loss.backward()
+                optimizer.step()
+                losses.append(float(loss))
+            ei = ExpectedImprovement(model, train_Y.max())
+            candidate, value = optimize_acqf(ei, bounds=torch.stack([-torch.ones(dim, dtype=dtype, device=device),
+                                                                     torch.ones(dim, dtype=dtype, device=device)]),
+                                             q=1, num_restarts=8, raw_samples=256)
+        from bogp_b200.gp import FitConfig, fit_gp_adamw
+        fused, hist = fit_gp_adamw(SingleTaskGP(X, train_Y, likelihood=likelihood), FitConfig(), return_loss=True)
+        np.testing.assert_allclose(losses, hist[0], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(model.lengthscale.numpy(), fused.lengthscale.numpy(), rtol=1e-8)
+        assert model.outputscale == pytest.approx(fused.outputscale, rel=1e-8) and model.noise == pytest.approx(fused.noise, rel=1e-8)
+        assert candidate.shape == (1, dim) and float(value) > 0.0 and bool((candidate.abs() <= 1.0).all())
+        # baxus.py:304-343: explicit Matern-5/2 ARD kernel with Interval constraints, L-BFGS-B fit
+        covar_module = ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=dim, lengthscale_constraint=Interval(0.005, 10)),
+                                   outputscale_constraint=Interval(0.05, 10))
+        model2 = SingleTaskGP(X, train_Y, covar_module=covar_module, likelihood=likelihood)
+        mll2 = ExactMarginalLogLikelihood(model2.likelihood, model2)
+        with gpytorch.settings.max_cholesky_size(float("inf")):
+            fit_gpytorch_mll(mll2)
+        from bogp_b200.gp import mll_value_and_grad
+        l_lbfgs, g = mll_value_and_grad(model2, model2.raw_parameters)
+        adam = SingleTaskGP(X, train_Y, covar_module=covar_module, likelihood=likelihood).fit()
+        l_adam, _ = mll_value_and_grad(adam, adam.raw_parameters)
+        assert l_lbfgs <= l_adam + 1e-6
+        free = np.abs(model2.raw_parameters) < 15.0                      # a sigmoid pinned at a bound has no gradient left
+        assert np.abs(g[free]).max() < 1e-3
+        assert 0.005 <= float(model2.lengthscale.min()) and float(model2.lengthscale.max()) <= 10.0
+        mll2.eval()
+        post = mll2.model(X[:5])
+        lo_, hi_ = post.confidence_region()
+        assert lo_.shape == hi_.shape and bool((hi_ >= lo_).all())
+    finally:
+        shim.uninstall()
+
+
 def test_fused_fit_kernel_jitter_and_errors():
     from bogp_b200 import _lib
     from bogp_b200.gp import FitConfig, SingleTaskGP, fit_gp_adamw

@@ -184,3 +184,44 @@ def test_optimize_acqf_sharded_raw_samples_and_restarts_gloo():
     assert v0 == v1 and sx0 == sx1 == (8, 1, 3) and sv0 == sv1 == (8,)
     np.testing.assert_allclose(c0.reshape(-1), [0.7, 0.2, 0.55], atol=1e-4)
     assert abs(v0 - 1.0) < 1e-3
+
+
+def test_shim_exports_the_fit_protocol():
+    """Every name the reference's hand-rolled loops import for the GP fit (ei.py:7-14, baxus.py:10-21, demo_1d.py) resolves
+    under shim.install(), and the explicit kernel of baxus.py:306-319 selects the Matern-5/2 ARD model with Interval
+    constraints and no priors.  No device call."""
+    import torch
+    from bogp_b200 import shim
+    shim.install(force=True)
+    try:
+        import botorch
+        import gpytorch
+        from botorch.exceptions import ModelFittingError
+        from botorch.fit import fit_gpytorch_mll
+        from botorch.models import SingleTaskGP
+        from gpytorch.constraints import Interval
+        from gpytorch.kernels import MaternKernel, RBFKernel, ScaleKernel
+        from gpytorch.likelihoods import GaussianLikelihood
+        from gpytorch.mlls import ExactMarginalLogLikelihood
+        assert issubclass(ModelFittingError, Exception) and callable(fit_gpytorch_mll)
+        X, Y = torch.rand(12, 4, dtype=torch.double), torch.rand(12, dtype=torch.double)
+        with botorch.settings.validate_input_scaling(False), gpytorch.settings.max_cholesky_size(2000):
+            m = SingleTaskGP(X, Y, covar_module=ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=4, lengthscale_constraint=Interval(0.005, 10)),
+                                                            outputscale_constraint=Interval(0.05, 10)),
+                             likelihood=GaussianLikelihood(noise_constraint=Interval(1e-8, 1e-3)))
+        assert m.kind == "matern52" and m.noise_bounds == (1e-8, 1e-3)
+        assert m.fit_defaults.lengthscale_bounds == (0.005, 10.0) and m.fit_defaults.outputscale_bounds == (0.05, 10.0)
+        assert m.fit_defaults.lengthscale_prior is None and m.fit_defaults.outputscale_prior is None
+        assert SingleTaskGP(X, Y, covar_module=ScaleKernel(RBFKernel(ard_num_dims=4))).kind == "rbf"
+        mll = ExactMarginalLogLikelihood(m.likelihood, m)
+        (raw,) = m.parameters()
+        assert isinstance(raw, torch.nn.Parameter) and raw.shape == (7,) and float(raw.abs().sum()) == 0.0
+        opt = torch.optim.AdamW([{"params": m.parameters()}], lr=0.1)
+        assert opt.param_groups[0]["params"][0] is raw
+        m.train(); m.likelihood.train()
+        assert m(X) is None and mll.train() is mll
+        import pytest
+        with pytest.raises(NotImplementedError):
+            MaternKernel(nu=1.5)
+    finally:
+        shim.uninstall()
