@@ -30,6 +30,7 @@ SIGNATURES = {
     "bogp_last_error": (C.c_char_p, []),
     "bogp_version": (C.c_int, []),
     "bogp_kernel_launches": (_ll, []),
+    "bogp_h2d_bytes": (_ll, []),
     "bogp_timing_enable": (C.c_int, [C.c_int]),
     "bogp_timing_read": (C.c_int, [_dp, C.POINTER(_ll)]),
     "bogp_device_info": (C.c_int, [_ip, _ip, _ip]),
@@ -144,6 +145,11 @@ def device_info():
 
 def kernel_launches() -> int:
     return int(lib().bogp_kernel_launches())
+
+
+def h2d_bytes() -> int:
+    """Input bytes the Bartlett entry points have copied host -> device since the library was loaded."""
+    return int(lib().bogp_h2d_bytes())
 
 
 def timing_enable(on: bool) -> None:

@@ -794,7 +794,7 @@ extern "C" int bogp_bartlett_points_host(bogp_modeset_t h, const double* cand_ho
   double* cd = static_cast<double*>(h->io_scratch);
   float* od = reinterpret_cast<float*>(cd + (size_t)C * 3);
   int rc = 0;
-  cudaError_t e = cudaMemcpyAsync(cd, cand_host, (size_t)C * 3 * sizeof(double), cudaMemcpyHostToDevice, s);
+  cudaError_t e = bogp::h2d_async(cd, cand_host, (size_t)C * 3 * sizeof(double), s);
   if (e != cudaSuccess) { bogp::set_error("H2D: %s", cudaGetErrorString(e)); rc = BOGP_ERR_CUDA; }
   if (!rc) rc = bogp_bartlett_points(h, cd, C, atype, mf_method, od, stream);
   if (!rc) {

@@ -18,6 +18,8 @@ typedef std::complex<double> cplx;
 void set_error(const char* fmt, ...);
 // Number of kernels this library has launched (bench.py reports it as gpu_launches).
 void count_launch(int n = 1);
+// host -> device copy of a call's inputs on its stream, counted (bogp_h2d_bytes: what bench.py reports per step)
+cudaError_t h2d_async(void* dst, const void* src, size_t bytes, cudaStream_t s);
 // Event bracket around a dominant kernel (no-ops returning nullptr unless bogp_timing_enable(1)).
 bool timing_enabled();
 cudaEvent_t timing_begin(cudaStream_t s);

@@ -24,6 +24,12 @@ const char* last_error_cstr() { return g_err.c_str(); }
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
+static std::atomic<long long> g_h2d{0};
+cudaError_t h2d_async(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  g_h2d.fetch_add((long long)bytes, std::memory_order_relaxed);
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+}
+long long h2d_bytes() { return g_h2d.load(std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------- dominant-kernel timing (bench.py roofline)
 // When enabled, the launcher of a dominant kernel brackets it with a CUDA event pair recorded on the launching
@@ -178,6 +184,7 @@ void invert_lower(std::vector<double>& L, int n) {
 extern "C" const char* bogp_last_error(void) { return bogp::last_error_cstr(); }
 extern "C" int bogp_version(void) { return 100; }
 extern "C" long long bogp_kernel_launches(void) { return bogp::launches(); }
+extern "C" long long bogp_h2d_bytes(void) { return bogp::h2d_bytes(); }
 extern "C" int bogp_timing_enable(int on) { bogp::g_timing = on != 0; return 0; }
 extern "C" int bogp_timing_read(double* total_ms, long long* count) {
   double tot = 0.0;

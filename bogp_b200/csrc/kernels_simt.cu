@@ -425,8 +425,8 @@ int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     double* z_dev = r_dev + Nr;
     float2* E = reinterpret_cast<float2*>(base + off_tab);
     float2* PZ = reinterpret_cast<float2*>(base + off_tab + bytes_E);
-    BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
-    BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
+    BOGP_CUDA(h2d_async(r_dev, r_host, Nr * sizeof(double), s));
+    BOGP_CUDA(h2d_async(z_dev, z_host, Nz * sizeof(double), s));
     dim3 tg(std::max(1, std::min(64, (int)(((long long)(Nr + Nz) * h->max_Mp + 255) / 256))), d.F);
     grid_tables_kernel<<<tg, 256, 0, s>>>(d, r_dev, Nr, z_dev, Nz, E, PZ);
     bogp::count_launch();
@@ -451,9 +451,9 @@ int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const doub
     double* t_dev = z_dev + Nz;
     float2* E = reinterpret_cast<float2*>(base + off_tab);
     float2* PZ = reinterpret_cast<float2*>(base + off_tab + bytes_E);
-    BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
-    BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
-    BOGP_CUDA(cudaMemcpyAsync(t_dev, tilt_host, Nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    BOGP_CUDA(h2d_async(r_dev, r_host, Nr * sizeof(double), s));
+    BOGP_CUDA(h2d_async(z_dev, z_host, Nz * sizeof(double), s));
+    BOGP_CUDA(h2d_async(t_dev, tilt_host, Nt * sizeof(double), s));
     dim3 tg(std::max(1, std::min(64, (int)(((long long)(Nr + Nz) * h->max_Mp + 255) / 256))), d.F);
     grid_tables_kernel<<<tg, 256, 0, s>>>(d, r_dev, Nr, z_dev, Nz, E, PZ);
     bogp::count_launch();
@@ -477,9 +477,9 @@ int launch_grid_simt(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   double* z_dev = r_dev + Nr;
   double* t_dev = z_dev + Nz;
   double* cand = reinterpret_cast<double*>(base + off_tab);
-  BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
-  BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
-  BOGP_CUDA(cudaMemcpyAsync(t_dev, tilt_host, Nt * sizeof(double), cudaMemcpyHostToDevice, s));
+  BOGP_CUDA(h2d_async(r_dev, r_host, Nr * sizeof(double), s));
+  BOGP_CUDA(h2d_async(z_dev, z_host, Nz * sizeof(double), s));
+  BOGP_CUDA(h2d_async(t_dev, tilt_host, Nt * sizeof(double), s));
   make_grid_candidates_kernel<<<std::max(1, (int)std::min<long long>((C + 255) / 256, 148 * 8)), 256, 0, s>>>(r_dev, Nr, z_dev, Nz, t_dev, Nt, cand);
   bogp::count_launch();
   BOGP_CUDA(cudaGetLastError());

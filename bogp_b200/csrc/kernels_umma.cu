@@ -1286,8 +1286,8 @@ int launch_grid_umma(bogp_modeset_s* h, const double* r_host, int Nr, const doub
   }
   // two small pageable copies: the driver sends them inline with the command stream, which costs less GPU time than
   // one DMA from page-locked staging (measured: 8 us per step)
-  BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
-  BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
+  BOGP_CUDA(h2d_async(r_dev, r_host, Nr * sizeof(double), s));
+  BOGP_CUDA(h2d_async(z_dev, z_host, Nz * sizeof(double), s));
   const int nE = d.F * p.nrt * (kTileR / kTabRows), nB = d.F * ((Nz + kTabDepths - 1) / kTabDepths);
   umma_tables_kernel<<<nE + nB, kTabThreads, 0, s>>>(d, p, r_dev, z_dev, nE);
   count_launch();
@@ -1439,9 +1439,9 @@ int launch_grid_umma_tilt(bogp_modeset_s* h, const double* r_host, int Nr, const
   p.CkT_re = d.CkT_re; p.CkT_im = d.CkT_im;
   p.E = base + off_E; p.Bhi = base + off_Bhi; p.Blo = base + off_Blo;
   p.out = out_dev;
-  BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
-  BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
-  BOGP_CUDA(cudaMemcpyAsync(t_dev, tilt_host, Nt * sizeof(double), cudaMemcpyHostToDevice, s));
+  BOGP_CUDA(h2d_async(r_dev, r_host, Nr * sizeof(double), s));
+  BOGP_CUDA(h2d_async(z_dev, z_host, Nz * sizeof(double), s));
+  BOGP_CUDA(h2d_async(t_dev, tilt_host, Nt * sizeof(double), s));
   const int nE = d.F * nrt * (kTileR / kTabRows);
   {
     UParams pe = p;              // the E blocks of the shared table kernel read Nr / nrt / e offsets only

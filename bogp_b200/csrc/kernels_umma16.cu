@@ -147,7 +147,7 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint32_t a_lo, uint3
 // warp's try_wait returns) takes ~300 cycles, about the time the pipe needs for the MMAs still to be issued here, so the
 // next stage's first MMA reaches the queue as this stage's last one leaves it.
 #ifndef BOGP_U16_TURN_LEFT
-#define BOGP_U16_TURN_LEFT 4
+#define BOGP_U16_TURN_LEFT 4      // measured: 6 (turn passed after the first MMA of a K = 16 stage) is 1.5 % slower
 #endif
 template <int KS>
 __device__ __forceinline__ void issue_stage16(uint32_t d_re, uint32_t d_im, uint32_t a0, uint32_t blk, uint32_t bh, uint32_t bl,
@@ -300,8 +300,11 @@ __device__ __forceinline__ float lean_slot32(const FoldC& c, const float* reA, c
   return __fdividef(num, sum4(t0, t1, t2, t3));
 }
 
+// The lean instance has to stay at 88 registers: 640 x 88 = 56 320 leave 9 216 of the SM's 65 536 for the 128-thread
+// block of the streamed table kernel that runs next to it (at 89 the allocation granularity makes it 96 and the two no
+// longer fit one SM -- the launcher checks the compiled counts and falls back to the sequential table kernel).
 template <bool LEAN>
-__global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_constant__ HParams p) {
+__device__ __forceinline__ void umma16_grid_body(const HParams& p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
@@ -739,6 +742,11 @@ __global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel(const __grid_const
   }
 }
 
+// (nvcc does not take __launch_bounds__ and __maxnreg__ on the same kernel, and with __maxnreg__(88) alone the lean
+// instance compiles to 85 registers and runs 2 % slower: the launch bounds stay, the launcher checks the count.)
+__global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel_lean(const __grid_constant__ HParams p) { umma16_grid_body<true>(p); }
+__global__ void __launch_bounds__(kThr, 1) umma16_grid_kernel_general(const __grid_constant__ HParams p) { umma16_grid_body<false>(p); }
+
 // ------------------------------------------------------------------------------------------------ operand tables
 // byte offset of the 16-byte chunk (row, K chunk kc) inside a K-major no-swizzle block with nch chunks per row
 __device__ __forceinline__ size_t chunk_off(int row, int kc, int nch) {
@@ -1133,7 +1141,7 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
   p.Blo = p.Bhi + (((size_t)b_off + 255) & ~(size_t)255);
   p.out = out_dev;
   if (!e_cached) {
-    BOGP_CUDA(cudaMemcpyAsync(r_dev, r_host, Nr * sizeof(double), cudaMemcpyHostToDevice, s));
+    BOGP_CUDA(h2d_async(r_dev, r_host, Nr * sizeof(double), s));
     umma16_E_kernel<<<d.F * p.nrt * (kTile / kETabRows), 128, 0, s>>>(d, p, r_dev);
     count_launch();
     BOGP_CUDA(cudaGetLastError());
@@ -1141,7 +1149,7 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
   }
   // the depth vector stays on the device while it is the same (one grid for all time steps of a sweep)
   if (!(e_cached && c.z_cached.size() == (size_t)Nz && std::memcmp(c.z_cached.data(), z_host, (size_t)Nz * sizeof(double)) == 0)) {
-    BOGP_CUDA(cudaMemcpyAsync(z_dev, z_host, Nz * sizeof(double), cudaMemcpyHostToDevice, s));
+    BOGP_CUDA(h2d_async(z_dev, z_host, Nz * sizeof(double), s));
     c.z_cached.assign(z_host, z_host + Nz);
     c.phi_valid = false;
   }
@@ -1156,7 +1164,14 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
   const char* pdl_env = std::getenv("BOGP_UMMA_PDL");
   const char* ts_env = std::getenv("BOGP_UMMA_TABSTREAM");
   const bool chained = !timing_enabled() && !(pdl_env && pdl_env[0] == '0') && !(BOGP_UMMA_DBG && std::getenv("BOGP_UMMA_DBG"));
-  const bool stream_tabs = chained && lean && !(ts_env && ts_env[0] == '0');
+  static int fits_next_to_tables = -1;      // the compiled register counts decide whether the two kernels share an SM
+  if (fits_next_to_tables < 0) {
+    cudaFuncAttributes fa{}, fb{};
+    fits_next_to_tables = cudaFuncGetAttributes(&fa, umma16_grid_kernel_lean) == cudaSuccess &&
+                          cudaFuncGetAttributes(&fb, umma16_B_stream_kernel) == cudaSuccess &&
+                          ((fa.numRegs + 7) & ~7) * kThr + ((fb.numRegs + 7) & ~7) * kBThreads <= 65536;
+  }
+  const bool stream_tabs = chained && lean && fits_next_to_tables == 1 && !(ts_env && ts_env[0] == '0');
   const int nzb = (Nz + kBDepths - 1) / kBDepths;
   if (stream_tabs) {
     if (!c.tab_cnt) {
@@ -1202,7 +1217,7 @@ int launch_grid_umma16(bogp_modeset_s* h, const double* r_host, int Nr, const do
     p.dbg = dbg_dev;
   }
   const size_t smem = (size_t)p.smem_bar + 256;
-  auto kern = lean ? umma16_grid_kernel<true> : umma16_grid_kernel<false>;
+  auto kern = lean ? umma16_grid_kernel_lean : umma16_grid_kernel_general;
   BOGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t ev = timing_begin(s);
   if (!ev && !p.dbg && !(pdl_env && pdl_env[0] == '0')) {

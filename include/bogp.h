@@ -61,6 +61,10 @@ const char* bogp_last_error(void);
 int bogp_version(void);
 /* Kernels launched by this library since load (monotonic; bench.py reports the per-step difference). */
 long long bogp_kernel_launches(void);
+/* Bytes of call inputs (range / depth / tilt vectors, candidate lists) copied host -> device by the Bartlett entry points
+ * since load (monotonic): vectors that have not changed since the previous call on the same handle are not copied
+ * again.  bench.py reports the per-step difference as e2e.h2d_bytes_per_step. */
+long long bogp_h2d_bytes(void);
 /* Roofline instrumentation: while enabled, each launch of a dominant kernel (the Bartlett grid/points kernels, the
  * GP evaluation kernel) is bracketed by CUDA events on its own stream; bogp_timing_read() waits for them and returns
  * the summed kernel time and the number of launches since the last read. */
