@@ -100,6 +100,31 @@ def sharded_surface(evaluate_rows: Callable[[int, int], torch.Tensor], n_rows: i
     return local, (val, pos), full
 
 
+def sharded_candidates(evaluate: Callable[[int, int], torch.Tensor], n: int, *, maximize: bool = True, gather: bool = False,
+                       group: Optional[dist.ProcessGroup] = None):
+    """Scattered candidates and per-candidate environments (BASELINE configs[4]: 10^4 environments, each with its own mode
+    set -- the process pool of ref/projects/swellex96_inv/data/bo/obj.py:28-30): rank ``r`` evaluates the candidates
+    ``[lo, hi)`` of its slab with its own ``EnvBatch`` / ``bartlett_points`` call (``evaluate(lo, hi) -> values[hi - lo]``),
+    nothing but the 16-byte extremum record is exchanged.  Returns ``(local_values, (value, global index), all_values |
+    None)``; ``maximize=False`` for the ``cbf_ml`` objective the inversion minimises."""
+    local, (val, pos), full = sharded_surface(lambda lo, hi: evaluate(lo, hi).reshape(-1, 1), n, 1, maximize=maximize,
+                                              gather_surface=gather, group=group)
+    return local.reshape(-1), (val, pos[0]), None if full is None else full.reshape(-1)
+
+
+def sharded_tilt_volume(evaluate_tilts: Callable[[int, int], torch.Tensor], n_tilt: int, n_z: int, n_r: int, *,
+                        maximize: bool = True, group: Optional[dist.ProcessGroup] = None):
+    """The (tilt, depth, range) volume of BASELINE configs[3] split over the tilt axis: rank ``r`` evaluates the tilt planes
+    ``[lo, hi)`` (``evaluate_tilts(lo, hi) -> [hi - lo, n_z, n_r]``, one ``bartlett_grid(r, z, tilt[lo:hi])`` call -- a unit
+    of the tilt engine is a chunk of tilts of one depth, so whole planes keep its A-operand reuse).  Returns
+    ``(local_planes, (value, (tilt, depth, range) index))``."""
+    local, (val, pos), _ = sharded_surface(lambda lo, hi: evaluate_tilts(lo, hi).reshape(hi - lo, n_z * n_r), n_tilt, n_z * n_r,
+                                           maximize=maximize, group=group)
+    t, rest = pos
+    zr = tuple(int(x) for x in np.unravel_index(rest, (n_z, n_r))) if t >= 0 else (-1, -1)
+    return local.reshape(-1, n_z, n_r), (val, (t,) + zr)
+
+
 def reduce_records(recs, maximize: bool = True) -> Tuple[float, int]:
     """``(value, global flat index)`` of the extremum over the exchanged int64[world, 2] ``(index, value bits)`` records,
     with np.argmax's first-occurrence rule across ranks (ties -> lowest global index); records with index < 0 (a rank

@@ -186,6 +186,45 @@ def test_optimize_acqf_sharded_raw_samples_and_restarts_gloo():
     assert abs(v0 - 1.0) < 1e-3
 
 
+def _cand_worker(rank, world, port, vals, vol, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bogp_b200.sharding import sharded_candidates, sharded_tilt_volume
+        v = torch.as_tensor(vals)
+        local, (val, idx), full = sharded_candidates(lambda lo, hi: v[lo:hi], len(vals), maximize=False, gather=True)
+        V = torch.as_tensor(vol)
+        planes, (vmax, pos) = sharded_tilt_volume(lambda lo, hi: V[lo:hi], *vol.shape)
+        q.put((rank, len(local), val, idx, bool(torch.equal(full, v)), tuple(planes.shape), vmax, pos))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_candidates_and_tilt_volume_gloo(world):
+    """configs[4] / configs[3] sharding on CPU: candidate slabs (arg-min: the inversion minimises cbf_ml) with the gathered
+    values in global order, tilt planes with the (tilt, depth, range) index of the global maximum; every rank agrees."""
+    rng = np.random.default_rng(11)
+    vals = rng.random(23).astype(np.float32)
+    vals[7] = vals[19] = -1.0                                     # tie across ranks: the lower index wins
+    vol = rng.random((5, 4, 6)).astype(np.float32)
+    vol[3, 2, 5] = 9.0
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_cand_worker, args=(r, world, port, vals, vol, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    from bogp_b200.sharding import slab
+    for rank, n_local, val, idx, same, pshape, vmax, pos in res:
+        lo, hi = slab(23, rank, world)
+        assert n_local == hi - lo and val == -1.0 and idx == 7 and same
+        tl, th = slab(5, rank, world)
+        assert pshape == (th - tl, 4, 6) and vmax == 9.0 and pos == (3, 2, 5)
+
+
 def test_shim_exports_the_fit_protocol():
     """Every name the reference's hand-rolled loops import for the GP fit (ei.py:7-14, baxus.py:10-21, demo_1d.py) resolves
     under shim.install(), and the explicit kernel of baxus.py:306-319 selects the Matern-5/2 ARD model with Interval

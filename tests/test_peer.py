@@ -196,3 +196,64 @@ def test_peer_exchange_two_gpus_matches_nccl_allgather():
     for p in procs:
         p.join(60)
     assert [r[1] for r in res] == [True, True]
+
+
+def _shard_worker(rank: int, world: int, port: int, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        from bogp_b200 import mfp
+        from bogp_b200.envbatch import EnvBatch
+        from bogp_b200.modes import (INV_TONALS_3, REC_Z_21, SWELLEX_TONALS_13, pekeris_modes, perturbed_pekeris_batch,
+                                     synthetic_covariance)
+        from bogp_b200.sharding import sharded_candidates, sharded_tilt_volume
+        # configs[4]: per-candidate environments, slabs of candidates per rank, arg-min of the cbf_ml objective
+        truth = pekeris_modes(INV_TONALS_3, REC_Z_21)
+        K = synthetic_covariance(truth, 71.11, 1.07)
+        rng = np.random.default_rng(4)
+        Cn = 61
+        depths, cbs = rng.uniform(212.0, 222.0, Cn), rng.uniform(1600.0, 1700.0, Cn)
+        depths[40], cbs[40] = 217.0, 1650.0                       # the true environment sits in the second rank's slab
+        sets = perturbed_pekeris_batch(INV_TONALS_3, REC_Z_21, depths, cbs)
+        r, zs = np.full(Cn, 1.07), np.full(Cn, 71.11)
+
+        def score(lo, hi):
+            with EnvBatch(sets[lo:hi], r[lo:hi], zs[lo:hi], K) as eb:
+                return eb.bartlett(atype="cbf_ml", multifreq_method="product")
+
+        local, (val, idx), full = sharded_candidates(score, Cn, maximize=False, gather=True)
+        whole = score(0, Cn)
+        ok = idx == 40 and abs(val) < 2e-5 and bool(torch.equal(full, whole))
+        # configs[3]: the (tilt, depth, range) volume split over tilt planes
+        modes = pekeris_modes(SWELLEX_TONALS_13)
+        rr, zz, tilt = np.linspace(0.5, 9.0, 150), np.linspace(5.0, 195.0, 24), np.linspace(-2.0, 2.0, 5)
+        dms = mfp.DeviceModeSet(modes, synthetic_covariance(modes, zz[13], rr[77], tilt_deg=tilt[3]))
+        planes, (vmax, pos) = sharded_tilt_volume(lambda lo, hi: dms.bartlett_grid(rr, zz, tilt[lo:hi]), len(tilt), len(zz), len(rr))
+        vol = dms.bartlett_grid(rr, zz, tilt)
+        flat = int(vol.reshape(-1).argmax())
+        ok = ok and pos == tuple(int(x) for x in np.unravel_index(flat, tuple(vol.shape))) and pos == (3, 13, 77)
+        ok = ok and vmax == float(vol.reshape(-1)[flat])
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs on one box")
+def test_environment_batch_and_tilt_volume_sharded_over_two_gpus():
+    """BASELINE configs[4] (own mode set per candidate) and configs[3] (tilt volume) over two ranks: each rank scores its
+    slab with its own EnvBatch / tilt-plane call, the gathered values equal the one-GPU call bit for bit and the global
+    extremum is the truth (environment 40; tilt 3, depth 13, range 77)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert [r[1] for r in res] == [True, True]
+
