@@ -119,8 +119,16 @@ def check(fn: str, rc: int) -> None:
         raise BogpError(fn, rc, (lib().bogp_last_error() or b"").decode(errors="replace"))
 
 
+_FN: dict = {}
+
+
 def call(fn: str, *args) -> None:
-    check(fn, getattr(lib(), fn)(*args))
+    f = _FN.get(fn)
+    if f is None:
+        f = _FN[fn] = getattr(lib(), fn)
+    rc = f(*args)
+    if rc != OK:
+        check(fn, rc)
 
 
 def dptr(a):
@@ -133,8 +141,13 @@ def fptr(a):
 
 
 def current_stream_ptr() -> int:
+    """Raw ``cudaStream_t`` of torch's current stream on the current device (the C-level query when this torch has it: the
+    Stream object costs ~3 us per call, which the host-buffer entry points pay on every step)."""
     import torch
-    return int(torch.cuda.current_stream().cuda_stream)
+    try:
+        return int(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+    except AttributeError:
+        return int(torch.cuda.current_stream().cuda_stream)
 
 
 def device_info():

@@ -45,6 +45,8 @@ class DeviceModeSet:
     def __init__(self, modes: ModeSet, covariance_matrix: Optional[np.ndarray] = None):
         self.modes = modes
         self._h = C.c_void_p()
+        self._vec_cache: dict = {}
+        self._out_cache = None
         M = np.asarray(modes.n_modes, dtype=np.int32)
         k_re, k_im = _split_planes([np.asarray(k, dtype=np.complex128) for k in modes.k])
         pr_re, pr_im = _split_planes(modes.phi_rec)
@@ -69,6 +71,30 @@ class DeviceModeSet:
             self.close()
         except Exception:
             pass
+
+    # ------------------------------------------------------------------ per-call host work
+    def _vec(self, key: str, x, scale: float = 1.0):
+        """float64 C-contiguous copy of a grid vector (scaled: km -> m) and its ``double*``, kept while the caller passes
+        the same values -- a sweep calls with ONE grid for all its time steps (mfp.py:166-216), and the conversion plus the
+        ctypes pointer cost more than the comparison of 8 kB.  Returns ``(array, pointer)``."""
+        a = np.atleast_1d(np.asarray(x, dtype=np.float64))
+        raw = a.tobytes()
+        hit = self._vec_cache.get(key)
+        if hit is not None and hit[0] == raw:
+            return hit[1], hit[2]
+        v = np.ascontiguousarray(scale * a if scale != 1.0 else a)
+        ptr = _lib.dptr(v)
+        self._vec_cache[key] = (raw, v, ptr)
+        return v, ptr
+
+    def _out_ptr(self, out: np.ndarray):
+        """``float*`` of a host output array, kept per array object (the reference is held, so the id cannot be reused)."""
+        hit = self._out_cache
+        if hit is not None and hit[0] is out:
+            return hit[1]
+        ptr = _lib.fptr(out)
+        self._out_cache = (out, ptr)
+        return ptr
 
     # ------------------------------------------------------------------ inputs
     def set_covariance(self, K: np.ndarray) -> None:
@@ -126,9 +152,9 @@ class DeviceModeSet:
         is also exchanged with the other GPUs of the box (``pairs`` int64[world, 2] gets every rank's record) -- from
         inside the same kernel on the FP16-split engine.
         """
-        r_m = np.ascontiguousarray(1000.0 * np.atleast_1d(np.asarray(r_km, dtype=np.float64)))
-        zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
-        tt = None if tilt_deg is None else np.ascontiguousarray(np.atleast_1d(np.asarray(tilt_deg, dtype=np.float64)))
+        r_m, p_r = self._vec("r", r_km, 1000.0)
+        zz, p_z = self._vec("z", z)
+        tt, p_t = (None, None) if tilt_deg is None else self._vec("t", tilt_deg)
         Nt = 1 if tt is None else len(tt)
         shape = (len(zz), len(r_m)) if tt is None else (Nt, len(zz), len(r_m))
         if out is None:
@@ -143,19 +169,19 @@ class DeviceModeSet:
                 px, offset, pairs = peer
                 if not (pairs.is_cuda and pairs.dtype == torch.int64 and pairs.numel() == 2 * px.world and pairs.is_contiguous()):
                     raise ValueError("peer pairs must be a contiguous CUDA int64[world, 2] tensor")
-                _lib.call("bogp_bartlett_grid_argext_peer", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
-                          _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
+                _lib.call("bogp_bartlett_grid_argext_peer", self._h, p_r, len(r_m), p_z, len(zz),
+                          p_t, Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
                           C.c_void_p(out.data_ptr()), 1 if maximize else 0, px._h, int(offset), C.c_void_p(pairs.data_ptr()),
                           C.c_void_p(pair.data_ptr() + 8), C.c_void_p(pair.data_ptr()), C.c_void_p(scratch.data_ptr()),
                           scratch.numel() * scratch.element_size(), C.c_void_p(_lib.current_stream_ptr()))
                 return out
-            _lib.call("bogp_bartlett_grid_argext", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
-                      _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
+            _lib.call("bogp_bartlett_grid_argext", self._h, p_r, len(r_m), p_z, len(zz),
+                      p_t, Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
                       C.c_void_p(out.data_ptr()), 1 if maximize else 0, C.c_void_p(pair.data_ptr() + 8),
                       C.c_void_p(pair.data_ptr()), C.c_void_p(scratch.data_ptr()),
                       scratch.numel() * scratch.element_size(), C.c_void_p(_lib.current_stream_ptr()))
             return out
-        _lib.call("bogp_bartlett_grid", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz), _lib.dptr(tt), Nt,
+        _lib.call("bogp_bartlett_grid", self._h, p_r, len(r_m), p_z, len(zz), p_t, Nt,
                   _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
                   C.c_void_p(out.data_ptr()), C.c_void_p(_lib.current_stream_ptr()))
         return out
@@ -168,37 +194,50 @@ class DeviceModeSet:
         ``argext="max"|"min"`` also returns ``(value, unravelled index)`` of the extremum (collate.py:50), computed
         on the device while the surface is still there: ``(surface, (value, index))``.  With ``peer=(PeerExchange,
         index_offset)`` the call returns ``(surface, records)``: the int64[world, 2] ``(index_offset + index, value
-        bits)`` records of every rank of the box, exchanged over peer memory inside the same call."""
-        r_m = np.ascontiguousarray(1000.0 * np.atleast_1d(np.asarray(r_km, dtype=np.float64)))
-        zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
-        tt = None if tilt_deg is None else np.ascontiguousarray(np.atleast_1d(np.asarray(tilt_deg, dtype=np.float64)))
-        Nt = 1 if tt is None else len(tt)
-        shape = (len(zz), len(r_m)) if tt is None else (Nt, len(zz), len(r_m))
+        bits)`` records of every rank of the box, exchanged over peer memory inside the same call (the records of the
+        PREVIOUS call when the exchange is pipelined, ``PeerExchange.set_pipelined``).
+
+        The per-call host work is kept to a few microseconds (a step is ~0.19 ms end to end): converted grid vectors and
+        their pointers are reused while the caller passes the same values, see :meth:`_vec`."""
+        r_m, p_r = self._vec("r", r_km, 1000.0)
+        zz, p_z = self._vec("z", z)
+        if tilt_deg is None:
+            Nt, p_t, shape = 1, None, (len(zz), len(r_m))
+        else:
+            tt, p_t = self._vec("t", tilt_deg)
+            Nt = len(tt)
+            shape = (Nt, len(zz), len(r_m))
         if out is None:
             out = np.empty(shape, dtype=np.float32)
         elif out.shape != shape or out.dtype != np.float32 or not out.flags.c_contiguous:
             raise ValueError(f"out must be a C-contiguous float32 array of shape {shape}")
+        p_out = self._out_ptr(out)
+        stream = _lib.current_stream_ptr()
         if argext is not None:
             if argext not in ("max", "min"):
                 raise ValueError("argext must be 'max', 'min' or None")
             if peer is not None:
                 px, offset = peer
                 recs = np.zeros((px.world, 2), dtype=np.int64)
-                _lib.call("bogp_bartlett_grid_host_argmax_peer", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
-                          _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
-                          _lib.fptr(out), 1 if argext == "max" else 0, px._h, int(offset),
-                          recs.ctypes.data_as(C.POINTER(C.c_longlong)), C.c_void_p(_lib.current_stream_ptr()))
+                _lib.call("bogp_bartlett_grid_host_argmax_peer", self._h, p_r, len(r_m), p_z, len(zz),
+                          p_t, Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
+                          p_out, 1 if argext == "max" else 0, px._h, int(offset),
+                          recs.ctypes.data_as(C.POINTER(C.c_longlong)), stream)
                 return out, recs
             val, idx = C.c_float(), C.c_longlong()
-            _lib.call("bogp_bartlett_grid_host_argmax", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz),
-                      _lib.dptr(tt), Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
-                      _lib.fptr(out), 1 if argext == "max" else 0, C.byref(val), C.byref(idx),
-                      C.c_void_p(_lib.current_stream_ptr()))
-            pos = tuple(int(i) for i in np.unravel_index(idx.value, shape)) if idx.value >= 0 else tuple(-1 for _ in shape)
+            _lib.call("bogp_bartlett_grid_host_argmax", self._h, p_r, len(r_m), p_z, len(zz),
+                      p_t, Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine],
+                      p_out, 1 if argext == "max" else 0, C.byref(val), C.byref(idx), stream)
+            i = idx.value
+            if i < 0:
+                pos = tuple(-1 for _ in shape)
+            elif len(shape) == 2:
+                pos = divmod(i, shape[1])
+            else:
+                pos = tuple(int(k) for k in np.unravel_index(i, shape))
             return out, (val.value, pos)
-        _lib.call("bogp_bartlett_grid_host", self._h, _lib.dptr(r_m), len(r_m), _lib.dptr(zz), len(zz), _lib.dptr(tt),
-                  Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine], _lib.fptr(out),
-                  C.c_void_p(_lib.current_stream_ptr()))
+        _lib.call("bogp_bartlett_grid_host", self._h, p_r, len(r_m), p_z, len(zz), p_t,
+                  Nt, _lib.ATYPE[atype], _lib.MF_METHOD[multifreq_method], _lib.ENGINE[engine], p_out, stream)
         return out
 
     def bartlett_points(self, cand: Union[np.ndarray, torch.Tensor], *, atype: str = "cbf",
