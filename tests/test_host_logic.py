@@ -264,3 +264,35 @@ def test_shim_exports_the_fit_protocol():
             MaternKernel(nu=1.5)
     finally:
         shim.uninstall()
+
+
+def test_grid_vector_cache_follows_values_not_objects():
+    """DeviceModeSet._vec (the per-call host work of the grid entry points): the converted vector and its pointer are
+    reused while the VALUES are the same -- a new array object with equal values hits, the same object modified in
+    place misses -- and the km -> m scaling is applied once.  No device call."""
+    import ctypes as C
+    from bogp_b200 import mfp
+    d = mfp.DeviceModeSet.__new__(mfp.DeviceModeSet)
+    d._h, d._vec_cache, d._out_cache = C.c_void_p(), {}, None
+    r = np.linspace(0.1, 10.0, 64)
+    a1, p1 = d._vec("r", r, 1000.0)
+    np.testing.assert_array_equal(a1, 1000.0 * r)
+    assert a1.dtype == np.float64 and a1.flags.c_contiguous
+    a2, p2 = d._vec("r", r.copy(), 1000.0)                       # other object, same values: hit
+    assert a2 is a1 and p2 is p1
+    a3, _ = d._vec("r", list(r), 1000.0)                         # a list with the same values: hit
+    assert a3 is a1
+    r[5] += 0.25                                                  # same object, modified in place: miss
+    a4, p4 = d._vec("r", r, 1000.0)
+    assert a4 is not a1 and a4[5] == 1000.0 * r[5]
+    z = np.array([5.0, 6.0], dtype=np.float32)                    # other dtype, unscaled key
+    az, _ = d._vec("z", z)
+    assert az.dtype == np.float64 and az.tolist() == [5.0, 6.0]
+    assert d._vec("r", r, 1000.0)[0] is a4                        # keys do not evict each other
+    s0, _ = d._vec("z", 7.5)                                      # scalars become length-1 vectors
+    assert s0.shape == (1,) and s0[0] == 7.5
+    out = np.empty((2, 3), dtype=np.float32)
+    assert d._out_ptr(out) is d._out_ptr(out)
+    assert d._out_ptr(np.empty((2, 3), dtype=np.float32)) is not None
+    d._h = C.c_void_p()                                           # nothing to destroy
+
