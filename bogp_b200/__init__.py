@@ -4,7 +4,7 @@ Boundary A (matched-field objective): :mod:`bogp_b200.mfp`  -- ``MatchedFieldPro
 Boundary B (GP posterior + acquisition): :mod:`bogp_b200.gp`, :mod:`bogp_b200.acquisition`, :mod:`bogp_b200.optim`
 Sampling strategies and BAxUS: :mod:`bogp_b200.generation` (``MaxPosteriorSampling``), :mod:`bogp_b200.baxus`
 Callers of the path: :mod:`bogp_b200.oao`, :mod:`bogp_b200.strategy`, :mod:`bogp_b200.sweep`, :mod:`bogp_b200.shim`
-Data contract and synthetic inputs: :mod:`bogp_b200.modes`
+Data contract and synthetic inputs: :mod:`bogp_b200.modes`; KRAKEN ``.mod`` files -> ``ModeSet``: :mod:`bogp_b200.kraken_mod`
 Multi-GPU sharding and the peer-memory final reduction: :mod:`bogp_b200.sharding`
 C ABI underneath: ``include/bogp.h`` / ``bogp_b200/libbogp_sm100.so`` (``python -m bogp_b200.build``)
 """
