@@ -209,6 +209,29 @@ class SingleTaskGP:
             self._raw_version = -1
         return [self._raw]
 
+    def state_dict(self) -> dict:
+        """The raw hyper-parameters, for the warm start of ``initialize_model(x, y, model.state_dict())``
+        (ref/projects/swellex96_localization/data/demo_1d.py:92-100,162): ``{"raw_parameters": tensor[d + 3]}``."""
+        if self._raw is not None:
+            raw = self._raw.detach().clone()
+        else:
+            init = getattr(self, "raw_parameters", None)
+            raw = torch.zeros(self.train_X.shape[1] + 3, dtype=DT) if init is None else torch.as_tensor(init, dtype=DT).clone()
+        return {"raw_parameters": raw}
+
+    def load_state_dict(self, state_dict: dict, strict: bool = True) -> "SingleTaskGP":
+        """Hyper-parameters of another model of the same input dimension (demo_1d.py:98-99): the next fit starts from
+        them, and the posterior uses them until then."""
+        raw = state_dict.get("raw_parameters") if isinstance(state_dict, dict) else None
+        if raw is None or tuple(raw.shape) != (self.train_X.shape[1] + 3,):
+            if strict:
+                raise KeyError("load_state_dict: expected {'raw_parameters': tensor[d + 3]} of a model with the same input dimension")
+            return self
+        with torch.no_grad():
+            self.parameters()[0].copy_(torch.as_tensor(raw, dtype=DT))
+        self._sync_raw()
+        return self
+
     def _sync_raw(self) -> None:
         r = self._raw
         if r is None or r._version == self._raw_version:
@@ -356,6 +379,10 @@ class ScaleKernel:
 
 class ModelFittingError(RuntimeError):
     """``botorch.exceptions.ModelFittingError`` (baxus.py:12,344)."""
+
+
+class InputDataWarning(UserWarning):
+    """``botorch.exceptions.InputDataWarning`` (filtered at demo_1d.py:8,187); never raised here."""
 
 
 def _constrained(raw: np.ndarray, d: int, lsb, osb, noise_bounds):

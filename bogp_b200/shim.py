@@ -111,7 +111,8 @@ def install(force: bool = False) -> Dict[str, bool]:
         _module("botorch.optim", optimize_acqf=optim.optimize_acqf)
         _module("botorch.generation", MaxPosteriorSampling=generation.MaxPosteriorSampling)
         _module("botorch.fit", fit_gpytorch_mll=gp.fit_gpytorch_mll)
-        _module("botorch.exceptions", ModelFittingError=gp.ModelFittingError)
+        _module("botorch", fit_gpytorch_mll=gp.fit_gpytorch_mll)                     # `from botorch import fit_gpytorch_mll` (demo_1d.py:6)
+        _module("botorch.exceptions", ModelFittingError=gp.ModelFittingError, InputDataWarning=gp.InputDataWarning)
         _module("botorch.settings", validate_input_scaling=_NoOpSetting, debug=_NoOpSetting)
         done["botorch"] = True
     else:

@@ -262,6 +262,24 @@ def test_shim_exports_the_fit_protocol():
         import pytest
         with pytest.raises(NotImplementedError):
             MaternKernel(nu=1.5)
+        # demo_1d.py:6-8,92-100,162: `from botorch import fit_gpytorch_mll`, InputDataWarning, state_dict warm start
+        from botorch import fit_gpytorch_mll as top_level
+        from botorch.exceptions import InputDataWarning
+        assert top_level is fit_gpytorch_mll and issubclass(InputDataWarning, Warning)
+        with torch.no_grad():
+            raw.copy_(torch.linspace(-0.3, 0.3, 7, dtype=torch.double))
+        sd = m.state_dict()
+        m2 = SingleTaskGP(torch.rand(15, 4, dtype=torch.double), torch.rand(15, 1, dtype=torch.double),
+                          covar_module=ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=4, lengthscale_constraint=Interval(0.005, 10)),
+                                                   outputscale_constraint=Interval(0.05, 10)))
+        m2.load_state_dict(sd)
+        assert torch.equal(m2.parameters()[0].detach(), raw.detach())
+        sig = lambda v: 1.0 / (1.0 + np.exp(-v))                                    # noqa: E731
+        np.testing.assert_allclose(m2.lengthscale.numpy(), 0.005 + (10 - 0.005) * sig(np.linspace(-0.3, 0.3, 7)[:4]), rtol=1e-12)
+        assert m2.outputscale == pytest.approx(0.05 + (10 - 0.05) * sig(np.linspace(-0.3, 0.3, 7)[4]), rel=1e-12)
+        assert m2.mean_const == pytest.approx(0.3)
+        with pytest.raises(KeyError):
+            SingleTaskGP(torch.rand(5, 2, dtype=torch.double), torch.rand(5, dtype=torch.double)).load_state_dict(sd)
     finally:
         shim.uninstall()
 
