@@ -120,7 +120,12 @@ class Properties:
     minimize: bool = False
 
 
-class NoiselessFormattedObjective:
+class Objective:
+    """``oao.objective.Objective``: the base the configs annotate with (``format_objective(cfg, objective: Objective)``,
+    ref/projects/swellex96_localization/conf/optimization/run.py:18,34)."""
+
+
+class NoiselessFormattedObjective(Objective):
     """Wraps an objective callable ``f(params: dict) -> float`` (boundary A) for the optimiser loop."""
 
     noiseless = True

@@ -82,7 +82,7 @@ def install(force: bool = False) -> Dict[str, bool]:
         _module("oao.space", SearchParameter=oao.SearchParameter, SearchSpace=oao.SearchSpace,
                 SearchParameterBounds=oao.SearchParameterBounds, SearchSpaceBounds=oao.SearchSpaceBounds)
         _module("oao.objective", NoiselessFormattedObjective=oao.NoiselessFormattedObjective,
-                NoisyFormattedObjective=oao.NoisyFormattedObjective, Properties=oao.Properties)
+                NoisyFormattedObjective=oao.NoisyFormattedObjective, Properties=oao.Properties, Objective=oao.Objective)
         _module("oao.optimizer", BayesianOptimization=oao.BayesianOptimization, GridSearch=oao.GridSearch,
                 QuasiRandom=oao.QuasiRandom)
         _module("oao.results", get_results=oao.get_results)
