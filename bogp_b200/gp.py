@@ -90,6 +90,18 @@ class GPPosterior:
         return (mean + (L @ z.unsqueeze(-1)).squeeze(-1)).unsqueeze(-1)
 
 
+class _KernelView:
+    def __init__(self, kind: str, lengthscale: torch.Tensor):
+        self.kind, self.lengthscale = kind, lengthscale
+
+
+class _CovarView:
+    """Read-only view of a model's kernel in GPyTorch's attribute layout (``ScaleKernel(base_kernel)``)."""
+
+    def __init__(self, kind: str, lengthscale: torch.Tensor, outputscale: torch.Tensor):
+        self.base_kernel, self.outputscale = _KernelView(kind, lengthscale), outputscale
+
+
 class SingleTaskGP:
     """Exact GP: constant mean, ``outputscale * {Matern-5/2 | RBF}`` ARD kernel, homoskedastic noise."""
 
@@ -208,6 +220,16 @@ class SingleTaskGP:
             self._raw = torch.nn.Parameter(t)
             self._raw_version = -1
         return [self._raw]
+
+    @property
+    def covar_module(self):
+        """What the reference reads from a fitted model's kernel: ``model.covar_module.base_kernel.lengthscale`` -- the
+        trust region of ``create_candidate`` is scaled by it (ref/projects/swellex96_inv/data/bo/baxus.py:116) -- and
+        ``model.covar_module.outputscale``, as tensors on the training data's device (GPyTorch shapes: ``[1, d]`` and
+        ``[]``)."""
+        self._sync_raw()
+        dev = self.train_X.device
+        return _CovarView(self.kind, self.lengthscale.to(dev).reshape(1, -1), torch.tensor(self.outputscale, dtype=DT, device=dev))
 
     def state_dict(self) -> dict:
         """The raw hyper-parameters, for the warm start of ``initialize_model(x, y, model.state_dict())``

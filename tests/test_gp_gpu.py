@@ -434,6 +434,8 @@ def test_reference_fit_loops_run_unchanged_under_the_shim():
         np.testing.assert_allclose(model.lengthscale.numpy(), fused.lengthscale.numpy(), rtol=1e-8)
         assert model.outputscale == pytest.approx(fused.outputscale, rel=1e-8) and model.noise == pytest.approx(fused.noise, rel=1e-8)
         assert candidate.shape == (1, dim) and float(value) > 0.0 and bool((candidate.abs() <= 1.0).all())
+        weights = model.covar_module.base_kernel.lengthscale.detach().view(-1)         # baxus.py:116
+        assert weights.shape == (dim,) and weights.device.type == "cuda" and bool((weights > 0).all())
         # baxus.py:304-343: explicit Matern-5/2 ARD kernel with Interval constraints, L-BFGS-B fit
         covar_module = ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=dim, lengthscale_constraint=Interval(0.005, 10)),
                                    outputscale_constraint=Interval(0.05, 10))

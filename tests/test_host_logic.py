@@ -280,6 +280,10 @@ def test_shim_exports_the_fit_protocol():
         assert m2.mean_const == pytest.approx(0.3)
         with pytest.raises(KeyError):
             SingleTaskGP(torch.rand(5, 2, dtype=torch.double), torch.rand(5, dtype=torch.double)).load_state_dict(sd)
+        # baxus.py:116: the trust region is scaled by model.covar_module.base_kernel.lengthscale
+        w = m2.covar_module.base_kernel.lengthscale.detach().view(-1)
+        assert w.shape == (4,) and torch.equal(w, m2.lengthscale) and m2.covar_module.base_kernel.lengthscale.shape == (1, 4)
+        assert float(m2.covar_module.outputscale) == pytest.approx(m2.outputscale)
     finally:
         shim.uninstall()
 
